@@ -1,0 +1,125 @@
+"""Pin the numpy oracle (oracle/beast_oracle.py) to the golden vectors produced
+by the live reference (tests/golden/make_golden.py).  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import beast_oracle as O
+from conftest import rel_err
+
+TOL = 1e-5          # north-star tolerance for coefficients / trajectories
+
+
+def _layout(cfg):
+    return O.slot_layout(cfg["num_dof"], cfg["gripper_zero_order"], cfg["gripper_indices"])
+
+
+def _offset(cfg):
+    return 0 if cfg["llm_vocab_size"] is None else cfg["llm_vocab_size"] - cfg["vocab_size"]
+
+
+def test_times_knots_basis_bit_exact(golden_case):
+    name, cfg, g = golden_case
+    times = O.linspace_f32(0.0, 2 * math.pi, cfg["seq_len"])
+    assert times.dtype == np.float32 and np.array_equal(times, g["times"])
+    assert np.array_equal(O.knot_vector(cfg["num_basis"], cfg["degree_p"]), g["knots_joint"])
+    phi = O.bspline_basis(times, 2 * math.pi, cfg["num_basis"], cfg["degree_p"])
+    assert np.array_equal(phi, g["phi_joint"])
+    if "phi_grip" in g:
+        assert np.array_equal(O.bspline_basis(times, 2 * math.pi, cfg["num_basis"], 0), g["phi_grip"])
+    joint, grip = _layout(cfg)
+    assert joint == g["joint_indices"].tolist() and grip == g["gripper_indices"].tolist()
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_fit_within_tolerance(golden_case, literal):
+    name, cfg, g = golden_case
+    if literal and name == "cli_default":
+        pytest.skip("1600x1600 literal systems: covered by the per-DoF form")
+    joint, grip = _layout(cfg)
+    w = O.compute_weights(g["trajs"], g["times"], 2 * math.pi, cfg["num_basis"], cfg["degree_p"],
+                          joint, grip, literal=literal)
+    assert w.dtype == np.float32 and w.shape == g["params"].shape
+    assert rel_err(w, g["params"]) <= TOL
+
+
+def test_quantise_bit_exact_given_reference_coefficients(golden_case):
+    """tokens are bit-exact given identical fp32 coefficients."""
+    name, cfg, g = golden_case
+    D, nb, V = cfg["num_dof"], cfg["num_basis"], cfg["vocab_size"]
+    t = O.tokens_from_params(g["params"], g["w_min_default"], g["w_max_default"], V, D, nb, _offset(cfg))
+    assert t.dtype == np.int64 and np.array_equal(t, g["tokens_default"])
+    t = O.tokens_from_params(g["params"], g["w_min_fit"], g["w_max_fit"], V, D, nb, _offset(cfg))
+    assert np.array_equal(t, g["tokens_fit"])
+    t = O.tokens_from_params(g["params"], g["w_min_fit"], g["w_max_fit"], V, D, nb, 0)
+    assert np.array_equal(t, g["tokens_fit_nooffset"])
+
+
+def test_dequantise_bit_exact(golden_case):
+    name, cfg, g = golden_case
+    D, nb, V = cfg["num_dof"], cfg["num_basis"], cfg["vocab_size"]
+    c = O.decode(g["tokens_fit"], g["w_min_fit"], g["w_max_fit"], V, D, nb, _offset(cfg))
+    assert c.dtype == np.float32 and np.array_equal(c, g["decode_fit"])
+
+
+def test_reconstruct_within_tolerance(golden_case):
+    name, cfg, g = golden_case
+    joint, grip = _layout(cfg)
+    args = (2 * math.pi, cfg["num_basis"], cfg["degree_p"], joint, grip, g["w_min_fit"], g["w_max_fit"],
+            cfg["vocab_size"], _offset(cfg))
+    r = O.reconstruct_traj(g["tokens_fit"], g["times"], *args)
+    assert rel_err(r, g["recon_fit"]) <= TOL
+    r = O.reconstruct_traj(g["tokens_fit"], g["times"], *args, init_p=g["init_p"])
+    assert rel_err(r, g["recon_fit_initp"]) <= TOL
+    if "custom_times" in g:
+        r = O.reconstruct_traj(g["tokens_fit"], g["custom_times"], *args)
+        assert r.shape == g["recon_fit_custom_times"].shape
+        assert rel_err(r, g["recon_fit_custom_times"]) <= TOL
+    # default +-0.02 bounds
+    r = O.reconstruct_traj(g["tokens_default"], g["times"], 2 * math.pi, cfg["num_basis"], cfg["degree_p"],
+                           joint, grip, g["w_min_default"], g["w_max_default"], cfg["vocab_size"], _offset(cfg))
+    assert rel_err(r, g["recon_default"]) <= TOL
+
+
+def test_bounds(golden_case):
+    name, cfg, g = golden_case
+    # min/max and the hysteresis expansion are exact given the reference coefficients
+    lo, hi = O.bounds_minmax(g["params"])
+    assert np.array_equal(lo, g["w_min_minmax"]) and np.array_equal(hi, g["w_max_minmax"])
+    joint, grip = _layout(cfg)
+    w_ub = O.compute_weights(g["trajs_ub"], g["times"], 2 * math.pi, cfg["num_basis"], cfg["degree_p"], joint, grip)
+    lo2, hi2 = O.bounds_expand(w_ub, lo, hi)
+    assert rel_err(lo2, g["w_min_expand"]) <= TOL and rel_err(hi2, g["w_max_expand"]) <= TOL
+    # same entries were replaced
+    assert np.array_equal(lo2 != lo, g["w_min_expand"] != g["w_min_minmax"])
+    assert np.array_equal(hi2 != hi, g["w_max_expand"] != g["w_max_minmax"])
+
+
+def test_fit_parameters_quantile(golden_case):
+    name, cfg, g = golden_case
+    from beast_tokenizer_b200.synth import SyntheticLoader
+    joint, grip = _layout(cfg)
+    ws = []
+    for b in SyntheticLoader(int(g["fit_batches"]), 32, cfg["seq_len"], cfg["num_dof"], seed0=int(g["fit_seed0"])):
+        ws.append(O.compute_weights(b["actions"].numpy(), g["times"], 2 * math.pi, cfg["num_basis"],
+                                    cfg["degree_p"], joint, grip))
+    lo, hi = O.bounds_quantile(np.concatenate(ws, 0))
+    assert rel_err(lo, g["w_min_fit"]) <= TOL and rel_err(hi, g["w_max_fit"]) <= TOL
+
+
+def test_continuous_tokens(golden_case):
+    name, cfg, g = golden_case
+    D, nb = cfg["num_dof"], cfg["num_basis"]
+    n = O.normalize_tensor(g["params"], g["w_min_fit"], g["w_max_fit"])
+    n = n.reshape(-1, D, nb).transpose(0, 2, 1).reshape(-1, nb * D)
+    assert np.array_equal(n, g["cont_tokens_fit"])
+    assert int(g["recon_cont_raises"]) == 1      # upstream bug recorded (beast/utils.py:42)
+
+
+def test_llm_offset_helpers():
+    g = dict(np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "cfg2_d14.npz")))
+    off = 32000 - 256
+    assert np.array_equal(g["tokens_fit_nooffset"] + off, g["tokens_fit"])
+    assert np.array_equal(g["llm_tokens"], g["tokens_fit"])
+    assert np.array_equal(g["mp_tokens_3d"].reshape(g["tokens_fit"].shape[0], -1), g["tokens_fit_nooffset"])
