@@ -1,0 +1,145 @@
+// Shared device helpers for libbeast_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "beast_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define BEAST_HOST 1
+#endif
+
+#define BEAST_MAX_SLOTS BEAST_MAX_DOF
+
+namespace beast {
+
+// ---------------------------------------------------------------- plan
+struct Plan {
+    int T, D, nb, n_joint, degree_p, V;
+    float tau;
+    int slot_to_dof[BEAST_MAX_SLOTS];
+    // host copies
+    float* proj_joint_h;   // [nb*T]  [k][t]
+    float* proj_grip_h;    // [nb*T] or nullptr
+    float* phi_joint_h;    // [T*nb]  [t][k]
+    float* phi_grip_h;
+    // device copies (one allocation)
+    float* dev_block;
+    float* proj_joint_d;
+    float* proj_grip_d;
+    float* phi_joint_d;
+    float* phi_grip_d;
+    float* knots_joint_d;  // [nb+degree_p+1]
+    float* knots_grip_d;   // [nb+1]
+    int* slot_to_dof_d;
+    int num_sms;
+    int max_smem_optin;
+};
+
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+// ---------------------------------------------------------------- quantiser (bit-exact contract)
+// beast/beast_bspline_tokenizer.py:419 (clamp) + beast/utils.py:12-16: every step is one
+// separately rounded IEEE fp32 operation; the _rn intrinsics are never contracted into FMAs.
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+    // torch.clamp(x, lo, hi) == min(max(x, lo), hi)
+    return fminf(fmaxf(x, lo), hi);
+}
+
+__device__ __forceinline__ float quant_scale(float w_min, float w_max) {
+    return fmaxf(__fsub_rn(w_max, w_min), 1e-8f);               // utils.py:12
+}
+
+__device__ __forceinline__ long long quantize_one(float w, float w_min, float w_max, float scale, float vm1) {
+    float p = clampf(w, w_min, w_max);                          // tokenizer.py:419
+    float n = __fdiv_rn(__fsub_rn(p, w_min), scale);            // utils.py:13 (true division)
+    n = clampf(n, 0.0f, 1.0f);                                  // utils.py:14
+    return (long long)rintf(__fmul_rn(n, vm1));                 // utils.py:16 (half-to-even)
+}
+
+// beast/utils.py:23-25: float(tok)/(V-1), mul, add (two roundings), clamp.
+__device__ __forceinline__ float dequantize_one(long long tok, float w_min, float w_max, float vm1) {
+    float n = __fdiv_rn(__ll2float_rn(tok), vm1);
+    float c = __fadd_rn(__fmul_rn(n, __fsub_rn(w_max, w_min)), w_min);
+    return clampf(c, w_min, w_max);
+}
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();            // ~2 s at 2 GHz
+    }
+}
+// global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (before a bulk store)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace beast
+
+#define BEAST_CHECK_LAUNCH()                     \
+    do {                                         \
+        cudaError_t e__ = cudaGetLastError();    \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)

@@ -1,0 +1,84 @@
+// Plan: immutable per-tokenizer constants (geometry, projector / basis tables) on host and device.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "common.cuh"
+
+namespace beast {
+long long g_launch_count = 0;
+}
+using beast::Plan;
+
+static float* dup_h(const float* src, size_t n) {
+    if (!src) return nullptr;
+    float* p = (float*)malloc(n * sizeof(float));
+    if (p) memcpy(p, src, n * sizeof(float));
+    return p;
+}
+
+extern "C" const char* beast_version(void) { return "beast_b200 0.1 sm_100a"; }
+extern "C" int64_t beast_launch_count(void) { return beast::g_launch_count; }
+
+extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out) {
+    if (!d || !out) return BEAST_E_NULL;
+    *out = nullptr;
+    if (d->seq_len < 1 || d->num_basis < 1 || d->num_dof < 1 || d->num_dof > BEAST_MAX_DOF) return BEAST_E_SHAPE;
+    if (d->n_joint < 0 || d->n_joint > d->num_dof || d->vocab_size < 2 || d->degree_p < 0) return BEAST_E_SHAPE;
+    if (!d->slot_to_dof_h || !d->proj_joint_h || !d->phi_joint_h || !d->knots_joint_h) return BEAST_E_NULL;
+    const bool has_grip = d->n_joint < d->num_dof;
+    if (has_grip && (!d->proj_grip_h || !d->phi_grip_h || !d->knots_grip_h)) return BEAST_E_NULL;
+    for (int i = 0; i < d->num_dof; ++i)
+        if (d->slot_to_dof_h[i] < 0 || d->slot_to_dof_h[i] >= d->num_dof) return BEAST_E_SHAPE;
+
+    Plan* p = new (std::nothrow) Plan();
+    if (!p) return BEAST_E_NOMEM;
+    memset(p, 0, sizeof(Plan));
+    p->T = d->seq_len; p->D = d->num_dof; p->nb = d->num_basis; p->n_joint = d->n_joint;
+    p->degree_p = d->degree_p; p->V = d->vocab_size; p->tau = d->tau;
+    for (int i = 0; i < p->D; ++i) p->slot_to_dof[i] = d->slot_to_dof_h[i];
+    const size_t nt = (size_t)p->nb * p->T;
+    const size_t nkj = (size_t)p->nb + p->degree_p + 1, nkg = (size_t)p->nb + 1;
+    p->proj_joint_h = dup_h(d->proj_joint_h, nt);
+    p->phi_joint_h = dup_h(d->phi_joint_h, nt);
+    p->proj_grip_h = has_grip ? dup_h(d->proj_grip_h, nt) : nullptr;
+    p->phi_grip_h = has_grip ? dup_h(d->phi_grip_h, nt) : nullptr;
+
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // one device block: 4 tables + 2 knot vectors + slot map (all 4-byte elements)
+    const size_t total = 4 * nt + nkj + nkg + BEAST_MAX_SLOTS;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->dev_block, total * sizeof(float));
+    if (e != cudaSuccess) { beast_plan_destroy((beast_plan_t*)p); return (int)e; }
+    float* host = (float*)calloc(total, sizeof(float));
+    if (!host) { beast_plan_destroy((beast_plan_t*)p); return BEAST_E_NOMEM; }
+    size_t off = 0;
+    auto put = [&](const float* src, size_t n, float** dptr) {
+        if (src) memcpy(host + off, src, n * sizeof(float));
+        *dptr = p->dev_block + off;
+        off += n;
+    };
+    put(d->proj_joint_h, nt, &p->proj_joint_d);
+    put(has_grip ? d->proj_grip_h : nullptr, nt, &p->proj_grip_d);
+    put(d->phi_joint_h, nt, &p->phi_joint_d);
+    put(has_grip ? d->phi_grip_h : nullptr, nt, &p->phi_grip_d);
+    put(d->knots_joint_h, nkj, &p->knots_joint_d);
+    put(has_grip ? d->knots_grip_h : nullptr, nkg, &p->knots_grip_d);
+    memcpy(host + off, p->slot_to_dof, BEAST_MAX_SLOTS * sizeof(int));
+    p->slot_to_dof_d = (int*)(p->dev_block + off);
+    e = cudaMemcpy(p->dev_block, host, total * sizeof(float), cudaMemcpyHostToDevice);
+    free(host);
+    if (e != cudaSuccess) { beast_plan_destroy((beast_plan_t*)p); return (int)e; }
+    *out = (beast_plan_t*)p;
+    return BEAST_OK;
+}
+
+extern "C" int beast_plan_destroy(beast_plan_t* plan) {
+    if (!plan) return BEAST_OK;
+    Plan* p = (Plan*)plan;
+    free(p->proj_joint_h); free(p->proj_grip_h); free(p->phi_joint_h); free(p->phi_grip_h);
+    if (p->dev_block) cudaFree(p->dev_block);
+    delete p;
+    return BEAST_OK;
+}

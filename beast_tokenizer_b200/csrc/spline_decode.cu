@@ -1,0 +1,388 @@
+// K3 — fused dequantise + B-spline evaluation  (replaces decode, beast/beast_bspline_tokenizer.py:483-496,
+// reconstruct_traj :498-536 and UniformBSpline.get_traj_pos, mp/uni_bspline.py:114-177).
+//
+//   c[slot, k] = clamp(float(tok - offset)/(V-1) * (w_max - w_min) + w_min)       (beast/utils.py:20-26)
+//   c[joint slot, 0] = init_p[dof]                       when init_p is given     (:505-510)
+//   pos[t, dof(slot)] = sum_k Phi[t, k] * c[slot, k]                              (uni_bspline.py:165)
+//
+// Fast kernel (seq_len = 50, num_basis = 10, tokenizer's own times): the mirror image of K1 —
+// persistent CTAs, bulk-TMA ring for the int64 token tiles (+ init_p), one thread per
+// (trajectory, slot) column, Phi from the constant bank, [t][dof] rows staged in shared memory
+// and written back with bulk stores.
+// Generic kernel: any geometry, optional caller-supplied times [B, Tq] with the basis evaluated
+// in-kernel by the Cox-de Boor recursion in the reference's fp32 operation order
+// (basis_gn/uni_bspline_basis.py:82-113, phase_gn/linear_phase.py:22-23).
+#include <cstdlib>
+#include "common.cuh"
+
+namespace beast {
+
+constexpr int kDecComputeWarps = 7;
+constexpr int kDecComputeThreads = kDecComputeWarps * 32;
+constexpr int kDecThreads = kDecComputeThreads + 32;
+constexpr int kMaxEvalKnots = 320;       // generic path: num_basis + degree_p <= 319
+
+template <int T, int NB>
+struct alignas(16) DecTables {
+    static constexpr int NBP = (NB + 3) & ~3;
+    float fj[T * NBP];   // Phi_joint [t][k], k padded
+    float fg[T * NBP];
+};
+
+struct DecArgs {
+    const long long* tokens;
+    const float* init_p;
+    float* out;
+    const float* w_min;
+    const float* w_max;
+    long long offset;
+    float vm1;
+    int D, n_joint, S, n_tiles;
+    int slot_to_dof[BEAST_MAX_SLOTS];
+};
+
+__host__ __device__ inline uint32_t dec_round_up_128(uint32_t x) { return (x + 127u) & ~127u; }
+
+template <int T, int NB, bool GRIP>
+__device__ __forceinline__ void eval_column(const DecTables<T, NB>& tab, const float (&c)[NB], float* __restrict__ o,
+                                            int D) {
+    constexpr int NBP = DecTables<T, NB>::NBP;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc = fmaf(GRIP ? tab.fg[t * NBP + k] : tab.fj[t * NBP + k], c[k], acc);
+        o[t * D] = acc;
+    }
+}
+
+template <int T, int NB, int NS, int DT>
+__global__ void __launch_bounds__(kDecThreads, 1)
+decode_fast_kernel(const __grid_constant__ DecTables<T, NB> tab, const __grid_constant__ DecArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int D = DT ? DT : a.D;
+    const int S = a.S;
+    const bool has_init = a.init_p != nullptr;
+    const uint32_t tok_bytes = (uint32_t)S * NB * D * 8u;
+    const uint32_t ini_bytes = (uint32_t)S * D * 4u;
+    const uint32_t tok_stride = dec_round_up_128(tok_bytes);
+    const uint32_t in_stride = tok_stride + dec_round_up_128(ini_bytes);
+    const uint32_t out_bytes = (uint32_t)S * T * D * 4u;
+    const uint32_t out_stride = dec_round_up_128(out_bytes);
+    unsigned char* out_base = smem + NS * in_stride;
+    uint64_t* bars = (uint64_t*)(out_base + 2 * out_stride);
+    uint64_t* in_full = bars;
+    uint64_t* in_empty = bars + NS;
+    uint64_t* out_full = bars + 2 * NS;
+    uint64_t* out_empty = bars + 2 * NS + 2;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], kDecComputeWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], kDecComputeWarps); mbar_init(&out_empty[s], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int first = blockIdx.x, step = gridDim.x;
+    const int n_my = first < a.n_tiles ? (a.n_tiles - first + step - 1) / step : 0;
+    const size_t tile_tok = (size_t)S * NB * D, tile_ini = (size_t)S * D, tile_out = (size_t)S * T * D;
+    const uint32_t load_bytes = tok_bytes + (has_init ? ini_bytes : 0u);
+
+    if (warp == kDecComputeWarps) {
+        if (lane == 0) {
+            auto load = [&](int j) {
+                const int s = j % NS;
+                const size_t tile = (size_t)first + (size_t)j * step;
+                mbar_arrive_expect_tx(&in_full[s], load_bytes);
+                bulk_g2s(smem + s * in_stride, a.tokens + tile * tile_tok, tok_bytes, &in_full[s]);
+                if (has_init)
+                    bulk_g2s(smem + s * in_stride + tok_stride, a.init_p + tile * tile_ini, ini_bytes, &in_full[s]);
+            };
+            int issued = 0;
+            for (; issued < NS && issued < n_my; ++issued) load(issued);
+            for (int i = 0; i < n_my; ++i) {
+                const int ob = i & 1;
+                const size_t tile = (size_t)first + (size_t)i * step;
+                mbar_wait(&out_full[ob], (i >> 1) & 1);
+                bulk_s2g(a.out + tile * tile_out, out_base + ob * out_stride, out_bytes);
+                bulk_commit();
+                if (issued < n_my) {
+                    mbar_wait(&in_empty[issued % NS], ((issued / NS) - 1) & 1);
+                    load(issued);
+                    ++issued;
+                }
+                bulk_wait_read<1>();
+                if (i >= 1) mbar_arrive(&out_empty[(i - 1) & 1]);
+            }
+            bulk_wait_all<0>();
+        }
+        return;
+    }
+
+    const int nj = a.n_joint, ng = D - nj;
+    const bool active = tid < S * D;
+    int tl = 0, slot = 0;
+    if (active) {
+        if (tid < S * nj) { tl = tid / nj; slot = tid - tl * nj; }
+        else { const int c = tid - S * nj; tl = c / ng; slot = nj + (c - tl * ng); }
+    }
+    const int dof = a.slot_to_dof[slot];
+    float wmin[NB], wmax[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { wmin[k] = a.w_min[slot * NB + k]; wmax[k] = a.w_max[slot * NB + k]; }
+
+    for (int i = 0; i < n_my; ++i) {
+        const int s = i % NS;
+        mbar_wait(&in_full[s], (i / NS) & 1);
+        float c[NB];
+        if (active) {
+            const long long* tk = (const long long*)(smem + s * in_stride) + tl * (NB * D) + slot;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) c[k] = dequantize_one(tk[k * D] - a.offset, wmin[k], wmax[k], a.vm1);
+            if (has_init && slot < nj) c[0] = ((const float*)(smem + s * in_stride + tok_stride))[tl * D + dof];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&in_empty[s]);
+
+        const int ob = i & 1;
+        if (i >= 2) mbar_wait(&out_empty[ob], ((i >> 1) - 1) & 1);
+        if (active) {
+            float* o = (float*)(out_base + ob * out_stride) + tl * (T * D) + dof;
+            if (slot < nj) eval_column<T, NB, false>(tab, c, o, D);
+            else eval_column<T, NB, true>(tab, c, o, D);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full[ob]);
+    }
+}
+
+// Cox-de Boor on the knot vector `kn` (nb + p + 1 knots): N[0..nb) <- basis values at phase u.
+// Level 0 exactly as uni_bspline_basis.py:94-104 (basis nb-1 closed on the right); higher levels
+// as :106-113, terms with a zero denominator dropped.  In place, ascending i.
+__device__ inline void deboor_basis(const float* __restrict__ kn, int nb, int p, float u, float* N) {
+    const int n0 = nb + p;
+    for (int i = 0; i < n0; ++i) {
+        const bool in = (u >= kn[i]) && (i == nb - 1 ? (u <= kn[i + 1]) : (u < kn[i + 1]));
+        N[i] = in ? 1.0f : 0.0f;
+    }
+    for (int k = 1; k <= p; ++k) {
+        for (int i = 0; i < n0 - k; ++i) {
+            const float d1 = __fsub_rn(kn[i + k], kn[i]);
+            const float d2 = __fsub_rn(kn[i + k + 1], kn[i + 1]);
+            const bool h1 = d1 != 0.0f, h2 = d2 != 0.0f;
+            const float t1 = h1 ? __fmul_rn(__fdiv_rn(__fsub_rn(u, kn[i]), d1), N[i]) : 0.0f;
+            const float t2 = h2 ? __fmul_rn(__fdiv_rn(__fsub_rn(kn[i + k + 1], u), d2), N[i + 1]) : 0.0f;
+            N[i] = (h1 && h2) ? __fadd_rn(t1, t2) : (h1 ? t1 : t2);
+        }
+    }
+}
+
+// One thread per (trajectory, time sample): basis row from the plan's table or evaluated in-kernel,
+// then every slot.  FROM_TOKENS: coefficients dequantised on the fly; else read from `params`.
+template <bool FROM_TOKENS>
+__global__ void __launch_bounds__(128)
+decode_generic_kernel(const long long* __restrict__ tokens, const float* __restrict__ params, long long n_rows,
+                      int Tq, int D, int nb, int n_joint, int degree_p, const int* __restrict__ slot_to_dof,
+                      const float* __restrict__ phi_j, const float* __restrict__ phi_g,
+                      const float* __restrict__ times, const float* __restrict__ knots_j,
+                      const float* __restrict__ knots_g, float tau, const float* __restrict__ w_min,
+                      const float* __restrict__ w_max, float vm1, long long offset,
+                      const float* __restrict__ init_p, float* __restrict__ out) {
+    float Nj[kMaxEvalKnots];
+    float Ng[kMaxEvalKnots];
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_rows;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / Tq;
+        const int t = (int)(idx - b * Tq);
+        const float* rj;
+        const float* rg;
+        if (times) {
+            // linear_phase.py:22-23 with delay = 0: clip(t / tau, 0, 1)
+            const float u = clampf(__fdiv_rn(__fsub_rn(times[idx], 0.0f), tau), 0.0f, 1.0f);
+            deboor_basis(knots_j, nb, degree_p, u, Nj);
+            rj = Nj;
+            if (n_joint < D) deboor_basis(knots_g, nb, 0, u, Ng);
+            rg = Ng;
+        } else {
+            rj = phi_j + (long long)t * nb;
+            rg = phi_g + (long long)t * nb;
+        }
+        const long long row = (long long)D * nb;
+        for (int slot = 0; slot < D; ++slot) {
+            const int dof = slot_to_dof[slot];
+            const float* r = slot < n_joint ? rj : rg;
+            float acc = 0.0f;
+            for (int k = 0; k < nb; ++k) {
+                float c;
+                if (FROM_TOKENS) {
+                    const int j = slot * nb + k;
+                    c = dequantize_one(tokens[b * row + (long long)k * D + slot] - offset, w_min[j], w_max[j], vm1);
+                } else {
+                    c = params[b * row + (long long)slot * nb + k];
+                }
+                if (k == 0 && init_p && slot < n_joint) c = init_p[b * D + dof];
+                acc = fmaf(r[k], c, acc);
+            }
+            out[idx * D + dof] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dequantize_kernel(const long long* __restrict__ tokens, long long n, int D, int nb, const float* __restrict__ w_min,
+                  const float* __restrict__ w_max, float vm1, long long offset, float* __restrict__ params_out) {
+    const int row = D * nb;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / row;
+        const int c = (int)(idx - b * row);          // output position slot*nb + k
+        const int slot = c / nb, k = c - slot * nb;
+        params_out[idx] = dequantize_one(tokens[b * row + (long long)k * D + slot] - offset, w_min[c], w_max[c], vm1);
+    }
+}
+
+static bool dec_fast_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BEAST_B200_DISABLE_FAST"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+static inline bool dec_aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+static int dec_grid_for(long long n, int block, int num_sms) {
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)num_sms * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <int T, int NB, int NS, int DT>
+static int launch_dec_fast(const Plan* p, const long long* tokens, long long n_tiles, int S, const float* w_min,
+                           const float* w_max, long long offset, const float* init_p, float* out,
+                           cudaStream_t st) {
+    DecTables<T, NB> tab;
+    constexpr int NBP = DecTables<T, NB>::NBP;
+    for (int t = 0; t < T; ++t)
+        for (int k = 0; k < NBP; ++k) {
+            tab.fj[t * NBP + k] = k < NB ? p->phi_joint_h[t * NB + k] : 0.0f;
+            tab.fg[t * NBP + k] = (k < NB && p->phi_grip_h) ? p->phi_grip_h[t * NB + k] : 0.0f;
+        }
+    DecArgs a;
+    a.tokens = tokens; a.init_p = init_p; a.out = out; a.w_min = w_min; a.w_max = w_max;
+    a.offset = offset; a.vm1 = (float)(p->V - 1);
+    a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
+    for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
+    const uint32_t in_stride = dec_round_up_128((uint32_t)S * NB * p->D * 8u) + dec_round_up_128((uint32_t)S * p->D * 4u);
+    const uint32_t out_stride = dec_round_up_128((uint32_t)S * T * p->D * 4u);
+    const size_t smem = (size_t)NS * in_stride + 2 * (size_t)out_stride + (2 * NS + 4) * sizeof(uint64_t);
+    if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<T, NB, NS, DT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
+    decode_fast_kernel<T, NB, NS, DT><<<grid, kDecThreads, smem, st>>>(tab, a);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+static int launch_generic(const Plan* p, const long long* tokens, const float* params, long long B, int Tq,
+                          const float* times, const float* w_min, const float* w_max, long long offset,
+                          const float* init_p, float* out, cudaStream_t st) {
+    if (times && p->nb + p->degree_p + 1 > kMaxEvalKnots) return BEAST_E_UNSUPPORTED;
+    const long long n_rows = B * Tq;
+    const int grid = dec_grid_for(n_rows, 128, p->num_sms);
+    if (tokens)
+        decode_generic_kernel<true><<<grid, 128, 0, st>>>(tokens, nullptr, n_rows, Tq, p->D, p->nb, p->n_joint,
+                                                          p->degree_p, p->slot_to_dof_d, p->phi_joint_d, p->phi_grip_d,
+                                                          times, p->knots_joint_d, p->knots_grip_d, p->tau, w_min,
+                                                          w_max, (float)(p->V - 1), offset, init_p, out);
+    else
+        decode_generic_kernel<false><<<grid, 128, 0, st>>>(nullptr, params, n_rows, Tq, p->D, p->nb, p->n_joint,
+                                                           p->degree_p, p->slot_to_dof_d, p->phi_joint_d,
+                                                           p->phi_grip_d, times, p->knots_joint_d, p->knots_grip_d,
+                                                           p->tau, nullptr, nullptr, 0.0f, 0, init_p, out);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+}  // namespace beast
+
+using namespace beast;
+
+extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B, const float* w_min,
+                                const float* w_max, int64_t offset, const float* init_p, float* traj_out,
+                                void* stream) {
+    const Plan* p = (const Plan*)plan;
+    if (!p || !w_min || !w_max || (B > 0 && (!tokens || !traj_out))) return BEAST_E_NULL;
+    if (B < 0) return BEAST_E_SHAPE;
+    if (B == 0) return BEAST_OK;
+    if (((uintptr_t)tokens & 7u) || ((uintptr_t)traj_out & 3u) || ((uintptr_t)init_p & 3u)) return BEAST_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = p->T, D = p->D, nb = p->nb;
+    long long done = 0;
+    if (T == 50 && nb == 10 && !dec_fast_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
+        (!init_p || dec_aligned16(init_p))) {
+        const int S = (kDecComputeThreads / D) & ~3;
+        if (S >= 4 && B >= S) {
+            const long long n_tiles = B / S;
+            int rc;
+            if (D == 14)
+                rc = launch_dec_fast<50, 10, 3, 14>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
+            else if (D == 7)
+                rc = launch_dec_fast<50, 10, 3, 7>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
+            else
+                rc = launch_dec_fast<50, 10, 3, 0>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
+            if (rc == BEAST_OK) done = n_tiles * S;
+            else if (rc != BEAST_E_UNSUPPORTED) return rc;
+        }
+    }
+    if (done < B)
+        return launch_generic(p, (const long long*)tokens + done * (long long)D * nb, nullptr, B - done, T, nullptr,
+                              w_min, w_max, offset, init_p ? init_p + done * D : nullptr,
+                              traj_out + done * (long long)T * D, st);
+    return BEAST_OK;
+}
+
+extern "C" int beast_decode_times_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B,
+                                      const float* w_min, const float* w_max, int64_t offset, const float* init_p,
+                                      const float* times, int32_t Tq, float* traj_out, void* stream) {
+    const Plan* p = (const Plan*)plan;
+    if (!p || !w_min || !w_max || (B > 0 && (!tokens || !traj_out || !times))) return BEAST_E_NULL;
+    if (B < 0 || Tq < 0) return BEAST_E_SHAPE;
+    if (B == 0 || Tq == 0) return BEAST_OK;
+    return launch_generic(p, (const long long*)tokens, nullptr, B, Tq, times, w_min, w_max, offset, init_p, traj_out,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int beast_eval_f32(const beast_plan_t* plan, const float* params, int64_t B, const float* init_p,
+                              const float* times, int32_t Tq, float* traj_out, void* stream) {
+    const Plan* p = (const Plan*)plan;
+    if (!p || (B > 0 && (!params || !traj_out))) return BEAST_E_NULL;
+    if (B < 0 || Tq < 0) return BEAST_E_SHAPE;
+    if (B == 0) return BEAST_OK;
+    const int tq = times ? Tq : p->T;
+    if (tq == 0) return BEAST_OK;
+    return launch_generic(p, nullptr, params, B, tq, times, nullptr, nullptr, 0, init_p, traj_out,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int beast_dequantize_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B, const float* w_min,
+                                    const float* w_max, int64_t offset, float* params_out, void* stream) {
+    const Plan* p = (const Plan*)plan;
+    if (!p || !w_min || !w_max || (B > 0 && (!tokens || !params_out))) return BEAST_E_NULL;
+    if (B < 0) return BEAST_E_SHAPE;
+    if (B == 0) return BEAST_OK;
+    const long long n = (long long)B * p->D * p->nb;
+    dequantize_kernel<<<dec_grid_for(n, 256, p->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)tokens, n, p->D, p->nb, w_min, w_max, (float)(p->V - 1), offset, params_out);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}

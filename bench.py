@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — BEAST tokenizer hot path on B200: trajectories/s, encode + decode.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload = BASELINE.json configs[1]: bimanual tokenizer (num_dof=14, num_basis=10, seq_len=50,
+vocab 256, grippers [6, 13] zero-order, llm_vocab_size=32000), batch 65 536 per GPU, synthetic
+trajectories.  One step = encode (K1) of one batch + reconstruct_traj (K3) of one batch of tokens.
+
+  value   device-resident throughput: inputs already in HBM, C-ABI calls on preallocated buffers,
+          timed with CUDA events on the launching stream, max over ranks.
+  e2e     the same step through the public Python API from pinned HOST memory: H2D of the
+          trajectories, both kernels, D2H of tokens and reconstructed trajectories inside the
+          timed region.
+  roofline  per-launch CUDA-event duration of the dominant kernel (encode) against the measured
+          HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the oracle's literal port of the reference algorithm on the host cores (rank 0, N=1).
+
+`--impl reference` times that CPU port alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 65536
+T, D, NB, V = 50, 14, 10, 256
+GRIP = [6, 13]
+LLM_VOCAB = 32000
+WORKLOAD = ("bimanual num_dof=14 num_basis=10 seq_len=50 vocab=256 gripper_indices=[6,13] "
+            "gripper_zero_order llm_vocab_size=32000, encode+reconstruct_traj batch 65536/GPU")
+ENC_BYTES = 4 * T * D + 8 * NB * D + 4 * NB * D       # 4480 B / trajectory
+DEC_BYTES = 8 * NB * D + 4 * T * D                    # 3920 B / trajectory
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks", 0x100: "display_clock"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+CPU_CHUNK = 2048
+
+
+def make_port():
+    """oracle/reference_port_torch.py: the reference's own sequence of torch CPU ops (basis rebuilt
+    per call, dense block-diagonal basis, one 120x120 LU per trajectory — mp/uni_bspline.py:539-586),
+    bit-identical to the live reference on the golden vectors."""
+    from oracle.reference_port_torch import ReferencePort
+    return ReferencePort(num_dof=D, num_basis=NB, seq_len=T, vocab_size=V, degree_p=4, gripper_zero_order=True,
+                         gripper_indices=GRIP, llm_vocab_size=LLM_VOCAB)
+
+
+def port_step(port, x):
+    tokens, _ = port.encode(x)
+    return port.reconstruct_traj(tokens)
+
+
+def cpu_threads():
+    import torch
+    return int(torch.get_num_threads())
+
+
+def cpu_baseline(budget_s=12.0):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1)."""
+    from beast_tokenizer_b200.synth import synth
+    port = make_port()
+    x = synth(CPU_CHUNK, T, D, seed=2)
+    port_step(port, x[:256])                     # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        port_step(port, x)
+        n += CPU_CHUNK
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return {"value": n / el, "unit": "trajectories/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"{n} trajectories in chunks of {CPU_CHUNK} (torch-CPU port of the reference's op sequence, "
+                      f"encode + reconstruct_traj), {el:.1f} s; host has {os.cpu_count()} logical cores"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (torch-CPU port) on this box's host cores."""
+    if rank != 0:
+        return
+    from beast_tokenizer_b200.synth import synth
+    port = make_port()
+    x = synth(CPU_CHUNK, T, D, seed=2)
+    for _ in range(max(1, min(args.warmup, 2))):
+        port_step(port, x[:512])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port_step(port, x)
+    el = time.perf_counter() - t0
+    n = args.steps * CPU_CHUNK
+    val = n / el
+    line = {
+        "impl": "reference", "metric": "trajectories/sec encode+decode", "value": val, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": CPU_CHUNK},
+        "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": f"{CPU_CHUNK} trajectories per step x {args.steps} steps (bounded sample of the "
+                                   f"65536-trajectory batch), torch-CPU port of the reference's op sequence; host has "
+                                   f"{os.cpu_count()} logical cores"},
+        "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer, _lib
+    from beast_tokenizer_b200.synth import SyntheticLoader, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    tok = BEASTBsplineTokenizer(num_dof=D, num_basis=NB, seq_len=T, vocab_size=V, gripper_zero_order=True,
+                                gripper_indices=GRIP, device=f"cuda:{local_rank}", llm_vocab_size=LLM_VOCAB)
+    tok.fit_parameters(SyntheticLoader(100, 32, T, D, seed0=1), verbose=False)
+    plan = tok._plan()
+    lib = plan._lib
+    lo, hi = tok._bounds(dev)
+    offset = LLM_VOCAB - V
+
+    # ---- device-resident leg: R rotating buffer sets, each larger than L2 in aggregate; the decode of a
+    # step reads tokens written two steps earlier, so no step input is L2-resident when it is read.
+    R = 4
+    xs = [synth(B, T, D, seed=2 + 1000 * rank + i, device=dev) for i in range(R)]
+    toks = [torch.empty((B, NB * D), device=dev, dtype=torch.int64) for _ in range(R)]
+    pars = [torch.empty((B, NB * D), device=dev, dtype=torch.float32) for _ in range(R)]
+    outs = [torch.empty((B, T, D), device=dev, dtype=torch.float32) for _ in range(R)]
+    stream = _lib.stream_ptr(dev)
+
+    def enc(i):
+        _lib.check(lib.beast_encode_f32(plan.handle, _lib.ptr(xs[i]), B, _lib.ptr(lo), _lib.ptr(hi), offset,
+                                        _lib.ptr(pars[i]), _lib.ptr(toks[i]), stream), "encode")
+
+    def dec(i):
+        _lib.check(lib.beast_decode_f32(plan.handle, _lib.ptr(toks[i]), B, _lib.ptr(lo), _lib.ptr(hi), offset,
+                                        None, _lib.ptr(outs[i]), stream), "decode")
+
+    for i in range(R):
+        enc(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for j in range(args.warmup):
+        enc(j % R)
+        dec((j + 2) % R)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    n0 = _lib.launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for j in range(K):
+        ev[j][0].record()
+        enc(j % R)
+        ev[j][1].record()
+        dec((j + 2) % R)
+        ev[j][2].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0
+    if world > 1:
+        dist.barrier()
+    ms_total = t_start.elapsed_time(t_end)
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+
+    # ---- end-to-end leg: public API, pinned host input, results back on the host
+    xh = [synth(B, T, D, seed=50 + 1000 * rank + i).pin_memory() for i in range(2)]
+    tok_h = torch.empty((B, NB * D), dtype=torch.int64).pin_memory()
+    rec_h = torch.empty((B, T, D), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        tokens, _ = tok.encode(xh[i % 2])
+        rec = tok.reconstruct_traj(tokens)
+        tok_h.copy_(tokens, non_blocking=True)
+        rec_h.copy_(rec, non_blocking=True)
+
+    Ke = max(3, min(K, 10))
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for i in range(Ke):
+        e2e_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - w0))
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms, enc_ms, dec_ms = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        enc_gbs = ENC_BYTES * B / (enc_ms * 1e-3) / 1e9
+        dec_gbs = DEC_BYTES * B / (dec_ms * 1e-3) / 1e9
+        line = {
+            "metric": "trajectories/sec encode+decode", "value": world * B * K / (ms_total * 1e-3),
+            "unit": "trajectories/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "parallelism": f"dp{world} (batch sharded, no collective)",
+                       "l2": f"{R} rotating buffer sets ({R * (ENC_BYTES + DEC_BYTES) * B / 1e6:.0f} MB) > 126 MB L2; "
+                             "decode reads tokens written two steps earlier"},
+            "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "trajectories/s",
+                    "h2d_bytes_per_step": 4 * T * D * B, "d2h_bytes_per_step": (8 * NB * D + 4 * T * D) * B,
+                    "steps": Ke, "ms_per_step": e2e_ms / Ke,
+                    "path": "BEASTBsplineTokenizer.encode(pinned host) -> reconstruct_traj -> tokens+trajectories to pinned host"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "encode_fast_kernel (K1)", "achieved": enc_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": enc_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": ENC_BYTES * B, "ms_per_launch": enc_ms},
+            "roofline_decode": {"bound": "hbm", "kernel": "decode_fast_kernel (K3)", "achieved": dec_gbs, "peak": peak,
+                                "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
+                                "bytes_per_launch": DEC_BYTES * B, "ms_per_launch": dec_ms},
+            "kernel_rates": {"encode_traj_per_s": B / (enc_ms * 1e-3), "decode_traj_per_s": B / (dec_ms * 1e-3)},
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                tr = json.load(open(traffic_file))
+                line["roofline"]["traffic"] = tr.get("encode_fast_kernel")
+                line["roofline_decode"]["traffic"] = tr.get("decode_fast_kernel")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

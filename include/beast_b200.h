@@ -1,0 +1,147 @@
+/*
+ * beast_b200.h — C ABI of libbeast_b200.so: the B200 (sm_100a) implementation of the
+ * BEAST tokenizer hot path.
+ *
+ * The reference (Dont4rootMe/beast_tokenizer) has no FFI layer: the path sits behind plain
+ * Python classes.  Each entry point below replaces the torch/numpy/`tokenizers` call
+ * sequence of one reference method; the Python classes in beast_tokenizer_b200/ (same names
+ * and signatures as the reference's) are the only callers.  Citations are relative to the
+ * reference tree.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = BEAST_E_* argument error, >0 = cudaError_t;
+ *   - nothing throws, nothing synchronises the device, nothing allocates device memory
+ *     except beast_plan_create (small constant tables, freed by beast_plan_destroy);
+ *   - the caller owns every buffer and passes its stream (cudaStream_t as void*);
+ *   - pointers are DEVICE pointers unless the name ends in _h;
+ *   - a plan is immutable after creation: calls on it are thread-safe per stream.
+ */
+#ifndef BEAST_B200_H
+#define BEAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEAST_MAX_DOF 64
+
+enum {
+    BEAST_OK = 0,
+    BEAST_E_NULL = -1,       /* required pointer is NULL */
+    BEAST_E_SHAPE = -2,      /* bad size / dimension */
+    BEAST_E_ALIGN = -3,      /* pointer not aligned for its element type */
+    BEAST_E_UNSUPPORTED = -4,
+    BEAST_E_NOMEM = -5
+};
+
+/* Geometry of one tokenizer (constructor arguments of BEASTBsplineTokenizer,
+ * beast/beast_bspline_tokenizer.py:47-116) plus the precomputed constant tables.
+ * All table pointers are HOST pointers, copied at plan creation.
+ *   slot_to_dof_h[num_dof] : joint_indices followed by gripper_indices (:56-70, :351-358)
+ *   proj_joint_h [num_basis*seq_len] row-major [k][t] : P = (Phi^T Phi + 1e-9 I)^-1 Phi^T, the
+ *        closed form of the ridge solve at MP_lite_PyTorch/mp_pytorch/mp/uni_bspline.py:559-586
+ *   proj_grip_h  same for the degree-0 gripper spline (NULL when n_joint == num_dof)
+ *   phi_joint_h  [seq_len*num_basis] row-major [t][k] : basis at the tokenizer's own times
+ *        (basis_gn/uni_bspline_basis.py:59-113); phi_grip_h likewise (NULL if no grippers)
+ *   knots_joint_h [num_basis+degree_p+1], knots_grip_h [num_basis+1] : knot vectors (:48-55),
+ *        used when the caller supplies its own evaluation times. */
+typedef struct beast_plan_desc {
+    int32_t seq_len;
+    int32_t num_dof;
+    int32_t num_basis;
+    int32_t n_joint;
+    int32_t degree_p;
+    int32_t vocab_size;
+    float   tau;            /* fp32(duration): phase = clip(t / tau, 0, 1), linear_phase.py:22-23 */
+    const int32_t* slot_to_dof_h;
+    const float* proj_joint_h;
+    const float* proj_grip_h;
+    const float* phi_joint_h;
+    const float* phi_grip_h;
+    const float* knots_joint_h;
+    const float* knots_grip_h;
+} beast_plan_desc_t;
+
+typedef struct beast_plan beast_plan_t;
+
+int beast_plan_create(const beast_plan_desc_t* desc, beast_plan_t** plan_out);
+int beast_plan_destroy(beast_plan_t* plan);
+
+/* Library / build information: "beast_b200 <version> sm_100a". */
+const char* beast_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t beast_launch_count(void);
+
+/* ---- K1: fused fit + quantise.  Replaces BEASTBsplineTokenizer.encode
+ * (beast/beast_bspline_tokenizer.py:399-428) and compute_weights (:344-360):
+ *   traj   [B, seq_len, num_dof] fp32
+ *   params_out [B, num_dof*num_basis] fp32, UNclamped, '(d t)' slot layout     (nullable)
+ *   tokens_out [B, num_basis*num_dof] int64, '(t d)' layout, + offset           (nullable)
+ *   w_min / w_max [num_dof*num_basis] fp32 ('(d t)'); required when tokens_out != NULL
+ *   offset = llm_vocab_size - vocab_size or 0 (:424-426). */
+int beast_encode_f32(const beast_plan_t* plan, const float* traj, int64_t B,
+                     const float* w_min, const float* w_max, int64_t offset,
+                     float* params_out, int64_t* tokens_out, void* stream);
+
+/* Quantise given coefficients (the bit-exact contract of beast/utils.py:4-17 applied as in
+ * beast_bspline_tokenizer.py:419-426): params [B, D*nb] '(d t)' -> tokens [B, nb*D] '(t d)'. */
+int beast_quantize_f32(const beast_plan_t* plan, const float* params, int64_t B,
+                       const float* w_min, const float* w_max, int64_t offset,
+                       int64_t* tokens_out, void* stream);
+
+/* encode_continuous (:430-450, utils.py:29-35): params -> normalised [-1,1] '(t d)' fp32. */
+int beast_normalize_f32(const beast_plan_t* plan, const float* params, int64_t B,
+                        const float* w_min, const float* w_max, float* out, void* stream);
+
+/* ---- K3: fused dequantise + spline evaluation.  Replaces decode (:483-496) +
+ * reconstruct_traj (:498-536) + UniformBSpline.get_traj_pos (mp/uni_bspline.py:114-177):
+ *   tokens [B, nb*D] int64 '(t d)';  init_p [B, num_dof] fp32 or NULL (first control point
+ *   of every JOINT slot := init_p[:, dof], :505-510);  traj_out [B, seq_len, num_dof] fp32. */
+int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B,
+                     const float* w_min, const float* w_max, int64_t offset,
+                     const float* init_p, float* traj_out, void* stream);
+
+/* Same with caller-supplied evaluation times [B, Tq] (reconstruct_traj(times=...)):
+ * the basis is evaluated in-kernel (Cox-de Boor, same fp32 op order).  traj_out [B, Tq, num_dof]. */
+int beast_decode_times_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B,
+                           const float* w_min, const float* w_max, int64_t offset,
+                           const float* init_p, const float* times, int32_t Tq,
+                           float* traj_out, void* stream);
+
+/* decode() alone (:483-496, utils.py:20-26): tokens -> coefficients [B, D*nb] '(d t)'. */
+int beast_dequantize_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B,
+                         const float* w_min, const float* w_max, int64_t offset,
+                         float* params_out, void* stream);
+
+/* Evaluate given coefficients (reconstruct_traj_continuous after denormalise, :549-582):
+ * params [B, D*nb] '(d t)' (already de-normalised) -> traj_out. times/Tq as above or NULL/0. */
+int beast_eval_f32(const beast_plan_t* plan, const float* params, int64_t B,
+                   const float* init_p, const float* times, int32_t Tq,
+                   float* traj_out, void* stream);
+
+/* ---- K2: bounds.
+ * Column min/max of x [rows, cols] (update_weights_bounds :377-378; the reduction inside
+ * update_weights_bounds_per_batch :382-383).  accumulate != 0 folds into the existing
+ * contents of min_out / max_out (used when the rows arrive in several batches or shards). */
+int beast_minmax_f32(const float* x, int64_t rows, int32_t cols,
+                     float* min_out, float* max_out, int32_t accumulate, void* stream);
+
+/* update_weights_bounds_per_batch (:384-389): w_min[i] = bmin[i] where bmin[i] < w_min[i]-hyst,
+ * w_max[i] = bmax[i] where bmax[i] > w_max[i]+hyst. */
+int beast_bounds_expand_f32(const float* batch_min, const float* batch_max,
+                            float* w_min, float* w_max, int32_t n, float hyst, void* stream);
+
+/* Exact per-column order statistics for fit_parameters' np.quantile (:211-214):
+ * x [rows, cols]; for every column c and every j < nk writes the ks_h[j]-th smallest value
+ * (0-based) to out[j*cols + c].  scratch: at least beast_colselect_scratch_bytes() bytes. */
+int64_t beast_colselect_scratch_bytes(int64_t rows, int32_t cols, int32_t nk);
+int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
+                        const int64_t* ks_h, int32_t nk, float* out,
+                        void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEAST_B200_H */

@@ -1,0 +1,281 @@
+"""Parity of the CUDA spline path (through the C ABI) against the oracle and the golden vectors
+generated from the live reference.  Run on the B200 box:  pytest -m gpu."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden, rel_err
+from oracle import beast_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5      # north star: coefficients / trajectories within 1e-5 (normwise, SURVEY.md trap 2)
+
+
+def make_tok(cfg, g=None, bounds="fit"):
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    tok = BEASTBsplineTokenizer(device="cuda", **cfg)
+    if g is not None and bounds is not None:
+        tok.w_min.copy_(torch.from_numpy(g[f"w_min_{bounds}"]))
+        tok.w_max.copy_(torch.from_numpy(g[f"w_max_{bounds}"]))
+    return tok
+
+
+def layout(cfg):
+    return O.slot_layout(cfg["num_dof"], cfg["gripper_zero_order"], cfg["gripper_indices"])
+
+
+def offset(cfg):
+    return 0 if cfg["llm_vocab_size"] is None else cfg["llm_vocab_size"] - cfg["vocab_size"]
+
+
+def check_flips(tokens, ref_tokens, ref_params, w_min, w_max, cfg):
+    """Every token that differs from the reference's must be a +-1 bin flip whose reference
+    coefficient lies within the coefficient tolerance of a bin edge.  Returns the flip list."""
+    D, nb, V = cfg["num_dof"], cfg["num_basis"], cfg["vocab_size"]
+    diff = np.argwhere(tokens != ref_tokens)
+    scale_w = np.abs(ref_params).max()
+    flips = []
+    for b, pos in diff:
+        k, slot = divmod(int(pos), D)
+        c = slot * nb + k
+        w = float(ref_params[b, c])
+        lo, hi = float(w_min[c]), float(w_max[c])
+        assert abs(int(tokens[b, pos]) - int(ref_tokens[b, pos])) == 1, "flip larger than one bin"
+        x = (min(max(w, lo), hi) - lo) / max(hi - lo, 1e-8) * (V - 1)
+        dist_bins = abs((x - math.floor(x)) - 0.5)                 # distance to the rounding edge, in bins
+        dist_w = dist_bins * (hi - lo) / (V - 1)
+        assert dist_w <= TOL * scale_w, f"flip at {(b, pos)} is {dist_w:.3e} from a bin edge"
+        flips.append((int(b), int(pos), int(ref_tokens[b, pos]), int(tokens[b, pos]), dist_w))
+    return flips
+
+
+def test_encode_vs_golden(golden_case):
+    name, cfg, g = golden_case
+    tok = make_tok(cfg, g, "fit")
+    x = torch.from_numpy(g["trajs"])
+    tokens, pd = tok.encode(x)
+    assert tokens.dtype == torch.int64 and tokens.is_cuda and tokens.shape == g["tokens_fit"].shape
+    assert set(pd) == {"params", "init_pos", "init_vel", "end_pos", "end_vel"}
+    params = pd["params"].cpu().numpy()
+    assert params.dtype == np.float32
+    assert rel_err(params, g["params"]) <= TOL
+    flips = check_flips(tokens.cpu().numpy(), g["tokens_fit"], g["params"], g["w_min_fit"], g["w_max_fit"], cfg)
+    print(f"{name}: {len(flips)} / {tokens.numel()} bin flips vs reference: {flips[:5]}")
+    # the strict clause: tokens bit-exact given identical fp32 coefficients
+    strict = tok._quantize(torch.from_numpy(g["params"]), offset(cfg)).cpu().numpy()
+    assert np.array_equal(strict, g["tokens_fit"])
+    t2, _ = tok.encode(x, respect_llm_vocab_size=False)
+    assert np.array_equal(t2.cpu().numpy(), tokens.cpu().numpy() - offset(cfg))
+    # fused-kernel tokens == exact quantiser applied to the kernel's own coefficients
+    own = O.tokens_from_params(params, g["w_min_fit"], g["w_max_fit"], cfg["vocab_size"], cfg["num_dof"],
+                               cfg["num_basis"], offset(cfg))
+    assert np.array_equal(tokens.cpu().numpy(), own)
+
+
+def test_encode_default_bounds(golden_case):
+    name, cfg, g = golden_case
+    tok = make_tok(cfg)
+    tokens, pd = tok.encode(torch.from_numpy(g["trajs"]))
+    check_flips(tokens.cpu().numpy(), g["tokens_default"], g["params"], g["w_min_default"], g["w_max_default"], cfg)
+    strict = tok._quantize(torch.from_numpy(g["params"]), offset(cfg)).cpu().numpy()
+    assert np.array_equal(strict, g["tokens_default"])
+
+
+def test_decode_and_reconstruct_vs_golden(golden_case):
+    name, cfg, g = golden_case
+    tok = make_tok(cfg, g, "fit")
+    toks = torch.from_numpy(g["tokens_fit"])
+    coeff = tok.decode(toks).cpu().numpy()
+    assert np.array_equal(coeff, g["decode_fit"])                 # dequantiser is bit-exact
+    rec = tok.reconstruct_traj(toks)
+    assert rec.shape == g["recon_fit"].shape and rec.dtype == torch.float32
+    assert rel_err(rec.cpu().numpy(), g["recon_fit"]) <= TOL
+    rec = tok.reconstruct_traj(toks, init_p=torch.from_numpy(g["init_p"]))
+    assert rel_err(rec.cpu().numpy(), g["recon_fit_initp"]) <= TOL
+    if "custom_times" in g:
+        rec = tok.reconstruct_traj(toks, times=torch.from_numpy(g["custom_times"]))
+        assert rec.shape == g["recon_fit_custom_times"].shape
+        assert rel_err(rec.cpu().numpy(), g["recon_fit_custom_times"]) <= TOL
+    # 3-D token input and the LLM helpers
+    D, nb = cfg["num_dof"], cfg["num_basis"]
+    rec3 = tok.reconstruct_traj(toks.reshape(-1, nb, D))
+    assert rel_err(rec3.cpu().numpy(), g["recon_fit"]) <= TOL
+    with pytest.raises(ValueError):
+        tok.decode(toks.reshape(-1))
+    if cfg["llm_vocab_size"] is not None:
+        assert np.array_equal(tok.tokens_to_llm_tokens(torch.from_numpy(g["tokens_fit_nooffset"])).cpu().numpy(),
+                              g["llm_tokens"])
+        assert np.array_equal(tok.llm_tokens_to_mp_tokens(toks).cpu().numpy(), g["mp_tokens_3d"])
+        # the double subtraction of reconstruct_from_llm_tokens is reproduced (SURVEY.md trap 8)
+        assert rel_err(tok.reconstruct_from_llm_tokens(toks).cpu().numpy(), g["recon_from_llm"]) <= TOL
+
+
+def test_reconstruct_vs_oracle_default_bounds(golden_case):
+    name, cfg, g = golden_case
+    tok = make_tok(cfg)
+    rec = tok.reconstruct_traj(torch.from_numpy(g["tokens_default"])).cpu().numpy()
+    assert rel_err(rec, g["recon_default"]) <= TOL
+    joint, grip = layout(cfg)
+    ora = O.reconstruct_traj(g["tokens_default"], g["times"], 2 * math.pi, cfg["num_basis"], cfg["degree_p"], joint,
+                             grip, g["w_min_default"], g["w_max_default"], cfg["vocab_size"], offset(cfg))
+    assert rel_err(rec, ora) <= TOL
+
+
+def test_bounds_minmax_and_expand(golden_case):
+    name, cfg, g = golden_case
+    tok = make_tok(cfg)
+    x = torch.from_numpy(g["trajs"])
+    w = tok.compute_weights(x).cpu().numpy()
+    tok.update_weights_bounds(x)
+    lo, hi = O.bounds_minmax(w)
+    assert np.array_equal(tok.w_min.cpu().numpy(), lo) and np.array_equal(tok.w_max.cpu().numpy(), hi)   # exact
+    assert rel_err(lo, g["w_min_minmax"]) <= TOL and rel_err(hi, g["w_max_minmax"]) <= TOL
+    # hysteresis expansion inside encode(update_bounds=True)
+    x2 = torch.from_numpy(g["trajs_ub"])
+    w2 = tok.compute_weights(x2).cpu().numpy()
+    toks, _ = tok.encode(x2, update_bounds=True)
+    lo2, hi2 = O.bounds_expand(w2, lo, hi)
+    assert np.array_equal(tok.w_min.cpu().numpy(), lo2) and np.array_equal(tok.w_max.cpu().numpy(), hi2)
+    assert rel_err(lo2, g["w_min_expand"]) <= TOL and rel_err(hi2, g["w_max_expand"]) <= TOL
+    own = O.tokens_from_params(w2, lo2, hi2, cfg["vocab_size"], cfg["num_dof"], cfg["num_basis"], offset(cfg))
+    assert np.array_equal(toks.cpu().numpy(), own)
+    check_flips(toks.cpu().numpy(), g["tokens_ub"], O.compute_weights(
+        g["trajs_ub"], g["times"], 2 * math.pi, cfg["num_basis"], cfg["degree_p"], *layout(cfg)),
+        g["w_min_expand"], g["w_max_expand"], cfg)
+
+
+def test_fit_parameters_quantile(golden_case):
+    name, cfg, g = golden_case
+    from beast_tokenizer_b200.synth import SyntheticLoader
+    tok = make_tok(cfg)
+    loader = SyntheticLoader(int(g["fit_batches"]), 32, cfg["seq_len"], cfg["num_dof"], seed0=int(g["fit_seed0"]))
+    tok.fit_parameters(loader, verbose=False)
+    assert rel_err(tok.w_min.cpu().numpy(), g["w_min_fit"]) <= TOL
+    assert rel_err(tok.w_max.cpu().numpy(), g["w_max_fit"]) <= TOL
+    # exact order statistics: identical to numpy on the kernel's own coefficients
+    ws = torch.cat([tok.compute_weights(b["actions"]) for b in loader]).cpu().numpy()
+    assert np.array_equal(tok.w_min.cpu().numpy(), np.quantile(ws, 0.01, 0).astype(np.float32))
+    assert np.array_equal(tok.w_max.cpu().numpy(), np.quantile(ws, 0.99, 0).astype(np.float32))
+    # max_samples counts batches; errors of the reference
+    tok2 = make_tok(cfg)
+    tok2.fit_parameters(loader, max_samples=3, verbose=False)
+    assert np.array_equal(tok2.w_min.cpu().numpy(), np.quantile(ws[:96], 0.01, 0).astype(np.float32))
+    with pytest.raises(KeyError):
+        tok2.fit_parameters([{"obs": torch.zeros(1)}], verbose=False)
+    with pytest.raises(RuntimeError):
+        tok2.fit_parameters([], verbose=False)
+
+
+def test_continuous(golden_case):
+    name, cfg, g = golden_case
+    tok = make_tok(cfg, g, "fit")
+    n = tok._normalize(torch.from_numpy(g["params"])).cpu().numpy()
+    assert np.array_equal(n, g["cont_tokens_fit"])                # bit-exact given the reference coefficients
+    ct, pd = tok.encode_continuous(torch.from_numpy(g["trajs"]))
+    assert np.abs(ct.cpu().numpy() - g["cont_tokens_fit"]).max() <= 2.0 * TOL * np.abs(g["params"]).max() / \
+        max(float((g["w_max_fit"] - g["w_min_fit"]).min()), 1e-8) + 1e-6
+    rec = tok.reconstruct_traj_continuous(ct).cpu().numpy()
+    joint, grip = layout(cfg)
+    clipped = np.clip(pd["params"].cpu().numpy(), g["w_min_fit"], g["w_max_fit"])
+    ora = O.reconstruct_from_params(clipped, g["times"], 2 * math.pi, cfg["num_basis"], cfg["degree_p"], joint, grip)
+    assert np.abs(rec - ora).max() <= 1e-5 * max(np.abs(ora).max(), 1e-3) + 1e-6
+    with pytest.raises(ValueError):
+        tok.reconstruct_traj_continuous(ct[:, :-1])
+
+
+def test_fast_and_generic_paths_agree():
+    """The TMA fast path and the generic kernel accumulate in the same order: a trajectory gets
+    bit-identical coefficients and tokens wherever it sits in the batch (tile body or ragged tail)."""
+    from beast_tokenizer_b200.synth import synth
+    cfg = GOLDEN_CASES["cfg2_d14"]
+    g = load_golden("cfg2_d14")
+    tok = make_tok(cfg, g, "fit")
+    B = 16 * 37 + 11
+    x = synth(B, 50, 14, seed=77).cuda()
+    t1, p1 = tok.encode(x)
+    shift = 11
+    xr = torch.roll(x, shifts=shift, dims=0)
+    t2, p2 = tok.encode(xr)
+    assert torch.equal(torch.roll(t2, -shift, 0), t1)
+    assert torch.equal(torch.roll(p2["params"], -shift, 0), p1["params"])
+    r1 = tok.reconstruct_traj(t1)
+    r2 = tok.reconstruct_traj(torch.roll(t1, shift, 0))
+    assert torch.equal(torch.roll(r2, -shift, 0), r1)
+    ip = x[:, 0, :].contiguous()
+    r1 = tok.reconstruct_traj(t1, init_p=ip)
+    r2 = tok.reconstruct_traj(torch.roll(t1, shift, 0), init_p=torch.roll(ip, shift, 0))
+    assert torch.equal(torch.roll(r2, -shift, 0), r1)
+    assert torch.allclose(r1[:, 0, tok.joint_indices], ip[:, tok.joint_indices], atol=1e-7)   # B_0(0) = 1
+
+
+@pytest.mark.parametrize("name,batch", [("cfg2_d14", 65536), ("cfg1_d7", 32), ("cfg1_d7", 40000)])
+def test_full_size_vs_oracle_and_properties(name, batch):
+    """BASELINE.json sizes: oracle parity on a row sample, fused tokens == exact quantiser of the
+    kernel's coefficients everywhere, round trip, and edge batches."""
+    from beast_tokenizer_b200.synth import synth
+    cfg = GOLDEN_CASES[name]
+    g = load_golden(name)
+    tok = make_tok(cfg, g, "fit")
+    D, nb, V = cfg["num_dof"], cfg["num_basis"], cfg["vocab_size"]
+    x = synth(batch, cfg["seq_len"], D, seed=2).cuda()
+    tokens, pd = tok.encode(x)
+    params = pd["params"].cpu().numpy()
+    tk = tokens.cpu().numpy()
+    own = O.tokens_from_params(params, g["w_min_fit"], g["w_max_fit"], V, D, nb, offset(cfg))
+    assert np.array_equal(tk, own)
+    rows = np.random.default_rng(0).choice(batch, size=min(batch, 512), replace=False)
+    joint, grip = layout(cfg)
+    xs = x[torch.from_numpy(rows).cuda()].cpu().numpy()
+    w_ora = O.compute_weights(xs, g["times"], 2 * math.pi, nb, cfg["degree_p"], joint, grip)
+    assert rel_err(params[rows], w_ora) <= TOL
+    t_ora = O.tokens_from_params(w_ora, g["w_min_fit"], g["w_max_fit"], V, D, nb, offset(cfg))
+    check_flips(tk[rows], t_ora, w_ora, g["w_min_fit"], g["w_max_fit"], cfg)
+    rec = tok.reconstruct_traj(tokens)
+    r_ora = O.reconstruct_traj(tk[rows], g["times"], 2 * math.pi, nb, cfg["degree_p"], joint, grip, g["w_min_fit"],
+                               g["w_max_fit"], V, offset(cfg))
+    assert rel_err(rec[torch.from_numpy(rows).cuda()].cpu().numpy(), r_ora) <= TOL
+    # round trip: re-encoding the reconstruction lands in the same or a neighbouring bin
+    t_again, _ = tok.encode(rec)
+    assert int((t_again - tokens).abs().max()) <= 1
+    # bounds reduction at full size, against numpy on the kernel's coefficients
+    tok.update_weights_bounds(x)
+    assert np.array_equal(tok.w_min.cpu().numpy(), params.min(0))
+    assert np.array_equal(tok.w_max.cpu().numpy(), params.max(0))
+
+
+def test_empty_and_single():
+    cfg = GOLDEN_CASES["cfg2_d14"]
+    tok = make_tok(cfg)
+    t, pd = tok.encode(torch.zeros(0, 50, 14))
+    assert t.shape == (0, 140) and pd["params"].shape == (0, 140)
+    assert tok.reconstruct_traj(t).shape == (0, 50, 14)
+    x = torch.zeros(1, 50, 14)
+    t, pd = tok.encode(x)
+    assert t.shape == (1, 140)
+    assert np.array_equal(pd["params"].cpu().numpy(), np.zeros((1, 140), np.float32))
+    with pytest.raises(AssertionError):
+        tok.encode(torch.zeros(2, 49, 14))
+    with pytest.raises(IndexError):
+        tok.encode(torch.zeros(2, 50, 13))
+    # extra trailing DoF columns are ignored, like the reference's index selection
+    from beast_tokenizer_b200.synth import synth
+    y = synth(5, 50, 16, seed=3)
+    assert torch.equal(tok.encode(y)[0], tok.encode(y[..., :14])[0])
+
+
+def test_update_times_rebuilds_plan():
+    cfg = GOLDEN_CASES["cfg1_d7"]
+    g = load_golden("cfg1_d7")
+    tok = make_tok(cfg, g, "fit")
+    x = torch.from_numpy(g["trajs"])
+    a = tok.encode(x)[0]
+    tok.update_times(torch.linspace(0, 2 * math.pi, 25))
+    with pytest.raises(AssertionError):
+        tok.encode(x)
+    b = tok.encode(x[:, ::2][:, :25])[0]
+    assert b.shape == a.shape
+    tok.update_times(torch.from_numpy(g["times"]))
+    assert torch.equal(tok.encode(x)[0], a)

@@ -1,0 +1,158 @@
+"""CPU-only checks: host-side constants, the Python API surface that needs no GPU, the on-disk
+format, and that the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, GOLDEN_CASES, ROOT, load_golden
+
+
+def test_host_constants_match_reference_basis(golden_case):
+    from beast_tokenizer_b200.basis import build_constants, make_times
+    from oracle import beast_oracle as O
+    name, cfg, g = golden_case
+    joint, grip = O.slot_layout(cfg["num_dof"], cfg["gripper_zero_order"], cfg["gripper_indices"])
+    times = make_times(2 * math.pi, cfg["seq_len"])
+    c = build_constants(times, 2 * math.pi, cfg["num_basis"], cfg["degree_p"], joint, grip)
+    assert np.array_equal(c.times.numpy(), g["times"])
+    assert np.array_equal(c.phi_joint.numpy(), g["phi_joint"])          # bit-identical to mp.basis_gn.basis
+    assert np.array_equal(c.knots_joint.numpy(), g["knots_joint"])
+    if grip:
+        assert np.array_equal(c.phi_grip.numpy(), g["phi_grip"])
+    assert c.slot_to_dof == joint + grip
+    # the projector reproduces the reference's coefficients within the 1e-5 tolerance
+    x = torch.from_numpy(g["trajs"])
+    w = torch.einsum("kt,btd->bdk", c.proj_joint, x[..., joint]).reshape(x.shape[0], -1)
+    if grip:
+        wg = torch.einsum("kt,btd->bdk", c.proj_grip, x[..., grip]).reshape(x.shape[0], -1)
+        w = torch.cat([w, wg], 1)
+    err = np.abs(w.numpy() - g["params"]).max() / np.abs(g["params"]).max()
+    assert err <= 1e-5
+
+
+def test_library_exports_every_declared_symbol():
+    from beast_tokenizer_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "beast_b200.h")).read()
+    declared = set(re.findall(r"\b(beast_[a-z0-9_]+)\s*\(", header))
+    declared |= set(re.findall(r"\b(bpe_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/beast_b200.h but not exported"
+    assert declared == set(_lib.exported_symbols())
+    assert b"sm_100a" in lib.beast_version()
+    assert lib.beast_launch_count() == 0 or lib.beast_launch_count() > 0
+    # argument validation needs no GPU
+    assert lib.beast_plan_create(None, None) == -1
+    assert lib.beast_minmax_f32(None, 0, 0, None, None, 0, None) == -1
+
+
+def test_no_cpu_fallback():
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer, BeastB200Error
+    tok = BEASTBsplineTokenizer(num_dof=7, device="cpu")
+    with pytest.raises(BeastB200Error):
+        tok.encode(torch.zeros(2, 50, 7))
+    with pytest.raises(BeastB200Error):
+        tok.reconstruct_traj(torch.zeros(2, 70, dtype=torch.long))
+    if not torch.cuda.is_available():
+        tok = BEASTBsplineTokenizer(num_dof=7, device="cuda")
+        with pytest.raises(BeastB200Error):
+            tok.compute_weights(torch.zeros(2, 50, 7))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "beast_tokenizer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle's", ""), f"{f} mentions the oracle"
+
+
+def test_llm_vocab_size_api():
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    tok = BEASTBsplineTokenizer(num_dof=14, gripper_zero_order=True, gripper_indices=[13, 6], device="cpu")
+    assert tok.joint_indices == [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12] and tok.gripper_indices == [6, 13]
+    assert tok.joint_dof == 12 and tok.gripper_dof == 2 and tok.num_dof == 14
+    with pytest.raises(ValueError, match="LLM vocab size is not set"):
+        tok.tokens_to_llm_tokens(torch.zeros(1, 140, dtype=torch.long))
+    with pytest.raises(ValueError):
+        tok.llm_tokens_to_mp_tokens(torch.zeros(1, 140, dtype=torch.long))
+    with pytest.raises(TypeError):
+        tok.set_llm_vocab_size(3.5)
+    with pytest.raises(ValueError):
+        tok.set_llm_vocab_size(100)
+    tok.set_llm_vocab_size(32000)
+    assert tok._llm_vocab_offset() == 31744 and tok.get_config()["llm_vocab_size"] == 32000
+    t = torch.arange(280).reshape(2, 140)
+    assert torch.equal(tok.tokens_to_llm_tokens(t.reshape(2, 10, 14)), t + 31744)
+    assert tok.llm_tokens_to_mp_tokens(t + 31744).shape == (2, 10, 14)
+    tok.update_vlm_vocab_size(None)
+    assert tok.llm_vocab_size is None and "llm_vocab_size" not in tok._config
+    # gripper_indices are ignored unless gripper_zero_order (SURVEY.md trap 3)
+    tok = BEASTBsplineTokenizer(num_dof=7, gripper_indices=[6], device="cpu")
+    assert tok.gripper_indices == [] and tok.joint_dof == 7 and tok._config["gripper_indices"] == []
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_checkpoint_format_round_trip(name, tmp_path):
+    """Reads the reference's save_pretrained output and writes byte-identical JSON back."""
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    ref_dir = os.path.join(GOLDEN, f"{name}_pretrained")
+    tok = BEASTBsplineTokenizer.from_pretrained(ref_dir, device="cpu")
+    g = load_golden(name)
+    assert np.array_equal(tok.w_min.numpy(), g["w_min_fit"]) and np.array_equal(tok.w_max.numpy(), g["w_max_fit"])
+    tok.save_pretrained(tmp_path)
+    ours = json.load(open(tmp_path / "beast_tokenizer_config.json"))
+    theirs = json.load(open(os.path.join(ref_dir, "beast_tokenizer_config.json")))
+    assert ours == theirs
+    assert open(tmp_path / "beast_tokenizer_config.json").read() == \
+        open(os.path.join(ref_dir, "beast_tokenizer_config.json")).read()
+    sd = tok.state_dict()
+    assert set(sd) == {"config", "w_min", "w_max", "llm_vocab_size"}
+    tok2 = BEASTBsplineTokenizer(**{k: v for k, v in sd["config"].items() if k not in ("tokenizer_type",)})
+    tok2.load_state_dict(sd)
+    assert torch.equal(tok2.w_min, tok.w_min) and tok2.llm_vocab_size == tok.llm_vocab_size
+
+
+def test_from_pretrained_errors(tmp_path):
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    with pytest.raises(FileNotFoundError):
+        BEASTBsplineTokenizer.from_pretrained(tmp_path / "nope")
+    d = tmp_path / "bad"
+    d.mkdir()
+    json.dump({"config": {"tokenizer_type": "something_else"}}, open(d / "beast_tokenizer_config.json", "w"))
+    with pytest.raises(ValueError):
+        BEASTBsplineTokenizer.from_pretrained(d)
+
+
+def test_utils_match_oracle():
+    from beast_tokenizer_b200 import utils as U
+    from oracle import beast_oracle as O
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 0.03, (64, 40)).astype(np.float32)
+    lo = (-0.02 - rng.random(40) * 0.01).astype(np.float32)
+    hi = (0.02 + rng.random(40) * 0.01).astype(np.float32)
+    tx, tlo, thi = torch.from_numpy(x), torch.from_numpy(lo), torch.from_numpy(hi)
+    q = U.continuous_to_discrete(torch.clamp(tx, tlo, thi), tlo, thi, 256).numpy()
+    assert np.array_equal(q, O.continuous_to_discrete(np.clip(x, lo, hi), lo, hi, 256))
+    assert np.array_equal(U.discrete_to_continuous(torch.from_numpy(q), tlo, thi, 256).numpy(),
+                          O.discrete_to_continuous(q, lo, hi, 256))
+    n = U.normalize_tensor(tx, tlo, thi).numpy()
+    assert np.array_equal(n, O.normalize_tensor(x, lo, hi))
+    assert np.array_equal(U.denormalize_tensor(torch.from_numpy(n), tlo, thi).numpy(), O.denormalize_tensor(n, lo, hi))
+
+
+def test_synth_is_deterministic():
+    from beast_tokenizer_b200.synth import synth, SyntheticLoader
+    a, b = synth(4, 50, 14, 3), synth(4, 50, 14, 3)
+    assert torch.equal(a, b) and a.dtype == torch.float32 and a.shape == (4, 50, 14)
+    g = load_golden("cfg2_d14")
+    assert np.array_equal(synth(96, 50, 14, 2).numpy(), g["trajs"])
+    batches = list(SyntheticLoader(2, 32, 50, 14, seed0=1))
+    assert len(batches) == 2 and batches[0]["actions"].shape == (32, 50, 14)

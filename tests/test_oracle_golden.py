@@ -123,3 +123,23 @@ def test_llm_offset_helpers():
     assert np.array_equal(g["tokens_fit_nooffset"] + off, g["tokens_fit"])
     assert np.array_equal(g["llm_tokens"], g["tokens_fit"])
     assert np.array_equal(g["mp_tokens_3d"].reshape(g["tokens_fit"].shape[0], -1), g["tokens_fit_nooffset"])
+
+
+def test_torch_reference_port_matches_golden(golden_case):
+    """The torch CPU port used as bench.py's CPU baseline reproduces the live reference."""
+    import torch
+    from oracle.reference_port_torch import ReferencePort
+    name, cfg, g = golden_case
+    port = ReferencePort(num_dof=cfg["num_dof"], num_basis=cfg["num_basis"], seq_len=cfg["seq_len"],
+                         vocab_size=cfg["vocab_size"], degree_p=cfg["degree_p"],
+                         gripper_zero_order=cfg["gripper_zero_order"], gripper_indices=cfg["gripper_indices"],
+                         llm_vocab_size=cfg["llm_vocab_size"])
+    assert np.array_equal(port.basis(port.times, cfg["degree_p"]).numpy(), g["phi_joint"])
+    port.w_min, port.w_max = torch.from_numpy(g["w_min_fit"]), torch.from_numpy(g["w_max_fit"])
+    tok, params = port.encode(torch.from_numpy(g["trajs"]))
+    assert rel_err(params.numpy(), g["params"]) <= 1e-6
+    assert (tok.numpy() != g["tokens_fit"]).mean() <= 1e-3
+    rec = port.reconstruct_traj(torch.from_numpy(g["tokens_fit"]))
+    assert rel_err(rec.numpy(), g["recon_fit"]) <= 1e-6
+    rec = port.reconstruct_traj(torch.from_numpy(g["tokens_fit"]), init_p=torch.from_numpy(g["init_p"]))
+    assert rel_err(rec.numpy(), g["recon_fit_initp"]) <= 1e-6
