@@ -6,9 +6,11 @@
 //   pos[t, dof(slot)] = sum_k Phi[t, k] * c[slot, k]                              (uni_bspline.py:165)
 //
 // Fast kernel (seq_len = 50, num_basis = 10, tokenizer's own times): the mirror image of K1 —
-// persistent CTAs, bulk-TMA ring for the int64 token tiles (+ init_p), one thread per
-// (trajectory, slot) column, Phi from the constant bank, [t][dof] rows staged in shared memory
-// and written back with bulk stores.
+// four CTAs per SM, each with one shared-memory stage: bulk-TMA load of the int64 token tile
+// (+ init_p), one thread per (trajectory, slot) column pulls its ten tokens into registers,
+// the [t][dof] output rows are staged over the consumed tile and leave with one bulk store.
+// Phi comes from the constant bank (uniform LDCU.128 loads); the degree-0 gripper basis has one
+// non-zero per sample and is walked interval by interval.
 // Generic kernel: any geometry, optional caller-supplied times [B, Tq] with the basis evaluated
 // in-kernel by the Cox-de Boor recursion in the reference's fp32 operation order
 // (basis_gn/uni_bspline_basis.py:82-113, phase_gn/linear_phase.py:22-23).
@@ -17,16 +19,16 @@
 
 namespace beast {
 
-constexpr int kDecComputeWarps = 7;
-constexpr int kDecComputeThreads = kDecComputeWarps * 32;
-constexpr int kDecThreads = kDecComputeThreads + 32;
+constexpr int kDecThreads = 224;
+constexpr int kDecCtasPerSm = 4;
 constexpr int kMaxEvalKnots = 320;       // generic path: num_basis + degree_p <= 319
 
 template <int T, int NB>
 struct alignas(16) DecTables {
     static constexpr int NBP = (NB + 3) & ~3;
     float fj[T * NBP];   // Phi_joint [t][k], k padded
-    float fg[T * NBP];
+    float fgv[T];        // Phi_grip[t][k(t)] — the single non-zero of row t
+    int gstart[NB + 1];  // rows gstart[k] <= t < gstart[k+1] belong to interval k
 };
 
 struct DecArgs {
@@ -41,84 +43,59 @@ struct DecArgs {
     int slot_to_dof[BEAST_MAX_SLOTS];
 };
 
-__host__ __device__ inline uint32_t dec_round_up_128(uint32_t x) { return (x + 127u) & ~127u; }
-
-template <int T, int NB, bool GRIP>
-__device__ __forceinline__ void eval_column(const DecTables<T, NB>& tab, const float (&c)[NB], float* __restrict__ o,
-                                            int D) {
+template <int T, int NB>
+__device__ __forceinline__ void eval_joint(const DecTables<T, NB>& tab, const float (&c)[NB], float* __restrict__ o,
+                                           int D) {
     constexpr int NBP = DecTables<T, NB>::NBP;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         float acc = 0.0f;
 #pragma unroll
-        for (int k = 0; k < NB; ++k) acc = fmaf(GRIP ? tab.fg[t * NBP + k] : tab.fj[t * NBP + k], c[k], acc);
+        for (int k = 0; k < NB; ++k) acc = fmaf(tab.fj[t * NBP + k], c[k], acc);
         o[t * D] = acc;
     }
 }
 
-template <int T, int NB, int NS, int DT>
-__global__ void __launch_bounds__(kDecThreads, 1)
+template <int T, int NB>
+__device__ __forceinline__ void eval_grip(const DecTables<T, NB>& tab, const float (&c)[NB], float* __restrict__ o,
+                                          int D) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const int t1 = tab.gstart[k + 1];
+        for (int t = tab.gstart[k]; t < t1; ++t) o[t * D] = fmaf(tab.fgv[t], c[k], 0.0f);
+    }
+}
+
+template <int T, int NB, int DT>
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
 decode_fast_kernel(const __grid_constant__ DecTables<T, NB> tab, const __grid_constant__ DecArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar;
     const int D = DT ? DT : a.D;
     const int S = a.S;
     const bool has_init = a.init_p != nullptr;
     const uint32_t tok_bytes = (uint32_t)S * NB * D * 8u;
     const uint32_t ini_bytes = (uint32_t)S * D * 4u;
-    const uint32_t tok_stride = dec_round_up_128(tok_bytes);
-    const uint32_t in_stride = tok_stride + dec_round_up_128(ini_bytes);
     const uint32_t out_bytes = (uint32_t)S * T * D * 4u;
-    const uint32_t out_stride = dec_round_up_128(out_bytes);
-    unsigned char* out_base = smem + NS * in_stride;
-    uint64_t* bars = (uint64_t*)(out_base + 2 * out_stride);
-    uint64_t* in_full = bars;
-    uint64_t* in_empty = bars + NS;
-    uint64_t* out_full = bars + 2 * NS;
-    uint64_t* out_empty = bars + 2 * NS + 2;
+    const uint32_t load_bytes = tok_bytes + (has_init ? ini_bytes : 0u);
+    const long long* s_tok = (const long long*)smem;
+    const float* s_ini = (const float*)(smem + tok_bytes);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], kDecComputeWarps); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], kDecComputeWarps); mbar_init(&out_empty[s], 1); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
+    const int tid = threadIdx.x;
     const int first = blockIdx.x, step = gridDim.x;
     const int n_my = first < a.n_tiles ? (a.n_tiles - first + step - 1) / step : 0;
     const size_t tile_tok = (size_t)S * NB * D, tile_ini = (size_t)S * D, tile_out = (size_t)S * T * D;
-    const uint32_t load_bytes = tok_bytes + (has_init ? ini_bytes : 0u);
-
-    if (warp == kDecComputeWarps) {
-        if (lane == 0) {
-            auto load = [&](int j) {
-                const int s = j % NS;
-                const size_t tile = (size_t)first + (size_t)j * step;
-                mbar_arrive_expect_tx(&in_full[s], load_bytes);
-                bulk_g2s(smem + s * in_stride, a.tokens + tile * tile_tok, tok_bytes, &in_full[s]);
-                if (has_init)
-                    bulk_g2s(smem + s * in_stride + tok_stride, a.init_p + tile * tile_ini, ini_bytes, &in_full[s]);
-            };
-            int issued = 0;
-            for (; issued < NS && issued < n_my; ++issued) load(issued);
-            for (int i = 0; i < n_my; ++i) {
-                const int ob = i & 1;
-                const size_t tile = (size_t)first + (size_t)i * step;
-                mbar_wait(&out_full[ob], (i >> 1) & 1);
-                bulk_s2g(a.out + tile * tile_out, out_base + ob * out_stride, out_bytes);
-                bulk_commit();
-                if (issued < n_my) {
-                    mbar_wait(&in_empty[issued % NS], ((issued / NS) - 1) & 1);
-                    load(issued);
-                    ++issued;
-                }
-                bulk_wait_read<1>();
-                if (i >= 1) mbar_arrive(&out_empty[(i - 1) & 1]);
-            }
-            bulk_wait_all<0>();
-        }
-        return;
+    auto load = [&](size_t tile) {
+        mbar_arrive_expect_tx(&full_bar, load_bytes);
+        bulk_g2s(smem, a.tokens + tile * tile_tok, tok_bytes, &full_bar);
+        if (has_init) bulk_g2s(smem + tok_bytes, a.init_p + tile * tile_ini, ini_bytes, &full_bar);
+    };
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_fence_init();
+        if (n_my > 0) load((size_t)first);
     }
+    __syncthreads();
 
     const int nj = a.n_joint, ng = D - nj;
     const bool active = tid < S * D;
@@ -133,29 +110,33 @@ decode_fast_kernel(const __grid_constant__ DecTables<T, NB> tab, const __grid_co
     for (int k = 0; k < NB; ++k) { wmin[k] = a.w_min[slot * NB + k]; wmax[k] = a.w_max[slot * NB + k]; }
 
     for (int i = 0; i < n_my; ++i) {
-        const int s = i % NS;
-        mbar_wait(&in_full[s], (i / NS) & 1);
+        const size_t tile = (size_t)first + (size_t)i * step;
+        mbar_wait(&full_bar, i & 1);
         float c[NB];
         if (active) {
-            const long long* tk = (const long long*)(smem + s * in_stride) + tl * (NB * D) + slot;
+            const long long* tk = s_tok + tl * (NB * D) + slot;
 #pragma unroll
             for (int k = 0; k < NB; ++k) c[k] = dequantize_one(tk[k * D] - a.offset, wmin[k], wmax[k], a.vm1);
-            if (has_init && slot < nj) c[0] = ((const float*)(smem + s * in_stride + tok_stride))[tl * D + dof];
+            if (has_init && slot < nj) c[0] = s_ini[tl * D + dof];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&in_empty[s]);
-
-        const int ob = i & 1;
-        if (i >= 2) mbar_wait(&out_empty[ob], ((i >> 1) - 1) & 1);
+        __syncthreads();                                   // tokens are in registers; the tile may be overwritten
         if (active) {
-            float* o = (float*)(out_base + ob * out_stride) + tl * (T * D) + dof;
-            if (slot < nj) eval_column<T, NB, false>(tab, c, o, D);
-            else eval_column<T, NB, true>(tab, c, o, D);
+            float* o = (float*)smem + tl * (T * D) + dof;
+            if (slot < nj) eval_joint<T, NB>(tab, c, o, D);
+            else eval_grip<T, NB>(tab, c, o, D);
         }
         fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&out_full[ob]);
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(a.out + tile * tile_out, smem, out_bytes);
+            bulk_commit();
+            if (i + 1 < n_my) {
+                bulk_wait_read<0>();
+                load(tile + step);
+            }
+        }
     }
+    if (tid == 0) bulk_wait_all<0>();
 }
 
 // Cox-de Boor on the knot vector `kn` (nb + p + 1 knots): N[0..nb) <- basis values at phase u.
@@ -257,35 +238,62 @@ static int dec_grid_for(long long n, int block, int num_sms) {
     return (int)g;
 }
 
-template <int T, int NB, int NS, int DT>
+// Degree-0 basis structure: one non-zero per row, rows of an interval contiguous.
+template <int T, int NB>
+static bool dec_grip_structure(const float* fg, float* fgv, int* gstart) {
+    int k_prev = 0;
+    for (int k = 0; k <= NB; ++k) gstart[k] = -1;
+    gstart[0] = 0;
+    for (int t = 0; t < T; ++t) {
+        int kk = -1;
+        for (int k = 0; k < NB; ++k) {
+            if (fg[t * NB + k] != 0.0f) {
+                if (kk >= 0) return false;
+                kk = k;
+            }
+        }
+        if (kk < 0) { fgv[t] = 0.0f; kk = k_prev; }
+        else fgv[t] = fg[t * NB + kk];
+        if (kk < k_prev) return false;
+        for (int k = k_prev + 1; k <= kk; ++k) gstart[k] = t;
+        k_prev = kk;
+    }
+    for (int k = k_prev + 1; k <= NB; ++k) gstart[k] = T;
+    return true;
+}
+
+template <int T, int NB, int DT>
 static int launch_dec_fast(const Plan* p, const long long* tokens, long long n_tiles, int S, const float* w_min,
                            const float* w_max, long long offset, const float* init_p, float* out,
                            cudaStream_t st) {
     DecTables<T, NB> tab;
     constexpr int NBP = DecTables<T, NB>::NBP;
     for (int t = 0; t < T; ++t)
-        for (int k = 0; k < NBP; ++k) {
-            tab.fj[t * NBP + k] = k < NB ? p->phi_joint_h[t * NB + k] : 0.0f;
-            tab.fg[t * NBP + k] = (k < NB && p->phi_grip_h) ? p->phi_grip_h[t * NB + k] : 0.0f;
-        }
+        for (int k = 0; k < NBP; ++k) tab.fj[t * NBP + k] = k < NB ? p->phi_joint_h[t * NB + k] : 0.0f;
+    if (p->phi_grip_h) {
+        if (!dec_grip_structure<T, NB>(p->phi_grip_h, tab.fgv, tab.gstart)) return BEAST_E_UNSUPPORTED;
+    } else {
+        for (int t = 0; t < T; ++t) tab.fgv[t] = 0.0f;
+        for (int k = 0; k <= NB; ++k) tab.gstart[k] = 0;
+    }
     DecArgs a;
     a.tokens = tokens; a.init_p = init_p; a.out = out; a.w_min = w_min; a.w_max = w_max;
     a.offset = offset; a.vm1 = (float)(p->V - 1);
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
-    const uint32_t in_stride = dec_round_up_128((uint32_t)S * NB * p->D * 8u) + dec_round_up_128((uint32_t)S * p->D * 4u);
-    const uint32_t out_stride = dec_round_up_128((uint32_t)S * T * p->D * 4u);
-    const size_t smem = (size_t)NS * in_stride + 2 * (size_t)out_stride + (2 * NS + 4) * sizeof(uint64_t);
+    static_assert(8 * NB + 4 <= 4 * T, "token tile (+ init_p) must fit under the output tile");
+    const size_t smem = (size_t)S * T * p->D * 4u;
     if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<T, NB, NS, DT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<T, NB, DT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_smem = smem;
     }
-    const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
-    decode_fast_kernel<T, NB, NS, DT><<<grid, kDecThreads, smem, st>>>(tab, a);
+    const long long cap = (long long)p->num_sms * kDecCtasPerSm;
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    decode_fast_kernel<T, NB, DT><<<grid, kDecThreads, smem, st>>>(tab, a);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -329,16 +337,16 @@ extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens,
     long long done = 0;
     if (T == 50 && nb == 10 && !dec_fast_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
         (!init_p || dec_aligned16(init_p))) {
-        const int S = (kDecComputeThreads / D) & ~3;
+        const int S = (kDecThreads / D) & ~3;
         if (S >= 4 && B >= S) {
             const long long n_tiles = B / S;
             int rc;
             if (D == 14)
-                rc = launch_dec_fast<50, 10, 3, 14>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
+                rc = launch_dec_fast<50, 10, 14>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
             else if (D == 7)
-                rc = launch_dec_fast<50, 10, 3, 7>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
+                rc = launch_dec_fast<50, 10, 7>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
             else
-                rc = launch_dec_fast<50, 10, 3, 0>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
+                rc = launch_dec_fast<50, 10, 0>(p, (const long long*)tokens, n_tiles, S, w_min, w_max, offset, init_p, traj_out, st);
             if (rc == BEAST_OK) done = n_tiles * S;
             else if (rc != BEAST_E_UNSUPPORTED) return rc;
         }

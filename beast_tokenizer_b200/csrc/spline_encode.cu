@@ -7,14 +7,16 @@
 // per spline (joint degree_p, gripper degree 0), computed once on the host.
 //
 // Fast kernel (seq_len = 50, num_basis = 10 — every BASELINE config): HBM-bound streaming.
-//   * persistent CTAs, one per SM; tile = S trajectories (S*D <= 224 columns);
-//   * warp 7 / lane 0 is the copy thread: 1-D bulk TMA (cp.async.bulk, UBLKCP) global->shared into a
-//     3-deep ring, and bulk shared->global stores of the staged outputs — every HBM byte moves in
-//     16-byte-aligned bursts, none through registers;
-//   * warps 0-6: one thread per (trajectory, slot) column: 50 LDS + 500 FFMA whose P operand comes
-//     straight from the constant bank (the table travels as a __grid_constant__ kernel parameter),
-//     then the exact quantiser, staged '(t d)' int64 tokens + '(d t)' fp32 coefficients;
-//   * full/empty mbarriers per stage, no CTA-wide barrier in the steady state.
+//   * tile = S trajectories (S*D <= 224 columns, 44.8 KB); each CTA owns ONE shared-memory stage and
+//     walks its tiles; four CTAs are resident per SM, so while one waits for its bulk copy the
+//     others compute (latency hiding across CTAs instead of a ring inside one);
+//   * every HBM byte moves by 1-D bulk TMA (cp.async.bulk, SASS UBLKCP): global->shared completes on
+//     an mbarrier; the outputs are staged over the consumed input tile and leave with bulk
+//     shared->global stores — 16-byte-aligned bursts, nothing through registers;
+//   * one thread per (trajectory, slot) column: 50 LDS + 500 FFMA whose P operand comes from the
+//     constant bank (the table travels as a __grid_constant__ kernel parameter and is read with
+//     uniform LDCU.128 loads), then the exact quantiser; joint columns fill warps 0-5, gripper
+//     columns warp 6 (degree-0 projector = one non-zero per sample, walked interval by interval).
 // Generic kernel: any geometry, one thread per column, same accumulation order (bit-identical
 // coefficients), plain loads/stores.  Also handles the ragged tail of the fast path.
 #include <cstdlib>
@@ -22,17 +24,18 @@
 
 namespace beast {
 
-constexpr int kComputeWarps = 7;
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreads = kComputeThreads + 32;
+constexpr int kEncThreads = 224;
+constexpr int kEncCtasPerSm = 4;
 
-// Projector tables as the kernel sees them: [t][k] with k padded to a multiple of 4 so that one
-// 16-byte uniform constant load (LDCU.128) feeds four FFMAs.
+// Projector tables as the kernel sees them.  Joint: [t][k] with k padded to a multiple of 4 so one
+// 16-byte uniform constant load (LDCU.128) feeds four FFMAs.  Gripper (degree 0): sample t belongs
+// to exactly one interval k, P_grip[k][t] = pgv[t] for gstart[k] <= t < gstart[k+1], zero elsewhere.
 template <int T, int NB>
 struct alignas(16) EncTables {
     static constexpr int NBP = (NB + 3) & ~3;
     float pj[T * NBP];
-    float pg[T * NBP];
+    float pgv[T];
+    int gstart[NB + 1];
 };
 
 struct EncArgs {
@@ -47,11 +50,9 @@ struct EncArgs {
     int slot_to_dof[BEAST_MAX_SLOTS];
 };
 
-__host__ __device__ inline uint32_t round_up_128(uint32_t x) { return (x + 127u) & ~127u; }
-
-template <int T, int NB, bool GRIP>
-__device__ __forceinline__ void fit_column(const EncTables<T, NB>& tab, const float* __restrict__ y, int D,
-                                           float (&acc)[NB]) {
+template <int T, int NB>
+__device__ __forceinline__ void fit_joint(const EncTables<T, NB>& tab, const float* __restrict__ y, int D,
+                                          float (&acc)[NB]) {
     constexpr int NBP = EncTables<T, NB>::NBP;
 #pragma unroll
     for (int k = 0; k < NB; ++k) acc[k] = 0.0f;
@@ -59,117 +60,87 @@ __device__ __forceinline__ void fit_column(const EncTables<T, NB>& tab, const fl
     for (int t = 0; t < T; ++t) {
         const float v = y[t * D];
 #pragma unroll
-        for (int k = 0; k < NB; ++k) acc[k] = fmaf(GRIP ? tab.pg[t * NBP + k] : tab.pj[t * NBP + k], v, acc[k]);
+        for (int k = 0; k < NB; ++k) acc[k] = fmaf(tab.pj[t * NBP + k], v, acc[k]);
     }
 }
 
-template <int T, int NB, int NS, int DT>
-__global__ void __launch_bounds__(kThreads, 1)
+// Same sums as the dense form (the skipped terms are exact zeros), t ascending inside each interval.
+template <int T, int NB>
+__device__ __forceinline__ void fit_grip(const EncTables<T, NB>& tab, const float* __restrict__ y, int D,
+                                         float (&acc)[NB]) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        float s = 0.0f;
+        const int t1 = tab.gstart[k + 1];
+        for (int t = tab.gstart[k]; t < t1; ++t) s = fmaf(tab.pgv[t], y[t * D], s);
+        acc[k] = s;
+    }
+}
+
+template <int T, int NB, int DT>
+__global__ void __launch_bounds__(kEncThreads, kEncCtasPerSm)
 encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_constant__ EncArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar;
     const int D = DT ? DT : a.D;          // compile-time DoF count for the common shapes (7, 14)
     const int S = a.S;
     const uint32_t in_bytes = (uint32_t)S * T * D * 4u;
     const uint32_t tok_bytes = (uint32_t)S * NB * D * 8u;
     const uint32_t par_bytes = (uint32_t)S * NB * D * 4u;
-    const uint32_t in_stride = round_up_128(in_bytes);
-    const uint32_t tok_stride = round_up_128(tok_bytes);
-    const uint32_t out_stride = tok_stride + round_up_128(par_bytes);
-    unsigned char* out_base = smem + NS * in_stride;
-    uint64_t* bars = (uint64_t*)(out_base + 2 * out_stride);
-    uint64_t* in_full = bars;
-    uint64_t* in_empty = bars + NS;
-    uint64_t* out_full = bars + 2 * NS;
-    uint64_t* out_empty = bars + 2 * NS + 2;
+    const bool want_tok = a.tokens_out != nullptr, want_par = a.params_out != nullptr;
+    // outputs are staged over the consumed input tile: tokens first, coefficients after them
+    long long* s_tok = (long long*)smem;
+    float* s_par = (float*)(smem + (want_tok ? tok_bytes : 0u));
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], kComputeWarps); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&out_full[s], kComputeWarps); mbar_init(&out_empty[s], 1); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
+    const int tid = threadIdx.x;
     const int first = blockIdx.x, step = gridDim.x;
     const int n_my = first < a.n_tiles ? (a.n_tiles - first + step - 1) / step : 0;
     const size_t tile_in = (size_t)S * T * D, tile_out = (size_t)S * NB * D;
-
-    if (warp == kComputeWarps) {
-        // ---------------- copy thread ----------------
-        if (lane == 0) {
-            int issued = 0;
-            for (; issued < NS && issued < n_my; ++issued) {
-                const size_t tile = (size_t)first + (size_t)issued * step;
-                mbar_arrive_expect_tx(&in_full[issued], in_bytes);
-                bulk_g2s(smem + issued * in_stride, a.traj + tile * tile_in, in_bytes, &in_full[issued]);
-            }
-            for (int i = 0; i < n_my; ++i) {
-                const int ob = i & 1;
-                const size_t tile = (size_t)first + (size_t)i * step;
-                mbar_wait(&out_full[ob], (i >> 1) & 1);
-                if (a.tokens_out) bulk_s2g(a.tokens_out + tile * tile_out, out_base + ob * out_stride, tok_bytes);
-                if (a.params_out)
-                    bulk_s2g(a.params_out + tile * tile_out, out_base + ob * out_stride + tok_stride, par_bytes);
-                bulk_commit();
-                if (issued < n_my) {
-                    const int s = issued % NS;
-                    const size_t nt = (size_t)first + (size_t)issued * step;
-                    mbar_wait(&in_empty[s], ((issued / NS) - 1) & 1);
-                    mbar_arrive_expect_tx(&in_full[s], in_bytes);
-                    bulk_g2s(smem + s * in_stride, a.traj + nt * tile_in, in_bytes, &in_full[s]);
-                    ++issued;
-                }
-                bulk_wait_read<1>();                       // store of tile i-1 has left its staging buffer
-                if (i >= 1) mbar_arrive(&out_empty[(i - 1) & 1]);
-            }
-            bulk_wait_all<0>();
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_fence_init();
+        if (n_my > 0) {
+            mbar_arrive_expect_tx(&full_bar, in_bytes);
+            bulk_g2s(smem, a.traj + (size_t)first * tile_in, in_bytes, &full_bar);
         }
-        return;
     }
+    __syncthreads();
 
-    // ---------------- compute threads: one (trajectory, slot) column each ----------------
+    // one (trajectory, slot) column per thread; joint columns first so that warps are uniform
     const int nj = a.n_joint, ng = D - nj;
-    const int ncols = S * D;
-    const bool active = tid < ncols;
+    const bool active = tid < S * D;
     int tl = 0, slot = 0;
     if (active) {
         if (tid < S * nj) { tl = tid / nj; slot = tid - tl * nj; }
         else { const int c = tid - S * nj; tl = c / ng; slot = nj + (c - tl * ng); }
     }
     const int dof = a.slot_to_dof[slot];
-    const bool want_tok = a.tokens_out != nullptr, want_par = a.params_out != nullptr;
-    float wmin[NB], wmax[NB], wscale[NB];
+    float wmin[NB], wmax[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
         wmin[k] = want_tok ? a.w_min[slot * NB + k] : 0.0f;
         wmax[k] = want_tok ? a.w_max[slot * NB + k] : 0.0f;
-        wscale[k] = quant_scale(wmin[k], wmax[k]);
     }
 
     for (int i = 0; i < n_my; ++i) {
-        const int s = i % NS;
-        mbar_wait(&in_full[s], (i / NS) & 1);
+        const size_t tile = (size_t)first + (size_t)i * step;
+        mbar_wait(&full_bar, i & 1);
         float acc[NB];
         if (active) {
-            const float* y = (const float*)(smem + s * in_stride) + tl * (T * D) + dof;
-            if (slot < nj) fit_column<T, NB, false>(tab, y, D, acc);
-            else fit_column<T, NB, true>(tab, y, D, acc);
+            const float* y = (const float*)smem + tl * (T * D) + dof;
+            if (slot < nj) fit_joint<T, NB>(tab, y, D, acc);
+            else fit_grip<T, NB>(tab, y, D, acc);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&in_empty[s]);
-
-        const int ob = i & 1;
-        if (i >= 2) mbar_wait(&out_empty[ob], ((i >> 1) - 1) & 1);
+        __syncthreads();                                   // every column has been read
         if (active) {
-            unsigned char* o = out_base + ob * out_stride;
             if (want_tok) {
-                long long* to = (long long*)o + tl * (NB * D) + slot;
+                long long* to = s_tok + tl * (NB * D) + slot;
 #pragma unroll
                 for (int k = 0; k < NB; ++k)
-                    to[k * D] = quantize_one(acc[k], wmin[k], wmax[k], wscale[k], a.vm1) + a.offset;
+                    to[k * D] = quantize_one(acc[k], wmin[k], wmax[k], quant_scale(wmin[k], wmax[k]), a.vm1) + a.offset;
             }
             if (want_par) {
-                float* po = (float*)(o + tok_stride) + tl * (NB * D) + slot * NB;
+                float* po = s_par + tl * (NB * D) + slot * NB;
                 if (NB % 2 == 0) {
 #pragma unroll
                     for (int k = 0; k < NB; k += 2) *(float2*)(po + k) = make_float2(acc[k], acc[k + 1]);
@@ -179,10 +150,20 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
                 }
             }
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&out_full[ob]);
+        fence_async_smem();                                // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            if (want_tok) bulk_s2g(a.tokens_out + tile * tile_out, s_tok, tok_bytes);
+            if (want_par) bulk_s2g(a.params_out + tile * tile_out, s_par, par_bytes);
+            bulk_commit();
+            if (i + 1 < n_my) {
+                bulk_wait_read<0>();                       // staging buffer drained -> refill it
+                mbar_arrive_expect_tx(&full_bar, in_bytes);
+                bulk_g2s(smem, a.traj + (tile + step) * tile_in, in_bytes, &full_bar);
+            }
+        }
     }
+    if (tid == 0) bulk_wait_all<0>();
 }
 
 // One thread per (trajectory, slot) column; any geometry.  Accumulates in the same order
@@ -254,35 +235,62 @@ static int grid_for(long long n, int block, int num_sms) {
     return (int)g;
 }
 
-template <int T, int NB, int NS, int DT>
+// Degree-0 projector structure: exactly one non-zero per sample, intervals contiguous in t.
+template <int T, int NB>
+static bool grip_structure(const float* pg, float* pgv, int* gstart) {
+    int k_prev = 0;
+    for (int k = 0; k <= NB; ++k) gstart[k] = -1;
+    gstart[0] = 0;
+    for (int t = 0; t < T; ++t) {
+        int kk = -1;
+        for (int k = 0; k < NB; ++k) {
+            if (pg[k * T + t] != 0.0f) {
+                if (kk >= 0) return false;
+                kk = k;
+            }
+        }
+        if (kk < 0) { pgv[t] = 0.0f; kk = k_prev; }        // sample outside every interval: contributes 0
+        else pgv[t] = pg[kk * T + t];
+        if (kk < k_prev) return false;
+        for (int k = k_prev + 1; k <= kk; ++k) gstart[k] = t;
+        k_prev = kk;
+    }
+    for (int k = k_prev + 1; k <= NB; ++k) gstart[k] = T;
+    return true;
+}
+
+template <int T, int NB, int DT>
 static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int S, const float* w_min,
                        const float* w_max, long long offset, float* params_out, long long* tokens_out,
                        cudaStream_t st) {
     EncTables<T, NB> tab;
     constexpr int NBP = EncTables<T, NB>::NBP;
     for (int t = 0; t < T; ++t)
-        for (int k = 0; k < NBP; ++k) {
-            tab.pj[t * NBP + k] = k < NB ? p->proj_joint_h[k * T + t] : 0.0f;
-            tab.pg[t * NBP + k] = (k < NB && p->proj_grip_h) ? p->proj_grip_h[k * T + t] : 0.0f;
-        }
+        for (int k = 0; k < NBP; ++k) tab.pj[t * NBP + k] = k < NB ? p->proj_joint_h[k * T + t] : 0.0f;
+    if (p->proj_grip_h) {
+        if (!grip_structure<T, NB>(p->proj_grip_h, tab.pgv, tab.gstart)) return BEAST_E_UNSUPPORTED;
+    } else {
+        for (int t = 0; t < T; ++t) tab.pgv[t] = 0.0f;
+        for (int k = 0; k <= NB; ++k) tab.gstart[k] = 0;
+    }
     EncArgs a;
     a.traj = traj; a.params_out = params_out; a.tokens_out = tokens_out;
     a.w_min = w_min; a.w_max = w_max; a.offset = offset; a.vm1 = (float)(p->V - 1);
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
-    const uint32_t in_stride = round_up_128((uint32_t)S * T * p->D * 4u);
-    const uint32_t out_stride = round_up_128((uint32_t)S * NB * p->D * 8u) + round_up_128((uint32_t)S * NB * p->D * 4u);
-    const size_t smem = (size_t)NS * in_stride + 2 * (size_t)out_stride + (2 * NS + 4) * sizeof(uint64_t);
+    const size_t smem = (size_t)S * T * p->D * 4u;       // outputs (12 B * NB per column) alias the 4*T B input
+    static_assert(12 * NB <= 4 * T, "staged outputs must fit over the input tile");
     if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(encode_fast_kernel<T, NB, NS, DT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(encode_fast_kernel<T, NB, DT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_smem = smem;
     }
-    const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
-    encode_fast_kernel<T, NB, NS, DT><<<grid, kThreads, smem, st>>>(tab, a);
+    const long long cap = (long long)p->num_sms * kEncCtasPerSm;
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    encode_fast_kernel<T, NB, DT><<<grid, kEncThreads, smem, st>>>(tab, a);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -296,29 +304,29 @@ extern "C" int beast_encode_f32(const beast_plan_t* plan, const float* traj, int
                                 const float* w_max, int64_t offset, float* params_out, int64_t* tokens_out,
                                 void* stream) {
     const Plan* p = (const Plan*)plan;
-    if (!p || (B > 0 && !traj)) return BEAST_E_NULL;
+    if (!p) return BEAST_E_NULL;
     if (B < 0) return BEAST_E_SHAPE;
-    if (!params_out && !tokens_out) return BEAST_E_NULL;
-    if (tokens_out && (!w_min || !w_max)) return BEAST_E_NULL;
     if (B == 0) return BEAST_OK;
+    if (!traj || (!params_out && !tokens_out)) return BEAST_E_NULL;
+    if (tokens_out && (!w_min || !w_max)) return BEAST_E_NULL;
     if (((uintptr_t)traj & 3u) || ((uintptr_t)params_out & 3u) || ((uintptr_t)tokens_out & 7u)) return BEAST_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int T = p->T, D = p->D, nb = p->nb;
     long long done = 0;
     if (T == 50 && nb == 10 && !fast_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
         (!tokens_out || aligned16(tokens_out))) {
-        const int S = (kComputeThreads / D) & ~3;
+        const int S = (kEncThreads / D) & ~3;
         if (S >= 4 && B >= S) {
             const long long n_tiles = B / S;
             int rc;
             if (D == 14)
-                rc = launch_fast<50, 10, 3, 14>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
+                rc = launch_fast<50, 10, 14>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
                                                 (long long*)tokens_out, st);
             else if (D == 7)
-                rc = launch_fast<50, 10, 3, 7>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
+                rc = launch_fast<50, 10, 7>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
                                                (long long*)tokens_out, st);
             else
-                rc = launch_fast<50, 10, 3, 0>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
+                rc = launch_fast<50, 10, 0>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
                                                (long long*)tokens_out, st);
             if (rc == BEAST_OK) done = n_tiles * S;
             else if (rc != BEAST_E_UNSUPPORTED) return rc;

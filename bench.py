@@ -207,47 +207,74 @@ def main():
     toks = [torch.empty((B, NB * D), device=dev, dtype=torch.int64) for _ in range(R)]
     pars = [torch.empty((B, NB * D), device=dev, dtype=torch.float32) for _ in range(R)]
     outs = [torch.empty((B, T, D), device=dev, dtype=torch.float32) for _ in range(R)]
-    stream = _lib.stream_ptr(dev)
-
     def enc(i):
         _lib.check(lib.beast_encode_f32(plan.handle, _lib.ptr(xs[i]), B, _lib.ptr(lo), _lib.ptr(hi), offset,
-                                        _lib.ptr(pars[i]), _lib.ptr(toks[i]), stream), "encode")
+                                        _lib.ptr(pars[i]), _lib.ptr(toks[i]), _lib.stream_ptr(dev)), "encode")
 
     def dec(i):
         _lib.check(lib.beast_decode_f32(plan.handle, _lib.ptr(toks[i]), B, _lib.ptr(lo), _lib.ptr(hi), offset,
-                                        None, _lib.ptr(outs[i]), stream), "decode")
+                                        None, _lib.ptr(outs[i]), _lib.stream_ptr(dev)), "decode")
+
+    def step(j):
+        enc(j % R)
+        dec((j + 2) % R)
 
     for i in range(R):
         enc(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
     for j in range(args.warmup):
-        enc(j % R)
-        dec((j + 2) % R)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+        step(j)
     torch.cuda.synchronize()
     K = args.steps
+
+    # (a) per-kernel durations: CUDA events around every launch of the K timed steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    n0 = _lib.launch_count()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
     for j in range(K):
         ev[j][0].record()
         enc(j % R)
         ev[j][1].record()
         dec((j + 2) % R)
         ev[j][2].record()
+    torch.cuda.synchronize()
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+
+    # (b) throughput: exactly K steps back to back, captured once into a CUDA graph (the launches are
+    # the same C-ABI calls; the graph only removes the host launch gap between 60 us kernels)
+    launch_mode = "cuda_graph"
+    graph = None
+    if os.environ.get("BEAST_BENCH_NO_GRAPH") != "1":
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for j in range(K):
+                    step(j)
+            graph.replay()                       # one untimed replay (graph upload)
+            torch.cuda.synchronize()
+        except Exception as exc:                 # pragma: no cover
+            print(f"[bench] graph capture failed ({exc}); timing plain stream launches", file=sys.stderr)
+            graph = None
+    if graph is None:
+        launch_mode = "stream"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    if graph is not None:
+        graph.replay()
+    else:
+        for j in range(K):
+            step(j)
     t_end.record()
     torch.cuda.synchronize()
-    launches = _lib.launch_count() - n0
+    launches = (2 * K) if graph is not None else (_lib.launch_count() - n0)
     if world > 1:
         dist.barrier()
     ms_total = t_start.elapsed_time(t_end)
-    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
 
     # ---- end-to-end leg: public API, pinned host input, results back on the host
     xh = [synth(B, T, D, seed=50 + 1000 * rank + i).pin_memory() for i in range(2)]
@@ -294,6 +321,7 @@ def main():
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "parallelism": f"dp{world} (batch sharded, no collective)",
+                       "launch": launch_mode,
                        "l2": f"{R} rotating buffer sets ({R * (ENC_BYTES + DEC_BYTES) * B / 1e6:.0f} MB) > 126 MB L2; "
                              "decode reads tokens written two steps earlier"},
             "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "trajectories/s",
