@@ -5,10 +5,10 @@
 //   c[joint slot, 0] = init_p[dof]                       when init_p is given     (:505-510)
 //   pos[t, dof(slot)] = sum_k Phi[t, k] * c[slot, k]                              (uni_bspline.py:165)
 //
-// Fast kernel (seq_len = 50, num_basis = 10, tokenizer's own times): the mirror image of K1 —
-// four CTAs per SM, each with one shared-memory stage: bulk-TMA load of the int64 token tile
-// (+ init_p), one thread per (trajectory, slot) column pulls its ten tokens into registers,
-// the [t][dof] output rows are staged over the consumed tile and leave with one bulk store.
+// Fast kernel (seq_len = 50, num_basis = 10, tokenizer's own times): the mirror image of K1 — one
+// persistent CTA per SM cycling five shared-memory stages; bulk-TMA load of the int64 token tile
+// (+ init_p), one thread per (trajectory, slot) column pulls its ten tokens into registers, the
+// [t][dof] output rows are staged over the consumed tile and leave with one bulk store.
 // Phi comes from the constant bank (uniform LDCU.128 loads); the degree-0 gripper basis has one
 // non-zero per sample and is walked interval by interval.
 // Generic kernel: any geometry, optional caller-supplied times [B, Tq] with the basis evaluated
@@ -19,8 +19,11 @@
 
 namespace beast {
 
-constexpr int kDecThreads = 224;
-constexpr int kDecCtasPerSm = 4;
+constexpr int kDecGroupWarps = 7;
+constexpr int kDecGroups = 2;
+constexpr int kDecStages = 5;
+constexpr int kDecThreads = (kDecGroups * kDecGroupWarps + 1) * 32;
+constexpr int kDecColumns = kDecGroupWarps * 32;
 constexpr int kMaxEvalKnots = 320;       // generic path: num_basis + degree_p <= 319
 
 template <int T, int NB>
@@ -66,11 +69,15 @@ __device__ __forceinline__ void eval_grip(const DecTables<T, NB>& tab, const flo
     }
 }
 
+// Persistent CTA, one per SM; same stage life cycle as K1 (spline_encode.cu): bulk load of the token
+// tile (+ init_p) -> one 7-warp group pulls its tokens into registers and evaluates -> [t][dof] rows
+// staged over the tile -> bulk store -> reload.
 template <int T, int NB, int DT>
-__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm)
+__global__ void __launch_bounds__(kDecThreads, 1)
 decode_fast_kernel(const __grid_constant__ DecTables<T, NB> tab, const __grid_constant__ DecArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ __align__(8) uint64_t full_bar[kDecStages];
+    __shared__ __align__(8) uint64_t out_full_bar[kDecStages];
     const int D = DT ? DT : a.D;
     const int S = a.S;
     const bool has_init = a.init_p != nullptr;
@@ -78,65 +85,80 @@ decode_fast_kernel(const __grid_constant__ DecTables<T, NB> tab, const __grid_co
     const uint32_t ini_bytes = (uint32_t)S * D * 4u;
     const uint32_t out_bytes = (uint32_t)S * T * D * 4u;
     const uint32_t load_bytes = tok_bytes + (has_init ? ini_bytes : 0u);
-    const long long* s_tok = (const long long*)smem;
-    const float* s_ini = (const float*)(smem + tok_bytes);
+    const uint32_t stride = (out_bytes + 127u) & ~127u;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int first = blockIdx.x, step = gridDim.x;
     const int n_my = first < a.n_tiles ? (a.n_tiles - first + step - 1) / step : 0;
     const size_t tile_tok = (size_t)S * NB * D, tile_ini = (size_t)S * D, tile_out = (size_t)S * T * D;
-    auto load = [&](size_t tile) {
-        mbar_arrive_expect_tx(&full_bar, load_bytes);
-        bulk_g2s(smem, a.tokens + tile * tile_tok, tok_bytes, &full_bar);
-        if (has_init) bulk_g2s(smem + tok_bytes, a.init_p + tile * tile_ini, ini_bytes, &full_bar);
-    };
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+        for (int s = 0; s < kDecStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&out_full_bar[s], kDecGroupWarps); }
         mbar_fence_init();
-        if (n_my > 0) load((size_t)first);
     }
     __syncthreads();
 
+    if (warp == kDecGroups * kDecGroupWarps) {
+        if (lane == 0) {
+            auto load = [&](int j) {
+                const int s = j % kDecStages;
+                const size_t tile = (size_t)first + (size_t)j * step;
+                mbar_arrive_expect_tx(&full_bar[s], load_bytes);
+                bulk_g2s(smem + s * stride, a.tokens + tile * tile_tok, tok_bytes, &full_bar[s]);
+                if (has_init) bulk_g2s(smem + s * stride + tok_bytes, a.init_p + tile * tile_ini, ini_bytes, &full_bar[s]);
+            };
+            for (int j = 0; j < kDecStages && j < n_my; ++j) load(j);
+            for (int i = 0; i < n_my; ++i) {
+                const int s = i % kDecStages;
+                const size_t tile = (size_t)first + (size_t)i * step;
+                mbar_wait(&out_full_bar[s], (i / kDecStages) & 1);
+                bulk_s2g(a.out + tile * tile_out, smem + s * stride, out_bytes);
+                bulk_commit();
+                if (i + kDecStages < n_my) {
+                    bulk_wait_read<0>();
+                    load(i + kDecStages);
+                }
+            }
+            bulk_wait_all<0>();
+        }
+        return;
+    }
+
+    const int group = warp / kDecGroupWarps;
+    const int gtid = tid - group * (kDecGroupWarps * 32);
     const int nj = a.n_joint, ng = D - nj;
-    const bool active = tid < S * D;
+    const bool active = gtid < S * D;
     int tl = 0, slot = 0;
     if (active) {
-        if (tid < S * nj) { tl = tid / nj; slot = tid - tl * nj; }
-        else { const int c = tid - S * nj; tl = c / ng; slot = nj + (c - tl * ng); }
+        if (gtid < S * nj) { tl = gtid / nj; slot = gtid - tl * nj; }
+        else { const int c = gtid - S * nj; tl = c / ng; slot = nj + (c - tl * ng); }
     }
     const int dof = a.slot_to_dof[slot];
     float wmin[NB], wmax[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) { wmin[k] = a.w_min[slot * NB + k]; wmax[k] = a.w_max[slot * NB + k]; }
+    const float rcp_vm1 = __frcp_rn(a.vm1);
 
-    for (int i = 0; i < n_my; ++i) {
-        const size_t tile = (size_t)first + (size_t)i * step;
-        mbar_wait(&full_bar, i & 1);
+    for (int i = group; i < n_my; i += kDecGroups) {
+        const int s = i % kDecStages;
+        unsigned char* stage = smem + s * stride;
+        mbar_wait(&full_bar[s], (i / kDecStages) & 1);
         float c[NB];
         if (active) {
-            const long long* tk = s_tok + tl * (NB * D) + slot;
+            const long long* tk = (const long long*)stage + tl * (NB * D) + slot;
 #pragma unroll
-            for (int k = 0; k < NB; ++k) c[k] = dequantize_one(tk[k * D] - a.offset, wmin[k], wmax[k], a.vm1);
-            if (has_init && slot < nj) c[0] = s_ini[tl * D + dof];
+            for (int k = 0; k < NB; ++k) c[k] = dequantize_fast(tk[k * D] - a.offset, wmin[k], wmax[k], a.vm1, rcp_vm1);
+            if (has_init && slot < nj) c[0] = ((const float*)(stage + tok_bytes))[tl * D + dof];
         }
-        __syncthreads();                                   // tokens are in registers; the tile may be overwritten
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kDecGroupWarps * 32) : "memory");   // tokens are in registers
         if (active) {
-            float* o = (float*)smem + tl * (T * D) + dof;
+            float* o = (float*)stage + tl * (T * D) + dof;
             if (slot < nj) eval_joint<T, NB>(tab, c, o, D);
             else eval_grip<T, NB>(tab, c, o, D);
         }
         fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            bulk_s2g(a.out + tile * tile_out, smem, out_bytes);
-            bulk_commit();
-            if (i + 1 < n_my) {
-                bulk_wait_read<0>();
-                load(tile + step);
-            }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full_bar[s]);
     }
-    if (tid == 0) bulk_wait_all<0>();
 }
 
 // Cox-de Boor on the knot vector `kn` (nb + p + 1 knots): N[0..nb) <- basis values at phase u.
@@ -282,7 +304,7 @@ static int launch_dec_fast(const Plan* p, const long long* tokens, long long n_t
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
     static_assert(8 * NB + 4 <= 4 * T, "token tile (+ init_p) must fit under the output tile");
-    const size_t smem = (size_t)S * T * p->D * 4u;
+    const size_t smem = (size_t)kDecStages * ((((size_t)S * T * p->D * 4u) + 127u) & ~(size_t)127u);
     if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -291,8 +313,7 @@ static int launch_dec_fast(const Plan* p, const long long* tokens, long long n_t
         if (e != cudaSuccess) return (int)e;
         attr_smem = smem;
     }
-    const long long cap = (long long)p->num_sms * kDecCtasPerSm;
-    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
     decode_fast_kernel<T, NB, DT><<<grid, kDecThreads, smem, st>>>(tab, a);
     count_launch();
     BEAST_CHECK_LAUNCH();
@@ -337,7 +358,7 @@ extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens,
     long long done = 0;
     if (T == 50 && nb == 10 && !dec_fast_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
         (!init_p || dec_aligned16(init_p))) {
-        const int S = (kDecThreads / D) & ~3;
+        const int S = (kDecColumns / D) & ~3;
         if (S >= 4 && B >= S) {
             const long long n_tiles = B / S;
             int rc;

@@ -7,9 +7,9 @@
 // per spline (joint degree_p, gripper degree 0), computed once on the host.
 //
 // Fast kernel (seq_len = 50, num_basis = 10 — every BASELINE config): HBM-bound streaming.
-//   * tile = S trajectories (S*D <= 224 columns, 44.8 KB); each CTA owns ONE shared-memory stage and
-//     walks its tiles; four CTAs are resident per SM, so while one waits for its bulk copy the
-//     others compute (latency hiding across CTAs instead of a ring inside one);
+//   * tile = S trajectories (S*D <= 224 columns, 44.8 KB); one persistent CTA per SM cycles five
+//     shared-memory stages through load -> compute -> staged outputs -> store, two 7-warp groups
+//     computing two tiles at once while the other stages have bulk copies in flight;
 //   * every HBM byte moves by 1-D bulk TMA (cp.async.bulk, SASS UBLKCP): global->shared completes on
 //     an mbarrier; the outputs are staged over the consumed input tile and leave with bulk
 //     shared->global stores — 16-byte-aligned bursts, nothing through registers;
@@ -24,8 +24,15 @@
 
 namespace beast {
 
-constexpr int kEncThreads = 224;
-constexpr int kEncCtasPerSm = 4;
+constexpr int kEncGroupWarps = 7;                       // 224 columns per tile
+constexpr int kEncGroups = 2;                           // tiles computed concurrently per SM
+constexpr int kEncStages = 5;                           // 5 x 44.8 KB of the 227 KB shared memory
+constexpr int kEncThreads = (kEncGroups * kEncGroupWarps + 1) * 32;
+constexpr int kEncColumns = kEncGroupWarps * 32;
+
+__device__ __forceinline__ void group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kEncGroupWarps * 32) : "memory");
+}
 
 // Projector tables as the kernel sees them.  Joint: [t][k] with k padded to a multiple of 4 so one
 // 16-byte uniform constant load (LDCU.128) feeds four FFMAs.  Gripper (degree 0): sample t belongs
@@ -47,6 +54,7 @@ struct EncArgs {
     long long offset;
     float vm1;
     int D, n_joint, S, n_tiles;
+    int debug_skip;        // perf debugging only (BEAST_B200_DEBUG_SKIP=1): move the data, skip the arithmetic
     int slot_to_dof[BEAST_MAX_SLOTS];
 };
 
@@ -77,70 +85,99 @@ __device__ __forceinline__ void fit_grip(const EncTables<T, NB>& tab, const floa
     }
 }
 
+// Persistent CTA, one per SM.  kEncStages tiles of shared memory cycle through
+//   bulk load in flight -> computed by one 7-warp group -> outputs staged over the tile -> bulk store -> reload.
+// Two groups compute two different tiles at once; the copy thread (warp 14, lane 0) issues every
+// bulk copy.  full[s] (tx-count) hands a stage to its group, out_full[s] (7 warp arrivals) hands it back.
 template <int T, int NB, int DT>
-__global__ void __launch_bounds__(kEncThreads, kEncCtasPerSm)
+__global__ void __launch_bounds__(kEncThreads, 1)
 encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_constant__ EncArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ __align__(8) uint64_t full_bar[kEncStages];
+    __shared__ __align__(8) uint64_t out_full_bar[kEncStages];
     const int D = DT ? DT : a.D;          // compile-time DoF count for the common shapes (7, 14)
     const int S = a.S;
     const uint32_t in_bytes = (uint32_t)S * T * D * 4u;
     const uint32_t tok_bytes = (uint32_t)S * NB * D * 8u;
     const uint32_t par_bytes = (uint32_t)S * NB * D * 4u;
+    const uint32_t stride = (in_bytes + 127u) & ~127u;
     const bool want_tok = a.tokens_out != nullptr, want_par = a.params_out != nullptr;
-    // outputs are staged over the consumed input tile: tokens first, coefficients after them
-    long long* s_tok = (long long*)smem;
-    float* s_par = (float*)(smem + (want_tok ? tok_bytes : 0u));
+    const uint32_t par_off = want_tok ? tok_bytes : 0u;   // outputs staged over the consumed input tile
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int first = blockIdx.x, step = gridDim.x;
     const int n_my = first < a.n_tiles ? (a.n_tiles - first + step - 1) / step : 0;
     const size_t tile_in = (size_t)S * T * D, tile_out = (size_t)S * NB * D;
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+        for (int s = 0; s < kEncStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&out_full_bar[s], kEncGroupWarps); }
         mbar_fence_init();
-        if (n_my > 0) {
-            mbar_arrive_expect_tx(&full_bar, in_bytes);
-            bulk_g2s(smem, a.traj + (size_t)first * tile_in, in_bytes, &full_bar);
-        }
     }
     __syncthreads();
 
-    // one (trajectory, slot) column per thread; joint columns first so that warps are uniform
-    const int nj = a.n_joint, ng = D - nj;
-    const bool active = tid < S * D;
-    int tl = 0, slot = 0;
-    if (active) {
-        if (tid < S * nj) { tl = tid / nj; slot = tid - tl * nj; }
-        else { const int c = tid - S * nj; tl = c / ng; slot = nj + (c - tl * ng); }
-    }
-    const int dof = a.slot_to_dof[slot];
-    float wmin[NB], wmax[NB];
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-        wmin[k] = want_tok ? a.w_min[slot * NB + k] : 0.0f;
-        wmax[k] = want_tok ? a.w_max[slot * NB + k] : 0.0f;
+    if (warp == kEncGroups * kEncGroupWarps) {
+        // ---------------- copy thread ----------------
+        if (lane == 0) {
+            auto load = [&](int j) {
+                const int s = j % kEncStages;
+                mbar_arrive_expect_tx(&full_bar[s], in_bytes);
+                bulk_g2s(smem + s * stride, a.traj + ((size_t)first + (size_t)j * step) * tile_in, in_bytes, &full_bar[s]);
+            };
+            for (int j = 0; j < kEncStages && j < n_my; ++j) load(j);
+            for (int i = 0; i < n_my; ++i) {
+                const int s = i % kEncStages;
+                const size_t tile = (size_t)first + (size_t)i * step;
+                mbar_wait(&out_full_bar[s], (i / kEncStages) & 1);
+                if (want_tok) bulk_s2g(a.tokens_out + tile * tile_out, smem + s * stride, tok_bytes);
+                if (want_par) bulk_s2g(a.params_out + tile * tile_out, smem + s * stride + par_off, par_bytes);
+                bulk_commit();
+                if (i + kEncStages < n_my) {
+                    bulk_wait_read<0>();                   // the stage has been drained -> refill it
+                    load(i + kEncStages);
+                }
+            }
+            bulk_wait_all<0>();
+        }
+        return;
     }
 
-    for (int i = 0; i < n_my; ++i) {
-        const size_t tile = (size_t)first + (size_t)i * step;
-        mbar_wait(&full_bar, i & 1);
+    // ---------------- compute groups: one (trajectory, slot) column per thread ----------------
+    const int group = warp / kEncGroupWarps;
+    const int gtid = tid - group * (kEncGroupWarps * 32);
+    const int nj = a.n_joint, ng = D - nj;
+    const bool active = gtid < S * D;
+    int tl = 0, slot = 0;
+    if (active) {
+        if (gtid < S * nj) { tl = gtid / nj; slot = gtid - tl * nj; }     // joint columns first: uniform warps
+        else { const int c = gtid - S * nj; tl = c / ng; slot = nj + (c - tl * ng); }
+    }
+    const int dof = a.slot_to_dof[slot];
+    QuantCol qc[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+        qc[k].init(want_tok ? a.w_min[slot * NB + k] : 0.0f, want_tok ? a.w_max[slot * NB + k] : 0.0f);
+
+    for (int i = group; i < n_my; i += kEncGroups) {
+        const int s = i % kEncStages;
+        unsigned char* stage = smem + s * stride;
+        mbar_wait(&full_bar[s], (i / kEncStages) & 1);
         float acc[NB];
         if (active) {
-            const float* y = (const float*)smem + tl * (T * D) + dof;
-            if (slot < nj) fit_joint<T, NB>(tab, y, D, acc);
+            const float* y = (const float*)stage + tl * (T * D) + dof;
+            if (a.debug_skip) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) acc[k] = y[k * D];
+            } else if (slot < nj) fit_joint<T, NB>(tab, y, D, acc);
             else fit_grip<T, NB>(tab, y, D, acc);
         }
-        __syncthreads();                                   // every column has been read
+        group_barrier(group);                              // every column of the tile has been read
         if (active) {
             if (want_tok) {
-                long long* to = s_tok + tl * (NB * D) + slot;
+                long long* to = (long long*)stage + tl * (NB * D) + slot;
 #pragma unroll
-                for (int k = 0; k < NB; ++k)
-                    to[k * D] = quantize_one(acc[k], wmin[k], wmax[k], quant_scale(wmin[k], wmax[k]), a.vm1) + a.offset;
+                for (int k = 0; k < NB; ++k) to[k * D] = quantize_col(acc[k], qc[k], a.vm1) + a.offset;
             }
             if (want_par) {
-                float* po = s_par + tl * (NB * D) + slot * NB;
+                float* po = (float*)(stage + par_off) + tl * (NB * D) + slot * NB;
                 if (NB % 2 == 0) {
 #pragma unroll
                     for (int k = 0; k < NB; k += 2) *(float2*)(po + k) = make_float2(acc[k], acc[k + 1]);
@@ -151,19 +188,9 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
             }
         }
         fence_async_smem();                                // generic-proxy writes -> visible to the bulk store
-        __syncthreads();
-        if (tid == 0) {
-            if (want_tok) bulk_s2g(a.tokens_out + tile * tile_out, s_tok, tok_bytes);
-            if (want_par) bulk_s2g(a.params_out + tile * tile_out, s_par, par_bytes);
-            bulk_commit();
-            if (i + 1 < n_my) {
-                bulk_wait_read<0>();                       // staging buffer drained -> refill it
-                mbar_arrive_expect_tx(&full_bar, in_bytes);
-                bulk_g2s(smem, a.traj + (tile + step) * tile_in, in_bytes, &full_bar);
-            }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full_bar[s]);
     }
-    if (tid == 0) bulk_wait_all<0>();
 }
 
 // One thread per (trajectory, slot) column; any geometry.  Accumulates in the same order
@@ -277,8 +304,10 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
     a.traj = traj; a.params_out = params_out; a.tokens_out = tokens_out;
     a.w_min = w_min; a.w_max = w_max; a.offset = offset; a.vm1 = (float)(p->V - 1);
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
+    { const char* e = getenv("BEAST_B200_DEBUG_SKIP"); a.debug_skip = (e && e[0] == '1') ? 1 : 0; }
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
-    const size_t smem = (size_t)S * T * p->D * 4u;       // outputs (12 B * NB per column) alias the 4*T B input
+    // outputs (12 B * NB per column) alias the 4*T B per column input tile
+    const size_t smem = (size_t)kEncStages * ((((size_t)S * T * p->D * 4u) + 127u) & ~(size_t)127u);
     static_assert(12 * NB <= 4 * T, "staged outputs must fit over the input tile");
     if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
     static size_t attr_smem = 0;
@@ -288,8 +317,7 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
         if (e != cudaSuccess) return (int)e;
         attr_smem = smem;
     }
-    const long long cap = (long long)p->num_sms * kEncCtasPerSm;
-    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
     encode_fast_kernel<T, NB, DT><<<grid, kEncThreads, smem, st>>>(tab, a);
     count_launch();
     BEAST_CHECK_LAUNCH();
@@ -315,7 +343,7 @@ extern "C" int beast_encode_f32(const beast_plan_t* plan, const float* traj, int
     long long done = 0;
     if (T == 50 && nb == 10 && !fast_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
         (!tokens_out || aligned16(tokens_out))) {
-        const int S = (kEncThreads / D) & ~3;
+        const int S = (kEncColumns / D) & ~3;
         if (S >= 4 && B >= S) {
             const long long n_tiles = B / S;
             int rc;

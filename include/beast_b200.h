@@ -141,6 +141,12 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
                         const int64_t* ks_h, int32_t nk, float* out,
                         void* scratch, void* stream);
 
+/* Device self-test of the exact invariant-divisor division inside K1 / K3 (csrc/common.cuh) against
+ * IEEE division: n_divisors random divisors x 2^24 + 2^22 numerators each, and float(tok)/(V-1)
+ * for every V <= vmax.  mismatches[0..1] (device, 2 x uint64) receive the number of differing results. */
+int beast_selftest_div(int32_t n_divisors, int32_t vmax, uint64_t seed, unsigned long long* mismatches,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

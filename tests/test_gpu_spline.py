@@ -279,3 +279,44 @@ def test_update_times_rebuilds_plan():
     assert b.shape == a.shape
     tok.update_times(torch.from_numpy(g["times"]))
     assert torch.equal(tok.encode(x)[0], a)
+
+
+def test_invariant_division_is_exact():
+    """The FMA-corrected reciprocal division inside the fused quantiser / dequantiser returns the
+    bits of IEEE division: 512 divisors x 21M numerators, and tok/(V-1) for every V <= 70000."""
+    from beast_tokenizer_b200 import _lib
+    lib = _lib.load()
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _lib.check(lib.beast_selftest_div(512, 70000, 1234, _lib.ptr(out), _lib.stream_ptr(torch.device("cuda", 0))),
+               "beast_selftest_div")
+    torch.cuda.synchronize()
+    assert out.tolist() == [0, 0], f"division mismatches (quantiser, dequantiser): {out.tolist()}"
+
+
+def test_clamped_and_extreme_bounds():
+    """Coefficients clamped at a bound (numerator exactly 0), degenerate and huge bounds: the fused
+    kernels agree with the exact oracle quantiser / dequantiser."""
+    from beast_tokenizer_b200.synth import synth
+    cfg = GOLDEN_CASES["cfg2_d14"]
+    tok = make_tok(cfg)
+    x = synth(16 * 9 + 3, 50, 14, seed=5)
+    rng = np.random.default_rng(1)
+    lo = (-0.01 * rng.random(140)).astype(np.float32)
+    hi = (0.01 * rng.random(140)).astype(np.float32)
+    lo[3], hi[3] = 0.005, 0.005            # zero width -> scale clamps to 1e-8
+    lo[7], hi[7] = -1e38, 1e38             # divisor above the fast-division range
+    lo[11], hi[11] = -1e-30, 1e-30         # divisor below the fast-division range
+    lo[20], hi[20] = -1e25, 1e25
+    tok.w_min.copy_(torch.from_numpy(lo)); tok.w_max.copy_(torch.from_numpy(hi))
+    tokens, pd = tok.encode(x)
+    params = pd["params"].cpu().numpy()
+    own = O.tokens_from_params(params, lo, hi, 256, 14, 10, offset(cfg))
+    assert np.array_equal(tokens.cpu().numpy(), own)
+    assert (tokens.cpu().numpy() == offset(cfg)).mean() > 0.1          # many clamped-at-minimum tokens
+    coeff = tok.decode(tokens).cpu().numpy()
+    assert np.array_equal(coeff, O.decode(tokens.cpu().numpy(), lo, hi, 256, 14, 10, offset(cfg)), equal_nan=True)
+    rec = tok.reconstruct_traj(tokens).cpu().numpy()
+    joint, grip = layout(cfg)
+    ora = O.reconstruct_from_params(coeff, tok.times.numpy(), 2 * math.pi, 10, 4, joint, grip)
+    fin = np.isfinite(ora) & (np.abs(ora) < 1e20)
+    assert np.abs(rec[fin] - ora[fin]).max() <= 1e-5 * np.abs(ora[fin]).max()
