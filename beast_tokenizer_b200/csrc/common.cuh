@@ -54,11 +54,13 @@ __device__ __forceinline__ float quant_scale(float w_min, float w_max) {
 // (IEEE reciprocal), then two FMA residual corrections.  After the first correction q is a faithful
 // quotient, so the second residual is exact and Markstein's theorem gives q2 == RN(a / b) — the
 // same bits as the reference's true division, without div.rn's data-dependent slow path (taken
-// for a == 0, i.e. for every clamped coefficient).  Valid while 1/b, a/b and the residuals stay
-// in the normal range: callers check div_fast_ok(b) once per divisor and fall back to __fdiv_rn.
-// Verified against __fdiv_rn on ~10^10 operand pairs by beast_selftest_div (tests/test_gpu_spline.py).
+// for a == 0, i.e. for every clamped coefficient).  Bit-exact for 2^-27 <= b <= 2^100 (callers check
+// div_fast_ok(b) once per divisor and fall back to __fdiv_rn) whenever a / b >= 2^-60: then every
+// residual is a normal number.  For a smaller (possibly subnormal) quotient the last bit may
+// differ, but the token is bin 0 either way ((V-1) * 2^-60 rounds to 0).  Verified against __fdiv_rn on ~10^10 operand
+// pairs by beast_selftest_div (tests/test_gpu_spline.py).
 __device__ __forceinline__ bool div_fast_ok(float b) {
-    return b >= 7.8886090522101181e-31f && b <= 1.2676506002282294e+30f;   // 2^-100 .. 2^100
+    return b >= 7.4505805969238281e-09f && b <= 1.2676506002282294e+30f;   // 2^-27 .. 2^100
 }
 __device__ __forceinline__ float div_invariant(float a, float b, float y) {
     float q = __fmul_rn(a, y);

@@ -11,7 +11,8 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-// Divisor d: a float in [2^-100, 2^100]; a few special significands (1.0, all ones, 1+ulp) are forced.
+// Divisor d: a float in [2^-27, 2^100) (the quantiser's divisor is clamped to >= 1e-8 > 2^-27);
+// a few special significands (1.0, all ones, 1+ulp) are forced.
 __device__ float selftest_divisor(int d, uint64_t seed) {
     const uint64_t h = splitmix64(seed ^ (uint64_t)d * 0x100000001B3ull);
     uint32_t mant = (uint32_t)(h & 0x7FFFFFu);
@@ -21,7 +22,7 @@ __device__ float selftest_divisor(int d, uint64_t seed) {
     else if (sel == 2) mant = 1;
     else if (sel == 3) mant = 0x7FFFFEu;
     else if (sel == 4) mant = 0x400000u;
-    const int e = (int)((h >> 32) % 200u) - 100 + 127;          // exponent 2^-100 .. 2^99
+    const int e = (int)((h >> 32) % 127u) - 27 + 127;           // exponent 2^-27 .. 2^99
     return __uint_as_float(((uint32_t)e << 23) | mant);
 }
 
@@ -46,9 +47,19 @@ __global__ void selftest_div_kernel(int n_div, uint64_t seed, unsigned long long
         }
         const float want = __fdiv_rn(a, b);
         const float got = div_invariant(a, b, y);
-        // below 2^-60 the quotient cannot influence a token (n * (V-1) rounds to 0): require only < 2^-50
-        const bool ok = (__float_as_uint(want) == __float_as_uint(got)) || (want < 8.6736174e-19f && got < 8.8817842e-16f && got >= 0.0f);
-        bad += ok ? 0 : 1;
+        // Bit-equal whenever the quotient is >= 2^-60 (then a >= 2^-87 and every residual is a normal
+        // number).  A smaller quotient can never reach bin 1 ((V-1) * 2^-60 < 0.5 for V <= 2^31), so
+        // there only "non-negative and < 2^-60" is required.
+        const bool ok = (__float_as_uint(want) == __float_as_uint(got)) ||
+                        (want < 8.6736174e-19f && got < 8.6736174e-19f && got >= 0.0f);
+        if (!ok) {
+            ++bad;
+            const unsigned long long slot = atomicAdd(&mism[2], 1ull);
+            if (slot < 8) {                                     // keep a few examples: (a, b, want, got) bit patterns
+                mism[4 + 2 * slot] = ((unsigned long long)__float_as_uint(a) << 32) | bb;
+                mism[5 + 2 * slot] = ((unsigned long long)__float_as_uint(want) << 32) | __float_as_uint(got);
+            }
+        }
     }
     if (bad) atomicAdd(&mism[0], bad);
 }
@@ -82,7 +93,7 @@ extern "C" int beast_selftest_div(int32_t n_divisors, int32_t vmax, uint64_t see
     if (!mismatches) return BEAST_E_NULL;
     if (n_divisors < 0 || n_divisors > 65535 || vmax < 2) return BEAST_E_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(mismatches, 0, 2 * sizeof(unsigned long long), st);
+    cudaError_t e = cudaMemsetAsync(mismatches, 0, 20 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return (int)e;
     if (n_divisors > 0) {
         selftest_div_kernel<<<dim3(296, n_divisors), 256, 0, st>>>(n_divisors, seed, mismatches);

@@ -143,7 +143,8 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
 
 /* Device self-test of the exact invariant-divisor division inside K1 / K3 (csrc/common.cuh) against
  * IEEE division: n_divisors random divisors x 2^24 + 2^22 numerators each, and float(tok)/(V-1)
- * for every V <= vmax.  mismatches[0..1] (device, 2 x uint64) receive the number of differing results. */
+ * for every V <= vmax.  mismatches (device, 20 x uint64): [0], [1] = number of differing results of the
+ * two forms, [2] = examples recorded, [4..19] = up to 8 x (a|b, want|got) bit patterns. */
 int beast_selftest_div(int32_t n_divisors, int32_t vmax, uint64_t seed, unsigned long long* mismatches,
                        void* stream);
 

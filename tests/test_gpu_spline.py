@@ -286,11 +286,14 @@ def test_invariant_division_is_exact():
     bits of IEEE division: 512 divisors x 21M numerators, and tok/(V-1) for every V <= 70000."""
     from beast_tokenizer_b200 import _lib
     lib = _lib.load()
-    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    out = torch.zeros(20, dtype=torch.int64, device="cuda")
     _lib.check(lib.beast_selftest_div(512, 70000, 1234, _lib.ptr(out), _lib.stream_ptr(torch.device("cuda", 0))),
                "beast_selftest_div")
     torch.cuda.synchronize()
-    assert out.tolist() == [0, 0], f"division mismatches (quantiser, dequantiser): {out.tolist()}"
+    res = out.tolist()
+    examples = [tuple(np.array([v >> 32 & 0xffffffff, v & 0xffffffff], dtype=np.uint32).view(np.float32).tolist())
+                for v in res[4:4 + 2 * min(res[2], 8)]]
+    assert res[:2] == [0, 0], f"division mismatches (quantiser, dequantiser): {res[:2]}; (a,b),(want,got): {examples}"
 
 
 def test_clamped_and_extreme_bounds():
