@@ -107,6 +107,48 @@ def spline_case(ref, name, *, num_dof, num_basis, seq_len, vocab_size, degree_p=
     return tok
 
 
+def bpe_case(ref, name, *, bpe_vocab_size, fit_batches, fit_seed0, max_sequences=None):
+    """BEASTBsplineBPETokenizer on the bimanual config: train (HF byte-level BPE under the hood),
+    save, encode to ragged ids, decode back."""
+    base = ref.BEASTBsplineTokenizer.__new__(ref.BEASTBsplineTokenizer)
+    cfg = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
+               gripper_indices=[6, 13], device="cpu")
+    base = ref.BEASTBsplineTokenizer(**cfg)
+    g2 = dict(np.load(os.path.join(HERE, "cfg2_d14.npz")))
+    base.w_min.copy_(torch.from_numpy(g2["w_min_fit"]))
+    base.w_max.copy_(torch.from_numpy(g2["w_max_fit"]))
+    tok = ref.BEASTBsplineBPETokenizer.from_beast(base, bpe_vocab_size=bpe_vocab_size)
+    loader = SyntheticLoader(fit_batches, 32, 50, 14, seed0=fit_seed0)
+    state = tok.fit_from_trajectories(loader, show_progress=False, max_sequences=max_sequences)
+    sd = os.path.join(HERE, f"{name}_pretrained")
+    tok.save_pretrained(sd)
+    x = torch.from_numpy(g2["trajs"])
+    ids, pd, mp = tok.encode(x, return_mp_tokens=True)
+    out = {
+        "min_token": np.int64(state.min_token), "max_token": np.int64(state.max_token),
+        "fit_batches": np.int64(fit_batches), "fit_seed0": np.int64(fit_seed0),
+        "max_sequences": np.int64(-1 if max_sequences is None else max_sequences),
+        "bpe_vocab_size": np.int64(bpe_vocab_size),
+        "mp_tokens": npy(mp), "params": npy(pd["params"]),
+        "ids_flat": np.asarray([i for row in ids for i in row], dtype=np.int64),
+        "ids_len": np.asarray([len(r) for r in ids], dtype=np.int64),
+        "bpe_to_mp": npy(tok.bpe_to_mp_tokens(ids)),
+        "recon": npy(tok.reconstruct_traj(ids)),
+        "decode": npy(tok.decode(ids)),
+    }
+    # the training corpus (MP tokens of the loader) so that trainers can be compared without refitting
+    seqs = []
+    for b in loader:
+        t, _ = tok.encode_to_mp_tokens(b["actions"])
+        seqs.append(npy(t))
+    corpus = np.concatenate(seqs, 0)
+    if max_sequences is not None:
+        corpus = corpus[:max_sequences]
+    out["corpus_bins"] = corpus.astype(np.uint8) if corpus.max() < 256 else corpus
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 def main():
     ref = import_reference()
     import tokenizers
@@ -128,6 +170,9 @@ def main():
     # the CLI-default degenerate shape (train/train_beast.py:34-36): nb > T, degree 0
     spline_case(ref, "cli_default", num_dof=32, num_basis=50, seq_len=10, vocab_size=1000, degree_p=0,
                 batch=8, seed=21, fit_batches=6, fit_seed0=400)
+    # BPE on top of the bimanual tokenizer (configs[3]/[4] at a size the reference finishes in seconds)
+    bpe_case(ref, "bpe_d14", bpe_vocab_size=640, fit_batches=40, fit_seed0=1000)
+    bpe_case(ref, "bpe_d14_small", bpe_vocab_size=400, fit_batches=8, fit_seed0=2000, max_sequences=200)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,89 @@
+"""Pin the C BPE oracle (oracle/bpe_oracle.c) to the reference: golden files written by the live
+reference (HF tokenizers under FIGBPE) and, where the `tokenizers` wheel is importable, the
+library itself on fresh corpora.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+from oracle.bpe_oracle import OracleBPE, pretokenize
+
+BPE_CASES = ["bpe_d14", "bpe_d14_small"]
+
+
+def ref_files(name):
+    d = os.path.join(GOLDEN, f"{name}_pretrained", "bpe_tokenizer")
+    return (open(os.path.join(d, "vocab.json"), encoding="utf-8").read(),
+            open(os.path.join(d, "merges.txt"), encoding="utf-8").read())
+
+
+@pytest.mark.parametrize("name", BPE_CASES)
+def test_train_reproduces_reference_files(name):
+    g = load_golden(name)
+    vocab_json, merges_txt = ref_files(name)
+    o = OracleBPE.train(g["corpus_bins"].astype(np.int64), int(g["bpe_vocab_size"]))
+    assert (o.min_token, o.max_token) == (int(g["min_token"]), int(g["max_token"]))
+    assert o.merges_txt() == merges_txt
+    assert o.vocab_json() == vocab_json                       # byte-identical vocab.json
+    assert json.loads(vocab_json) == o.vocab_dict()
+
+
+@pytest.mark.parametrize("name", BPE_CASES)
+def test_encode_decode_match_reference(name):
+    g = load_golden(name)
+    vocab_json, merges_txt = ref_files(name)
+    o = OracleBPE.from_strings(json.loads(vocab_json), merges_txt.splitlines()[1:])
+    ids_ref = np.split(g["ids_flat"], np.cumsum(g["ids_len"])[:-1])
+    mn = int(g["min_token"])
+    for row, want in zip(g["mp_tokens"], ids_ref):
+        got = o.encode(row - mn)
+        assert got == want.tolist()
+        assert np.array_equal(o.decode(got) + mn, row)
+    assert np.array_equal(g["bpe_to_mp"], g["mp_tokens"])
+
+
+def test_pretokenizer_examples():
+    """SURVEY.md Appendix A.2 examples (probed against the library)."""
+    def pieces(s):
+        cp = [ord(c) for c in s]
+        ws = pretokenize(cp)
+        idx = [i for i, w in enumerate(ws) if w] + [len(cp)]
+        return [s[a:b] for a, b in zip(idx[:-1], idx[1:])]
+    assert pieces("ab  cd") == ["ab", " ", " cd"]
+    assert pieces("ab \n cd") == ["ab", " \n", " cd"]
+    assert pieces(" 12ab") == [" 12", "ab"]
+    assert pieces("x'll") == ["x", "'ll"]
+    assert pieces("\x00\x01'tA") == ["\x00\x01'", "tA"]
+    assert pieces("a\x85b\xa0") == ["a", "\x85", "b", "\xa0"]
+    assert pieces("  ") == ["  "]
+
+
+def test_against_live_library():
+    tokenizers = pytest.importorskip("tokenizers")
+    from tokenizers import ByteLevelBPETokenizer, pre_tokenizers
+    from tokenizers.trainers import BpeTrainer
+    rng = np.random.default_rng(7)
+    pt = pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=True)
+    for trial in range(600):
+        n = int(rng.integers(1, 50))
+        cp = rng.integers(0, 256, n) if trial % 2 else rng.choice([32, 39, 115, 116, 114, 101, 108, 65, 48, 10, 160, 33], n)
+        starts = np.zeros(n, np.uint8)
+        for _, (a, _b) in pt.pre_tokenize_str("".join(map(chr, cp))):
+            starts[a] = 1
+        assert np.array_equal(pretokenize(cp), starts), cp.tolist()
+    for bins, vs in ((rng.integers(0, 256, (600, 140)), 500), (rng.integers(30, 100, (300, 70)), 420),
+                     (rng.choice([97, 98, 99], (100, 40)), 300)):
+        mn, mx = int(bins.min()), int(bins.max())
+        hf = ByteLevelBPETokenizer()
+        trainer = BpeTrainer(vocab_size=vs, min_frequency=2, show_progress=False, special_tokens=[],
+                             initial_alphabet=[chr(i) for i in range(mx - mn + 1)], max_token_length=10000)
+        hf._tokenizer.train_from_iterator(["".join(map(chr, r - mn)) for r in bins], trainer=trainer)
+        o = OracleBPE.train(bins, vs)
+        assert o.vocab_dict() == hf.get_vocab()
+        model = json.loads(hf._tokenizer.to_str())["model"]
+        hf_merges = [m if isinstance(m, str) else " ".join(m) for m in model["merges"]]
+        assert o.merges_lines() == hf_merges
+        for r in bins[:50]:
+            assert o.encode(r - mn) == hf.encode("".join(map(chr, r - mn)), add_special_tokens=False).ids
