@@ -2,6 +2,10 @@
 behind the reference's Python API (Dont4rootMe/beast_tokenizer, package `beast`)."""
 from .base_tokenizer import TokenizerBase
 from .beast_bspline_tokenizer import BEASTBsplineTokenizer, CONFIG_FILENAME
+from .beast_bspline_bpe_tokenizer import BEASTBsplineBPETokenizer
+from .beast_bpe_trainer import FIGBPE, FIGBPEState
+from .bpe_model import B200ByteLevelBPE
 from ._lib import BeastB200Error
 
-__all__ = ["TokenizerBase", "BEASTBsplineTokenizer", "CONFIG_FILENAME", "BeastB200Error"]
+__all__ = ["TokenizerBase", "BEASTBsplineTokenizer", "BEASTBsplineBPETokenizer", "FIGBPE", "FIGBPEState",
+           "B200ByteLevelBPE", "CONFIG_FILENAME", "BeastB200Error"]

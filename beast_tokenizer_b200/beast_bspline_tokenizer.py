@@ -486,11 +486,14 @@ class BEASTBsplineTokenizer(TokenizerBase):
     @torch.no_grad()
     def reconstruct_traj(self, tokens, times=None, **kwargs):
         """tokens -> trajectories [B, T, D] (reference :498-536): one fused K3 launch."""
+        offset = self._llm_vocab_offset() if self.llm_vocab_size is not None else 0   # decode() default
+        return self._reconstruct_from_mp_tokens(tokens, offset, times, **kwargs)
+
+    def _reconstruct_from_mp_tokens(self, tokens, offset, times=None, **kwargs):
         plan = self._plan()
         dev = plan.device
         tokens = self._flatten_tokens(tokens, dev)
         B = tokens.shape[0]
-        offset = self._llm_vocab_offset() if self.llm_vocab_size is not None else 0   # decode() default
         lo, hi = self._bounds(dev)
         init_p = self._init_p(kwargs, dev, B)
         with torch.cuda.device(dev):

@@ -1,0 +1,238 @@
+"""Byte-level BPE model (vocabulary + merge table) with device-side tables for the K5 kernels.
+
+Stands in for HF `tokenizers.ByteLevelBPETokenizer` as used by the reference
+(beast/beast_bpe_trainer.py:61-74, beast/beast_bspline_bpe_tokenizer.py:175-247, 336-388): same
+vocab.json / merges.txt / tokenizer.json files, same ids.  Applying the model (ids <-> bins) runs
+on the GPU through libbeast_b200.so (bpe_encode / bpe_decode); there is no host implementation.
+"""
+import ctypes as C
+import json
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def bytes_to_unicode() -> List[int]:
+    """GPT-2 byte -> character map of the ByteLevel pre-tokenizer: printable
+    bytes map to themselves, the other 68 to U+0100.. in byte order."""
+    out, n = [], 0
+    for b in range(256):
+        if 33 <= b <= 126 or 161 <= b <= 172 or 174 <= b <= 255:
+            out.append(b)
+        else:
+            out.append(256 + n)
+            n += 1
+    return out
+
+
+B2U = bytes_to_unicode()
+U2B = {c: b for b, c in enumerate(B2U)}
+
+
+class Encoding:
+    """Minimal stand-in for tokenizers.Encoding (only `.ids` is used by the reference)."""
+
+    def __init__(self, ids):
+        self.ids = ids
+
+
+class B200ByteLevelBPE:
+    """vocab: token strings (byte-level characters) in id order; merges: [(id_a, id_b, id_new)]."""
+
+    def __init__(self, vocab: Sequence[str], merges: Sequence[Tuple[int, int, int]]):
+        self.tokens: List[str] = list(vocab)
+        self.merges: List[Tuple[int, int, int]] = [tuple(int(x) for x in m) for m in merges]
+        self._vocab: Dict[str, int] = {t: i for i, t in enumerate(self.tokens)}
+        self._dev_tables = {}
+
+    # ------------------------------------------------------------------ construction / files
+    @classmethod
+    def from_vocab_merges(cls, vocab: Dict[str, int], merge_pairs: Sequence[Tuple[str, str]]):
+        by_id = sorted(vocab.items(), key=lambda kv: kv[1])
+        if [i for _, i in by_id] != list(range(len(by_id))):
+            raise ValueError("vocabulary ids must be 0..n-1")
+        merges = []
+        for a, b in merge_pairs:
+            if a not in vocab or b not in vocab or (a + b) not in vocab:
+                raise ValueError(f"merge {a!r} {b!r} refers to tokens outside the vocabulary")
+            merges.append((vocab[a], vocab[b], vocab[a + b]))
+        return cls([t for t, _ in by_id], merges)
+
+    @classmethod
+    def from_file(cls, vocab_path: str, merges_path: str):
+        """Same inputs as ByteLevelBPETokenizer.from_file (reference bpe_tokenizer.py:379-382)."""
+        with open(vocab_path, encoding="utf-8") as f:
+            vocab = json.load(f)
+        pairs = []
+        with open(merges_path, encoding="utf-8") as f:
+            for i, line in enumerate(f.read().split("\n")):
+                if (i == 0 and line.startswith("#version")) or not line:
+                    continue
+                a, b = line.split(" ")
+                pairs.append((a, b))
+        return cls.from_vocab_merges(vocab, pairs)
+
+    @classmethod
+    def from_hf(cls, tokenizer):
+        """Import a trained HF ByteLevelBPETokenizer / Tokenizer (e.g. one the reference produced)."""
+        inner = getattr(tokenizer, "_tokenizer", tokenizer)
+        model = json.loads(inner.to_str())["model"]
+        pairs = [tuple(m.split(" ")) if isinstance(m, str) else tuple(m) for m in model["merges"]]
+        return cls.from_vocab_merges(model["vocab"], pairs)
+
+    def to_hf(self):
+        """A real tokenizers.ByteLevelBPETokenizer with this vocabulary (needs the `tokenizers` wheel)."""
+        from tokenizers import ByteLevelBPETokenizer
+        return ByteLevelBPETokenizer(vocab=dict(self._vocab), merges=[(a, b) for a, b in self.merge_strings()])
+
+    def get_vocab(self) -> Dict[str, int]:
+        return dict(self._vocab)
+
+    def get_vocab_size(self) -> int:
+        return len(self.tokens)
+
+    def token_to_id(self, token: str) -> Optional[int]:
+        return self._vocab.get(token)
+
+    def id_to_token(self, i: int) -> Optional[str]:
+        return self.tokens[i] if 0 <= i < len(self.tokens) else None
+
+    def merge_strings(self) -> List[Tuple[str, str]]:
+        return [(self.tokens[a], self.tokens[b]) for a, b, _ in self.merges]
+
+    def vocab_json(self) -> str:
+        """The bytes HF's save_model writes: compact JSON in id order, non-ASCII unescaped."""
+        return json.dumps(self._vocab, ensure_ascii=False, separators=(",", ":"))
+
+    def merges_txt(self) -> str:
+        return "#version: 0.2\n" + "".join(f"{a} {b}\n" for a, b in self.merge_strings())
+
+    def save_model(self, directory: str, prefix: Optional[str] = None) -> List[str]:
+        name = (lambda n: f"{prefix}-{n}" if prefix else n)
+        vp, mp = os.path.join(directory, name("vocab.json")), os.path.join(directory, name("merges.txt"))
+        with open(vp, "w", encoding="utf-8") as f:
+            f.write(self.vocab_json())
+        with open(mp, "w", encoding="utf-8") as f:
+            f.write(self.merges_txt())
+        return [vp, mp]
+
+    def tokenizer_json(self) -> str:
+        """tokenizer.json exactly as ByteLevelBPETokenizer.save writes it (tokenizers 0.2x layout)."""
+        bl = lambda prefix, trim: {"type": "ByteLevel", "add_prefix_space": prefix, "trim_offsets": trim,
+                                   "use_regex": True}
+        doc = {
+            "version": "1.0", "truncation": None, "padding": None, "added_tokens": [], "normalizer": None,
+            "pre_tokenizer": bl(False, True), "post_processor": bl(True, False), "decoder": bl(True, True),
+            "model": {"type": "BPE", "dropout": None, "unk_token": None, "continuing_subword_prefix": None,
+                      "end_of_word_suffix": None, "fuse_unk": False, "byte_fallback": False, "ignore_merges": False,
+                      "vocab": self._vocab, "merges": [list(p) for p in self.merge_strings()]},
+        }
+        return json.dumps(doc, indent=2, ensure_ascii=False)
+
+    def save(self, path: str, pretty: bool = True):
+        with open(path, "w", encoding="utf-8") as f:
+            f.write(self.tokenizer_json())
+
+    # ------------------------------------------------------------------ device tables
+    def token_bytes(self, i: int) -> bytes:
+        return bytes(U2B[ord(c)] for c in self.tokens[i] if ord(c) in U2B)
+
+    def _tables(self, dev: torch.device):
+        key = (dev.type, dev.index)
+        if key in self._dev_tables:
+            return self._dev_tables[key]
+        V = len(self.tokens)
+        if V > 65535:
+            raise _lib.BeastB200Error("BPE vocabularies above 65535 entries are not supported")
+        b2i = np.full(256, -1, dtype=np.int16)
+        for b in range(256):
+            b2i[b] = self._vocab.get(chr(B2U[b]), -1)
+        rank = np.full(V * V, 0xFFFFFFFF, dtype=np.uint32)
+        for r, (a, b, c) in enumerate(self.merges):
+            k = a * V + b
+            if rank[k] == 0xFFFFFFFF:
+                rank[k] = (r << 16) | c
+        off = np.zeros(V + 1, dtype=np.int32)
+        chunks = []
+        for i in range(V):
+            # HF's ByteLevel decoder maps characters back to bytes; a token holding any other
+            # character (the unused raw chr(i) alphabet entries) contributes its own UTF-8 bytes
+            tok = self.tokens[i]
+            tb = bytes(U2B[ord(c)] for c in tok) if all(ord(c) in U2B for c in tok) else tok.encode("utf-8")
+            chunks.append(tb)
+            off[i + 1] = off[i] + len(tb)
+        blob = np.frombuffer(b"".join(chunks) or b"\x00", dtype=np.uint8).copy()
+        t = dict(V=V, b2i=torch.from_numpy(b2i).to(dev), rank=torch.from_numpy(rank.view(np.int32)).to(dev),
+                 off=torch.from_numpy(off).to(dev), blob=torch.from_numpy(blob).to(dev))
+        self._dev_tables[key] = t
+        return t
+
+    # ------------------------------------------------------------------ apply (GPU)
+    def encode_bins(self, bins: torch.Tensor, min_token: int, max_token: Optional[int]):
+        """bins [N, L] int64 (CUDA) -> (flat ids int32, offsets int64 [N+1], status int32 [N]).
+        status bit 0 / 1 = a bin below min_token / above max_token (reference :182-192)."""
+        dev = bins.device
+        if dev.type != "cuda":
+            raise _lib.BeastB200Error("BPE encode runs on the GPU only (no CPU fallback)")
+        lib = _lib.load()
+        t = self._tables(dev)
+        bins = bins.to(torch.int64).contiguous()
+        N, L = bins.shape
+        max_shift = 255 if max_token is None else int(max_token) - int(min_token)
+        stride = 2 * L
+        padded = torch.empty((N, stride), device=dev, dtype=torch.int16)
+        lens = torch.empty(N, device=dev, dtype=torch.int32)
+        status = torch.empty(N, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(lib.bpe_encode(_lib.ptr(bins), N, L, int(min_token), max_shift, _lib.ptr(t["b2i"]),
+                                      _lib.ptr(t["rank"]), t["V"], _lib.ptr(padded), stride, _lib.ptr(lens),
+                                      _lib.ptr(status), st), "bpe_encode")
+            offsets = torch.zeros(N + 1, device=dev, dtype=torch.int64)
+            torch.cumsum(lens, 0, out=offsets[1:])
+            total = int(offsets[-1].item()) if N else 0
+            flat = torch.empty(max(total, 1), device=dev, dtype=torch.int32)
+            _lib.check(lib.bpe_compact(_lib.ptr(padded), stride, _lib.ptr(lens), _lib.ptr(offsets), N, _lib.ptr(flat),
+                                       st), "bpe_compact")
+        return flat[:total], offsets, status
+
+    def decode_ids(self, flat: torch.Tensor, offsets: torch.Tensor, L: int, min_token: int):
+        """CSR ids (CUDA) -> (bins int64 [N, L], status int32 [N], decoded length int32 [N])."""
+        dev = flat.device
+        if dev.type != "cuda":
+            raise _lib.BeastB200Error("BPE decode runs on the GPU only (no CPU fallback)")
+        lib = _lib.load()
+        t = self._tables(dev)
+        flat = flat.to(torch.int32).contiguous()
+        offsets = offsets.to(dev, torch.int64).contiguous()
+        N = offsets.numel() - 1
+        bins = torch.empty((N, L), device=dev, dtype=torch.int64)
+        status = torch.empty(N, device=dev, dtype=torch.int32)
+        declen = torch.empty(N, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.bpe_decode(_lib.ptr(flat), _lib.ptr(offsets), N, L, int(min_token), _lib.ptr(t["off"]),
+                                      _lib.ptr(t["blob"]), t["V"], _lib.ptr(bins), _lib.ptr(status), _lib.ptr(declen),
+                                      _lib.stream_ptr(dev)), "bpe_decode")
+        return bins, status, declen
+
+    # ------------------------------------------------------------------ HF-shaped convenience (single strings, on the GPU)
+    def encode(self, text: str, add_special_tokens: bool = False) -> Encoding:
+        cps = [ord(c) for c in text]
+        if any(c > 255 for c in cps):
+            raise ValueError("only codepoints 0..255 (<= 256-bin tokenizers) are supported")
+        if not cps:
+            return Encoding([])
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if dev is None:
+            raise _lib.BeastB200Error("BPE encode runs on the GPU only (no CPU fallback)")
+        flat, _, _ = self.encode_bins(torch.tensor([cps], dtype=torch.int64, device=dev), 0, None)
+        return Encoding(flat.cpu().tolist())
+
+    def decode(self, ids: Sequence[int], skip_special_tokens: bool = True) -> str:
+        """Token strings -> bytes -> text for ONE id list (a table lookup, kept for API parity with the
+        HF object; batches go through decode_ids on the GPU)."""
+        return bytes(U2B[ord(c)] for i in ids for c in self.tokens[i] if ord(c) in U2B).decode("utf-8", "replace")

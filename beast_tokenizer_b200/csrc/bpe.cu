@@ -1,0 +1,574 @@
+// K4 / K5 — byte-level BPE over discretised BEAST bins on the GPU.
+//
+// The reference trains and applies HF `tokenizers`' ByteLevelBPETokenizer on chr(bin - min_token)
+// strings (beast/beast_bpe_trainer.py:61-98, beast/beast_bspline_bpe_tokenizer.py:175-247).  These
+// kernels implement the same algorithm on integer symbols:
+//
+//   symbolise   bins -> GPT-2 pre-tokenisation -> UTF-8 bytes -> symbol ids, word-start flag in bit 15
+//   count       adjacent-pair histogram, dense V x V int32 (L2-resident: 16 MB at V = 2048)
+//   argmax      max count, ties -> smallest (a, b)  ==  smallest flat index a*V + b
+//   merge       per sequence, left to right, non-overlapping, in-place compaction; the count changes
+//               are confined to column a, row b, column c, row c of the histogram and are collected
+//               in a 4 x V delta block (summed over GPUs with one small all-reduce when sharded)
+//   encode      per word: repeatedly merge the lowest-rank pair, leftmost first
+//   decode      ids -> token bytes -> UTF-8 -> codepoints + min_token
+//
+// Corpus layout: POSITION-MAJOR sym[p * n_stride + seq] (uint16): one thread owns one sequence and
+// walks p, so every warp access is a contiguous 64-byte row — the serial per-sequence state
+// machines (pre-tokeniser, merge) run at full coalescing without any shuffling.
+#include "common.cuh"
+
+namespace beast {
+
+constexpr int kBpeBlock = 128;
+constexpr uint16_t kWordStart = 0x8000u;
+constexpr uint16_t kIdMask = 0x7fffu;
+constexpr int kMaxWord = 512;            // longest sequence (in byte-level symbols) encode handles
+
+// GPT-2 pre-tokeniser character classes for codepoints 0..255
+enum { CLS_O = 0, CLS_L = 1, CLS_N = 2, CLS_S = 3 };
+__device__ __forceinline__ int cp_class(int c) {
+    if (c == 32 || (c >= 9 && c <= 13) || c == 133 || c == 160) return CLS_S;
+    if ((c >= 48 && c <= 57) || c == 178 || c == 179 || c == 185 || (c >= 188 && c <= 190)) return CLS_N;
+    if ((c >= 65 && c <= 90) || (c >= 97 && c <= 122) || c == 170 || c == 181 || c == 186 ||
+        (c >= 192 && c <= 214) || (c >= 216 && c <= 246) || c >= 248)
+        return CLS_L;
+    return CLS_O;
+}
+
+// Length of the pre-token starting at codepoint i of cp[0..n) (shared memory).
+__device__ __forceinline__ int pretoken_len(const uint8_t* cp, int i, int n) {
+    const int c = cp[i];
+    if (c == 39 && i + 1 < n) {                              // 's|'t|'re|'ve|'m|'ll|'d
+        const int d = cp[i + 1];
+        if (d == 's' || d == 't' || d == 'm' || d == 'd') return 2;
+        if (i + 2 < n) {
+            const int e = cp[i + 2];
+            if ((d == 'r' && e == 'e') || (d == 'v' && e == 'e') || (d == 'l' && e == 'l')) return 3;
+        }
+    }
+    int start = i;
+    if (c == 32 && i + 1 < n && cp_class(cp[i + 1]) != CLS_S) start = i + 1;     // " ?" prefix
+    const int k = cp_class(cp[start]);
+    if (k != CLS_S) {                                        // one run of L, N or O
+        int j = start + 1;
+        while (j < n && cp_class(cp[j]) == k) ++j;
+        return j - i;
+    }
+    int j = i + 1;                                           // whitespace run [i, j)
+    while (j < n && cp_class(cp[j]) == CLS_S) ++j;
+    if (j == n) return j - i;                                // \s+(?!\S) at end of text
+    if (j - i >= 2) return j - 1 - i;                        // \s+(?!\S): leave the last blank
+    return 1;                                                // \s+
+}
+
+// Cooperative load of kBpeBlock rows of bins into shared memory as shifted bytes.
+// status: bit 0 = a value below min_token, bit 1 = a value above max_token (per sequence).
+__device__ __forceinline__ void stage_rows(const long long* __restrict__ bins, long long base, long long N, int L,
+                                           long long min_token, long long max_shift, uint8_t* s_cp, int LP,
+                                           int* s_status) {
+    const long long rows = (N - base) < kBpeBlock ? (N - base) : kBpeBlock;
+    for (long long idx = threadIdx.x; idx < rows * L; idx += blockDim.x) {
+        const int r = (int)(idx / L), p = (int)(idx - (long long)r * L);
+        const long long v = bins[(base + r) * L + p] - min_token;
+        if (v < 0) atomicOr(&s_status[r], 1);
+        else if (v > max_shift) atomicOr(&s_status[r], 2);
+        s_cp[r * LP + p] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+// ---------------------------------------------------------------- alphabet discovery
+__global__ void __launch_bounds__(256)
+bpe_minmax_kernel(const long long* __restrict__ bins, long long n, long long* mn, long long* mx) {
+    long long a = 0x7fffffffffffffffLL, b = -0x7fffffffffffffffLL - 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = bins[i];
+        a = v < a ? v : a;
+        b = v > b ? v : b;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, b, o);
+        a = a2 < a ? a2 : a;
+        b = b2 > b ? b2 : b;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mn, a); atomicMax(mx, b); }
+}
+
+// seen[b] = 1 for every UTF-8 byte that occurs (the byte-level characters "seen in words", A.3)
+__global__ void __launch_bounds__(256)
+bpe_seen_kernel(const long long* __restrict__ bins, long long n, long long min_token, int* seen, int* err) {
+    __shared__ int s_seen[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_seen[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = bins[i] - min_token;
+        if (v < 0 || v > 255) { *err = 1; continue; }
+        if (v < 128) s_seen[v] = 1;
+        else { s_seen[0xC0 | (v >> 6)] = 1; s_seen[0x80 | (v & 0x3F)] = 1; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) if (s_seen[i]) seen[i] = 1;
+}
+
+// ---------------------------------------------------------------- symbolise
+__global__ void __launch_bounds__(kBpeBlock)
+bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token,
+                     const short* __restrict__ byte_to_id, uint16_t* __restrict__ sym, int* __restrict__ len,
+                     long long n_stride, int* err) {
+    extern __shared__ uint8_t s_raw[];
+    const int LP = L + 1;
+    uint8_t* s_cp = s_raw;
+    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP + 3) & ~(size_t)3));
+    __shared__ short s_b2i[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
+    for (int i = threadIdx.x; i < kBpeBlock; i += blockDim.x) s_status[i] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kBpeBlock;
+    stage_rows(bins, base, N, L, min_token, 255, s_cp, LP, s_status);
+    __syncthreads();
+    const long long seq = base + threadIdx.x;
+    if (seq >= N) return;
+    if (s_status[threadIdx.x]) *err = 1;
+    const uint8_t* cp = s_cp + threadIdx.x * LP;
+    uint16_t* out = sym + seq;
+    int m = 0, i = 0;
+    while (i < L) {
+        const int pl = pretoken_len(cp, i, L);
+        uint16_t flag = kWordStart;
+        for (int q = i; q < i + pl; ++q) {
+            const int c = cp[q];
+            if (c < 128) {
+                const int id = s_b2i[c];
+                if (id >= 0) { out[(long long)m * n_stride] = (uint16_t)id | flag; flag = 0; ++m; }
+            } else {
+                const int i0 = s_b2i[0xC0 | (c >> 6)], i1 = s_b2i[0x80 | (c & 0x3F)];
+                if (i0 >= 0) { out[(long long)m * n_stride] = (uint16_t)i0 | flag; flag = 0; ++m; }
+                if (i1 >= 0) { out[(long long)m * n_stride] = (uint16_t)i1 | flag; flag = 0; ++m; }
+            }
+        }
+        i += pl;
+    }
+    len[seq] = m;
+}
+
+// ---------------------------------------------------------------- pair histogram
+__global__ void __launch_bounds__(256)
+bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
+                 int V, int* __restrict__ hist) {
+    for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
+         seq += (long long)gridDim.x * blockDim.x) {
+        const int n = len[seq];
+        if (n < 2) continue;
+        const uint16_t* s = sym + seq;
+        int prev = s[0] & kIdMask;
+        for (int q = 1; q < n; ++q) {
+            const uint16_t cur = s[(long long)q * n_stride];
+            if (!(cur & kWordStart)) atomicAdd(&hist[(long long)prev * V + (cur & kIdMask)], 1);
+            prev = cur & kIdMask;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- arg-max with the trainer's tie-break
+// key = count << 32 | ~flat: the largest key is the largest count and, among equals, the smallest
+// flat index a*V + b, i.e. the lexicographically smallest (a, b).
+__global__ void __launch_bounds__(256)
+bpe_argmax_kernel(const int* __restrict__ hist, int V, int n_active, unsigned long long* __restrict__ result) {
+    unsigned long long best = 0;
+    const long long total = (long long)n_active * n_active;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i / n_active), b = (int)(i - (long long)a * n_active);
+        const unsigned int flat = (unsigned int)a * (unsigned int)V + (unsigned int)b;
+        const int c = hist[flat];
+        if (c > 0) {
+            const unsigned long long key = ((unsigned long long)(unsigned int)c << 32) | (0xffffffffu - flat);
+            best = key > best ? key : best;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long s_best[8];
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_best[w] > best ? s_best[w] : best;
+        if (best) atomicMax(result, best);
+    }
+}
+
+// ---------------------------------------------------------------- merge (a, b) -> c
+// delta block: [0] column a (pairs (x, a) lost), [1] row b (pairs (b, y) lost),
+//              [2] column c (pairs (x, c) gained), [3] row c (pairs (c, y) gained).
+// Block-private copies live in shared memory (4*V ints) and are flushed once per block.
+__global__ void __launch_bounds__(256)
+bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N, long long n_stride, int a, int b,
+                 int c, int V, int* __restrict__ delta) {
+    extern __shared__ int s_delta[];
+    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
+    __syncthreads();
+    int* col_a = s_delta;
+    int* row_b = s_delta + V;
+    int* col_c = s_delta + 2 * V;
+    int* row_c = s_delta + 3 * V;
+    for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
+         seq += (long long)gridDim.x * blockDim.x) {
+        const int n = len[seq];
+        if (n < 2) continue;
+        uint16_t* s = sym + seq;
+        int q = 0, o = 0;
+        uint16_t cur = s[0];
+        bool prev_merged = false;
+        int prev_old = 0, prev_new = 0;                      // ids of the previous old / emitted symbol
+        while (q < n) {
+            const uint16_t nxt = (q + 1 < n) ? s[(long long)(q + 1) * n_stride] : (uint16_t)kWordStart;
+            const int cid = cur & kIdMask;
+            if (cid == a && q + 1 < n && (nxt & kIdMask) == b && !(nxt & kWordStart)) {
+                if (!(cur & kWordStart) && q > 0) {          // pair with the left neighbour changes
+                    atomicAdd(&col_a[prev_old], -1);         // (old left, a) disappears
+                    atomicAdd(&col_c[prev_new], 1);          // (new left, c) appears
+                }
+                const uint16_t w = (uint16_t)c | (cur & kWordStart);
+                s[(long long)o * n_stride] = w;
+                prev_merged = true;
+                prev_old = b;
+                prev_new = c;
+                ++o;
+                q += 2;
+                cur = (q < n) ? s[(long long)q * n_stride] : (uint16_t)0;
+            } else {
+                if (prev_merged && !(cur & kWordStart)) {    // right neighbour of a merge
+                    atomicAdd(&row_b[cid], -1);              // (b, y) disappears
+                    atomicAdd(&row_c[cid], 1);               // (c, y) appears
+                }
+                if (o != q) s[(long long)o * n_stride] = cur;
+                prev_merged = false;
+                prev_old = cid;
+                prev_new = cid;
+                ++o;
+                ++q;
+                cur = nxt;
+            }
+        }
+        if (o != n) len[seq] = o;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
+        const int d = s_delta[i];
+        if (d) atomicAdd(&delta[i], d);
+    }
+}
+
+// hist += delta (after the optional cross-GPU sum), then the merged pair is gone for good.
+__global__ void __launch_bounds__(1024)
+bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, int b, int c, int V) {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) hist[(long long)i * V + a] += delta[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < V; i += blockDim.x) hist[(long long)b * V + i] += delta[V + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < V; i += blockDim.x) hist[(long long)i * V + c] += delta[2 * V + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < V; i += blockDim.x) hist[(long long)c * V + i] += delta[3 * V + i];
+    __syncthreads();
+    if (threadIdx.x == 0) hist[(long long)a * V + b] = 0;
+    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) delta[i] = 0;
+}
+
+// ---------------------------------------------------------------- encode (K5a)
+// rank_tab[a*V + b] = rank << 16 | new_id, or 0xffffffff.  One thread per sequence; the word being
+// merged lives in local memory with its pair keys cached, so a merge costs one scan + two lookups.
+__global__ void __launch_bounds__(kBpeBlock)
+bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token, long long max_shift,
+                  const short* __restrict__ byte_to_id, const unsigned int* __restrict__ rank_tab, int V,
+                  uint16_t* __restrict__ ids_out, int out_stride, int* __restrict__ len_out,
+                  int* __restrict__ status_out) {
+    extern __shared__ uint8_t s_raw[];
+    const int LP = L + 1;
+    uint8_t* s_cp = s_raw;
+    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP + 3) & ~(size_t)3));
+    __shared__ short s_b2i[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
+    for (int i = threadIdx.x; i < kBpeBlock; i += blockDim.x) s_status[i] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kBpeBlock;
+    stage_rows(bins, base, N, L, min_token, max_shift, s_cp, LP, s_status);
+    __syncthreads();
+    const long long seq = base + threadIdx.x;
+    if (seq >= N) return;
+    status_out[seq] = s_status[threadIdx.x];
+    if (s_status[threadIdx.x]) { len_out[seq] = 0; return; }
+    const uint8_t* cp = s_cp + threadIdx.x * LP;
+    uint16_t* out = ids_out + seq * (long long)out_stride;
+    uint16_t w[kMaxWord];
+    unsigned int key[kMaxWord];
+    int m = 0, i = 0;
+    while (i < L) {
+        const int pl = pretoken_len(cp, i, L);
+        int wl = 0;
+        for (int q = i; q < i + pl; ++q) {
+            const int c = cp[q];
+            if (c < 128) {
+                const int id = s_b2i[c];
+                if (id >= 0) w[wl++] = (uint16_t)id;
+            } else {
+                const int i0 = s_b2i[0xC0 | (c >> 6)], i1 = s_b2i[0x80 | (c & 0x3F)];
+                if (i0 >= 0) w[wl++] = (uint16_t)i0;
+                if (i1 >= 0) w[wl++] = (uint16_t)i1;
+            }
+        }
+        i += pl;
+        for (int q = 0; q + 1 < wl; ++q) key[q] = __ldg(&rank_tab[(size_t)w[q] * V + w[q + 1]]);
+        while (wl >= 2) {
+            unsigned int best = 0xffffffffu, best_rank = 0xffffffffu;
+            int bp = -1;
+            for (int q = 0; q + 1 < wl; ++q) {               // lowest rank, leftmost first
+                const unsigned int kq = key[q];
+                if (kq != 0xffffffffu && (kq >> 16) < best_rank) { best = kq; best_rank = kq >> 16; bp = q; }
+            }
+            if (bp < 0) break;
+            w[bp] = (uint16_t)(best & 0xffffu);
+            for (int q = bp + 1; q + 1 < wl; ++q) { w[q] = w[q + 1]; key[q] = key[q + 1]; }
+            --wl;
+            if (bp > 0) key[bp - 1] = __ldg(&rank_tab[(size_t)w[bp - 1] * V + w[bp]]);
+            if (bp + 1 < wl) key[bp] = __ldg(&rank_tab[(size_t)w[bp] * V + w[bp + 1]]);
+        }
+        for (int q = 0; q < wl; ++q) out[m++] = w[q];
+    }
+    len_out[seq] = m;
+}
+
+// padded rows -> CSR (offsets are an exclusive scan of len, computed by the caller)
+__global__ void __launch_bounds__(256)
+bpe_compact_kernel(const uint16_t* __restrict__ padded, int stride, const int* __restrict__ len,
+                   const long long* __restrict__ offsets, long long N, int* __restrict__ flat) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long seq = (long long)blockIdx.x * (blockDim.x >> 5) + warp; seq < N;
+         seq += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const int n = len[seq];
+        const long long off = offsets[seq];
+        for (int q = lane; q < n; q += 32) flat[off + q] = padded[seq * (long long)stride + q];
+    }
+}
+
+// ---------------------------------------------------------------- decode (K5b)
+// ids (CSR) -> token bytes -> UTF-8 -> codepoints + min_token.  status: 1 = id out of range,
+// 2 = invalid UTF-8, 3 = decoded length != L (the reference's ValueError, bpe_tokenizer.py:241-244).
+__global__ void __launch_bounds__(kBpeBlock)
+bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
+                  long long min_token, const int* __restrict__ tok_off, const uint8_t* __restrict__ tok_bytes,
+                  int n_vocab, long long* __restrict__ bins_out, int* __restrict__ status_out,
+                  int* __restrict__ declen_out) {
+    extern __shared__ uint8_t s_raw[];
+    const int LP = L + 1;
+    uint8_t* s_cp = s_raw;                                   // decoded codepoints, [kBpeBlock][LP]
+    const long long base = (long long)blockIdx.x * kBpeBlock;
+    const long long seq = base + threadIdx.x;
+    int status = 0, cnt = 0;
+    if (seq < N) {
+        uint8_t* cp = s_cp + threadIdx.x * LP;
+        int pending = 0, acc = 0;
+        for (long long p = offsets[seq]; p < offsets[seq + 1] && !status; ++p) {
+            const int id = flat[p];
+            if (id < 0 || id >= n_vocab) { status = 1; break; }
+            for (int q = tok_off[id]; q < tok_off[id + 1]; ++q) {
+                const int bt = tok_bytes[q];
+                int out_c = -1;
+                if (pending) {
+                    if ((bt & 0xC0) != 0x80) { status = 2; break; }
+                    acc = (acc << 6) | (bt & 0x3F);
+                    if (--pending == 0) out_c = acc;
+                } else if (bt < 0x80) out_c = bt;
+                else if ((bt & 0xE0) == 0xC0) { acc = bt & 0x1F; pending = 1; }
+                else if ((bt & 0xF0) == 0xE0) { acc = bt & 0x0F; pending = 2; }
+                else if ((bt & 0xF8) == 0xF0) { acc = bt & 0x07; pending = 3; }
+                else { status = 2; break; }
+                if (out_c >= 0) {
+                    if (out_c > 255) { status = 2; break; }  // cannot be a shifted bin of a <=256-bin tokenizer
+                    if (cnt < L) cp[cnt] = (uint8_t)out_c;
+                    ++cnt;
+                }
+            }
+        }
+        if (!status && pending) status = 2;
+        if (!status && cnt != L) status = 3;
+        status_out[seq] = status;
+        declen_out[seq] = cnt;
+    }
+    __syncthreads();
+    const long long rows = (N - base) < kBpeBlock ? (N - base) : kBpeBlock;
+    for (long long idx = threadIdx.x; idx < rows * L; idx += blockDim.x) {
+        const int r = (int)(idx / L), p = (int)(idx - (long long)r * L);
+        bins_out[(base + r) * L + p] = (long long)s_cp[r * LP + p] + min_token;
+    }
+}
+
+static int bpe_grid(long long n, int block) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)sms * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static size_t stage_smem(int L) { return (((size_t)kBpeBlock * (L + 1) + 3) & ~(size_t)3) + kBpeBlock * sizeof(int); }
+
+}  // namespace beast
+
+using namespace beast;
+
+extern "C" int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, int64_t* minmax, int32_t* seen,
+                             int32_t* err, int32_t phase, void* stream) {
+    if (!bins || n < 1) return n == 0 ? BEAST_OK : BEAST_E_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 0) {
+        if (!minmax) return BEAST_E_NULL;
+        bpe_minmax_kernel<<<bpe_grid(n, 256), 256, 0, st>>>((const long long*)bins, n, (long long*)minmax,
+                                                           (long long*)minmax + 1);
+    } else {
+        if (!seen || !err) return BEAST_E_NULL;
+        bpe_seen_kernel<<<bpe_grid(n, 256), 256, 0, st>>>((const long long*)bins, n, min_token, seen, err);
+    }
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
+                             uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (!bins || !byte_to_id || !sym || !len || !err) return BEAST_E_NULL;
+    if (N < 0 || L < 1 || n_stride < N || 2 * L > 32767) return BEAST_E_SHAPE;
+    const size_t smem = stage_smem(L);
+    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(bpe_symbolize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
+    bpe_symbolize_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+        (const long long*)bins, N, L, min_token, byte_to_id, sym, len, n_stride, err);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
+                               int32_t* hist, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (!sym || !len || !hist) return BEAST_E_NULL;
+    if (N < 0 || V < 1 || V > 32767) return BEAST_E_SHAPE;
+    bpe_count_kernel<<<bpe_grid(N, 256), 256, 0, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, hist);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream) {
+    if (!hist || !result) return BEAST_E_NULL;
+    if (V < 1 || n_active < 1 || n_active > V || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(result, 0, sizeof(uint64_t), st);
+    if (e != cudaSuccess) return (int)e;
+    bpe_argmax_kernel<<<bpe_grid((long long)n_active * n_active, 256 * 4), 256, 0, st>>>(
+        hist, V, n_active, (unsigned long long*)result);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
+                               int32_t c, int32_t V, int32_t* delta, void* stream) {
+    if (!delta) return BEAST_E_NULL;
+    if (V < 1 || a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V || c > 32767) return BEAST_E_SHAPE;
+    if (N == 0) return BEAST_OK;
+    if (!sym || !len) return BEAST_E_NULL;
+    const size_t smem = (size_t)4 * V * sizeof(int);
+    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (N + 255) / 256;
+    const long long cap = (long long)sms * 6;
+    if (grid > cap) grid = cap;
+    bpe_merge_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, a, b, c, V, delta);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream) {
+    if (!hist || !delta) return BEAST_E_NULL;
+    if (V < 1 || a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V) return BEAST_E_SHAPE;
+    bpe_apply_delta_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, delta, a, b, c, V);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
+                          const int16_t* byte_to_id, const uint32_t* rank_tab, int32_t V, uint16_t* ids_padded,
+                          int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (!bins || !byte_to_id || !rank_tab || !ids_padded || !len_out || !status_out) return BEAST_E_NULL;
+    if (N < 0 || L < 1 || 2 * L > kMaxWord || out_stride < 2 * L || V < 1 || V > 65535) return BEAST_E_SHAPE;
+    const size_t smem = stage_smem(L);
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(bpe_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
+    bpe_encode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+        (const long long*)bins, N, L, min_token, max_shift, byte_to_id, rank_tab, V, ids_padded, out_stride, len_out,
+        status_out);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int32_t* len, const int64_t* offsets,
+                           int64_t N, int32_t* flat, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (!ids_padded || !len || !offsets || !flat) return BEAST_E_NULL;
+    bpe_compact_kernel<<<bpe_grid(N, 8), 256, 0, (cudaStream_t)stream>>>(ids_padded, stride, len,
+                                                                        (const long long*)offsets, N, flat);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,
+                          const int32_t* tok_off, const uint8_t* tok_bytes, int32_t n_vocab, int64_t* bins_out,
+                          int32_t* status_out, int32_t* declen_out, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (!offsets || !tok_off || !tok_bytes || !bins_out || !status_out || !declen_out) return BEAST_E_NULL;
+    if (N < 0 || L < 1 || n_vocab < 1) return BEAST_E_SHAPE;
+    const size_t smem = (size_t)kBpeBlock * (L + 1);
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(bpe_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
+    bpe_decode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+        flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out, status_out,
+        declen_out);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}

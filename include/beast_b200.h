@@ -141,6 +141,52 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
                         const int64_t* ks_h, int32_t nk, float* out,
                         void* scratch, void* stream);
 
+/* ---- K4 / K5: byte-level BPE over discretised bins.  Replaces the HF `tokenizers` calls under
+ * FIGBPE (beast/beast_bpe_trainer.py:61-98: ByteLevelBPETokenizer + BpeTrainer.train_from_iterator) and
+ * BEASTBsplineBPETokenizer._discrete_to_bpe / _bpe_to_discrete (beast/beast_bspline_bpe_tokenizer.py:
+ * 175-247: tokenizer.encode(...).ids / tokenizer.decode).  Algorithm: SURVEY.md Appendix A.
+ * Corpus layout: position-major symbols sym[p * n_stride + seq] (uint16, bit 15 = first symbol of a
+ * pre-token), len[seq] live symbols; sequences may be sharded over GPUs, the V x V pair histogram is
+ * replicated.  All functions below take DEVICE pointers.
+ *
+ * bpe_scan_bins  phase 0: minmax[0] = min(minmax[0], bins), minmax[1] = max(minmax[1], bins)
+ *                         (caller initialises to INT64_MAX / INT64_MIN; global min_token / max_token, A.1);
+ *                phase 1: seen[b] = 1 for every UTF-8 byte of chr(bin - min_token) (alphabet, A.3);
+ *                         *err = 1 if a shifted bin is outside 0..255.
+ * bpe_symbolize  bins [N, L] int64 -> sym / len through the GPT-2 pre-tokeniser (A.2) and the byte-level
+ *                expansion (A.3); byte_to_id[256] int16 (-1 = not in the vocabulary: dropped).
+ * bpe_count_pairs  hist[a*V + b] += #adjacent (a, b) inside pre-tokens (int32, V x V).
+ * bpe_argmax     result = count << 32 | (0xffffffff - (a*V + b)) of the best pair (0 if none): maximum
+ *                count, ties -> smallest (a, b) (BpeTrainer's heap order).
+ * bpe_apply_merge  replace (a, b) by c left to right, non-overlapping, compacting in place; the count
+ *                changes are ADDED to delta[4*V] = {column a lost, row b lost, column c gained, row c gained}.
+ * bpe_apply_delta  hist += delta (after the cross-GPU sum when sharded); hist[a][b] = 0; delta = 0.
+ * bpe_encode     bins -> ids: per pre-token repeatedly merge the lowest-rank pair, leftmost first (A.5).
+ *                rank_tab[a*V + b] = rank << 16 | new_id or 0xffffffff.  ids_padded [N, out_stride >= 2L]
+ *                uint16, len_out [N], status_out [N]: bit 0 = bin below min_token, bit 1 = bin above
+ *                min_token + max_shift (the two range ValueErrors of bpe_tokenizer.py:182-192).
+ * bpe_compact    padded rows -> CSR flat int32 (offsets = exclusive scan of len, by the caller).
+ * bpe_decode     CSR ids -> bins [N, L] int64 (A.6); status 1 = unknown id, 2 = invalid UTF-8,
+ *                3 = decoded length != L (bpe_tokenizer.py:241-244); declen_out = decoded length. */
+int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, int64_t* minmax, int32_t* seen,
+                  int32_t* err, int32_t phase, void* stream);
+int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
+                  uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err, void* stream);
+int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
+                    int32_t* hist, void* stream);
+int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream);
+int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
+                    int32_t c, int32_t V, int32_t* delta, void* stream);
+int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
+int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
+               const int16_t* byte_to_id, const uint32_t* rank_tab, int32_t V, uint16_t* ids_padded,
+               int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream);
+int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int32_t* len, const int64_t* offsets,
+                int64_t N, int32_t* flat, void* stream);
+int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,
+               const int32_t* tok_off, const uint8_t* tok_bytes, int32_t n_vocab, int64_t* bins_out,
+               int32_t* status_out, int32_t* declen_out, void* stream);
+
 /* Device self-test of the exact invariant-divisor division inside K1 / K3 (csrc/common.cuh) against
  * IEEE division: n_divisors random divisors x 2^24 + 2^22 numerators each, and float(tok)/(V-1)
  * for every V <= vmax.  mismatches (device, 20 x uint64): [0], [1] = number of differing results of the

@@ -218,8 +218,7 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     for (int c = 0; c < 512; ++c) {
         char_to_id[c] = -1;
         if (!in_alpha[c]) continue;
-        if (tk.n >= vocab_size) break;                       /* vocab_size smaller than the alphabet: HF keeps them all; */
-        char_to_id[c] = tk.n;                                /* we mirror by truncating only when ids run out (not hit in tests) */
+        char_to_id[c] = tk.n;                                /* the whole alphabet is kept even if it exceeds vocab_size */
         tk.chars[tk.off[tk.n]] = (uint16_t)c;
         tk.off[tk.n + 1] = tk.off[tk.n] + 1;
         tk.n++;
@@ -230,7 +229,7 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
         for (int q = 0; q < words[w].len; ++q) sym[words[w].off + q] = char_to_id[g_b2u[pool[words[w].off + q]]];
     free(pool);
 
-    const int V = vocab_size;
+    const int V = vocab_size > tk.n ? vocab_size : tk.n;     /* caller sizes vocab_off / merges for max(vocab_size, 512) */
     long long* cnt = (long long*)calloc((size_t)V * V, sizeof(long long));
     for (size_t w = 0; w < n_words; ++w) {
         const int* s = sym + words[w].off;

@@ -44,10 +44,11 @@ class OracleBPE:
         bins = np.ascontiguousarray(bins, dtype=np.int64)
         assert bins.ndim == 2
         min_token, max_token = int(bins.min()), int(bins.max())
-        off = np.zeros(vocab_size + 1, dtype=np.int32)
+        cap_v = max(vocab_size, 512)
+        off = np.zeros(cap_v + 1, dtype=np.int32)
         cap = 4 * 1024 * 1024
         chars = np.zeros(cap, dtype=np.uint16)
-        merges = np.zeros(3 * vocab_size, dtype=np.int32)
+        merges = np.zeros(3 * cap_v, dtype=np.int32)
         nv, nm = C.c_int32(0), C.c_int32(0)
         rc = lib().bpe_oracle_train(bins.ctypes.data, bins.shape[0], bins.shape[1], min_token, max_token, vocab_size,
                                     min_frequency, off.ctypes.data, chars.ctypes.data, cap, merges.ctypes.data,

@@ -1,0 +1,199 @@
+"""CPU-only checks of the BPE host logic: file formats, alphabet construction, and the sharded
+training protocol (world_size 2, gloo) with a numpy engine standing in for the GPU kernels."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+from oracle.bpe_oracle import OracleBPE, pretokenize
+
+
+def test_model_files_round_trip(tmp_path):
+    from beast_tokenizer_b200 import B200ByteLevelBPE, BEASTBsplineBPETokenizer
+    for name in ("bpe_d14", "bpe_d14_small"):
+        src = os.path.join(GOLDEN, f"{name}_pretrained")
+        tok = BEASTBsplineBPETokenizer.from_pretrained(src, device="cpu")
+        out = tmp_path / name
+        tok.save_pretrained(out)
+        for f in ("beast_tokenizer_config.json", "bpe_tokenizer/vocab.json", "bpe_tokenizer/merges.txt",
+                  "bpe_tokenizer/tokenizer.json"):
+            assert open(os.path.join(src, f), encoding="utf-8").read() == open(out / f, encoding="utf-8").read(), f
+        sd = tok.state_dict()
+        assert sd["bpe"] == {"min_token": 0, "max_token": 255, "vocab_size": tok.bpe_vocab_size,
+                             "tokenizer_dir": "bpe_tokenizer"}
+        m = tok.bpe_tokenizer
+        assert m.get_vocab_size() == tok.bpe_vocab_size and m.token_to_id(m.id_to_token(300)) == 300
+    with pytest.raises(ValueError):          # a base-tokenizer checkpoint is not a BPE checkpoint
+        BEASTBsplineBPETokenizer.from_pretrained(os.path.join(GOLDEN, "cfg2_d14_pretrained"), device="cpu")
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    with pytest.raises(ValueError):
+        BEASTBsplineTokenizer.from_pretrained(os.path.join(GOLDEN, "bpe_d14_pretrained"), device="cpu")
+    with pytest.raises(FileNotFoundError):
+        BEASTBsplineBPETokenizer.from_pretrained(tmp_path / "missing")
+
+
+def test_ctor_errors_and_from_beast():
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer, BEASTBsplineTokenizer
+    base = BEASTBsplineTokenizer(num_dof=7, device="cpu", llm_vocab_size=1000)
+    base.w_min.fill_(-0.5)
+    tok = BEASTBsplineBPETokenizer.from_beast(base, bpe_vocab_size=300)
+    assert tok.bpe_vocab_size == 300 and tok.use_bpe and tok.llm_vocab_size == 1000
+    assert torch.equal(tok.w_min, base.w_min) and tok.sequence_length == 70
+    assert tok.get_config()["tokenizer_type"] == "beast_bspline_bpe"
+    with pytest.raises(TypeError):
+        BEASTBsplineBPETokenizer(7, base_tokenizer=base)
+    with pytest.raises(TypeError):
+        BEASTBsplineBPETokenizer(base_tokenizer=base, num_basis=3)
+    with pytest.raises(TypeError):
+        BEASTBsplineBPETokenizer(base_tokenizer=object())
+    with pytest.raises(TypeError):
+        BEASTBsplineBPETokenizer.from_beast(object())
+    with pytest.raises(RuntimeError, match="has not been trained"):
+        tok._require_bpe()
+    from beast_tokenizer_b200 import FIGBPE
+    with pytest.raises(RuntimeError):
+        FIGBPE().get_state()
+    with pytest.raises(ValueError):
+        FIGBPE(show_progress=False).fit_from_sequences([[], []])
+
+
+def test_alphabet_matches_oracle():
+    from beast_tokenizer_b200.beast_bpe_trainer import build_alphabet
+    rng = np.random.default_rng(0)
+    for lo, hi in ((0, 256), (40, 91), (100, 230)):
+        bins = rng.integers(lo, hi, (50, 40))
+        o = OracleBPE.train(bins, 10)          # vocab_size below the alphabet: no merges, alphabet only
+        seen = np.zeros(256, np.int32)
+        for v in np.unique(bins - bins.min()):
+            for b in chr(int(v)).encode("utf-8"):
+                seen[b] = 1
+        tokens, b2i = build_alphabet(int(bins.min()), int(bins.max()), seen)
+        assert tokens == o.token_strings() and len(o.merges) == 0      # HF keeps the whole alphabet
+        assert all((b2i[b] >= 0) == bool(seen[b]) or chr(b) in tokens for b in range(256))
+
+
+# ---------------------------------------------------------------- sharded protocol on CPU (gloo)
+class NumpyEngine:
+    """Same interface as GpuBpeEngine, numpy on the CPU (test double for the orchestration)."""
+
+    def __init__(self, bins, min_token, byte_to_id, V):
+        self.V = V
+        self.words = []
+        for row in np.asarray(bins):
+            cp = (row - min_token).astype(np.uint8)
+            ws = pretokenize(cp)
+            seq = []
+            for c, w in zip(cp.tolist(), ws.tolist()):
+                bs = chr(c).encode("utf-8")
+                for j, b in enumerate(bs):
+                    seq.append([int(byte_to_id[b]), bool(w) and j == 0])
+            self.words.append(seq)
+        self.hist = torch.zeros((V, V), dtype=torch.int32)
+        for seq in self.words:
+            for (x, _), (y, wy) in zip(seq[:-1], seq[1:]):
+                if not wy:
+                    self.hist[x, y] += 1
+        self.delta = torch.zeros(4 * V, dtype=torch.int32)
+
+    def argmax(self, n_active):
+        h = self.hist[:n_active, :n_active]
+        m = int(h.max())
+        if m <= 0:
+            return 0, -1, -1
+        flat = int(torch.nonzero(h.reshape(-1) == m)[0])
+        return m, flat // n_active, flat % n_active
+
+    def merge(self, a, b, c):
+        from collections import Counter
+        V, d, net = self.V, self.delta, Counter()
+        for seq in self.words:
+            for (x, _), (y, wy) in zip(seq[:-1], seq[1:]):
+                if not wy:
+                    net[(x, y)] -= 1
+            out, q = [], 0
+            while q < len(seq):
+                if q + 1 < len(seq) and seq[q][0] == a and seq[q + 1][0] == b and not seq[q + 1][1]:
+                    out.append([c, seq[q][1]]); q += 2
+                else:
+                    out.append(seq[q]); q += 1
+            seq[:] = out
+            for (x, _), (y, wy) in zip(seq[:-1], seq[1:]):
+                if not wy:
+                    net[(x, y)] += 1
+        for (x, y), n in net.items():
+            if n == 0 or (x, y) == (a, b):
+                continue
+            if n < 0:
+                if y == a: d[x] += n
+                elif x == b: d[V + y] += n
+                else: raise AssertionError(("lost pair outside column a / row b", x, y, n))
+            else:
+                if y == c: d[2 * V + x] += n
+                elif x == c: d[3 * V + y] += n
+                else: raise AssertionError(("gained pair outside column c / row c", x, y, n))
+
+    def apply_delta(self, a, b, c):
+        V, d = self.V, self.delta.clone()
+        self.hist[:, a] += d[:V]; self.hist[b, :] += d[V:2 * V]; self.hist[:, c] += d[2 * V:3 * V]; self.hist[c, :] += d[3 * V:]
+        self.hist[a, b] = 0
+        self.delta.zero_()
+
+
+def numpy_scan(bins, coll):
+    bins = np.asarray(bins)
+    lo = torch.tensor([int(bins.min())]); hi = torch.tensor([int(bins.max())])
+    coll.reduce_(lo, "min"); coll.reduce_(hi, "max")
+    mn, mx = int(lo), int(hi)
+    seen = torch.zeros(256, dtype=torch.int32)
+    for v in np.unique(bins - mn):
+        for b in chr(int(v)).encode("utf-8"):
+            seen[b] = 1
+    coll.reduce_(seen, "max")
+    return mn, mx, seen.numpy()
+
+
+def _worker(rank, world, port, bins, vocab, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from beast_tokenizer_b200.beast_bpe_trainer import _Collective, train_bpe
+    shard = bins[rank::world]
+    tok, mn, mx = train_bpe(shard, vocab, 2, engine_factory=NumpyEngine, scan=numpy_scan, coll=_Collective())
+    q.put((rank, tok.merges_txt(), tok.vocab_json(), mn, mx))
+    dist.destroy_process_group()
+
+
+def test_single_rank_protocol_matches_oracle():
+    from beast_tokenizer_b200.beast_bpe_trainer import _Collective, train_bpe
+    rng = np.random.default_rng(5)
+    bins = rng.integers(30, 120, (60, 30))
+    tok, mn, mx = train_bpe(bins, 260, 2, engine_factory=NumpyEngine, scan=numpy_scan, coll=_Collective(enabled=False))
+    o = OracleBPE.train(bins, 260)
+    assert tok.merges_txt() == o.merges_txt() and tok.vocab_json() == o.vocab_json()
+
+
+def test_sharded_training_two_ranks_gloo():
+    """Two processes, each with half of the sequences: min/max, seen bytes, histogram and per-merge
+    deltas are all-reduced; both ranks end with the unsharded oracle's merges and vocabulary."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(11)
+    bins = rng.integers(20, 140, (80, 24))
+    bins[::2] += 60                                  # the two shards see different value ranges
+    o = OracleBPE.train(bins, 300)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bins, 300, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, merges_txt, vocab_json, mn, mx in results:
+        assert merges_txt == o.merges_txt() and vocab_json == o.vocab_json()
+        assert (mn, mx) == (int(bins.min()), int(bins.max()))

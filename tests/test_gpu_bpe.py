@@ -1,0 +1,163 @@
+"""GPU BPE path (trainer, encode, decode) against the reference's golden files and the C oracle.
+Run on the B200 box:  pytest -m gpu."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, GOLDEN_CASES, load_golden, rel_err
+from oracle.bpe_oracle import OracleBPE
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_files(name):
+    d = os.path.join(GOLDEN, f"{name}_pretrained", "bpe_tokenizer")
+    return (open(os.path.join(d, "vocab.json"), encoding="utf-8").read(),
+            open(os.path.join(d, "merges.txt"), encoding="utf-8").read(),
+            open(os.path.join(d, "tokenizer.json"), encoding="utf-8").read())
+
+
+def ragged(g):
+    return [r.tolist() for r in np.split(g["ids_flat"], np.cumsum(g["ids_len"])[:-1])]
+
+
+@pytest.mark.parametrize("name", ["bpe_d14", "bpe_d14_small"])
+def test_trainer_reproduces_reference_files(name):
+    from beast_tokenizer_b200 import FIGBPE
+    g = load_golden(name)
+    vocab_json, merges_txt, tok_json = ref_files(name)
+    fig = FIGBPE(vocab_size=int(g["bpe_vocab_size"]), show_progress=False)
+    state = fig.fit_from_bins(torch.from_numpy(g["corpus_bins"].astype(np.int64)).cuda())
+    assert (state.min_token, state.max_token) == (int(g["min_token"]), int(g["max_token"]))
+    assert state.tokenizer.merges_txt() == merges_txt            # byte-identical merges.txt
+    assert state.tokenizer.vocab_json() == vocab_json            # byte-identical vocab.json
+    assert state.tokenizer.tokenizer_json() == tok_json          # and tokenizer.json
+    # the list-of-rows entry point of the reference API
+    st2 = FIGBPE(vocab_size=int(g["bpe_vocab_size"]), show_progress=False).fit_from_sequences(
+        [row for row in g["corpus_bins"][:64].astype(np.int64)])
+    o = OracleBPE.train(g["corpus_bins"][:64].astype(np.int64), int(g["bpe_vocab_size"]))
+    assert st2.tokenizer.merges_txt() == o.merges_txt() and st2.tokenizer.vocab_json() == o.vocab_json()
+
+
+@pytest.mark.parametrize("name", ["bpe_d14", "bpe_d14_small"])
+def test_encode_decode_vs_reference(name):
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
+    g = load_golden(name)
+    g2 = load_golden("cfg2_d14")
+    tok = BEASTBsplineBPETokenizer.from_pretrained(os.path.join(GOLDEN, f"{name}_pretrained"), device="cuda")
+    want = ragged(g)
+    mp = torch.from_numpy(g["mp_tokens"])
+    assert tok._discrete_to_bpe(mp) == want                       # ids bit-exact
+    assert tok._discrete_to_bpe(g["mp_tokens"]) == want            # numpy input
+    assert tok._discrete_to_bpe([r.tolist() for r in g["mp_tokens"][:5]]) == want[:5]
+    assert tok._discrete_to_bpe(g["mp_tokens"][3].tolist()) == [want[3]]
+    back = tok.bpe_to_mp_tokens(want)
+    assert back.dtype == torch.long and back.is_cuda and np.array_equal(back.cpu().numpy(), g["mp_tokens"])
+    assert np.array_equal(tok.decode(want).cpu().numpy(), g["decode"])
+    assert rel_err(tok.reconstruct_traj(want).cpu().numpy(), g["recon"]) <= 1e-5
+    # full pipeline from trajectories: ids equal wherever the MP tokens equal the reference's
+    ids, pd, mp_ours = tok.encode(torch.from_numpy(g2["trajs"]), return_mp_tokens=True)
+    same = (mp_ours.cpu().numpy() == g["mp_tokens"]).all(1)
+    assert same.mean() > 0.9
+    for i in np.nonzero(same)[0]:
+        assert ids[i] == want[i]
+    flat, offsets, _ = tok.encode_csr(torch.from_numpy(g2["trajs"]))
+    assert flat.dtype == torch.int32 and offsets[-1].item() == sum(len(r) for r in ids)
+    assert torch.equal(tok.reconstruct_traj_csr(flat, offsets), tok.reconstruct_traj(ids))
+    # ragged API shapes
+    out2 = tok.encode(torch.from_numpy(g2["trajs"][:4]))
+    assert len(out2) == 2 and isinstance(out2[0], list) and isinstance(out2[0][0], list)
+
+
+@pytest.mark.parametrize("kind,n,vocab", [("uniform", 20000, 1024), ("normal", 30000, 2048), ("letters", 3000, 700),
+                                          ("narrow", 4000, 400)])
+def test_trainer_vs_oracle_large(kind, n, vocab):
+    """Synthetic corpora at sizes the C oracle trains in seconds: merges, vocabulary and ids identical."""
+    from beast_tokenizer_b200 import FIGBPE
+    rng = np.random.default_rng(3)
+    if kind == "uniform":
+        bins = rng.integers(0, 256, (n, 140))
+    elif kind == "normal":
+        bins = np.clip(rng.normal(128, 28, (n, 140)).round(), 0, 255).astype(np.int64)
+    elif kind == "letters":                                        # long pre-tokens, repeated symbols (aaa -> Xa)
+        bins = rng.choice([97, 97, 97, 98, 99, 32], (n, 60)) + 7
+    else:
+        bins = rng.integers(40, 91, (n, 140))
+    o = OracleBPE.train(bins, vocab)
+    state = FIGBPE(vocab_size=vocab, show_progress=False).fit_from_bins(torch.from_numpy(bins).cuda())
+    assert state.tokenizer.merges_txt() == o.merges_txt()
+    assert state.tokenizer.vocab_json() == o.vocab_json()
+    assert (state.min_token, state.max_token) == (o.min_token, o.max_token)
+    # encode / decode a held-out batch (includes values never seen in training for "narrow")
+    test = rng.integers(int(bins.min()), int(bins.max()) + 1, (512, bins.shape[1]))
+    flat, offsets, status = state.tokenizer.encode_bins(torch.from_numpy(test).cuda(), state.min_token, state.max_token)
+    assert int(status.max()) == 0
+    fl, of = flat.cpu().numpy(), offsets.cpu().numpy()
+    for i in range(0, 512, 7):
+        assert fl[of[i]:of[i + 1]].tolist() == o.encode(test[i] - o.min_token)
+    dec, st, ln = state.tokenizer.decode_ids(flat, offsets, bins.shape[1], state.min_token)
+    assert int(st.max()) == 0 and np.array_equal(dec.cpu().numpy(), test)
+
+
+def test_fit_from_trajectories_and_files(tmp_path):
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer, BEASTBsplineTokenizer, FIGBPEState
+    from beast_tokenizer_b200.synth import SyntheticLoader, synth
+    g2 = load_golden("cfg2_d14")
+    cfg = {k: v for k, v in GOLDEN_CASES["cfg2_d14"].items() if k != "llm_vocab_size"}
+    base = BEASTBsplineTokenizer(device="cuda", **cfg)
+    base.w_min.copy_(torch.from_numpy(g2["w_min_fit"])); base.w_max.copy_(torch.from_numpy(g2["w_max_fit"]))
+    tok = BEASTBsplineBPETokenizer.from_beast(base, bpe_vocab_size=512)
+    with pytest.raises(RuntimeError):
+        tok.encode(synth(2, 50, 14, 0))
+    loader = SyntheticLoader(30, 32, 50, 14, seed0=1000)
+    state = tok.fit_from_trajectories(loader, show_progress=False, max_sequences=900)
+    assert isinstance(state, FIGBPEState) and tok.bpe_tokenizer is state.tokenizer
+    corpus = torch.cat([tok.encode_to_mp_tokens(b["actions"])[0] for b in loader])[:900].cpu().numpy()
+    o = OracleBPE.train(corpus, 512)
+    assert state.tokenizer.merges_txt() == o.merges_txt() and state.tokenizer.vocab_json() == o.vocab_json()
+    assert (tok.bpe_min_token, tok.bpe_max_token) == (o.min_token, o.max_token)
+    x = synth(40, 50, 14, seed=9)
+    ids, pd, mp = tok.encode(x, return_mp_tokens=True)
+    for i in range(40):
+        assert ids[i] == o.encode(mp[i].cpu().numpy() - o.min_token)
+    assert torch.equal(tok.bpe_to_mp_tokens(ids), mp)
+    assert torch.equal(tok.reconstruct_traj(ids), base.reconstruct_traj(mp))
+    tok.save_pretrained(tmp_path)
+    tok2 = BEASTBsplineBPETokenizer.from_pretrained(tmp_path, device="cuda")
+    assert tok2.encode(x)[0] == ids and tok2.bpe_max_token == tok.bpe_max_token
+    hf = pytest.importorskip("tokenizers")
+    ref_tok = hf.ByteLevelBPETokenizer.from_file(str(tmp_path / "bpe_tokenizer" / "vocab.json"),
+                                                 str(tmp_path / "bpe_tokenizer" / "merges.txt"))
+    row = mp[0].cpu().numpy() - tok.bpe_min_token
+    assert ref_tok.encode("".join(map(chr, row)), add_special_tokens=False).ids == ids[0]   # the library reads our files
+    tok3 = BEASTBsplineBPETokenizer.from_beast(base, bpe_vocab_size=512)
+    tok3.set_bpe_tokenizer(ref_tok, min_token=tok.bpe_min_token, max_token=tok.bpe_max_token)   # and we read its objects
+    assert tok3.encode(x)[0] == ids
+    with pytest.raises(TypeError):
+        tok3.set_bpe_tokenizer(object())
+
+
+def test_bpe_errors():
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
+    g = load_golden("bpe_d14")
+    tok = BEASTBsplineBPETokenizer.from_pretrained(os.path.join(GOLDEN, "bpe_d14_pretrained"), device="cuda")
+    mp = g["mp_tokens"][:4].copy()
+    tok.bpe_min_token, tok.bpe_max_token = 5, 200
+    bad = mp.copy(); bad[1, 3] = 2
+    with pytest.raises(ValueError, match="smaller than the configured BPE minimum"):
+        tok._discrete_to_bpe(np.clip(bad, 2, 200))
+    bad = np.clip(mp, 5, 200); bad[2, 7] = 231
+    with pytest.raises(ValueError, match="greater than the configured BPE maximum"):
+        tok._discrete_to_bpe(bad)
+    tok.bpe_min_token, tok.bpe_max_token = 0, 255
+    ids = tok._discrete_to_bpe(mp)
+    with pytest.raises(ValueError, match="Decoded sequence has length"):
+        tok.bpe_to_mp_tokens([ids[0][:-1], ids[1]])
+    with pytest.raises(ValueError):
+        tok.bpe_to_mp_tokens([[10 ** 6]])
+    with pytest.raises(ValueError):
+        tok._discrete_to_bpe(torch.zeros(2, 2, 2, dtype=torch.long))
+    assert tok._discrete_to_bpe(torch.zeros(0, 140, dtype=torch.long)) == []
