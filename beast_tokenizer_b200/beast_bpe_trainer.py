@@ -213,8 +213,10 @@ class FIGBPE:
 
     def fit_from_bins(self, bins: torch.Tensor) -> FIGBPEState:
         """bins [N, L] int64 on the GPU (this rank's shard when sharded)."""
+        # process_group=False forces a local (unsharded) fit even under torch.distributed
+        coll = _Collective(enabled=False) if self.process_group is False else _Collective(self.process_group)
         tok, mn, mx = train_bpe(bins.to(self._device(), torch.int64).contiguous(), self.vocab_size, self.min_frequency,
-                                coll=_Collective(self.process_group), show_progress=self.show_progress)
+                                coll=coll, show_progress=self.show_progress)
         self.tokenizer, self.min_token, self.max_token = tok, mn, mx
         return FIGBPEState(tokenizer=tok, min_token=mn, max_token=mx)
 

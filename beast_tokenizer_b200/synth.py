@@ -36,3 +36,16 @@ class SyntheticLoader:
     def __iter__(self):
         for i in range(self.num_batches):
             yield {self.key: synth(self.batch, self.seq_len, self.num_dof, self.seed0 + i, self.device)}
+
+
+def synth_device(batch: int, seq_len: int, num_dof: int, seed: int, device) -> torch.Tensor:
+    """Same distribution as `synth`, every draw made by the device generator (bench-scale inputs:
+    1.6 M trajectories would take minutes from the CPU generator)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(int(seed))
+    amp = 0.02 * torch.randn(batch, 1, num_dof, generator=g, device=dev)
+    freq = 3.0 * torch.rand(batch, 1, num_dof, generator=g, device=dev)
+    phase = 2.0 * math.pi * torch.rand(batch, 1, num_dof, generator=g, device=dev)
+    noise = 0.002 * torch.randn(batch, seq_len, num_dof, generator=g, device=dev)
+    t = torch.linspace(0.0, 1.0, seq_len, device=dev).view(1, seq_len, 1)
+    return (amp * torch.sin(2.0 * math.pi * freq * t + phase) + noise).to(torch.float32).contiguous()

@@ -156,7 +156,126 @@ def run_reference(args, rank):
                                    f"{os.cpu_count()} logical cores"},
         "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    try:                                                   # BPE-train merges/s of the reference trainer, bounded sample
+        import numpy as np
+        import torch
+        n = 16384
+        tokens, _ = port.encode(synth(n, T, D, seed=1000)[:n])
+        bins = (tokens - (LLM_VOCAB - V)).numpy()
+        cpu = hf_train_cpu(bins, BPE_VOCAB)
+        line["bpe_train"] = {"metric": "BPE-train merges/sec", "value": cpu["merges"] / cpu["seconds"], "unit": "merges/s",
+                             "engine": cpu["engine"], "merges": cpu["merges"], "seconds": cpu["seconds"],
+                             "sample": f"{n} sequences x 140 bins (bounded sample; the trainer is ~linear in the corpus)"}
+    except Exception as exc:                               # pragma: no cover
+        line["bpe_train"] = {"unavailable": str(exc)}
     print(json.dumps(line), flush=True)
+
+
+BPE_VOCAB = 2048
+BPE_BATCHES, BPE_BATCH = 50_000, 32          # BASELINE configs[3]: 50k batches x 32 = 1.6 M sequences
+BPE_CHUNKS = 200                             # corpus generated as 200 chunks of 250 batches, dealt round-robin to ranks
+BPE_CPU_SAMPLE = 65_536
+
+
+def hf_train_cpu(bins_np, vocab):
+    """The reference's trainer: HF tokenizers' BpeTrainer behind FIGBPE._fit_from_strings
+    (beast/beast_bpe_trainer.py:61-98) on the host cores; the C oracle if the wheel is absent."""
+    mn, mx = int(bins_np.min()), int(bins_np.max())
+    try:
+        from tokenizers import ByteLevelBPETokenizer
+        from tokenizers.trainers import BpeTrainer
+    except ImportError:
+        from oracle.bpe_oracle import OracleBPE
+        t0 = time.perf_counter()
+        o = OracleBPE.train(bins_np, vocab)
+        return {"engine": "oracle/bpe_oracle.c (1 thread)", "seconds": time.perf_counter() - t0, "merges": len(o.merges),
+                "merges_txt": o.merges_txt()}
+    t0 = time.perf_counter()
+    strings = ["".join(map(chr, (row - mn).astype(int))) for row in bins_np]
+    t1 = time.perf_counter()
+    hf = ByteLevelBPETokenizer()
+    trainer = BpeTrainer(vocab_size=vocab, min_frequency=2, show_progress=False, special_tokens=[],
+                         initial_alphabet=[chr(i) for i in range(mx - mn + 1)], max_token_length=10000)
+    hf._tokenizer.train_from_iterator(strings, trainer=trainer)
+    t2 = time.perf_counter()
+    model = json.loads(hf._tokenizer.to_str())["model"]
+    merges = [m if isinstance(m, str) else " ".join(m) for m in model["merges"]]
+    import tokenizers
+    return {"engine": f"tokenizers {tokenizers.__version__} BpeTrainer (rayon, {os.cpu_count()} logical cores)",
+            "seconds": t2 - t1, "string_build_seconds": t1 - t0, "merges": len(merges),
+            "merges_txt": "#version: 0.2\n" + "".join(m + "\n" for m in merges)}
+
+
+def bpe_legs(tok, dev, rank, world, dist, with_cpu):
+    """BPE-train merges/s on the 1.6 M-sequence corpus sharded over the ranks (strong scaling), and
+    BPE encode / decode sequences/s on 1 M trajectories (rank 0's GPU)."""
+    import torch
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer, FIGBPE
+    from beast_tokenizer_b200.synth import synth_device
+    per_chunk = BPE_BATCHES * BPE_BATCH // BPE_CHUNKS
+    mine = [c for c in range(BPE_CHUNKS) if c % world == rank]
+    bins = torch.cat([tok.encode(synth_device(per_chunk, T, D, 1000 + c, dev), respect_llm_vocab_size=False)[0]
+                      for c in mine])
+    torch.cuda.synchronize()
+    fig = FIGBPE(vocab_size=BPE_VOCAB, show_progress=False, device=str(dev))
+    fig.fit_from_bins(bins[:4096])                    # warm-up: kernels loaded, NCCL channels up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    state = fig.fit_from_bins(bins)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    secs = float(dt.item())
+    n_merges = len(state.tokenizer.merges)
+    out = {"metric": "BPE-train merges/sec", "value": n_merges / secs, "unit": "merges/s", "seconds": secs,
+           "merges": n_merges, "vocab": BPE_VOCAB, "sequences": BPE_BATCHES * BPE_BATCH, "n_gpus": world,
+           "scaling": "strong", "sharding": f"{BPE_CHUNKS} chunks of {per_chunk} sequences round-robin over ranks; "
+           "min/max, seen bytes, histogram and per-merge 4xV deltas all-reduced (NCCL)"}
+    if rank != 0:
+        return out, None
+    if with_cpu:
+        # the reference trainer on the same bins, bounded sample; the GPU trainer on that sample must agree
+        sample = synth_bins_sample(tok, dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st_s = FIGBPE(vocab_size=BPE_VOCAB, show_progress=False, device=str(dev), process_group=False).fit_from_bins(sample)
+        torch.cuda.synchronize()
+        g_secs = time.perf_counter() - t0
+        cpu = hf_train_cpu(sample.cpu().numpy(), BPE_VOCAB)
+        out["cpu_baseline"] = {"value": cpu["merges"] / cpu["seconds"], "unit": "merges/s", "kind": "reference",
+                               "engine": cpu["engine"], "seconds": cpu["seconds"],
+                               "sample": f"{BPE_CPU_SAMPLE} of the 1.6 M sequences (trainer cost is ~linear in the corpus)",
+                               "gpu_same_sample": {"seconds": g_secs, "merges_per_s": len(st_s.tokenizer.merges) / g_secs},
+                               "merge_table_identical": cpu["merges_txt"] == st_s.tokenizer.merges_txt()}
+    # BPE encode + reconstruct (configs[4]) on device-resident CSR
+    btok = BEASTBsplineBPETokenizer.from_beast(tok, bpe_vocab_size=BPE_VOCAB, device=str(dev))
+    btok.set_llm_vocab_size(None)
+    btok.set_bpe_tokenizer(state.tokenizer, min_token=state.min_token, max_token=state.max_token)
+    nb = 1 << 20
+    x = synth_device(nb, T, D, 5, dev)
+    mp, _ = btok.encode_to_mp_tokens(x)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    flat, offsets = btok._discrete_to_bpe_csr(mp)    # warm-up
+    torch.cuda.synchronize()
+    ev[0].record()
+    flat, offsets = btok._discrete_to_bpe_csr(mp)
+    ev[1].record()
+    back = btok._bpe_csr_to_discrete(flat, offsets)
+    ev[2].record()
+    torch.cuda.synchronize()
+    apply = {"workload": "BPE encode / decode of 1 048 576 sequences x 140 bins, 2048-entry table, device CSR",
+             "encode_seq_per_s": nb / (ev[0].elapsed_time(ev[1]) * 1e-3),
+             "decode_seq_per_s": nb / (ev[1].elapsed_time(ev[2]) * 1e-3),
+             "ids_per_sequence": float(flat.numel()) / nb, "round_trip_exact": bool(torch.equal(back, mp))}
+    return out, apply
+
+
+def synth_bins_sample(tok, dev):
+    from beast_tokenizer_b200.synth import synth_device
+    return tok.encode(synth_device(BPE_CPU_SAMPLE, T, D, 1000, dev), respect_llm_vocab_size=False)[0]
 
 
 def main():
@@ -167,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bpe", action="store_true", help="skip the BPE-train / BPE-apply legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -306,6 +426,12 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
+    bpe_train = bpe_apply = None
+    if not args.no_bpe:
+        del xs, toks, pars, outs, xh
+        torch.cuda.empty_cache()
+        bpe_train, bpe_apply = bpe_legs(tok, dev, rank, world, dist, world == 1 and not args.no_cpu_baseline)
+
     if world > 1:
         t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,6 +472,10 @@ def main():
                 line["roofline_decode"]["traffic"] = tr.get("decode_fast_kernel")
             except Exception:
                 pass
+        if bpe_train is not None:
+            line["bpe_train"] = bpe_train
+        if bpe_apply is not None:
+            line["bpe_apply"] = bpe_apply
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
