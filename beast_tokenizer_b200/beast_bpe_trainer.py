@@ -111,6 +111,38 @@ class GpuBpeEngine:
             _lib.check(self.lib.bpe_apply_delta(_lib.ptr(self.hist), _lib.ptr(self.delta), a, b, c, self.V,
                                                 _lib.stream_ptr(self.dev)), "bpe_apply_delta")
 
+    def run_fast(self, coll: "_Collective", n_tokens: int, vocab_size: int, min_frequency: int):
+        """Sync-free merge loop: arg-max, stop rules, id assignment and the merge log all stay on the
+        device (bpe_train_step); the host only enqueues iterations (plus the NCCL all-reduce of the
+        delta block when sharded) and reads the log once.  Returns [(a, b, new_id, count)] assuming every merge creates a NEW token string; the
+        caller verifies that and falls back to the exact host-driven loop otherwise."""
+        max_merges = int(vocab_size) - int(n_tokens)
+        if max_merges <= 0:
+            return []
+        dev = self.dev
+        with torch.cuda.device(dev):
+            ctl = torch.zeros(8, device=dev, dtype=torch.int32)
+            ctl[4] = n_tokens
+            log = torch.zeros(4 * max_merges, device=dev, dtype=torch.int32)
+            self.result.zero_()
+
+            def step(phase):
+                _lib.check(self.lib.bpe_train_step(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, self.V,
+                                                   _lib.ptr(self.hist), _lib.ptr(self.delta), _lib.ptr(ctl),
+                                                   _lib.ptr(log), _lib.ptr(self.result), int(vocab_size),
+                                                   int(min_frequency), max_merges, phase, _lib.stream_ptr(dev)),
+                           "bpe_train_step")
+
+            # plain stream launches: ~60 us of host enqueue per merge, never a sync (capturing the
+            # iteration into a CUDA graph costs more to instantiate than 1 700 replays save)
+            for _ in range(max_merges):
+                step(0)
+                coll.reduce_(self.delta, "sum")
+                step(1)
+            ctl_h = ctl.cpu().tolist()
+            n = ctl_h[5]
+            return log[:4 * n].cpu().view(-1, 4).tolist()
+
 
 def scan_bins_gpu(bins: torch.Tensor, coll: _Collective):
     """Global min / max token and the set of UTF-8 bytes seen (A.1, A.3)."""
@@ -154,6 +186,20 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
     coll.reduce_(eng.hist, "sum")                       # replicated global histogram
     index = {t: i for i, t in enumerate(tokens)}
     merges: List[tuple] = []
+    if hasattr(eng, "run_fast") and not show_progress:
+        log = eng.run_fast(coll, len(tokens), vocab_size, min_frequency)
+        fast_tokens, fast_index, ok = list(tokens), dict(index), True
+        for a, b, c, _count in log:
+            new = fast_tokens[a] + fast_tokens[b]
+            if new in fast_index or c != len(fast_tokens):
+                ok = False                              # an existing string must keep its id: replay exactly
+                break
+            fast_index[new] = c
+            fast_tokens.append(new)
+        if ok:
+            return B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log]), min_token, max_token
+        eng = engine_factory(bins, min_token, byte_to_id, V)
+        coll.reduce_(eng.hist, "sum")
     bar = tqdm(total=max(vocab_size - len(tokens), 0), desc="BPE merges", leave=False) if (show_progress and tqdm) else None
     while len(tokens) < vocab_size:
         count, a, b = eng.argmax(len(tokens))

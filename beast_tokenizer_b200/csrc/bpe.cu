@@ -25,6 +25,16 @@ constexpr uint16_t kWordStart = 0x8000u;
 constexpr uint16_t kIdMask = 0x7fffu;
 constexpr int kMaxWord = 512;            // longest sequence (in byte-level symbols) encode handles
 
+// Device-side control block of the sync-free training loop (bpe_train_step).
+struct BpeCtl {
+    int a, b, c, count;     // the merge selected for this iteration
+    int n_tokens;           // vocabulary size so far (= next new id)
+    int n_merges;           // merges logged
+    int done;               // sticky: no pair reached min_frequency, or the vocabulary is full
+    int pad;
+};
+
+
 // GPT-2 pre-tokeniser character classes for codepoints 0..255
 enum { CLS_O = 0, CLS_L = 1, CLS_N = 2, CLS_S = 3 };
 __device__ __forceinline__ int cp_class(int c) {
@@ -173,7 +183,12 @@ bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, 
 // key = count << 32 | ~flat: the largest key is the largest count and, among equals, the smallest
 // flat index a*V + b, i.e. the lexicographically smallest (a, b).
 __global__ void __launch_bounds__(256)
-bpe_argmax_kernel(const int* __restrict__ hist, int V, int n_active, unsigned long long* __restrict__ result) {
+bpe_argmax_kernel(const int* __restrict__ hist, int V, int n_active, const BpeCtl* __restrict__ ctl,
+                  unsigned long long* __restrict__ result) {
+    if (ctl) {
+        if (ctl->done) return;
+        n_active = ctl->n_tokens;
+    }
     unsigned long long best = 0;
     const long long total = (long long)n_active * n_active;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -203,57 +218,102 @@ bpe_argmax_kernel(const int* __restrict__ hist, int V, int n_active, unsigned lo
 // delta block: [0] column a (pairs (x, a) lost), [1] row b (pairs (b, y) lost),
 //              [2] column c (pairs (x, c) gained), [3] row c (pairs (c, y) gained).
 // Block-private copies live in shared memory (4*V ints) and are flushed once per block.
-__global__ void __launch_bounds__(256)
-bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N, long long n_stride, int a, int b,
-                 int c, int V, int* __restrict__ delta) {
-    extern __shared__ int s_delta[];
-    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
-    __syncthreads();
+// One thread per sequence.  Loads are issued kMergeChunk at a time (independent addresses, all in
+// flight together) because a symbol-at-a-time walk is bound by memory latency, not bandwidth.
+//   pass 1 (read-only): first position q0 whose id is a and whose successor is b inside the same
+//           pre-token (b with the word-start bit clear is the 16-bit value b itself);
+//   pass 2 (only if found): streaming rewrite from q0 — an `a` is held back one step, so no look-ahead
+//           is needed: next symbol == b -> emit c (merge), otherwise emit the held symbol unchanged.
+constexpr int kMergeChunk = 8;
+
+__device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int* __restrict__ len, long long N,
+                                                long long n_stride, int a, int b, int c, int V, int* s_delta) {
     int* col_a = s_delta;
     int* row_b = s_delta + V;
     int* col_c = s_delta + 2 * V;
     int* row_c = s_delta + 3 * V;
+    const uint16_t bsym = (uint16_t)b;
     for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
          seq += (long long)gridDim.x * blockDim.x) {
         const int n = len[seq];
         if (n < 2) continue;
         uint16_t* s = sym + seq;
-        int q = 0, o = 0;
-        uint16_t cur = s[0];
-        bool prev_merged = false;
-        int prev_old = 0, prev_new = 0;                      // ids of the previous old / emitted symbol
-        while (q < n) {
-            const uint16_t nxt = (q + 1 < n) ? s[(long long)(q + 1) * n_stride] : (uint16_t)kWordStart;
-            const int cid = cur & kIdMask;
-            if (cid == a && q + 1 < n && (nxt & kIdMask) == b && !(nxt & kWordStart)) {
-                if (!(cur & kWordStart) && q > 0) {          // pair with the left neighbour changes
-                    atomicAdd(&col_a[prev_old], -1);         // (old left, a) disappears
-                    atomicAdd(&col_c[prev_new], 1);          // (new left, c) appears
+        int q0 = -1;
+        {
+            bool prev_a = false;
+            for (int q = 0; q < n && q0 < 0; q += kMergeChunk) {
+                uint16_t v[kMergeChunk];
+#pragma unroll
+                for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
+#pragma unroll
+                for (int j = 0; j < kMergeChunk; ++j) {
+                    if (q0 < 0 && prev_a && v[j] == bsym) q0 = q + j - 1;
+                    prev_a = (v[j] & kIdMask) == a;
                 }
-                const uint16_t w = (uint16_t)c | (cur & kWordStart);
-                s[(long long)o * n_stride] = w;
-                prev_merged = true;
-                prev_old = b;
-                prev_new = c;
-                ++o;
-                q += 2;
-                cur = (q < n) ? s[(long long)q * n_stride] : (uint16_t)0;
-            } else {
-                if (prev_merged && !(cur & kWordStart)) {    // right neighbour of a merge
-                    atomicAdd(&row_b[cid], -1);              // (b, y) disappears
-                    atomicAdd(&row_c[cid], 1);               // (c, y) appears
-                }
-                if (o != q) s[(long long)o * n_stride] = cur;
-                prev_merged = false;
-                prev_old = cid;
-                prev_new = cid;
-                ++o;
-                ++q;
-                cur = nxt;
             }
         }
-        if (o != n) len[seq] = o;
+        if (q0 < 0) continue;
+        int o = q0;
+        bool prev_merged = false, pend = false;
+        uint16_t pend_sym = 0;
+        int prev_old = q0 > 0 ? (s[(long long)(q0 - 1) * n_stride] & kIdMask) : 0;   // old / emitted left neighbour ids
+        int prev_new = prev_old;
+        auto emit_plain = [&](uint16_t x) {
+            const int id = x & kIdMask;
+            if (prev_merged && !(x & kWordStart)) {          // right neighbour of a merge
+                atomicAdd(&row_b[id], -1);                   // (b, y) disappears
+                atomicAdd(&row_c[id], 1);                    // (c, y) appears
+            }
+            s[(long long)o * n_stride] = x;
+            prev_merged = false;
+            prev_old = id;
+            prev_new = id;
+            ++o;
+        };
+        for (int q = q0; q < n; q += kMergeChunk) {
+            uint16_t v[kMergeChunk];
+#pragma unroll
+            for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
+#pragma unroll
+            for (int j = 0; j < kMergeChunk; ++j) {
+                if (q + j >= n) break;
+                const uint16_t cur = v[j];
+                if (pend) {
+                    pend = false;
+                    if (cur == bsym) {                       // merge (held a, b) -> c
+                        if (!(pend_sym & kWordStart)) {      // the pair with the left neighbour changes
+                            atomicAdd(&col_a[prev_old], -1); // (old left, a) disappears
+                            atomicAdd(&col_c[prev_new], 1);  // (new left, c) appears
+                        }
+                        s[(long long)o * n_stride] = (uint16_t)c | (pend_sym & kWordStart);
+                        prev_merged = true;
+                        prev_old = b;
+                        prev_new = c;
+                        ++o;
+                        continue;
+                    }
+                    emit_plain(pend_sym);
+                }
+                if ((cur & kIdMask) == a) { pend = true; pend_sym = cur; }
+                else emit_plain(cur);
+            }
+        }
+        if (pend) emit_plain(pend_sym);
+        len[seq] = o;
     }
+}
+
+__global__ void __launch_bounds__(256)
+bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N, long long n_stride, int a, int b,
+                 int c, int V, const BpeCtl* __restrict__ ctl, int* __restrict__ delta) {
+    extern __shared__ int s_delta[];
+    if (ctl) {                                               // sync-free loop: the merge comes from device memory
+        if (ctl->done) return;
+        a = ctl->a; b = ctl->b; c = ctl->c;
+    }
+    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
+    __syncthreads();
+    merge_sequences(sym, len, N, n_stride, a, b, c, V, s_delta);
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
         const int d = s_delta[i];
@@ -261,9 +321,35 @@ bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N,
     }
 }
 
+// Decode the arg-max key, apply the stop rules of BpeTrainer (vocabulary full, count < min_frequency),
+// assign the next id, log the merge.  One thread; also re-arms the arg-max result.
+__global__ void bpe_select_kernel(unsigned long long* __restrict__ result, BpeCtl* __restrict__ ctl,
+                                  int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges) {
+    const unsigned long long key = *result;
+    *result = 0;
+    if (ctl->done) return;
+    const int count = (int)(key >> 32);
+    if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges) {
+        ctl->done = 1;
+        return;
+    }
+    const unsigned int flat = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
+    ctl->a = (int)(flat / (unsigned int)V);
+    ctl->b = (int)(flat % (unsigned int)V);
+    ctl->c = ctl->n_tokens++;
+    ctl->count = count;
+    int* e = log + 4 * ctl->n_merges++;
+    e[0] = ctl->a; e[1] = ctl->b; e[2] = ctl->c; e[3] = count;
+}
+
 // hist += delta (after the optional cross-GPU sum), then the merged pair is gone for good.
 __global__ void __launch_bounds__(1024)
-bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, int b, int c, int V) {
+bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, int b, int c, int V,
+                       const BpeCtl* __restrict__ ctl) {
+    if (ctl) {
+        if (ctl->done) return;
+        a = ctl->a; b = ctl->b; c = ctl->c;
+    }
     for (int i = threadIdx.x; i < V; i += blockDim.x) hist[(long long)i * V + a] += delta[i];
     __syncthreads();
     for (int i = threadIdx.x; i < V; i += blockDim.x) hist[(long long)b * V + i] += delta[V + i];
@@ -477,7 +563,7 @@ extern "C" int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint
     cudaError_t e = cudaMemsetAsync(result, 0, sizeof(uint64_t), st);
     if (e != cudaSuccess) return (int)e;
     bpe_argmax_kernel<<<bpe_grid((long long)n_active * n_active, 256 * 4), 256, 0, st>>>(
-        hist, V, n_active, (unsigned long long*)result);
+        hist, V, n_active, nullptr, (unsigned long long*)result);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -503,7 +589,7 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
     long long grid = (N + 255) / 256;
     const long long cap = (long long)sms * 6;
     if (grid > cap) grid = cap;
-    bpe_merge_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, a, b, c, V, delta);
+    bpe_merge_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, a, b, c, V, nullptr, delta);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -512,8 +598,48 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
 extern "C" int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream) {
     if (!hist || !delta) return BEAST_E_NULL;
     if (V < 1 || a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V) return BEAST_E_SHAPE;
-    bpe_apply_delta_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, delta, a, b, c, V);
+    bpe_apply_delta_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, delta, a, b, c, V, nullptr);
     count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+// One iteration of the sync-free training loop.  phase 0: arg-max -> select -> merge (fills delta);
+// phase 1: hist += delta.  The caller runs [phase 0, all-reduce(delta) when sharded, phase 1] up to
+// (vocab_size - alphabet) times without reading anything back; ctl / log are read once at the end.
+extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
+                              int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t vocab_size,
+                              int32_t min_frequency, int32_t max_merges, int32_t phase, void* stream) {
+    if (!hist || !delta || !ctl || !log || !result) return BEAST_E_NULL;
+    if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
+    if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase == 1) {
+        bpe_apply_delta_kernel<<<1, 1024, 0, st>>>(hist, delta, 0, 0, 0, V, (const BpeCtl*)ctl);
+        count_launch();
+        BEAST_CHECK_LAUNCH();
+        return BEAST_OK;
+    }
+    const size_t smem = (size_t)4 * V * sizeof(int);
+    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // the arg-max grid is sized for the full table: n_active lives on the device
+    bpe_argmax_kernel<<<sms * 4, 256, 0, st>>>(hist, V, V, (const BpeCtl*)ctl, (unsigned long long*)result);
+    bpe_select_kernel<<<1, 1, 0, st>>>((unsigned long long*)result, (BpeCtl*)ctl, log, V, vocab_size, min_frequency,
+                                      max_merges);
+    long long grid = (N + 255) / 256;
+    const long long cap = (long long)sms * 6;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    bpe_merge_kernel<<<(unsigned)grid, 256, smem, st>>>(sym, len, N, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, delta);
+    count_launch(3);
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
 }

@@ -178,6 +178,14 @@ int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* resul
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
                     int32_t c, int32_t V, int32_t* delta, void* stream);
 int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
+/* Sync-free training loop: one iteration = phase 0 (arg-max, select with BpeTrainer's stop rules —
+ * vocabulary full / count < min_frequency —, merge into delta) [+ all-reduce(delta) when sharded] + phase 1
+ * (hist += delta).  ctl: 8 x int32 device block {a, b, c, count, n_tokens, n_merges, done, pad}, caller sets
+ * n_tokens = alphabet size and zeroes the rest; log: int32 [4 * max_merges] receives (a, b, new_id, count) per
+ * merge; result: the arg-max scratch word (zeroed by the caller once).  Nothing is read back until the end. */
+int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
+                   int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t vocab_size,
+                   int32_t min_frequency, int32_t max_merges, int32_t phase, void* stream);
 int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
                const int16_t* byte_to_id, const uint32_t* rank_tab, int32_t V, uint16_t* ids_padded,
                int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream);
