@@ -151,7 +151,9 @@ class BEASTBsplineTokenizer(TokenizerBase):
         return (self.w_min.to(dev, torch.float32).contiguous(), self.w_max.to(dev, torch.float32).contiguous())
 
     def _prep_trajs(self, trajs, dev):
-        trajs = trajs.to(dev, dtype=torch.float32)
+        # pinned host batches are uploaded asynchronously on the current stream (stream-ordered before
+        # the kernel), so callers can overlap the copy of one chunk with the compute of another
+        trajs = trajs.to(dev, dtype=torch.float32, non_blocking=bool(trajs.device.type == "cpu" and trajs.is_pinned()))
         if trajs.dim() != 3:
             raise AssertionError(f"expected trajectories [batch, time, dof], got {tuple(trajs.shape)}")
         if trajs.shape[1] != self.times.numel():

@@ -110,6 +110,22 @@ __device__ __forceinline__ float dequantize_fast(long long tok, float w_min, flo
     return clampf(c, w_min, w_max);
 }
 
+// ---------------------------------------------------------------- packed fp32 FMA (Blackwell FFMA2)
+// fma.rn.f32x2: two IEEE fp32 FMAs per instruction (SASS FFMA2, which takes a uniform-register pair
+// and a broadcast scalar directly).  Bit-identical to two fmaf calls; halves the issue slots of the
+// K = 50 / N = 10 contractions in K1 / K3.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ float lo_f32(unsigned long long v) { return __uint_as_float((unsigned int)v); }
+__device__ __forceinline__ float hi_f32(unsigned long long v) { return __uint_as_float((unsigned int)(v >> 32)); }
+// acc.{lo,hi} = fma(a.{lo,hi}, b, acc.{lo,hi})
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, float a_lo, float a_hi, float b) {
+    const unsigned long long a = pack_f32x2(a_lo, a_hi);
+    const unsigned long long bb = pack_f32x2(b, b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(bb));
+}
+
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

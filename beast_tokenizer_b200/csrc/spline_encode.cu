@@ -13,9 +13,10 @@
 //   * every HBM byte moves by 1-D bulk TMA (cp.async.bulk, SASS UBLKCP): global->shared completes on
 //     an mbarrier; the outputs are staged over the consumed input tile and leave with bulk
 //     shared->global stores — 16-byte-aligned bursts, nothing through registers;
-//   * one thread per (trajectory, slot) column: 50 LDS + 500 FFMA whose P operand comes from the
-//     constant bank (the table travels as a __grid_constant__ kernel parameter and is read with
-//     uniform LDCU.128 loads), then the exact quantiser; joint columns fill warps 0-5, gripper
+//   * one thread per (trajectory, slot) column: 50 LDS + 250 packed FFMA2 (fma.rn.f32x2: two fp32
+//     FMAs per instruction) whose P operand pair comes from the constant bank (the table travels as
+//     a __grid_constant__ kernel parameter and is read with uniform LDCU.128 loads straight into the
+//     uniform-register operand of FFMA2), then the exact quantiser; joint columns fill warps 0-5, gripper
 //     columns warp 6 (degree-0 projector = one non-zero per sample, walked interval by interval).
 // Generic kernel: any geometry, one thread per column, same accumulation order (bit-identical
 // coefficients), plain loads/stores.  Also handles the ragged tail of the fast path.
@@ -62,14 +63,21 @@ template <int T, int NB>
 __device__ __forceinline__ void fit_joint(const EncTables<T, NB>& tab, const float* __restrict__ y, int D,
                                           float (&acc)[NB]) {
     constexpr int NBP = EncTables<T, NB>::NBP;
+    constexpr int NP = NB / 2;
+    unsigned long long acc2[NP > 0 ? NP : 1];             // (k, k+1) accumulator pairs -> FFMA2
+    float tail = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NB; ++k) acc[k] = 0.0f;
+    for (int p = 0; p < NP; ++p) acc2[p] = 0ull;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const float v = y[t * D];
 #pragma unroll
-        for (int k = 0; k < NB; ++k) acc[k] = fmaf(tab.pj[t * NBP + k], v, acc[k]);
+        for (int p = 0; p < NP; ++p) ffma2_bcast(acc2[p], tab.pj[t * NBP + 2 * p], tab.pj[t * NBP + 2 * p + 1], v);
+        if (NB & 1) tail = fmaf(tab.pj[t * NBP + NB - 1], v, tail);
     }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { acc[2 * p] = lo_f32(acc2[p]); acc[2 * p + 1] = hi_f32(acc2[p]); }
+    if (NB & 1) acc[NB - 1] = tail;
 }
 
 // Same sums as the dense form (the skipped terms are exact zeros), t ascending inside each interval.
