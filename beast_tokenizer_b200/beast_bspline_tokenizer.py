@@ -338,9 +338,17 @@ class BEASTBsplineTokenizer(TokenizerBase):
 
     @torch.no_grad()
     def update_weights_bounds(self, demos):
-        """Global per-column min / max of the coefficients (reference :362-378)."""
-        weights = self.compute_weights(demos)
-        lo, hi = self._minmax(weights)
+        """Global per-column min / max of the coefficients (reference :362-378): one fused launch,
+        the coefficients are reduced in registers and never written."""
+        plan = self._plan()
+        dev = plan.device
+        x = self._prep_trajs(demos, dev)
+        n = self.num_dof * self.num_basis
+        lo = torch.empty(n, device=dev, dtype=torch.float32)
+        hi = torch.empty(n, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(plan._lib.beast_fit_minmax_f32(plan.handle, _lib.ptr(x), x.shape[0], _lib.ptr(lo), _lib.ptr(hi), 0,
+                                                      _lib.stream_ptr(dev)), "beast_fit_minmax_f32")
         self.w_min.copy_(lo.to(self.w_min.device))
         self.w_max.copy_(hi.to(self.w_max.device))
 

@@ -10,18 +10,6 @@
 
 namespace beast {
 
-// float atomics through the order-preserving integer views (outputs hold +inf / -inf initially).
-__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
-    v = __fadd_rn(v, 0.0f);                                  // -0.0 -> +0.0 (its int view is INT_MIN)
-    if (v >= 0.0f) atomicMin((int*)addr, __float_as_int(v));
-    else atomicMax((unsigned int*)addr, __float_as_uint(v));
-}
-__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
-    v = __fadd_rn(v, 0.0f);
-    if (v >= 0.0f) atomicMax((int*)addr, __float_as_int(v));
-    else atomicMin((unsigned int*)addr, __float_as_uint(v));
-}
-
 __global__ void minmax_init_kernel(float* mn, float* mx, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { mn[i] = __int_as_float(0x7f800000); mx[i] = __int_as_float(0xff800000); }

@@ -52,6 +52,8 @@ struct EncArgs {
     long long* tokens_out;
     const float* w_min;
     const float* w_max;
+    float* bmin;           // optional [D*NB]: column min / max of the coefficients (order-preserving atomics)
+    float* bmax;
     long long offset;
     float vm1;
     int D, n_joint, S, n_tiles;
@@ -164,6 +166,11 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
     for (int k = 0; k < NB; ++k)
         qc[k].init(want_tok ? a.w_min[slot * NB + k] : 0.0f, want_tok ? a.w_max[slot * NB + k] : 0.0f);
 
+    const bool want_mm = a.bmin != nullptr;
+    float tmin[NB], tmax[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { tmin[k] = __int_as_float(0x7f800000); tmax[k] = __int_as_float(0xff800000); }
+
     for (int i = group; i < n_my; i += kEncGroups) {
         const int s = i % kEncStages;
         unsigned char* stage = smem + s * stride;
@@ -176,6 +183,10 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
                 for (int k = 0; k < NB; ++k) acc[k] = y[k * D];
             } else if (slot < nj) fit_joint<T, NB>(tab, y, D, acc);
             else fit_grip<T, NB>(tab, y, D, acc);
+        }
+        if (want_mm && active) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) { tmin[k] = fminf(tmin[k], acc[k]); tmax[k] = fmaxf(tmax[k], acc[k]); }
         }
         group_barrier(group);                              // every column of the tile has been read
         if (active) {
@@ -199,6 +210,14 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&out_full_bar[s]);
     }
+    if (want_mm && active && n_my > group) {
+        // a thread keeps its (slot) columns for the whole launch: one pair of atomics per coefficient
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            atomic_min_f32(a.bmin + slot * NB + k, tmin[k]);
+            atomic_max_f32(a.bmax + slot * NB + k, tmax[k]);
+        }
+    }
 }
 
 // One thread per (trajectory, slot) column; any geometry.  Accumulates in the same order
@@ -208,7 +227,8 @@ encode_generic_kernel(const float* __restrict__ traj, long long ncol, int T, int
                       const int* __restrict__ slot_to_dof, const float* __restrict__ Pj,
                       const float* __restrict__ Pg, const float* __restrict__ w_min,
                       const float* __restrict__ w_max, float vm1, long long offset,
-                      float* __restrict__ params_out, long long* __restrict__ tokens_out) {
+                      float* __restrict__ params_out, long long* __restrict__ tokens_out,
+                      float* __restrict__ bmin, float* __restrict__ bmax) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < ncol;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long b = idx / D;
@@ -221,6 +241,7 @@ encode_generic_kernel(const float* __restrict__ traj, long long ncol, int T, int
             const float* pk = P + (long long)k * T;
             for (int t = 0; t < T; ++t) acc = fmaf(__ldg(pk + t), __ldg(y + (long long)t * D), acc);
             if (params_out) params_out[b * (long long)D * nb + (long long)slot * nb + k] = acc;
+            if (bmin) { atomic_min_f32(bmin + slot * nb + k, acc); atomic_max_f32(bmax + slot * nb + k, acc); }
             if (tokens_out) {
                 const float lo = w_min[slot * nb + k], hi = w_max[slot * nb + k];
                 tokens_out[b * (long long)D * nb + (long long)k * D + slot] =
@@ -297,7 +318,7 @@ static bool grip_structure(const float* pg, float* pgv, int* gstart) {
 template <int T, int NB, int DT>
 static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int S, const float* w_min,
                        const float* w_max, long long offset, float* params_out, long long* tokens_out,
-                       cudaStream_t st) {
+                       float* bmin, float* bmax, cudaStream_t st) {
     EncTables<T, NB> tab;
     constexpr int NBP = EncTables<T, NB>::NBP;
     for (int t = 0; t < T; ++t)
@@ -310,7 +331,7 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
     }
     EncArgs a;
     a.traj = traj; a.params_out = params_out; a.tokens_out = tokens_out;
-    a.w_min = w_min; a.w_max = w_max; a.offset = offset; a.vm1 = (float)(p->V - 1);
+    a.w_min = w_min; a.w_max = w_max; a.bmin = bmin; a.bmax = bmax; a.offset = offset; a.vm1 = (float)(p->V - 1);
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
     { const char* e = getenv("BEAST_B200_DEBUG_SKIP"); a.debug_skip = (e && e[0] == '1') ? 1 : 0; }
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
@@ -332,6 +353,47 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
     return BEAST_OK;
 }
 
+
+// Shared body of beast_encode_f32 / beast_fit_minmax_f32.
+static int encode_impl(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
+                       long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
+                       cudaStream_t st) {
+    const int T = p->T, D = p->D, nb = p->nb;
+    long long done = 0;
+    if (T == 50 && nb == 10 && !fast_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
+        (!tokens_out || aligned16(tokens_out))) {
+        const int S = (kEncColumns / D) & ~3;
+        if (S >= 4 && B >= S) {
+            const long long n_tiles = B / S;
+            int rc;
+            if (D == 14)
+                rc = launch_fast<50, 10, 14>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
+            else if (D == 7)
+                rc = launch_fast<50, 10, 7>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
+            else
+                rc = launch_fast<50, 10, 0>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
+            if (rc == BEAST_OK) done = n_tiles * S;
+            else if (rc != BEAST_E_UNSUPPORTED) return rc;
+        }
+    }
+    if (done < B) {
+        const long long ncol = (B - done) * D;
+        encode_generic_kernel<<<grid_for(ncol, 256, p->num_sms), 256, 0, st>>>(
+            traj + done * (long long)T * D, ncol, T, D, nb, p->n_joint, p->slot_to_dof_d, p->proj_joint_d,
+            p->proj_grip_d, w_min, w_max, (float)(p->V - 1), offset,
+            params_out ? params_out + done * (long long)D * nb : nullptr,
+            tokens_out ? tokens_out + done * (long long)D * nb : nullptr, bmin, bmax);
+        count_launch();
+        BEAST_CHECK_LAUNCH();
+    }
+    return BEAST_OK;
+}
+
+__global__ void bounds_init_kernel(float* mn, float* mx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mn[i] = __int_as_float(0x7f800000); mx[i] = __int_as_float(0xff800000); }
+}
+
 }  // namespace beast
 
 using namespace beast;
@@ -346,39 +408,26 @@ extern "C" int beast_encode_f32(const beast_plan_t* plan, const float* traj, int
     if (!traj || (!params_out && !tokens_out)) return BEAST_E_NULL;
     if (tokens_out && (!w_min || !w_max)) return BEAST_E_NULL;
     if (((uintptr_t)traj & 3u) || ((uintptr_t)params_out & 3u) || ((uintptr_t)tokens_out & 7u)) return BEAST_E_ALIGN;
+    return encode_impl(p, traj, B, w_min, w_max, offset, params_out, (long long*)tokens_out, nullptr, nullptr,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int beast_fit_minmax_f32(const beast_plan_t* plan, const float* traj, int64_t B, float* min_out,
+                                    float* max_out, int32_t accumulate, void* stream) {
+    const Plan* p = (const Plan*)plan;
+    if (!p || !min_out || !max_out) return BEAST_E_NULL;
+    if (B < 0) return BEAST_E_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    const int T = p->T, D = p->D, nb = p->nb;
-    long long done = 0;
-    if (T == 50 && nb == 10 && !fast_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
-        (!tokens_out || aligned16(tokens_out))) {
-        const int S = (kEncColumns / D) & ~3;
-        if (S >= 4 && B >= S) {
-            const long long n_tiles = B / S;
-            int rc;
-            if (D == 14)
-                rc = launch_fast<50, 10, 14>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
-                                                (long long*)tokens_out, st);
-            else if (D == 7)
-                rc = launch_fast<50, 10, 7>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
-                                               (long long*)tokens_out, st);
-            else
-                rc = launch_fast<50, 10, 0>(p, traj, n_tiles, S, w_min, w_max, offset, params_out,
-                                               (long long*)tokens_out, st);
-            if (rc == BEAST_OK) done = n_tiles * S;
-            else if (rc != BEAST_E_UNSUPPORTED) return rc;
-        }
-    }
-    if (done < B) {
-        const long long ncol = (B - done) * D;
-        encode_generic_kernel<<<grid_for(ncol, 256, p->num_sms), 256, 0, st>>>(
-            traj + done * (long long)T * D, ncol, T, D, nb, p->n_joint, p->slot_to_dof_d, p->proj_joint_d,
-            p->proj_grip_d, w_min, w_max, (float)(p->V - 1), offset,
-            params_out ? params_out + done * (long long)D * nb : nullptr,
-            tokens_out ? (long long*)tokens_out + done * (long long)D * nb : nullptr);
+    const int n = p->D * p->nb;
+    if (!accumulate) {
+        bounds_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(min_out, max_out, n);
         count_launch();
         BEAST_CHECK_LAUNCH();
     }
-    return BEAST_OK;
+    if (B == 0) return BEAST_OK;
+    if (!traj) return BEAST_E_NULL;
+    if ((uintptr_t)traj & 3u) return BEAST_E_ALIGN;
+    return encode_impl(p, traj, B, nullptr, nullptr, 0, nullptr, nullptr, min_out, max_out, st);
 }
 
 extern "C" int beast_quantize_f32(const beast_plan_t* plan, const float* params, int64_t B, const float* w_min,

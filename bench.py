@@ -266,11 +266,59 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu):
     back = btok._bpe_csr_to_discrete(flat, offsets)
     ev[2].record()
     torch.cuda.synchronize()
+    xs_api = x[:65536]
+    btok.encode(xs_api[:1024])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ids_list, _ = btok.encode(xs_api)                 # API-faithful: ragged List[List[int]] on the host
+    t1 = time.perf_counter()
+    rec_api = btok.reconstruct_traj(ids_list)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
     apply = {"workload": "BPE encode / decode of 1 048 576 sequences x 140 bins, 2048-entry table, device CSR",
+             "api_list_path": {"batch": 65536, "encode_traj_per_s": 65536 / (t1 - t0),
+                               "reconstruct_traj_per_s": 65536 / (t2 - t1),
+                               "note": "BEASTBsplineBPETokenizer.encode -> List[List[int]] -> reconstruct_traj; "
+                                       "dominated by building / flattening 65 536 Python lists"},
              "encode_seq_per_s": nb / (ev[0].elapsed_time(ev[1]) * 1e-3),
              "decode_seq_per_s": nb / (ev[1].elapsed_time(ev[2]) * 1e-3),
              "ids_per_sequence": float(flat.numel()) / nb, "round_trip_exact": bool(torch.equal(back, mp))}
     return out, apply
+
+
+def bounds_leg(tok, dev):
+    """BASELINE configs[2]: weight bounds over 100 000 trajectories — the fused min/max reduction
+    (update_weights_bounds) and the reference-faithful quantile fit (fit_parameters)."""
+    import torch
+    from beast_tokenizer_b200.synth import synth_device
+    n = 100_000
+    x = synth_device(n, T, D, 7, dev)
+    saved = (tok.w_min.clone(), tok.w_max.clone())
+    tok.update_weights_bounds(x)                      # warm-up
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        tok.update_weights_bounds(x)
+    e1.record()
+    torch.cuda.synchronize()
+    mm_ms = e0.elapsed_time(e1) / reps
+    out = {"workload": "100 000 trajectories [100000, 50, 14] resident in HBM",
+           "update_weights_bounds": {"ms": mm_ms, "traj_per_s": n / (mm_ms * 1e-3),
+                                     "GBps_read": 4 * T * D * n / (mm_ms * 1e-3) / 1e9}}
+    for label, bs in (("3125 batches x 32 (the reference's loader shape)", 32), ("25 batches x 4000", 4000)):
+        batches = [{"actions": x[i:i + bs]} for i in range(0, n, bs)]
+        tok.fit_parameters(batches[:4], verbose=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tok.fit_parameters(batches, verbose=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out.setdefault("fit_parameters", {})[label] = {"seconds": dt, "traj_per_s": n / dt}
+    tok.w_min.copy_(saved[0])
+    tok.w_max.copy_(saved[1])
+    return out
 
 
 def synth_bins_sample(tok, dev):
@@ -441,6 +489,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
+    bounds = bounds_leg(tok, dev) if rank == 0 else None
     bpe_train = bpe_apply = None
     if not args.no_bpe:
         del xs, toks, pars, outs, xh
@@ -488,6 +537,8 @@ def main():
                 line["roofline_decode"]["traffic"] = tr.get("decode_fast_kernel")
             except Exception:
                 pass
+        if bounds is not None:
+            line["bounds"] = bounds
         if bpe_train is not None:
             line["bpe_train"] = bpe_train
         if bpe_apply is not None:

@@ -128,6 +128,11 @@ int beast_eval_f32(const beast_plan_t* plan, const float* params, int64_t B,
 int beast_minmax_f32(const float* x, int64_t rows, int32_t cols,
                      float* min_out, float* max_out, int32_t accumulate, void* stream);
 
+/* update_weights_bounds fused (:362-378): column min / max of the fitted coefficients straight from the
+ * trajectories — K1 without any output but 2 x D*nb floats (2 800 B read per trajectory). */
+int beast_fit_minmax_f32(const beast_plan_t* plan, const float* traj, int64_t B, float* min_out,
+                         float* max_out, int32_t accumulate, void* stream);
+
 /* update_weights_bounds_per_batch (:384-389): w_min[i] = bmin[i] where bmin[i] < w_min[i]-hyst,
  * w_max[i] = bmax[i] where bmax[i] > w_max[i]+hyst. */
 int beast_bounds_expand_f32(const float* batch_min, const float* batch_max,
