@@ -551,12 +551,17 @@ class BEASTBsplineTokenizer(TokenizerBase):
         return out
 
     # ------------------------------------------------------------------ evaluation
-    def compute_reconstruction_error(self, raw_traj):
+    def compute_reconstruction_error(self, raw_traj, return_tokens: bool = False):
+        """(mean squared error, mean signed error) of encode -> reconstruct (reference :589-597).
+        `return_tokens=True` also returns the tokens — the call train/eval.py:34 makes upstream, where
+        the one-argument signature makes it fail."""
         raw_traj = raw_traj.to(self._cuda(), dtype=torch.float32)
         if len(raw_traj.shape) == 2:
             raw_traj = raw_traj.unsqueeze(0)
-        tokens, _ = self.encode(raw_traj)
+        tokens = self.encode(raw_traj)[0]
         reconstruct_trajs = self.reconstruct_traj(tokens)
         error_l2 = torch.mean((raw_traj - reconstruct_trajs) ** 2)
         error_l1 = torch.mean(raw_traj - reconstruct_trajs)
+        if return_tokens:
+            return error_l2, error_l1, tokens
         return error_l2, error_l1

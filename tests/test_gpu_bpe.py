@@ -171,3 +171,21 @@ def test_bpe_errors():
     with pytest.raises(ValueError):
         tok._discrete_to_bpe(torch.zeros(2, 2, 2, dtype=torch.long))
     assert tok._discrete_to_bpe(torch.zeros(0, 140, dtype=torch.long)) == []
+
+
+def test_train_cli_flow(tmp_path):
+    """The reference's train_beast.py flow (fit -> save -> BPE -> save -> eval) on synthetic loaders,
+    at a 256-bin configuration the BPE path supports."""
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
+    from beast_tokenizer_b200.train_beast import main
+    main(["--device", "cuda", "--num-basis", "10", "--degree", "4", "--vocab-size", "256", "--actions-len", "50",
+          "--actions-dof", "14", "--train-batches", "40", "--eval-batches", "5", "--bpe-vocab-size", "500",
+          "--beast-checkpoint-dir", str(tmp_path / "beast"), "--bpe-checkpoint-dir", str(tmp_path / "bpe"),
+          "--eval-results-dir", str(tmp_path / "eval")])
+    stats = json.load(open(tmp_path / "eval" / "total_stats.json"))["synthetic"]
+    assert set(stats) == {f"{a}_{b}" for a in ("mean", "std", "max", "min") for b in ("l2", "l1")}
+    assert 0 <= stats["mean_l2"] < 1e-4
+    tok = BEASTBsplineBPETokenizer.from_pretrained(tmp_path / "bpe", device="cuda")
+    assert tok.bpe_tokenizer.get_vocab_size() == 500
+    errs = json.load(open(tmp_path / "eval" / "synthetic" / "errors.json"))
+    assert len(errs["errors_l2"]) == 5 and len(errs["mean_tokens_length"]) == 5 * 32
