@@ -218,13 +218,27 @@ bpe_argmax_kernel(const int* __restrict__ hist, int V, int n_active, const BpeCt
 // delta block: [0] column a (pairs (x, a) lost), [1] row b (pairs (b, y) lost),
 //              [2] column c (pairs (x, c) gained), [3] row c (pairs (c, y) gained).
 // Block-private copies live in shared memory (4*V ints) and are flushed once per block.
-// One thread per sequence.  Loads are issued kMergeChunk at a time (independent addresses, all in
-// flight together) because a symbol-at-a-time walk is bound by memory latency, not bandwidth.
+// One thread per sequence, one warp per 32 consecutive sequences, and the warp walks the positions in
+// LOCK STEP: at every step all lanes touch the same row p of the position-major corpus, so loads and
+// stores stay 64-byte contiguous even though each lane runs its own state machine.  Loads are issued
+// kMergeChunk rows at a time (independent addresses in flight: the walk is latency-bound otherwise).
 //   pass 1 (read-only): first position q0 whose id is a and whose successor is b inside the same
 //           pre-token (b with the word-start bit clear is the 16-bit value b itself);
-//   pass 2 (only if found): streaming rewrite from q0 — an `a` is held back one step, so no look-ahead
-//           is needed: next symbol == b -> emit c (merge), otherwise emit the held symbol unchanged.
+//   pass 2 (only if some lane found one): streaming rewrite from the warp's smallest q0 — an `a` is held
+//           back one step, so no look-ahead is needed: next symbol == b -> emit c (merge), otherwise
+//           emit the held symbol unchanged.  Nothing is written before a lane's first merge.
 constexpr int kMergeChunk = 8;
+
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 
 __device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int* __restrict__ len, long long N,
                                                 long long n_stride, int a, int b, int c, int V, int* s_delta) {
@@ -233,30 +247,39 @@ __device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int*
     int* col_c = s_delta + 2 * V;
     int* row_c = s_delta + 3 * V;
     const uint16_t bsym = (uint16_t)b;
-    for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
-         seq += (long long)gridDim.x * blockDim.x) {
-        const int n = len[seq];
-        if (n < 2) continue;
-        uint16_t* s = sym + seq;
+    const int lane = threadIdx.x & 31;
+    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N;
+         base += (long long)gridDim.x * blockDim.x) {
+        const long long seq = base + lane;
+        const bool valid = seq < N;
+        const int n = valid ? len[seq] : 0;
+        uint16_t* s = sym + (valid ? seq : 0);
+        const int nmax = warp_max_i(n);
         int q0 = -1;
         {
             bool prev_a = false;
-            for (int q = 0; q < n && q0 < 0; q += kMergeChunk) {
-                uint16_t v[kMergeChunk];
+            for (int q = 0; q < nmax; q += kMergeChunk) {
+                if (q < n && q0 < 0) {
+                    uint16_t v[kMergeChunk];
 #pragma unroll
-                for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
+                    for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
 #pragma unroll
-                for (int j = 0; j < kMergeChunk; ++j) {
-                    if (q0 < 0 && prev_a && v[j] == bsym) q0 = q + j - 1;
-                    prev_a = (v[j] & kIdMask) == a;
+                    for (int j = 0; j < kMergeChunk; ++j) {
+                        if (q0 < 0 && prev_a && v[j] == bsym) q0 = q + j - 1;
+                        prev_a = (v[j] & kIdMask) == a;
+                    }
                 }
+                if (__all_sync(0xffffffffu, q0 >= 0 || q + kMergeChunk >= n)) break;
             }
         }
-        if (q0 < 0) continue;
-        int o = q0;
-        bool prev_merged = false, pend = false;
+        if (!__any_sync(0xffffffffu, q0 >= 0)) continue;
+        const bool mine = q0 >= 0;
+        const int qs = warp_min_i(mine ? q0 : 0x7fffffff) & ~(kMergeChunk - 1);
+        const int nact = warp_max_i(mine ? n : 0);
+        int o = qs;
+        bool prev_merged = false, pend = false, dirty = false;
         uint16_t pend_sym = 0;
-        int prev_old = q0 > 0 ? (s[(long long)(q0 - 1) * n_stride] & kIdMask) : 0;   // old / emitted left neighbour ids
+        int prev_old = (mine && qs > 0) ? (s[(long long)(qs - 1) * n_stride] & kIdMask) : 0;   // left neighbour ids (old / emitted)
         int prev_new = prev_old;
         auto emit_plain = [&](uint16_t x) {
             const int id = x & kIdMask;
@@ -264,13 +287,14 @@ __device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int*
                 atomicAdd(&row_b[id], -1);                   // (b, y) disappears
                 atomicAdd(&row_c[id], 1);                    // (c, y) appears
             }
-            s[(long long)o * n_stride] = x;
+            if (dirty) s[(long long)o * n_stride] = x;
             prev_merged = false;
             prev_old = id;
             prev_new = id;
             ++o;
         };
-        for (int q = q0; q < n; q += kMergeChunk) {
+        for (int q = qs; q < nact; q += kMergeChunk) {
+            if (!mine || q >= n) continue;
             uint16_t v[kMergeChunk];
 #pragma unroll
             for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
@@ -286,6 +310,7 @@ __device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int*
                             atomicAdd(&col_c[prev_new], 1);  // (new left, c) appears
                         }
                         s[(long long)o * n_stride] = (uint16_t)c | (pend_sym & kWordStart);
+                        dirty = true;
                         prev_merged = true;
                         prev_old = b;
                         prev_new = c;
@@ -298,8 +323,10 @@ __device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int*
                 else emit_plain(cur);
             }
         }
-        if (pend) emit_plain(pend_sym);
-        len[seq] = o;
+        if (mine) {
+            if (pend) emit_plain(pend_sym);
+            len[seq] = o;
+        }
     }
 }
 

@@ -118,6 +118,13 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
     const int first = blockIdx.x, step = gridDim.x;
     const int n_my = first < a.n_tiles ? (a.n_tiles - first + step - 1) / step : 0;
     const size_t tile_in = (size_t)S * T * D, tile_out = (size_t)S * NB * D;
+    // optional column min / max of the coefficients: CTA-level partials (shared-memory atomics),
+    // then one global atomic per column and CTA
+    __shared__ float s_mn[BEAST_MAX_SLOTS * NB];
+    __shared__ float s_mx[BEAST_MAX_SLOTS * NB];
+    const bool want_mm = a.bmin != nullptr;
+    if (want_mm)
+        for (int c = tid; c < D * NB; c += blockDim.x) { s_mn[c] = __int_as_float(0x7f800000); s_mx[c] = __int_as_float(0xff800000); }
     if (tid == 0) {
         for (int s = 0; s < kEncStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&out_full_bar[s], kEncGroupWarps); }
         mbar_fence_init();
@@ -166,7 +173,6 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
     for (int k = 0; k < NB; ++k)
         qc[k].init(want_tok ? a.w_min[slot * NB + k] : 0.0f, want_tok ? a.w_max[slot * NB + k] : 0.0f);
 
-    const bool want_mm = a.bmin != nullptr;
     float tmin[NB], tmax[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) { tmin[k] = __int_as_float(0x7f800000); tmax[k] = __int_as_float(0xff800000); }
@@ -210,12 +216,18 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&out_full_bar[s]);
     }
-    if (want_mm && active && n_my > group) {
-        // a thread keeps its (slot) columns for the whole launch: one pair of atomics per coefficient
+    if (want_mm) {
+        // a thread keeps its (slot) columns for the whole launch: registers -> shared -> global
+        if (active && n_my > group) {
 #pragma unroll
-        for (int k = 0; k < NB; ++k) {
-            atomic_min_f32(a.bmin + slot * NB + k, tmin[k]);
-            atomic_max_f32(a.bmax + slot * NB + k, tmax[k]);
+            for (int k = 0; k < NB; ++k) {
+                atomic_min_f32(&s_mn[slot * NB + k], tmin[k]);
+                atomic_max_f32(&s_mx[slot * NB + k], tmax[k]);
+            }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(kEncGroups + 1), "r"(kEncGroups * kEncGroupWarps * 32) : "memory");
+        for (int c = tid; c < D * NB; c += kEncGroups * kEncGroupWarps * 32) {
+            if (s_mn[c] <= s_mx[c]) { atomic_min_f32(a.bmin + c, s_mn[c]); atomic_max_f32(a.bmax + c, s_mx[c]); }
         }
     }
 }
