@@ -65,7 +65,7 @@ def build_alphabet(min_token: int, max_token: int, seen_bytes: Sequence[int]):
 
 
 class GpuBpeEngine:
-    """Device state of one shard: position-major symbols, lengths, replicated V x V histogram."""
+    """Device state of one shard: chunk-major symbols, lengths, replicated V x V histogram."""
 
     def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int):
         self.lib = _lib.load()
@@ -74,11 +74,13 @@ class GpuBpeEngine:
         self.V = V
         self.stride = max(self.N, 1)
         with torch.cuda.device(self.dev):
-            self.sym = torch.empty((2 * self.L, self.stride), device=self.dev, dtype=torch.int16)
+            # chunk-major corpus: [ceil(2L / 8) chunks, sequences, 8 symbols] uint16 (see csrc/bpe.cu)
+            self.sym = torch.empty(((2 * self.L + 7) // 8, self.stride, 8), device=self.dev, dtype=torch.int16)
             self.len = torch.zeros(self.stride, device=self.dev, dtype=torch.int32)
             self.hist = torch.zeros((V, V), device=self.dev, dtype=torch.int32)
             self.delta = torch.zeros(4 * V, device=self.dev, dtype=torch.int32)
             self.result = torch.zeros(1, device=self.dev, dtype=torch.int64)
+            self.work = torch.zeros(4 + 2 * self.stride, device=self.dev, dtype=torch.int32)   # scan -> rewrite work list
             err = torch.zeros(1, device=self.dev, dtype=torch.int32)
             b2i = torch.from_numpy(byte_to_id).to(self.dev)
             st = _lib.stream_ptr(self.dev)
@@ -103,8 +105,8 @@ class GpuBpeEngine:
     def merge(self, a: int, b: int, c: int):
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.bpe_apply_merge(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, a, b, c,
-                                                self.V, _lib.ptr(self.delta), _lib.stream_ptr(self.dev)),
-                       "bpe_apply_merge")
+                                                self.V, _lib.ptr(self.delta), _lib.ptr(self.work),
+                                                _lib.stream_ptr(self.dev)), "bpe_apply_merge")
 
     def apply_delta(self, a: int, b: int, c: int):
         with torch.cuda.device(self.dev):
@@ -129,8 +131,9 @@ class GpuBpeEngine:
             def step(phase):
                 _lib.check(self.lib.bpe_train_step(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, self.V,
                                                    _lib.ptr(self.hist), _lib.ptr(self.delta), _lib.ptr(ctl),
-                                                   _lib.ptr(log), _lib.ptr(self.result), int(vocab_size),
-                                                   int(min_frequency), max_merges, phase, _lib.stream_ptr(dev)),
+                                                   _lib.ptr(log), _lib.ptr(self.result), _lib.ptr(self.work),
+                                                   int(vocab_size), int(min_frequency), max_merges, phase,
+                                                   _lib.stream_ptr(dev)),
                            "bpe_train_step")
 
             # plain stream launches: ~60 us of host enqueue per merge, never a sync (capturing the

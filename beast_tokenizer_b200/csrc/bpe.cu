@@ -13,9 +13,10 @@
 //   encode      per word: repeatedly merge the lowest-rank pair, leftmost first
 //   decode      ids -> token bytes -> UTF-8 -> codepoints + min_token
 //
-// Corpus layout: POSITION-MAJOR sym[p * n_stride + seq] (uint16): one thread owns one sequence and
-// walks p, so every warp access is a contiguous 64-byte row — the serial per-sequence state
-// machines (pre-tokeniser, merge) run at full coalescing without any shuffling.
+// Corpus layout: CHUNK-MAJOR — 8 consecutive symbols (16 bytes) of one sequence form a chunk and chunk c
+// of all sequences is contiguous: sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)] (uint16).  One thread
+// owns one sequence; a warp reads / writes chunk c of its 32 sequences as 512 contiguous bytes, one
+// 128-bit access per lane, so the serial per-sequence state machines run at full coalescing.
 #include "common.cuh"
 
 namespace beast {
@@ -24,6 +25,16 @@ constexpr int kBpeBlock = 128;
 constexpr uint16_t kWordStart = 0x8000u;
 constexpr uint16_t kIdMask = 0x7fffu;
 constexpr int kMaxWord = 512;            // longest sequence (in byte-level symbols) encode handles
+
+// Corpus layout ("chunk-major"): the symbols of sequence `seq` live in 16-byte chunks of 8,
+// chunk c of all sequences contiguous:  sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)].
+// One thread owns one sequence; a warp reading chunk c of its 32 sequences touches 512 contiguous
+// bytes with one 128-bit load per lane.  Slots past len[seq] in the last chunk hold 0xffff.
+constexpr int kChunk = 8;
+constexpr uint16_t kPad = 0xffffu;
+__device__ __forceinline__ long long sym_index(int p, long long seq, long long n_stride) {
+    return ((long long)(p >> 3) * n_stride + seq) * kChunk + (p & 7);
+}
 
 // Device-side control block of the sync-free training loop (bpe_train_step).
 struct BpeCtl {
@@ -140,7 +151,6 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
     if (seq >= N) return;
     if (s_status[threadIdx.x]) *err = 1;
     const uint8_t* cp = s_cp + threadIdx.x * LP;
-    uint16_t* out = sym + seq;
     int m = 0, i = 0;
     while (i < L) {
         const int pl = pretoken_len(cp, i, L);
@@ -149,16 +159,17 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
             const int c = cp[q];
             if (c < 128) {
                 const int id = s_b2i[c];
-                if (id >= 0) { out[(long long)m * n_stride] = (uint16_t)id | flag; flag = 0; ++m; }
+                if (id >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)id | flag; flag = 0; ++m; }
             } else {
                 const int i0 = s_b2i[0xC0 | (c >> 6)], i1 = s_b2i[0x80 | (c & 0x3F)];
-                if (i0 >= 0) { out[(long long)m * n_stride] = (uint16_t)i0 | flag; flag = 0; ++m; }
-                if (i1 >= 0) { out[(long long)m * n_stride] = (uint16_t)i1 | flag; flag = 0; ++m; }
+                if (i0 >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)i0 | flag; flag = 0; ++m; }
+                if (i1 >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)i1 | flag; flag = 0; ++m; }
             }
         }
         i += pl;
     }
     len[seq] = m;
+    for (int q = m; q & 7; ++q) sym[sym_index(q, seq, n_stride)] = kPad;      // pad the last chunk
 }
 
 // ---------------------------------------------------------------- pair histogram
@@ -169,10 +180,9 @@ bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, 
          seq += (long long)gridDim.x * blockDim.x) {
         const int n = len[seq];
         if (n < 2) continue;
-        const uint16_t* s = sym + seq;
-        int prev = s[0] & kIdMask;
+        int prev = sym[sym_index(0, seq, n_stride)] & kIdMask;
         for (int q = 1; q < n; ++q) {
-            const uint16_t cur = s[(long long)q * n_stride];
+            const uint16_t cur = sym[sym_index(q, seq, n_stride)];
             if (!(cur & kWordStart)) atomicAdd(&hist[(long long)prev * V + (cur & kIdMask)], 1);
             prev = cur & kIdMask;
         }
@@ -218,17 +228,14 @@ bpe_argmax_kernel(const int* __restrict__ hist, int V, int n_active, const BpeCt
 // delta block: [0] column a (pairs (x, a) lost), [1] row b (pairs (b, y) lost),
 //              [2] column c (pairs (x, c) gained), [3] row c (pairs (c, y) gained).
 // Block-private copies live in shared memory (4*V ints) and are flushed once per block.
-// One thread per sequence, one warp per 32 consecutive sequences, and the warp walks the positions in
-// LOCK STEP: at every step all lanes touch the same row p of the position-major corpus, so loads and
-// stores stay 64-byte contiguous even though each lane runs its own state machine.  Loads are issued
-// kMergeChunk rows at a time (independent addresses in flight: the walk is latency-bound otherwise).
+// One thread per sequence, one warp per 32 consecutive sequences; the warp walks the chunks in LOCK
+// STEP, so every load / store is one 128-bit access per lane over 512 contiguous bytes.
 //   pass 1 (read-only): first position q0 whose id is a and whose successor is b inside the same
-//           pre-token (b with the word-start bit clear is the 16-bit value b itself);
-//   pass 2 (only if some lane found one): streaming rewrite from the warp's smallest q0 — an `a` is held
-//           back one step, so no look-ahead is needed: next symbol == b -> emit c (merge), otherwise
-//           emit the held symbol unchanged.  Nothing is written before a lane's first merge.
-constexpr int kMergeChunk = 8;
-
+//           pre-token (b with the word-start bit clear is the 16-bit value b itself; padding never matches);
+//   pass 2 (only if some lane found one): streaming rewrite from the warp's first hit chunk — an `a` is
+//           held back one step, so no look-ahead is needed: next symbol == b -> emit c (merge),
+//           otherwise emit the held symbol unchanged.  Emitted symbols are packed into a 128-bit
+//           register window and stored chunk-wise; nothing is stored before a lane's first merge.
 __device__ __forceinline__ int warp_max_i(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -239,108 +246,171 @@ __device__ __forceinline__ int warp_min_i(int v) {
     for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ uint16_t chunk_get(const uint4& w, int j) {        // j is a compile-time index
+    const unsigned int word = j < 2 ? w.x : (j < 4 ? w.y : (j < 6 ? w.z : w.w));
+    return (uint16_t)((j & 1) ? (word >> 16) : (word & 0xffffu));
+}
 
-__device__ __forceinline__ void merge_sequences(uint16_t* __restrict__ sym, int* __restrict__ len, long long N,
-                                                long long n_stride, int a, int b, int c, int V, int* s_delta) {
-    int* col_a = s_delta;
-    int* row_b = s_delta + V;
-    int* col_c = s_delta + 2 * V;
-    int* row_c = s_delta + 3 * V;
-    const uint16_t bsym = (uint16_t)b;
+// Scan kernel (pass 1): for every sequence the first position q0 whose id is a and whose successor is
+// b inside the same pre-token (b with the word-start bit clear is the 16-bit value b itself; padding
+// never matches).  One thread per sequence, the warp walks the chunks in lock step (512 contiguous
+// bytes per step).  SWAR search, two symbols per 32-bit word: most chunks contain no `a` at all and cost
+// four XOR-AND-ADD-ANDN groups.  Sequences with a hit are appended to the work list (warp-aggregated
+// atomic) — typically well under 1 % of the corpus after the first hundred merges.
+__global__ void __launch_bounds__(256)
+bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
+                int a, int b, const BpeCtl* __restrict__ ctl, int* __restrict__ work_count, int* __restrict__ work_seq,
+                int* __restrict__ work_q0) {
+    if (ctl) {
+        if (ctl->done) return;
+        a = ctl->a; b = ctl->b;
+    }
+    const uint4* sym4 = (const uint4*)sym;
     const int lane = threadIdx.x & 31;
+    const unsigned int A2 = (unsigned int)a | ((unsigned int)a << 16);
+    const unsigned int B2 = (unsigned int)b | ((unsigned int)b << 16);
     for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N;
          base += (long long)gridDim.x * blockDim.x) {
         const long long seq = base + lane;
         const bool valid = seq < N;
         const int n = valid ? len[seq] : 0;
-        uint16_t* s = sym + (valid ? seq : 0);
-        const int nmax = warp_max_i(n);
+        const int nch = (n + kChunk - 1) >> 3;
+        const long long row0 = valid ? seq : 0;
+        const int nch_max = warp_max_i(nch);
         int q0 = -1;
-        {
-            bool prev_a = false;
-            for (int q = 0; q < nmax; q += kMergeChunk) {
-                if (q < n && q0 < 0) {
-                    uint16_t v[kMergeChunk];
+        unsigned int carry = 0;                               // bit 15: previous chunk ended with `a`
+        for (int ci = 0; ci < nch_max; ++ci) {
+            if (ci < nch && q0 < 0) {
+                const uint4 w = __ldg(&sym4[(long long)ci * n_stride + row0]);
+                const unsigned int wd[4] = {w.x, w.y, w.z, w.w};
+                unsigned int fa[4];                           // bit 15 / 31: half-word has id == a
 #pragma unroll
-                    for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
+                for (int k = 0; k < 4; ++k) fa[k] = ~(((wd[k] ^ A2) & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+                if (carry | fa[0] | fa[1] | fa[2] | fa[3]) {
 #pragma unroll
-                    for (int j = 0; j < kMergeChunk; ++j) {
-                        if (q0 < 0 && prev_a && v[j] == bsym) q0 = q + j - 1;
-                        prev_a = (v[j] & kIdMask) == a;
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned int y = wd[k] ^ B2;        // fb: half-word == b exactly
+                        const unsigned int fb = ~((((y & 0x7fff7fffu) + 0x7fff7fffu)) | y) & 0x80008000u;
+                        const unsigned int h = ((fa[k] << 16) | (k ? fa[k - 1] >> 16 : carry)) & fb;
+                        if (h && q0 < 0) q0 = ci * kChunk + 2 * k + ((h & 0x8000u) ? 0 : 1) - 1;
                     }
                 }
-                if (__all_sync(0xffffffffu, q0 >= 0 || q + kMergeChunk >= n)) break;
+                carry = fa[3] >> 16;
             }
+            if (__all_sync(0xffffffffu, q0 >= 0 || ci + 1 >= nch)) break;
         }
-        if (!__any_sync(0xffffffffu, q0 >= 0)) continue;
-        const bool mine = q0 >= 0;
-        const int qs = warp_min_i(mine ? q0 : 0x7fffffff) & ~(kMergeChunk - 1);
-        const int nact = warp_max_i(mine ? n : 0);
-        int o = qs;
-        bool prev_merged = false, pend = false, dirty = false;
-        uint16_t pend_sym = 0;
-        int prev_old = (mine && qs > 0) ? (s[(long long)(qs - 1) * n_stride] & kIdMask) : 0;   // left neighbour ids (old / emitted)
-        int prev_new = prev_old;
-        auto emit_plain = [&](uint16_t x) {
-            const int id = x & kIdMask;
-            if (prev_merged && !(x & kWordStart)) {          // right neighbour of a merge
-                atomicAdd(&row_b[id], -1);                   // (b, y) disappears
-                atomicAdd(&row_c[id], 1);                    // (c, y) appears
+        const unsigned int hits = __ballot_sync(0xffffffffu, q0 >= 0);
+        if (hits) {
+            int slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(work_count, __popc(hits));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (q0 >= 0) {
+                const int slot = slot0 + __popc(hits & ((1u << lane) - 1u));
+                work_seq[slot] = (int)seq;
+                work_q0[slot] = q0;
             }
-            if (dirty) s[(long long)o * n_stride] = x;
-            prev_merged = false;
-            prev_old = id;
-            prev_new = id;
-            ++o;
-        };
-        for (int q = qs; q < nact; q += kMergeChunk) {
-            if (!mine || q >= n) continue;
-            uint16_t v[kMergeChunk];
-#pragma unroll
-            for (int j = 0; j < kMergeChunk; ++j) v[j] = (q + j < n) ? s[(long long)(q + j) * n_stride] : (uint16_t)0xffffu;
-#pragma unroll
-            for (int j = 0; j < kMergeChunk; ++j) {
-                if (q + j >= n) break;
-                const uint16_t cur = v[j];
-                if (pend) {
-                    pend = false;
-                    if (cur == bsym) {                       // merge (held a, b) -> c
-                        if (!(pend_sym & kWordStart)) {      // the pair with the left neighbour changes
-                            atomicAdd(&col_a[prev_old], -1); // (old left, a) disappears
-                            atomicAdd(&col_c[prev_new], 1);  // (new left, c) appears
-                        }
-                        s[(long long)o * n_stride] = (uint16_t)c | (pend_sym & kWordStart);
-                        dirty = true;
-                        prev_merged = true;
-                        prev_old = b;
-                        prev_new = c;
-                        ++o;
-                        continue;
-                    }
-                    emit_plain(pend_sym);
-                }
-                if ((cur & kIdMask) == a) { pend = true; pend_sym = cur; }
-                else emit_plain(cur);
-            }
-        }
-        if (mine) {
-            if (pend) emit_plain(pend_sym);
-            len[seq] = o;
         }
     }
 }
 
+// Rewrite kernel (pass 2): one thread per work-list entry.  Streaming state machine from the chunk of
+// q0: an `a` is held back one step, so no look-ahead is needed — next symbol == b -> emit c (merge),
+// otherwise emit the held symbol unchanged.  Emitted symbols are packed into a 128-bit register window
+// and stored chunk-wise (in place: the write position never overtakes the read position); nothing is
+// stored before the first merge.  Count changes go to the block-private delta block.
+__device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int* __restrict__ len, long long seq,
+                                                 int q0, long long n_stride, int a, int b, int c, int V,
+                                                 int* s_delta) {
+    int* col_a = s_delta;
+    int* row_b = s_delta + V;
+    int* col_c = s_delta + 2 * V;
+    int* row_c = s_delta + 3 * V;
+    const uint16_t bsym = (uint16_t)b;
+    uint4* sym4 = (uint4*)sym;
+    const int n = len[seq];
+    const int nch = (n + kChunk - 1) >> 3;
+    const int cs = q0 >> 3;
+    int o = cs * kChunk;                                      // output position
+    unsigned long long olo = 0ull, ohi = 0ull;                // 8 x 16-bit output window
+    bool prev_merged = false, pend = false, dirty = false;
+    uint16_t pend_sym = 0;
+    int prev_old = 0, prev_new = 0;                           // left neighbour ids (old / emitted)
+    if (cs > 0) {
+        const uint4 w = sym4[(long long)(cs - 1) * n_stride + seq];
+        prev_old = prev_new = (w.w >> 16) & kIdMask;
+    }
+    auto push = [&](uint16_t x) {                             // append to the window, store when a chunk fills
+        const int k = o & 7;
+        if (k < 4) olo |= (unsigned long long)x << (16 * k);
+        else ohi |= (unsigned long long)x << (16 * (k - 4));
+        ++o;
+        if ((o & 7) == 0) {
+            if (dirty)
+                sym4[(long long)((o >> 3) - 1) * n_stride + seq] =
+                    make_uint4((unsigned int)olo, (unsigned int)(olo >> 32), (unsigned int)ohi, (unsigned int)(ohi >> 32));
+            olo = 0ull;
+            ohi = 0ull;
+        }
+    };
+    auto emit_plain = [&](uint16_t x) {
+        const int id = x & kIdMask;
+        if (prev_merged && !(x & kWordStart)) {              // right neighbour of a merge
+            atomicAdd(&row_b[id], -1);                       // (b, y) disappears
+            atomicAdd(&row_c[id], 1);                        // (c, y) appears
+        }
+        prev_merged = false;
+        prev_old = id;
+        prev_new = id;
+        push(x);
+    };
+    for (int ci = cs; ci < nch; ++ci) {
+        const uint4 w = sym4[(long long)ci * n_stride + seq];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            if (ci * kChunk + j >= n) break;
+            const uint16_t cur = chunk_get(w, j);
+            if (pend) {
+                pend = false;
+                if (cur == bsym) {                           // merge (held a, b) -> c
+                    if (!(pend_sym & kWordStart)) {          // the pair with the left neighbour changes
+                        atomicAdd(&col_a[prev_old], -1);     // (old left, a) disappears
+                        atomicAdd(&col_c[prev_new], 1);      // (new left, c) appears
+                    }
+                    dirty = true;
+                    prev_merged = true;
+                    prev_old = b;
+                    prev_new = c;
+                    push((uint16_t)c | (pend_sym & kWordStart));
+                    continue;
+                }
+                emit_plain(pend_sym);
+            }
+            if ((cur & kIdMask) == a) { pend = true; pend_sym = cur; }
+            else emit_plain(cur);
+        }
+    }
+    if (pend) emit_plain(pend_sym);
+    const int n_new = o;
+    while (o & 7) push(kPad);                                 // pad and flush the last chunk
+    len[seq] = n_new;
+}
+
 __global__ void __launch_bounds__(256)
-bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N, long long n_stride, int a, int b,
-                 int c, int V, const BpeCtl* __restrict__ ctl, int* __restrict__ delta) {
+bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int a, int b, int c, int V,
+                   const BpeCtl* __restrict__ ctl, const int* __restrict__ work_count,
+                   const int* __restrict__ work_seq, const int* __restrict__ work_q0, int* __restrict__ delta) {
     extern __shared__ int s_delta[];
-    if (ctl) {                                               // sync-free loop: the merge comes from device memory
+    if (ctl) {
         if (ctl->done) return;
         a = ctl->a; b = ctl->b; c = ctl->c;
     }
+    const int n_work = *work_count;
+    if ((long long)blockIdx.x * blockDim.x >= n_work) return;       // nothing for this block
     for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
     __syncthreads();
-    merge_sequences(sym, len, N, n_stride, a, b, c, V, s_delta);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_work;
+         i += (long long)gridDim.x * blockDim.x)
+        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta);
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
         const int d = s_delta[i];
@@ -351,9 +421,11 @@ bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N,
 // Decode the arg-max key, apply the stop rules of BpeTrainer (vocabulary full, count < min_frequency),
 // assign the next id, log the merge.  One thread; also re-arms the arg-max result.
 __global__ void bpe_select_kernel(unsigned long long* __restrict__ result, BpeCtl* __restrict__ ctl,
-                                  int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges) {
+                                  int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges,
+                                  int* __restrict__ work_count) {
     const unsigned long long key = *result;
     *result = 0;
+    *work_count = 0;
     if (ctl->done) return;
     const int count = (int)(key >> 32);
     if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges) {
@@ -596,28 +668,45 @@ extern "C" int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint
     return BEAST_OK;
 }
 
-extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
-                               int32_t c, int32_t V, int32_t* delta, void* stream) {
-    if (!delta) return BEAST_E_NULL;
-    if (V < 1 || a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V || c > 32767) return BEAST_E_SHAPE;
-    if (N == 0) return BEAST_OK;
-    if (!sym || !len) return BEAST_E_NULL;
-    const size_t smem = (size_t)4 * V * sizeof(int);
+static int merge_grid(long long n) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    long long grid = (n + 255) / 256;
+    const long long cap = (long long)sms * 8;
+    if (grid > cap) grid = cap;
+    return grid < 1 ? 1 : (int)grid;
+}
+
+static int rewrite_smem_attr(size_t smem) {
     if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
     static size_t attr = 48 * 1024;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bpe_rewrite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = smem;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long grid = (N + 255) / 256;
-    const long long cap = (long long)sms * 6;
-    if (grid > cap) grid = cap;
-    bpe_merge_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, a, b, c, V, nullptr, delta);
-    count_launch();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
+                               int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream) {
+    if (!delta || !work) return BEAST_E_NULL;
+    if (V < 1 || a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V || c > 32766) return BEAST_E_SHAPE;
+    if (N == 0) return BEAST_OK;
+    if (!sym || !len) return BEAST_E_NULL;
+    const size_t smem = (size_t)4 * V * sizeof(int);
+    int rc = rewrite_smem_attr(smem);
+    if (rc != BEAST_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* work_count = work;                  // work = {count, pad[3], seq[N], q0[N]}
+    int* work_seq = work + 4;
+    int* work_q0 = work + 4 + N;
+    cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = merge_grid(N);
+    bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0);
+    bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta);
+    count_launch(2);
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
 }
@@ -635,9 +724,10 @@ extern "C" int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t
 // phase 1: hist += delta.  The caller runs [phase 0, all-reduce(delta) when sharded, phase 1] up to
 // (vocab_size - alphabet) times without reading anything back; ctl / log are read once at the end.
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
-                              int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t vocab_size,
-                              int32_t min_frequency, int32_t max_merges, int32_t phase, void* stream) {
-    if (!hist || !delta || !ctl || !log || !result) return BEAST_E_NULL;
+                              int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
+                              int32_t vocab_size, int32_t min_frequency, int32_t max_merges, int32_t phase,
+                              void* stream) {
+    if (!hist || !delta || !ctl || !log || !result || !work) return BEAST_E_NULL;
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
     if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -648,25 +738,25 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
         return BEAST_OK;
     }
     const size_t smem = (size_t)4 * V * sizeof(int);
-    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(bpe_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
-    }
+    int rc = rewrite_smem_attr(smem);
+    if (rc != BEAST_OK) return rc;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int* work_count = work;                  // work = {count, pad[3], seq[N], q0[N]}
+    int* work_seq = work + 4;
+    int* work_q0 = work + 4 + N;
     // the arg-max grid is sized for the full table: n_active lives on the device
     bpe_argmax_kernel<<<sms * 4, 256, 0, st>>>(hist, V, V, (const BpeCtl*)ctl, (unsigned long long*)result);
     bpe_select_kernel<<<1, 1, 0, st>>>((unsigned long long*)result, (BpeCtl*)ctl, log, V, vocab_size, min_frequency,
-                                      max_merges);
-    long long grid = (N + 255) / 256;
-    const long long cap = (long long)sms * 6;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    bpe_merge_kernel<<<(unsigned)grid, 256, smem, st>>>(sym, len, N, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, delta);
-    count_launch(3);
+                                      max_merges, work_count);
+    count_launch(2);
+    if (N > 0) {
+        const int grid = merge_grid(N);
+        bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count, work_seq, work_q0);
+        bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, work_count,
+                                                    work_seq, work_q0, delta);
+        count_launch(2);
+    }
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
 }

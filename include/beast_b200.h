@@ -150,8 +150,8 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  * FIGBPE (beast/beast_bpe_trainer.py:61-98: ByteLevelBPETokenizer + BpeTrainer.train_from_iterator) and
  * BEASTBsplineBPETokenizer._discrete_to_bpe / _bpe_to_discrete (beast/beast_bspline_bpe_tokenizer.py:
  * 175-247: tokenizer.encode(...).ids / tokenizer.decode).  Algorithm: SURVEY.md Appendix A.
- * Corpus layout: position-major symbols sym[p * n_stride + seq] (uint16, bit 15 = first symbol of a
- * pre-token), len[seq] live symbols; sequences may be sharded over GPUs, the V x V pair histogram is
+ * Corpus layout: chunk-major symbols sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)] (uint16, bit 15 = first
+ * symbol of a pre-token, 0xffff padding in the last 8-symbol chunk; ceil(2L / 8) chunks), len[seq] live symbols; sequences may be sharded over GPUs, the V x V pair histogram is
  * replicated.  All functions below take DEVICE pointers.
  *
  * bpe_scan_bins  phase 0: minmax[0] = min(minmax[0], bins), minmax[1] = max(minmax[1], bins)
@@ -165,6 +165,8 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  *                count, ties -> smallest (a, b) (BpeTrainer's heap order).
  * bpe_apply_merge  replace (a, b) by c left to right, non-overlapping, compacting in place; the count
  *                changes are ADDED to delta[4*V] = {column a lost, row b lost, column c gained, row c gained}.
+ *                Two kernels: a scan that lists the sequences containing the pair, a rewrite over that list;
+ *                work: int32 [4 + 2*N] scratch (list length, sequence ids, first-hit positions).
  * bpe_apply_delta  hist += delta (after the cross-GPU sum when sharded); hist[a][b] = 0; delta = 0.
  * bpe_encode     bins -> ids: per pre-token repeatedly merge the lowest-rank pair, leftmost first (A.5).
  *                rank_tab[a*V + b] = rank << 16 | new_id or 0xffffffff.  ids_padded [N, out_stride >= 2L]
@@ -181,7 +183,7 @@ int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t 
                     int32_t* hist, void* stream);
 int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream);
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
-                    int32_t c, int32_t V, int32_t* delta, void* stream);
+                    int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream);
 int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
 /* Sync-free training loop: one iteration = phase 0 (arg-max, select with BpeTrainer's stop rules —
  * vocabulary full / count < min_frequency —, merge into delta) [+ all-reduce(delta) when sharded] + phase 1
@@ -189,7 +191,7 @@ int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t
  * n_tokens = alphabet size and zeroes the rest; log: int32 [4 * max_merges] receives (a, b, new_id, count) per
  * merge; result: the arg-max scratch word (zeroed by the caller once).  Nothing is read back until the end. */
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
-                   int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t vocab_size,
+                   int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
                    int32_t min_frequency, int32_t max_merges, int32_t phase, void* stream);
 int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
                const int16_t* byte_to_id, const uint32_t* rank_tab, int32_t V, uint16_t* ids_padded,
