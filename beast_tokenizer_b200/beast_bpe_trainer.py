@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .beast_bspline_tokenizer import BEASTBsplineTokenizer
-from .bpe_model import B2U, B200ByteLevelBPE
+from .bpe_model import B2U, MAX_SHIFT, B200ByteLevelBPE, class_table_device, utf8_len
 
 try:
     from tqdm.auto import tqdm
@@ -67,15 +67,16 @@ def build_alphabet(min_token: int, max_token: int, seen_bytes: Sequence[int]):
 class GpuBpeEngine:
     """Device state of one shard: chunk-major symbols, lengths, replicated V x V histogram."""
 
-    def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int):
+    def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int, max_shift: int = 255):
         self.lib = _lib.load()
         self.dev = bins.device
         self.N, self.L = bins.shape
         self.V = V
         self.stride = max(self.N, 1)
+        cap = utf8_len(max_shift) * self.L                  # byte-level symbols per sequence
         with torch.cuda.device(self.dev):
-            # chunk-major corpus: [ceil(2L / 8) chunks, sequences, 8 symbols] uint16 (see csrc/bpe.cu)
-            self.sym = torch.empty(((2 * self.L + 7) // 8, self.stride, 8), device=self.dev, dtype=torch.int16)
+            # chunk-major corpus: [ceil(cap / 8) chunks, sequences, 8 symbols] uint16 (see csrc/bpe.cu)
+            self.sym = torch.empty(((cap + 7) // 8, self.stride, 8), device=self.dev, dtype=torch.int16)
             self.len = torch.zeros(self.stride, device=self.dev, dtype=torch.int32)
             self.hist = torch.zeros((V, V), device=self.dev, dtype=torch.int32)
             self.delta = torch.zeros(4 * V, device=self.dev, dtype=torch.int32)
@@ -85,12 +86,12 @@ class GpuBpeEngine:
             b2i = torch.from_numpy(byte_to_id).to(self.dev)
             st = _lib.stream_ptr(self.dev)
             _lib.check(self.lib.bpe_symbolize(_lib.ptr(bins), self.N, self.L, int(min_token), _lib.ptr(b2i),
-                                              _lib.ptr(self.sym), _lib.ptr(self.len), self.stride, _lib.ptr(err), st),
-                       "bpe_symbolize")
+                                              _lib.ptr(class_table_device(self.dev)), _lib.ptr(self.sym),
+                                              _lib.ptr(self.len), self.stride, _lib.ptr(err), st), "bpe_symbolize")
             _lib.check(self.lib.bpe_count_pairs(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, V,
                                                 _lib.ptr(self.hist), st), "bpe_count_pairs")
             if int(err.item()):
-                raise ValueError("discrete tokens outside the 0..255 range after subtracting min_token")
+                raise ValueError("discrete tokens outside the representable range after subtracting min_token")
 
     def argmax(self, n_active: int):
         with torch.cuda.device(self.dev):
@@ -160,9 +161,9 @@ def scan_bins_gpu(bins: torch.Tensor, coll: _Collective):
         coll.reduce_(lo, "min")
         coll.reduce_(hi, "max")
         min_token, max_token = int(lo.item()), int(hi.item())
-        if max_token - min_token > 255:
-            raise NotImplementedError("BPE over more than 256 distinct bin values (vocab_size > 256) is not supported "
-                                      "by the B200 path yet")
+        if max_token - min_token > MAX_SHIFT:
+            raise ValueError("BPE over more than 55 296 distinct bin values is not representable: chr() of the shifted "
+                             "bins would enter the surrogate range")
         seen = torch.zeros(256, device=dev, dtype=torch.int32)
         err = torch.zeros(1, device=dev, dtype=torch.int32)
         if bins.numel():
@@ -185,7 +186,9 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
     V = max(int(vocab_size), len(tokens))
     if V > 32767:
         raise NotImplementedError("bpe_vocab_size above 32767 is not supported")
-    eng = engine_factory(bins, min_token, byte_to_id, V)
+    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token)
+                           if engine_factory is GpuBpeEngine else engine_factory(bins, min_token, byte_to_id, V))
+    eng = make_engine()
     coll.reduce_(eng.hist, "sum")                       # replicated global histogram
     index = {t: i for i, t in enumerate(tokens)}
     merges: List[tuple] = []
@@ -201,7 +204,7 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
             fast_tokens.append(new)
         if ok:
             return B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log]), min_token, max_token
-        eng = engine_factory(bins, min_token, byte_to_id, V)
+        eng = make_engine()
         coll.reduce_(eng.hist, "sum")
     bar = tqdm(total=max(vocab_size - len(tokens), 0), desc="BPE merges", leave=False) if (show_progress and tqdm) else None
     while len(tokens) < vocab_size:

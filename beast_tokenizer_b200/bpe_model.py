@@ -32,6 +32,46 @@ def bytes_to_unicode() -> List[int]:
 B2U = bytes_to_unicode()
 U2B = {c: b for b, c in enumerate(B2U)}
 
+MAX_SHIFT = 0xD7FF                      # shifted bins are codepoints below the surrogate range
+# letters added to Unicode after Python 3.12's tables (15.0) that the reference's regex engine already knows
+_NEWER_LETTERS = (7305, 7306, 42955, 42956, 42957, 42970, 42971, 42972)
+_WHITE_SPACE = {9, 10, 11, 12, 13, 32, 133, 160, 5760, 8232, 8233, 8239, 8287, 12288} | set(range(8192, 8203))
+_CLASS_TABLE = None
+
+
+def class_table() -> np.ndarray:
+    """uint8 [0xD800]: GPT-2 pre-tokenizer class of every codepoint (0 other, 1 \\p{L}, 2 \\p{N}, 3 \\s) from the
+    Unicode general categories — what Oniguruma's \\p{L} / \\p{N} / \\s match (SURVEY.md Appendix A.2 extended
+    beyond Latin-1 for tokenizers with more than 256 bins).  Entries below 256 are not read by the kernels."""
+    global _CLASS_TABLE
+    if _CLASS_TABLE is None:
+        import unicodedata
+        tab = np.zeros(MAX_SHIFT + 1, dtype=np.uint8)
+        for c in range(MAX_SHIFT + 1):
+            if c in _WHITE_SPACE:
+                tab[c] = 3
+            else:
+                k = unicodedata.category(chr(c))[0]
+                tab[c] = 1 if k == "L" else 2 if k == "N" else 0
+        for c in _NEWER_LETTERS:
+            tab[c] = 1
+        _CLASS_TABLE = tab
+    return _CLASS_TABLE
+
+
+_CLASS_DEV = {}
+
+
+def class_table_device(dev: torch.device) -> torch.Tensor:
+    key = (dev.type, dev.index)
+    if key not in _CLASS_DEV:
+        _CLASS_DEV[key] = torch.from_numpy(class_table()).to(dev)
+    return _CLASS_DEV[key]
+
+
+def utf8_len(max_shift: int) -> int:
+    return 1 if max_shift < 0x80 else 2 if max_shift < 0x800 else 3
+
 
 class Encoding:
     """Minimal stand-in for tokenizers.Encoding (only `.ids` is used by the reference)."""
@@ -182,16 +222,18 @@ class B200ByteLevelBPE:
         t = self._tables(dev)
         bins = bins.to(torch.int64).contiguous()
         N, L = bins.shape
-        max_shift = 255 if max_token is None else int(max_token) - int(min_token)
-        stride = 2 * L
+        max_shift = MAX_SHIFT if max_token is None else int(max_token) - int(min_token)
+        if max_shift > MAX_SHIFT:
+            raise ValueError("BPE over more than 55 296 distinct bin values is not representable (surrogate range)")
+        stride = utf8_len(max_shift) * L
         padded = torch.empty((N, stride), device=dev, dtype=torch.int16)
         lens = torch.empty(N, device=dev, dtype=torch.int32)
         status = torch.empty(N, device=dev, dtype=torch.int32)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(lib.bpe_encode(_lib.ptr(bins), N, L, int(min_token), max_shift, _lib.ptr(t["b2i"]),
-                                      _lib.ptr(t["rank"]), t["V"], _lib.ptr(padded), stride, _lib.ptr(lens),
-                                      _lib.ptr(status), st), "bpe_encode")
+                                      _lib.ptr(class_table_device(dev)), _lib.ptr(t["rank"]), t["V"], _lib.ptr(padded),
+                                      stride, _lib.ptr(lens), _lib.ptr(status), st), "bpe_encode")
             offsets = torch.zeros(N + 1, device=dev, dtype=torch.int64)
             torch.cumsum(lens, 0, out=offsets[1:])
             total = int(offsets[-1].item()) if N else 0
@@ -222,8 +264,8 @@ class B200ByteLevelBPE:
     # ------------------------------------------------------------------ HF-shaped convenience (single strings, on the GPU)
     def encode(self, text: str, add_special_tokens: bool = False) -> Encoding:
         cps = [ord(c) for c in text]
-        if any(c > 255 for c in cps):
-            raise ValueError("only codepoints 0..255 (<= 256-bin tokenizers) are supported")
+        if any(c > MAX_SHIFT for c in cps):
+            raise ValueError("only codepoints below U+D800 are supported")
         if not cps:
             return Encoding([])
         dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None

@@ -48,7 +48,7 @@ struct BpeCtl {
 
 // GPT-2 pre-tokeniser character classes for codepoints 0..255
 enum { CLS_O = 0, CLS_L = 1, CLS_N = 2, CLS_S = 3 };
-__device__ __forceinline__ int cp_class(int c) {
+__device__ __forceinline__ int cp_class_latin1(int c) {
     if (c == 32 || (c >= 9 && c <= 13) || c == 133 || c == 160) return CLS_S;
     if ((c >= 48 && c <= 57) || c == 178 || c == 179 || c == 185 || (c >= 188 && c <= 190)) return CLS_N;
     if ((c >= 65 && c <= 90) || (c >= 97 && c <= 122) || c == 170 || c == 181 || c == 186 ||
@@ -57,8 +57,22 @@ __device__ __forceinline__ int cp_class(int c) {
     return CLS_O;
 }
 
+// Codepoints >= 256 (tokenizers with more than 256 bins) look their class up in a table built on the
+// host from the Unicode general categories (L*, N*, White_Space — Oniguruma's \p{L}, \p{N}, \s).
+__device__ __forceinline__ int cp_class(int c, const uint8_t* __restrict__ cls_tab) {
+    return c < 256 ? cp_class_latin1(c) : (int)__ldg(cls_tab + c);
+}
+
+// UTF-8 bytes of codepoint c (< 0x10000, never a surrogate here).
+__device__ __forceinline__ int utf8_encode(int c, int (&b)[3]) {
+    if (c < 0x80) { b[0] = c; return 1; }
+    if (c < 0x800) { b[0] = 0xC0 | (c >> 6); b[1] = 0x80 | (c & 0x3F); return 2; }
+    b[0] = 0xE0 | (c >> 12); b[1] = 0x80 | ((c >> 6) & 0x3F); b[2] = 0x80 | (c & 0x3F);
+    return 3;
+}
+
 // Length of the pre-token starting at codepoint i of cp[0..n) (shared memory).
-__device__ __forceinline__ int pretoken_len(const uint8_t* cp, int i, int n) {
+__device__ __forceinline__ int pretoken_len(const uint16_t* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
     const int c = cp[i];
     if (c == 39 && i + 1 < n) {                              // 's|'t|'re|'ve|'m|'ll|'d
         const int d = cp[i + 1];
@@ -69,24 +83,24 @@ __device__ __forceinline__ int pretoken_len(const uint8_t* cp, int i, int n) {
         }
     }
     int start = i;
-    if (c == 32 && i + 1 < n && cp_class(cp[i + 1]) != CLS_S) start = i + 1;     // " ?" prefix
-    const int k = cp_class(cp[start]);
+    if (c == 32 && i + 1 < n && cp_class(cp[i + 1], cls_tab) != CLS_S) start = i + 1;     // " ?" prefix
+    const int k = cp_class(cp[start], cls_tab);
     if (k != CLS_S) {                                        // one run of L, N or O
         int j = start + 1;
-        while (j < n && cp_class(cp[j]) == k) ++j;
+        while (j < n && cp_class(cp[j], cls_tab) == k) ++j;
         return j - i;
     }
     int j = i + 1;                                           // whitespace run [i, j)
-    while (j < n && cp_class(cp[j]) == CLS_S) ++j;
+    while (j < n && cp_class(cp[j], cls_tab) == CLS_S) ++j;
     if (j == n) return j - i;                                // \s+(?!\S) at end of text
     if (j - i >= 2) return j - 1 - i;                        // \s+(?!\S): leave the last blank
     return 1;                                                // \s+
 }
 
-// Cooperative load of kBpeBlock rows of bins into shared memory as shifted bytes.
+// Cooperative load of kBpeBlock rows of bins into shared memory as shifted 16-bit codepoints.
 // status: bit 0 = a value below min_token, bit 1 = a value above max_token (per sequence).
 __device__ __forceinline__ void stage_rows(const long long* __restrict__ bins, long long base, long long N, int L,
-                                           long long min_token, long long max_shift, uint8_t* s_cp, int LP,
+                                           long long min_token, long long max_shift, uint16_t* s_cp, int LP,
                                            int* s_status) {
     const long long rows = (N - base) < kBpeBlock ? (N - base) : kBpeBlock;
     for (long long idx = threadIdx.x; idx < rows * L; idx += blockDim.x) {
@@ -94,7 +108,7 @@ __device__ __forceinline__ void stage_rows(const long long* __restrict__ bins, l
         const long long v = bins[(base + r) * L + p] - min_token;
         if (v < 0) atomicOr(&s_status[r], 1);
         else if (v > max_shift) atomicOr(&s_status[r], 2);
-        s_cp[r * LP + p] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        s_cp[r * LP + p] = (uint16_t)(v < 0 ? 0 : (v > 0xD7FF ? 0xD7FF : v));
     }
 }
 
@@ -123,9 +137,10 @@ bpe_seen_kernel(const long long* __restrict__ bins, long long n, long long min_t
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long v = bins[i] - min_token;
-        if (v < 0 || v > 255) { *err = 1; continue; }
-        if (v < 128) s_seen[v] = 1;
-        else { s_seen[0xC0 | (v >> 6)] = 1; s_seen[0x80 | (v & 0x3F)] = 1; }
+        if (v < 0 || v > 0xD7FF) { *err = 1; continue; }
+        int bt[3];
+        const int nbt = utf8_encode((int)v, bt);
+        for (int q = 0; q < nbt; ++q) s_seen[bt[q]] = 1;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) if (s_seen[i]) seen[i] = 1;
@@ -134,36 +149,33 @@ bpe_seen_kernel(const long long* __restrict__ bins, long long n, long long min_t
 // ---------------------------------------------------------------- symbolise
 __global__ void __launch_bounds__(kBpeBlock)
 bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token,
-                     const short* __restrict__ byte_to_id, uint16_t* __restrict__ sym, int* __restrict__ len,
-                     long long n_stride, int* err) {
+                     const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
+                     uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int* err) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
-    uint8_t* s_cp = s_raw;
-    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP + 3) & ~(size_t)3));
+    uint16_t* s_cp = (uint16_t*)s_raw;
+    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP * 2 + 3) & ~(size_t)3));
     __shared__ short s_b2i[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
     for (int i = threadIdx.x; i < kBpeBlock; i += blockDim.x) s_status[i] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * kBpeBlock;
-    stage_rows(bins, base, N, L, min_token, 255, s_cp, LP, s_status);
+    stage_rows(bins, base, N, L, min_token, 0xD7FF, s_cp, LP, s_status);
     __syncthreads();
     const long long seq = base + threadIdx.x;
     if (seq >= N) return;
     if (s_status[threadIdx.x]) *err = 1;
-    const uint8_t* cp = s_cp + threadIdx.x * LP;
+    const uint16_t* cp = s_cp + threadIdx.x * LP;
     int m = 0, i = 0;
     while (i < L) {
-        const int pl = pretoken_len(cp, i, L);
+        const int pl = pretoken_len(cp, i, L, cls_tab);
         uint16_t flag = kWordStart;
         for (int q = i; q < i + pl; ++q) {
-            const int c = cp[q];
-            if (c < 128) {
-                const int id = s_b2i[c];
+            int bt[3];
+            const int nbt = utf8_encode(cp[q], bt);
+            for (int r = 0; r < nbt; ++r) {
+                const int id = s_b2i[bt[r]];
                 if (id >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)id | flag; flag = 0; ++m; }
-            } else {
-                const int i0 = s_b2i[0xC0 | (c >> 6)], i1 = s_b2i[0x80 | (c & 0x3F)];
-                if (i0 >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)i0 | flag; flag = 0; ++m; }
-                if (i1 >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)i1 | flag; flag = 0; ++m; }
             }
         }
         i += pl;
@@ -466,13 +478,13 @@ bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, i
 // merged lives in local memory with its pair keys cached, so a merge costs one scan + two lookups.
 __global__ void __launch_bounds__(kBpeBlock)
 bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token, long long max_shift,
-                  const short* __restrict__ byte_to_id, const unsigned int* __restrict__ rank_tab, int V,
-                  uint16_t* __restrict__ ids_out, int out_stride, int* __restrict__ len_out,
-                  int* __restrict__ status_out) {
+                  const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
+                  const unsigned int* __restrict__ rank_tab, int V, uint16_t* __restrict__ ids_out, int out_stride,
+                  int* __restrict__ len_out, int* __restrict__ status_out) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
-    uint8_t* s_cp = s_raw;
-    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP + 3) & ~(size_t)3));
+    uint16_t* s_cp = (uint16_t*)s_raw;
+    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP * 2 + 3) & ~(size_t)3));
     __shared__ short s_b2i[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
     for (int i = threadIdx.x; i < kBpeBlock; i += blockDim.x) s_status[i] = 0;
@@ -484,23 +496,20 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
     if (seq >= N) return;
     status_out[seq] = s_status[threadIdx.x];
     if (s_status[threadIdx.x]) { len_out[seq] = 0; return; }
-    const uint8_t* cp = s_cp + threadIdx.x * LP;
+    const uint16_t* cp = s_cp + threadIdx.x * LP;
     uint16_t* out = ids_out + seq * (long long)out_stride;
     uint16_t w[kMaxWord];
     unsigned int key[kMaxWord];
     int m = 0, i = 0;
     while (i < L) {
-        const int pl = pretoken_len(cp, i, L);
+        const int pl = pretoken_len(cp, i, L, cls_tab);
         int wl = 0;
         for (int q = i; q < i + pl; ++q) {
-            const int c = cp[q];
-            if (c < 128) {
-                const int id = s_b2i[c];
+            int bt[3];
+            const int nbt = utf8_encode(cp[q], bt);
+            for (int r = 0; r < nbt; ++r) {
+                const int id = s_b2i[bt[r]];
                 if (id >= 0) w[wl++] = (uint16_t)id;
-            } else {
-                const int i0 = s_b2i[0xC0 | (c >> 6)], i1 = s_b2i[0x80 | (c & 0x3F)];
-                if (i0 >= 0) w[wl++] = (uint16_t)i0;
-                if (i1 >= 0) w[wl++] = (uint16_t)i1;
             }
         }
         i += pl;
@@ -547,12 +556,12 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
                   int* __restrict__ declen_out) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
-    uint8_t* s_cp = s_raw;                                   // decoded codepoints, [kBpeBlock][LP]
+    uint16_t* s_cp = (uint16_t*)s_raw;                       // decoded codepoints, [kBpeBlock][LP]
     const long long base = (long long)blockIdx.x * kBpeBlock;
     const long long seq = base + threadIdx.x;
     int status = 0, cnt = 0;
     if (seq < N) {
-        uint8_t* cp = s_cp + threadIdx.x * LP;
+        uint16_t* cp = s_cp + threadIdx.x * LP;
         int pending = 0, acc = 0;
         for (long long p = offsets[seq]; p < offsets[seq + 1] && !status; ++p) {
             const int id = flat[p];
@@ -570,8 +579,8 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
                 else if ((bt & 0xF8) == 0xF0) { acc = bt & 0x07; pending = 3; }
                 else { status = 2; break; }
                 if (out_c >= 0) {
-                    if (out_c > 255) { status = 2; break; }  // cannot be a shifted bin of a <=256-bin tokenizer
-                    if (cnt < L) cp[cnt] = (uint8_t)out_c;
+                    if (out_c > 0xFFFF) { status = 2; break; }   // not a shifted bin
+                    if (cnt < L) cp[cnt] = (uint16_t)out_c;
                     ++cnt;
                 }
             }
@@ -600,7 +609,7 @@ static int bpe_grid(long long n, int block) {
     return (int)g;
 }
 
-static size_t stage_smem(int L) { return (((size_t)kBpeBlock * (L + 1) + 3) & ~(size_t)3) + kBpeBlock * sizeof(int); }
+static size_t stage_smem(int L) { return (((size_t)kBpeBlock * (L + 1) * 2 + 3) & ~(size_t)3) + kBpeBlock * sizeof(int); }
 
 }  // namespace beast
 
@@ -624,10 +633,11 @@ extern "C" int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, 
 }
 
 extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
-                             uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err, void* stream) {
+                             const uint8_t* cls_tab, uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err,
+                             void* stream) {
     if (N == 0) return BEAST_OK;
-    if (!bins || !byte_to_id || !sym || !len || !err) return BEAST_E_NULL;
-    if (N < 0 || L < 1 || n_stride < N || 2 * L > 32767) return BEAST_E_SHAPE;
+    if (!bins || !byte_to_id || !cls_tab || !sym || !len || !err) return BEAST_E_NULL;
+    if (N < 0 || L < 1 || n_stride < N || 3 * L > 32767) return BEAST_E_SHAPE;
     const size_t smem = stage_smem(L);
     if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
     static size_t attr = 48 * 1024;
@@ -638,7 +648,7 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
     }
     const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
     bpe_symbolize_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-        (const long long*)bins, N, L, min_token, byte_to_id, sym, len, n_stride, err);
+        (const long long*)bins, N, L, min_token, byte_to_id, cls_tab, sym, len, n_stride, err);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -762,11 +772,14 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
 }
 
 extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
-                          const int16_t* byte_to_id, const uint32_t* rank_tab, int32_t V, uint16_t* ids_padded,
-                          int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream) {
+                          const int16_t* byte_to_id, const uint8_t* cls_tab, const uint32_t* rank_tab, int32_t V,
+                          uint16_t* ids_padded, int32_t out_stride, int32_t* len_out, int32_t* status_out,
+                          void* stream) {
     if (N == 0) return BEAST_OK;
-    if (!bins || !byte_to_id || !rank_tab || !ids_padded || !len_out || !status_out) return BEAST_E_NULL;
-    if (N < 0 || L < 1 || 2 * L > kMaxWord || out_stride < 2 * L || V < 1 || V > 65535) return BEAST_E_SHAPE;
+    if (!bins || !byte_to_id || !cls_tab || !rank_tab || !ids_padded || !len_out || !status_out) return BEAST_E_NULL;
+    const int mult = max_shift < 0x80 ? 1 : (max_shift < 0x800 ? 2 : 3);       // UTF-8 bytes per bin
+    if (N < 0 || L < 1 || mult * L > kMaxWord || out_stride < mult * L || V < 1 || V > 65535 || max_shift > 0xD7FF)
+        return BEAST_E_SHAPE;
     const size_t smem = stage_smem(L);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
@@ -776,8 +789,8 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     }
     const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
     bpe_encode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-        (const long long*)bins, N, L, min_token, max_shift, byte_to_id, rank_tab, V, ids_padded, out_stride, len_out,
-        status_out);
+        (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
+        len_out, status_out);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -800,7 +813,7 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
     if (N == 0) return BEAST_OK;
     if (!offsets || !tok_off || !tok_bytes || !bins_out || !status_out || !declen_out) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_vocab < 1) return BEAST_E_SHAPE;
-    const size_t smem = (size_t)kBpeBlock * (L + 1);
+    const size_t smem = (size_t)kBpeBlock * (L + 1) * 2;
     static size_t attr = 48 * 1024;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(bpe_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -157,9 +157,10 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  * bpe_scan_bins  phase 0: minmax[0] = min(minmax[0], bins), minmax[1] = max(minmax[1], bins)
  *                         (caller initialises to INT64_MAX / INT64_MIN; global min_token / max_token, A.1);
  *                phase 1: seen[b] = 1 for every UTF-8 byte of chr(bin - min_token) (alphabet, A.3);
- *                         *err = 1 if a shifted bin is outside 0..255.
+ *                         *err = 1 if a shifted bin is outside 0..0xD7FF (1 / 2 / 3 UTF-8 bytes per bin).
  * bpe_symbolize  bins [N, L] int64 -> sym / len through the GPT-2 pre-tokeniser (A.2) and the byte-level
- *                expansion (A.3); byte_to_id[256] int16 (-1 = not in the vocabulary: dropped).
+ *                expansion (A.3); byte_to_id[256] int16 (-1 = not in the vocabulary: dropped); cls_tab[max
+ *                shifted bin + 1] uint8: character class of every codepoint >= 256 (0 other, 1 \p{L}, 2 \p{N}, 3 \s).
  * bpe_count_pairs  hist[a*V + b] += #adjacent (a, b) inside pre-tokens (int32, V x V).
  * bpe_argmax     result = count << 32 | (0xffffffff - (a*V + b)) of the best pair (0 if none): maximum
  *                count, ties -> smallest (a, b) (BpeTrainer's heap order).
@@ -178,7 +179,8 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
 int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, int64_t* minmax, int32_t* seen,
                   int32_t* err, int32_t phase, void* stream);
 int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
-                  uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err, void* stream);
+                  const uint8_t* cls_tab, uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err,
+                  void* stream);
 int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
                     int32_t* hist, void* stream);
 int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream);
@@ -194,8 +196,8 @@ int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int
                    int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
                    int32_t min_frequency, int32_t max_merges, int32_t phase, void* stream);
 int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
-               const int16_t* byte_to_id, const uint32_t* rank_tab, int32_t V, uint16_t* ids_padded,
-               int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream);
+               const int16_t* byte_to_id, const uint8_t* cls_tab, const uint32_t* rank_tab, int32_t V,
+               uint16_t* ids_padded, int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream);
 int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int32_t* len, const int64_t* offsets,
                 int64_t N, int32_t* flat, void* stream);
 int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,

@@ -19,7 +19,9 @@
  * Pinned against the live library (merges, vocabulary, ids) in tests/test_bpe_oracle.py and by the
  * golden files tests/golden/bpe_*.
  *
- * Restriction: shifted bins must be < 256 (vocab_size <= 256 tokenizers), vocab_size <= 8192.
+ * Shifted bins up to 0xD7FF (below the surrogates, which Python cannot hand to the library); the
+ * character classes of codepoints >= 256 are supplied by the caller (bpe_oracle_set_classes: Unicode
+ * general categories L*, N*, White_Space, as Oniguruma's \p{L} \p{N} \s).  vocab_size <= 8192.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -30,7 +32,8 @@
 #define CLS_N 2
 #define CLS_S 3
 
-static uint8_t g_cls[256];
+#define MAXCP 65536
+static uint8_t g_cls[MAXCP];
 static uint16_t g_b2u[256];     /* byte -> byte-level character (GPT-2 bytes_to_unicode) */
 static int g_init = 0;
 
@@ -60,8 +63,14 @@ static void init_tables(void) {
     g_init = 1;
 }
 
-/* A.2: mark the first codepoint of every pre-token.  cp[i] in 0..255. */
-static void pretokenize(const uint8_t* cp, int n, uint8_t* ws) {
+/* Classes of codepoints >= 256 (0 = other, 1 = letter, 2 = number, 3 = white space). */
+void bpe_oracle_set_classes(const uint8_t* tab, int n) {
+    init_tables();
+    for (int c = 256; c < n && c < MAXCP; ++c) g_cls[c] = tab[c];
+}
+
+/* A.2: mark the first codepoint of every pre-token. */
+static void pretokenize(const uint16_t* cp, int n, uint8_t* ws) {
     memset(ws, 0, (size_t)n);
     int i = 0;
     while (i < n) {
@@ -93,13 +102,17 @@ static void pretokenize(const uint8_t* cp, int n, uint8_t* ws) {
 }
 
 /* A.3: codepoints -> bytes with word-start flags on the first byte of each pre-token. */
-static int expand(const uint8_t* cp, const uint8_t* ws, int n, uint8_t* bytes, uint8_t* bws) {
+static int expand(const uint16_t* cp, const uint8_t* ws, int n, uint8_t* bytes, uint8_t* bws) {
     int m = 0;
     for (int i = 0; i < n; ++i) {
         int c = cp[i];
-        if (c < 128) { bytes[m] = (uint8_t)c; bws[m++] = ws[i]; }
-        else {
+        if (c < 0x80) { bytes[m] = (uint8_t)c; bws[m++] = ws[i]; }
+        else if (c < 0x800) {
             bytes[m] = (uint8_t)(0xC0 | (c >> 6)); bws[m++] = ws[i];
+            bytes[m] = (uint8_t)(0x80 | (c & 0x3F)); bws[m++] = 0;
+        } else {
+            bytes[m] = (uint8_t)(0xE0 | (c >> 12)); bws[m++] = ws[i];
+            bytes[m] = (uint8_t)(0x80 | ((c >> 6) & 0x3F)); bws[m++] = 0;
             bytes[m] = (uint8_t)(0x80 | (c & 0x3F)); bws[m++] = 0;
         }
     }
@@ -141,16 +154,17 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
                      int vocab_size, int min_frequency, int32_t* vocab_off, uint16_t* vocab_chars,
                      int64_t vocab_chars_cap, int32_t* merges, int32_t* n_vocab_out, int32_t* n_merges_out) {
     init_tables();
-    if (max_token - min_token > 255 || max_token < min_token) return -2;
+    if (max_token - min_token > 0xD7FF || max_token < min_token) return -2;
     if (vocab_size < 1 || vocab_size > 8192) return -2;
+    if (max_token - min_token + 69 > 8192) return -2;          /* dense V x V counts */
     const int R = (int)(max_token - min_token);
     const int L = (int)seq_len;
 
     /* pass 1: pre-tokenise, expand, collect unique words with counts */
-    uint8_t* cp = (uint8_t*)malloc((size_t)L + 1);
+    uint16_t* cp = (uint16_t*)malloc(((size_t)L + 1) * 2);
     uint8_t* ws = (uint8_t*)malloc((size_t)L + 1);
-    uint8_t* by = (uint8_t*)malloc((size_t)2 * L + 2);
-    uint8_t* bws = (uint8_t*)malloc((size_t)2 * L + 2);
+    uint8_t* by = (uint8_t*)malloc((size_t)3 * L + 3);
+    uint8_t* bws = (uint8_t*)malloc((size_t)3 * L + 3);
     size_t pool_cap = 1 << 20, pool_n = 0;
     uint8_t* pool = (uint8_t*)malloc(pool_cap);
     size_t words_cap = 1 << 16, n_words = 0;
@@ -163,8 +177,8 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     for (int64_t s = 0; s < n_seq; ++s) {
         for (int i = 0; i < L; ++i) {
             int64_t v = bins[s * L + i] - min_token;
-            if (v < 0 || v > 255) { free(cp); free(ws); free(by); free(bws); free(pool); free(words); free(ht); return -3; }
-            cp[i] = (uint8_t)v;
+            if (v < 0 || v > 0xD7FF) { free(cp); free(ws); free(by); free(bws); free(pool); free(words); free(ht); return -3; }
+            cp[i] = (uint16_t)v;
         }
         pretokenize(cp, L, ws);
         int m = expand(cp, ws, L, by, bws);
@@ -207,15 +221,14 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     free(cp); free(ws); free(by); free(bws); free(ht);
 
     /* alphabet: chr(0..R) U seen byte-level characters, ids by sorted codepoint (A.3) */
-    uint8_t in_alpha[512];
-    memset(in_alpha, 0, sizeof(in_alpha));
+    uint8_t* in_alpha = (uint8_t*)calloc(MAXCP, 1);
     for (int c = 0; c <= R; ++c) in_alpha[c] = 1;
     for (int b = 0; b < 256; ++b) if (seen[b]) in_alpha[g_b2u[b]] = 1;
     tokens_t tk;
     tk.n = 0; tk.off = vocab_off; tk.chars = vocab_chars; tk.cap_chars = (int)vocab_chars_cap;
-    int char_to_id[512];
+    int* char_to_id = (int*)malloc(sizeof(int) * MAXCP);
     tk.off[0] = 0;
-    for (int c = 0; c < 512; ++c) {
+    for (int c = 0; c < MAXCP; ++c) {
         char_to_id[c] = -1;
         if (!in_alpha[c]) continue;
         char_to_id[c] = tk.n;                                /* the whole alphabet is kept even if it exceeds vocab_size */
@@ -227,7 +240,7 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     int* sym = (int*)malloc((pool_n + 1) * sizeof(int));
     for (size_t w = 0; w < n_words; ++w)
         for (int q = 0; q < words[w].len; ++q) sym[words[w].off + q] = char_to_id[g_b2u[pool[words[w].off + q]]];
-    free(pool);
+    free(pool); free(in_alpha); free(char_to_id);
 
     const int V = vocab_size > tk.n ? vocab_size : tk.n;     /* caller sizes vocab_off / merges for max(vocab_size, 512) */
     long long* cnt = (long long*)calloc((size_t)V * V, sizeof(long long));
@@ -287,7 +300,7 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
 /* ------------------------------------------------------------------ encode / decode */
 typedef struct {
     int n_vocab, n_merges, V;
-    int char_to_id[512];
+    int* char_to_id;    /* [MAXCP] */
     int32_t* rank;      /* [V*V] merge rank or -1 */
     int32_t* newid;     /* [V*V] */
     int32_t* off;       /* [n_vocab+1] */
@@ -303,9 +316,10 @@ void* bpe_oracle_model_new(const int32_t* vocab_off, const uint16_t* vocab_chars
     memcpy(m->off, vocab_off, sizeof(int32_t) * (size_t)(n_vocab + 1));
     m->chars = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)(vocab_off[n_vocab] + 1));
     memcpy(m->chars, vocab_chars, sizeof(uint16_t) * (size_t)vocab_off[n_vocab]);
-    for (int c = 0; c < 512; ++c) m->char_to_id[c] = -1;
+    m->char_to_id = (int*)malloc(sizeof(int) * MAXCP);
+    for (int c = 0; c < MAXCP; ++c) m->char_to_id[c] = -1;
     for (int i = 0; i < n_vocab; ++i)
-        if (vocab_off[i + 1] - vocab_off[i] == 1 && vocab_chars[vocab_off[i]] < 512 && m->char_to_id[vocab_chars[vocab_off[i]]] < 0)
+        if (vocab_off[i + 1] - vocab_off[i] == 1 && m->char_to_id[vocab_chars[vocab_off[i]]] < 0)
             m->char_to_id[vocab_chars[vocab_off[i]]] = i;
     m->rank = (int32_t*)malloc(sizeof(int32_t) * (size_t)m->V * m->V);
     m->newid = (int32_t*)malloc(sizeof(int32_t) * (size_t)m->V * m->V);
@@ -320,18 +334,18 @@ void* bpe_oracle_model_new(const int32_t* vocab_off, const uint16_t* vocab_chars
 void bpe_oracle_model_free(void* p) {
     model_t* m = (model_t*)p;
     if (!m) return;
-    free(m->rank); free(m->newid); free(m->off); free(m->chars); free(m);
+    free(m->rank); free(m->newid); free(m->off); free(m->chars); free(m->char_to_id); free(m);
 }
 
-/* Encode one sequence of shifted bins (0..255).  ids_out must hold 2*n entries.  Returns the id count. */
+/* Encode one sequence of shifted bins.  ids_out must hold 3*n entries.  Returns the id count. */
 int bpe_oracle_encode(const void* p, const int64_t* shifted, int n, int32_t* ids_out) {
     const model_t* m = (const model_t*)p;
-    uint8_t* cp = (uint8_t*)malloc((size_t)n + 1);
+    uint16_t* cp = (uint16_t*)malloc(((size_t)n + 1) * 2);
     uint8_t* ws = (uint8_t*)malloc((size_t)n + 1);
-    uint8_t* by = (uint8_t*)malloc((size_t)2 * n + 2);
-    uint8_t* bws = (uint8_t*)malloc((size_t)2 * n + 2);
-    int* w = (int*)malloc(sizeof(int) * ((size_t)2 * n + 2));
-    for (int i = 0; i < n; ++i) cp[i] = (uint8_t)shifted[i];
+    uint8_t* by = (uint8_t*)malloc((size_t)3 * n + 3);
+    uint8_t* bws = (uint8_t*)malloc((size_t)3 * n + 3);
+    int* w = (int*)malloc(sizeof(int) * ((size_t)3 * n + 3));
+    for (int i = 0; i < n; ++i) cp[i] = (uint16_t)shifted[i];
     pretokenize(cp, n, ws);
     int mlen = expand(cp, ws, n, by, bws);
     int out = 0, i = 0;
@@ -391,7 +405,7 @@ int bpe_oracle_decode(const void* p, const int32_t* ids, int n, int64_t* out, in
 }
 
 /* Pre-tokeniser alone, for unit tests: ws_out[i] = 1 where a pre-token starts. */
-void bpe_oracle_pretokenize(const uint8_t* cp, int n, uint8_t* ws_out) {
+void bpe_oracle_pretokenize(const uint16_t* cp, int n, uint8_t* ws_out) {
     init_tables();
     pretokenize(cp, n, ws_out);
 }

@@ -26,7 +26,32 @@ def lib():
         _lib.bpe_oracle_decode.restype = C.c_int
         _lib.bpe_oracle_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib.bpe_oracle_pretokenize.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.bpe_oracle_set_classes.argtypes = [C.c_void_p, C.c_int]
+        tab = unicode_classes(0xD800)
+        _lib.bpe_oracle_set_classes(tab.ctypes.data, len(tab))
     return _lib
+
+
+# letters added after Python 3.12's Unicode 15.0 that the library's regex engine already knows
+_NEWER_LETTERS = (7305, 7306, 42955, 42956, 42957, 42970, 42971, 42972)
+_WHITE_SPACE = {9, 10, 11, 12, 13, 32, 133, 160, 5760, 8232, 8233, 8239, 8287, 12288} | set(range(8192, 8203))
+
+
+def unicode_classes(n):
+    """0 = other, 1 = \\p{L}, 2 = \\p{N}, 3 = \\s for codepoints < n (extended past
+    Latin-1; checked codepoint by codepoint against the library's pre-tokenizer in tests/test_bpe_oracle.py)."""
+    import unicodedata
+    tab = np.zeros(n, dtype=np.uint8)
+    for c in range(n):
+        if c in _WHITE_SPACE:
+            tab[c] = 3
+        else:
+            k = unicodedata.category(chr(c))[0]
+            tab[c] = 1 if k == "L" else 2 if k == "N" else 0
+    for c in _NEWER_LETTERS:
+        if c < n:
+            tab[c] = 1
+    return tab
 
 
 class OracleBPE:
@@ -102,7 +127,7 @@ class OracleBPE:
 
     def encode(self, shifted):
         shifted = np.ascontiguousarray(shifted, dtype=np.int64)
-        out = np.zeros(2 * len(shifted) + 2, dtype=np.int32)
+        out = np.zeros(3 * len(shifted) + 3, dtype=np.int32)
         n = lib().bpe_oracle_encode(self._m(), shifted.ctypes.data, len(shifted), out.ctypes.data)
         return out[:n].tolist()
 
@@ -123,7 +148,7 @@ class OracleBPE:
 
 
 def pretokenize(codepoints):
-    cp = np.ascontiguousarray(codepoints, dtype=np.uint8)
+    cp = np.ascontiguousarray(codepoints, dtype=np.uint16)
     ws = np.zeros(len(cp), dtype=np.uint8)
     lib().bpe_oracle_pretokenize(cp.ctypes.data, len(cp), ws.ctypes.data)
     return ws

@@ -107,11 +107,11 @@ def spline_case(ref, name, *, num_dof, num_basis, seq_len, vocab_size, degree_p=
     return tok
 
 
-def bpe_case(ref, name, *, bpe_vocab_size, fit_batches, fit_seed0, max_sequences=None):
+def bpe_case(ref, name, *, bpe_vocab_size, fit_batches, fit_seed0, max_sequences=None, vocab_size=256):
     """BEASTBsplineBPETokenizer on the bimanual config: train (HF byte-level BPE under the hood),
     save, encode to ragged ids, decode back."""
     base = ref.BEASTBsplineTokenizer.__new__(ref.BEASTBsplineTokenizer)
-    cfg = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
+    cfg = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=vocab_size, gripper_zero_order=True,
                gripper_indices=[6, 13], device="cpu")
     base = ref.BEASTBsplineTokenizer(**cfg)
     g2 = dict(np.load(os.path.join(HERE, "cfg2_d14.npz")))
@@ -144,7 +144,7 @@ def bpe_case(ref, name, *, bpe_vocab_size, fit_batches, fit_seed0, max_sequences
     corpus = np.concatenate(seqs, 0)
     if max_sequences is not None:
         corpus = corpus[:max_sequences]
-    out["corpus_bins"] = corpus.astype(np.uint8) if corpus.max() < 256 else corpus
+    out["corpus_bins"] = corpus.astype(np.uint8) if corpus.max() < 256 else corpus.astype(np.uint16)
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
@@ -173,6 +173,8 @@ def main():
     # BPE on top of the bimanual tokenizer (configs[3]/[4] at a size the reference finishes in seconds)
     bpe_case(ref, "bpe_d14", bpe_vocab_size=640, fit_batches=40, fit_seed0=1000)
     bpe_case(ref, "bpe_d14_small", bpe_vocab_size=400, fit_batches=8, fit_seed0=2000, max_sequences=200)
+    # a 1000-bin tokenizer (the CLI default vocab): shifted bins are codepoints up to U+03E7 (2-byte UTF-8)
+    bpe_case(ref, "bpe_v1000", bpe_vocab_size=1600, fit_batches=24, fit_seed0=3000, vocab_size=1000)
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ from oracle.bpe_oracle import OracleBPE, pretokenize
 
 def test_model_files_round_trip(tmp_path):
     from beast_tokenizer_b200 import B200ByteLevelBPE, BEASTBsplineBPETokenizer
-    for name in ("bpe_d14", "bpe_d14_small"):
+    for name in ("bpe_d14", "bpe_d14_small", "bpe_v1000"):
         src = os.path.join(GOLDEN, f"{name}_pretrained")
         tok = BEASTBsplineBPETokenizer.from_pretrained(src, device="cpu")
         out = tmp_path / name
@@ -22,7 +22,7 @@ def test_model_files_round_trip(tmp_path):
                   "bpe_tokenizer/tokenizer.json"):
             assert open(os.path.join(src, f), encoding="utf-8").read() == open(out / f, encoding="utf-8").read(), f
         sd = tok.state_dict()
-        assert sd["bpe"] == {"min_token": 0, "max_token": 255, "vocab_size": tok.bpe_vocab_size,
+        assert sd["bpe"] == {"min_token": 0, "max_token": tok.vocab_size - 1, "vocab_size": tok.bpe_vocab_size,
                              "tokenizer_dir": "bpe_tokenizer"}
         m = tok.bpe_tokenizer
         assert m.get_vocab_size() == tok.bpe_vocab_size and m.token_to_id(m.id_to_token(300)) == 300

@@ -10,7 +10,7 @@ import pytest
 from conftest import GOLDEN, load_golden
 from oracle.bpe_oracle import OracleBPE, pretokenize
 
-BPE_CASES = ["bpe_d14", "bpe_d14_small"]
+BPE_CASES = ["bpe_d14", "bpe_d14_small", "bpe_v1000"]
 
 
 def ref_files(name):
@@ -58,6 +58,7 @@ def test_pretokenizer_examples():
     assert pieces("\x00\x01'tA") == ["\x00\x01'", "tA"]
     assert pieces("a\x85b\xa0") == ["a", "\x85", "b", "\xa0"]
     assert pieces("  ") == ["  "]
+    assert pieces("a\u0416\u0661b \u2003x") == ["a\u0416", "\u0661", "b", " ", "\u2003", "x"]      # beyond Latin-1
 
 
 def test_against_live_library():
@@ -66,15 +67,17 @@ def test_against_live_library():
     from tokenizers.trainers import BpeTrainer
     rng = np.random.default_rng(7)
     pt = pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=True)
-    for trial in range(600):
+    for trial in range(900):
         n = int(rng.integers(1, 50))
-        cp = rng.integers(0, 256, n) if trial % 2 else rng.choice([32, 39, 115, 116, 114, 101, 108, 65, 48, 10, 160, 33], n)
+        cp = (rng.integers(0, 256, n) if trial % 3 == 1 else rng.integers(0, 0xD800, n) if trial % 3 == 2
+              else rng.choice([32, 39, 115, 116, 114, 101, 108, 65, 48, 10, 160, 33], n))
         starts = np.zeros(n, np.uint8)
         for _, (a, _b) in pt.pre_tokenize_str("".join(map(chr, cp))):
             starts[a] = 1
         assert np.array_equal(pretokenize(cp), starts), cp.tolist()
     for bins, vs in ((rng.integers(0, 256, (600, 140)), 500), (rng.integers(30, 100, (300, 70)), 420),
-                     (rng.choice([97, 98, 99], (100, 40)), 300)):
+                     (rng.choice([97, 98, 99], (100, 40)), 300), (rng.integers(0, 1000, (400, 100)), 1500),
+                     (rng.integers(1500, 4000, (200, 60)), 3000)):
         mn, mx = int(bins.min()), int(bins.max())
         hf = ByteLevelBPETokenizer()
         trainer = BpeTrainer(vocab_size=vs, min_frequency=2, show_progress=False, special_tokens=[],

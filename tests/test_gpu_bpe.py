@@ -24,7 +24,7 @@ def ragged(g):
     return [r.tolist() for r in np.split(g["ids_flat"], np.cumsum(g["ids_len"])[:-1])]
 
 
-@pytest.mark.parametrize("name", ["bpe_d14", "bpe_d14_small"])
+@pytest.mark.parametrize("name", ["bpe_d14", "bpe_d14_small", "bpe_v1000"])
 def test_trainer_reproduces_reference_files(name):
     from beast_tokenizer_b200 import FIGBPE
     g = load_golden(name)
@@ -42,7 +42,7 @@ def test_trainer_reproduces_reference_files(name):
     assert st2.tokenizer.merges_txt() == o.merges_txt() and st2.tokenizer.vocab_json() == o.vocab_json()
 
 
-@pytest.mark.parametrize("name", ["bpe_d14", "bpe_d14_small"])
+@pytest.mark.parametrize("name", ["bpe_d14", "bpe_d14_small", "bpe_v1000"])
 def test_encode_decode_vs_reference(name):
     from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
     g = load_golden(name)
@@ -73,7 +73,7 @@ def test_encode_decode_vs_reference(name):
 
 
 @pytest.mark.parametrize("kind,n,vocab", [("uniform", 20000, 1024), ("normal", 30000, 2048), ("letters", 3000, 700),
-                                          ("narrow", 4000, 400)])
+                                          ("narrow", 4000, 400), ("bins1000", 6000, 1800), ("bins5000", 2000, 5600)])
 def test_trainer_vs_oracle_large(kind, n, vocab):
     """Synthetic corpora at sizes the C oracle trains in seconds: merges, vocabulary and ids identical."""
     from beast_tokenizer_b200 import FIGBPE
@@ -84,6 +84,10 @@ def test_trainer_vs_oracle_large(kind, n, vocab):
         bins = np.clip(rng.normal(128, 28, (n, 140)).round(), 0, 255).astype(np.int64)
     elif kind == "letters":                                        # long pre-tokens, repeated symbols (aaa -> Xa)
         bins = rng.choice([97, 97, 97, 98, 99, 32], (n, 60)) + 7
+    elif kind == "bins1000":                                       # 1000-bin tokenizer: 2-byte UTF-8, classes past Latin-1
+        bins = np.clip(rng.normal(500, 120, (n, 140)).round(), 0, 999).astype(np.int64)
+    elif kind == "bins5000":                                       # 3-byte UTF-8
+        bins = rng.integers(0, 5000, (n, 100))
     else:
         bins = rng.integers(40, 91, (n, 140))
     o = OracleBPE.train(bins, vocab)
