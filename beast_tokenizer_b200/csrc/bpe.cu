@@ -24,7 +24,8 @@ namespace beast {
 constexpr int kBpeBlock = 128;
 constexpr uint16_t kWordStart = 0x8000u;
 constexpr uint16_t kIdMask = 0x7fffu;
-constexpr int kMaxWord = 512;            // longest sequence (in byte-level symbols) encode handles
+constexpr int kMaxWord = 512;            // longest pre-token (in byte-level symbols) of the common encode kernel
+constexpr int kMaxWordLong = 8192;       // long-sequence variant (e.g. 1600 bins x 2 bytes)
 
 // Corpus layout ("chunk-major"): the symbols of sequence `seq` live in 16-byte chunks of 8,
 // chunk c of all sequences contiguous:  sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)].
@@ -101,8 +102,8 @@ __device__ __forceinline__ int pretoken_len(const uint16_t* cp, int i, int n, co
 // status: bit 0 = a value below min_token, bit 1 = a value above max_token (per sequence).
 __device__ __forceinline__ void stage_rows(const long long* __restrict__ bins, long long base, long long N, int L,
                                            long long min_token, long long max_shift, uint16_t* s_cp, int LP,
-                                           int* s_status) {
-    const long long rows = (N - base) < kBpeBlock ? (N - base) : kBpeBlock;
+                                           int* s_status, int rows_per_block) {
+    const long long rows = (N - base) < rows_per_block ? (N - base) : rows_per_block;
     for (long long idx = threadIdx.x; idx < rows * L; idx += blockDim.x) {
         const int r = (int)(idx / L), p = (int)(idx - (long long)r * L);
         const long long v = bins[(base + r) * L + p] - min_token;
@@ -150,20 +151,20 @@ bpe_seen_kernel(const long long* __restrict__ bins, long long n, long long min_t
 __global__ void __launch_bounds__(kBpeBlock)
 bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token,
                      const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
-                     uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int* err) {
+                     uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int* err, int rows) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
     uint16_t* s_cp = (uint16_t*)s_raw;
-    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP * 2 + 3) & ~(size_t)3));
+    int* s_status = (int*)(s_raw + (((size_t)rows * LP * 2 + 3) & ~(size_t)3));
     __shared__ short s_b2i[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
-    for (int i = threadIdx.x; i < kBpeBlock; i += blockDim.x) s_status[i] = 0;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) s_status[i] = 0;
     __syncthreads();
-    const long long base = (long long)blockIdx.x * kBpeBlock;
-    stage_rows(bins, base, N, L, min_token, 0xD7FF, s_cp, LP, s_status);
+    const long long base = (long long)blockIdx.x * rows;
+    stage_rows(bins, base, N, L, min_token, 0xD7FF, s_cp, LP, s_status, rows);
     __syncthreads();
     const long long seq = base + threadIdx.x;
-    if (seq >= N) return;
+    if (threadIdx.x >= rows || seq >= N) return;
     if (s_status[threadIdx.x]) *err = 1;
     const uint16_t* cp = s_cp + threadIdx.x * LP;
     int m = 0, i = 0;
@@ -476,30 +477,31 @@ bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, i
 // ---------------------------------------------------------------- encode (K5a)
 // rank_tab[a*V + b] = rank << 16 | new_id, or 0xffffffff.  One thread per sequence; the word being
 // merged lives in local memory with its pair keys cached, so a merge costs one scan + two lookups.
+template <int MAXW>
 __global__ void __launch_bounds__(kBpeBlock)
 bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token, long long max_shift,
                   const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
                   const unsigned int* __restrict__ rank_tab, int V, uint16_t* __restrict__ ids_out, int out_stride,
-                  int* __restrict__ len_out, int* __restrict__ status_out) {
+                  int* __restrict__ len_out, int* __restrict__ status_out, int rows) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
     uint16_t* s_cp = (uint16_t*)s_raw;
-    int* s_status = (int*)(s_raw + (((size_t)kBpeBlock * LP * 2 + 3) & ~(size_t)3));
+    int* s_status = (int*)(s_raw + (((size_t)rows * LP * 2 + 3) & ~(size_t)3));
     __shared__ short s_b2i[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
-    for (int i = threadIdx.x; i < kBpeBlock; i += blockDim.x) s_status[i] = 0;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) s_status[i] = 0;
     __syncthreads();
-    const long long base = (long long)blockIdx.x * kBpeBlock;
-    stage_rows(bins, base, N, L, min_token, max_shift, s_cp, LP, s_status);
+    const long long base = (long long)blockIdx.x * rows;
+    stage_rows(bins, base, N, L, min_token, max_shift, s_cp, LP, s_status, rows);
     __syncthreads();
     const long long seq = base + threadIdx.x;
-    if (seq >= N) return;
+    if (threadIdx.x >= rows || seq >= N) return;
     status_out[seq] = s_status[threadIdx.x];
     if (s_status[threadIdx.x]) { len_out[seq] = 0; return; }
     const uint16_t* cp = s_cp + threadIdx.x * LP;
     uint16_t* out = ids_out + seq * (long long)out_stride;
-    uint16_t w[kMaxWord];
-    unsigned int key[kMaxWord];
+    uint16_t w[MAXW];
+    unsigned int key[MAXW];
     int m = 0, i = 0;
     while (i < L) {
         const int pl = pretoken_len(cp, i, L, cls_tab);
@@ -553,14 +555,14 @@ __global__ void __launch_bounds__(kBpeBlock)
 bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
                   long long min_token, const int* __restrict__ tok_off, const uint8_t* __restrict__ tok_bytes,
                   int n_vocab, long long* __restrict__ bins_out, int* __restrict__ status_out,
-                  int* __restrict__ declen_out) {
+                  int* __restrict__ declen_out, int rows_per_block) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
     uint16_t* s_cp = (uint16_t*)s_raw;                       // decoded codepoints, [kBpeBlock][LP]
-    const long long base = (long long)blockIdx.x * kBpeBlock;
+    const long long base = (long long)blockIdx.x * rows_per_block;
     const long long seq = base + threadIdx.x;
     int status = 0, cnt = 0;
-    if (seq < N) {
+    if (threadIdx.x < rows_per_block && seq < N) {
         uint16_t* cp = s_cp + threadIdx.x * LP;
         int pending = 0, acc = 0;
         for (long long p = offsets[seq]; p < offsets[seq + 1] && !status; ++p) {
@@ -591,7 +593,7 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
         declen_out[seq] = cnt;
     }
     __syncthreads();
-    const long long rows = (N - base) < kBpeBlock ? (N - base) : kBpeBlock;
+    const long long rows = (N - base) < rows_per_block ? (N - base) : rows_per_block;
     for (long long idx = threadIdx.x; idx < rows * L; idx += blockDim.x) {
         const int r = (int)(idx / L), p = (int)(idx - (long long)r * L);
         bins_out[(base + r) * L + p] = (long long)s_cp[r * LP + p] + min_token;
@@ -609,7 +611,13 @@ static int bpe_grid(long long n, int block) {
     return (int)g;
 }
 
-static size_t stage_smem(int L) { return (((size_t)kBpeBlock * (L + 1) * 2 + 3) & ~(size_t)3) + kBpeBlock * sizeof(int); }
+// rows of bins staged per block: as many as fit in ~180 KB of shared memory, at most one per thread
+static int stage_rows_per_block(int L) {
+    long long r = (180 * 1024) / ((long long)(L + 1) * 2 + 4);
+    if (r > kBpeBlock) r = kBpeBlock;
+    return (int)r;
+}
+static size_t stage_smem(int L, int rows) { return (((size_t)rows * (L + 1) * 2 + 3) & ~(size_t)3) + (size_t)rows * sizeof(int); }
 
 }  // namespace beast
 
@@ -638,17 +646,18 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
     if (N == 0) return BEAST_OK;
     if (!bins || !byte_to_id || !cls_tab || !sym || !len || !err) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_stride < N || 3 * L > 32767) return BEAST_E_SHAPE;
-    const size_t smem = stage_smem(L);
-    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
+    const int rows = stage_rows_per_block(L);
+    if (rows < 1) return BEAST_E_UNSUPPORTED;
+    const size_t smem = stage_smem(L, rows);
     static size_t attr = 48 * 1024;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(bpe_symbolize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = smem;
     }
-    const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
+    const long long grid = (N + rows - 1) / rows;
     bpe_symbolize_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-        (const long long*)bins, N, L, min_token, byte_to_id, cls_tab, sym, len, n_stride, err);
+        (const long long*)bins, N, L, min_token, byte_to_id, cls_tab, sym, len, n_stride, err, rows);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -778,19 +787,28 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     if (N == 0) return BEAST_OK;
     if (!bins || !byte_to_id || !cls_tab || !rank_tab || !ids_padded || !len_out || !status_out) return BEAST_E_NULL;
     const int mult = max_shift < 0x80 ? 1 : (max_shift < 0x800 ? 2 : 3);       // UTF-8 bytes per bin
-    if (N < 0 || L < 1 || mult * L > kMaxWord || out_stride < mult * L || V < 1 || V > 65535 || max_shift > 0xD7FF)
+    if (N < 0 || L < 1 || mult * L > kMaxWordLong || out_stride < mult * L || V < 1 || V > 65535 || max_shift > 0xD7FF)
         return BEAST_E_SHAPE;
-    const size_t smem = stage_smem(L);
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(bpe_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int rows = stage_rows_per_block(L);
+    if (rows < 1) return BEAST_E_UNSUPPORTED;
+    const size_t smem = stage_smem(L, rows);
+    const bool lng = mult * L > kMaxWord;
+    static size_t attr[2] = {48 * 1024, 48 * 1024};
+    if (smem > attr[lng]) {
+        cudaError_t e = lng ? cudaFuncSetAttribute(bpe_encode_kernel<kMaxWordLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(bpe_encode_kernel<kMaxWord>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr = smem;
+        attr[lng] = smem;
     }
-    const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
-    bpe_encode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-        (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
-        len_out, status_out);
+    const long long grid = (N + rows - 1) / rows;
+    if (lng)
+        bpe_encode_kernel<kMaxWordLong><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+            (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
+            len_out, status_out, rows);
+    else
+        bpe_encode_kernel<kMaxWord><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+            (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
+            len_out, status_out, rows);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -813,17 +831,19 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
     if (N == 0) return BEAST_OK;
     if (!offsets || !tok_off || !tok_bytes || !bins_out || !status_out || !declen_out) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_vocab < 1) return BEAST_E_SHAPE;
-    const size_t smem = (size_t)kBpeBlock * (L + 1) * 2;
+    const int rows = stage_rows_per_block(L);
+    if (rows < 1) return BEAST_E_UNSUPPORTED;
+    const size_t smem = (size_t)rows * (L + 1) * 2;
     static size_t attr = 48 * 1024;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(bpe_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = smem;
     }
-    const long long grid = (N + kBpeBlock - 1) / kBpeBlock;
+    const long long grid = (N + rows - 1) / rows;
     bpe_decode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
         flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out, status_out,
-        declen_out);
+        declen_out, rows);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;

@@ -57,7 +57,6 @@ struct EncArgs {
     long long offset;
     float vm1;
     int D, n_joint, S, n_tiles;
-    int debug_skip;        // perf debugging only (BEAST_B200_DEBUG_SKIP=1): move the data, skip the arithmetic
     int slot_to_dof[BEAST_MAX_SLOTS];
 };
 
@@ -184,10 +183,7 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
         float acc[NB];
         if (active) {
             const float* y = (const float*)stage + tl * (T * D) + dof;
-            if (a.debug_skip) {
-#pragma unroll
-                for (int k = 0; k < NB; ++k) acc[k] = y[k * D];
-            } else if (slot < nj) fit_joint<T, NB>(tab, y, D, acc);
+            if (slot < nj) fit_joint<T, NB>(tab, y, D, acc);
             else fit_grip<T, NB>(tab, y, D, acc);
         }
         if (want_mm && active) {
@@ -345,7 +341,6 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
     a.traj = traj; a.params_out = params_out; a.tokens_out = tokens_out;
     a.w_min = w_min; a.w_max = w_max; a.bmin = bmin; a.bmax = bmax; a.offset = offset; a.vm1 = (float)(p->V - 1);
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
-    { const char* e = getenv("BEAST_B200_DEBUG_SKIP"); a.debug_skip = (e && e[0] == '1') ? 1 : 0; }
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
     // outputs (12 B * NB per column) alias the 4*T B per column input tile
     const size_t smem = (size_t)kEncStages * ((((size_t)S * T * p->D * 4u) + 127u) & ~(size_t)127u);

@@ -193,3 +193,26 @@ def test_train_cli_flow(tmp_path):
     assert tok.bpe_tokenizer.get_vocab_size() == 500
     errs = json.load(open(tmp_path / "eval" / "synthetic" / "errors.json"))
     assert len(errs["errors_l2"]) == 5 and len(errs["mean_tokens_length"]) == 5 * 32
+
+
+def test_train_cli_flow_reference_defaults(tmp_path):
+    """The reference's train.sh configuration: 50 basis functions, degree 0, 1000 bins, actions [10, 32]
+    (sequences of 1600 bins, 2-byte UTF-8) — fit, BPE with vocab 2048, save, evaluate."""
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
+    from beast_tokenizer_b200.train_beast import main
+    from beast_tokenizer_b200.synth import synth
+    main(["--device", "cuda", "--train-batches", "12", "--eval-batches", "3", "--bpe-vocab-size", "2048",
+          "--beast-checkpoint-dir", str(tmp_path / "beast"), "--bpe-checkpoint-dir", str(tmp_path / "bpe"),
+          "--eval-results-dir", str(tmp_path / "eval")])
+    tok = BEASTBsplineBPETokenizer.from_pretrained(tmp_path / "bpe", device="cuda")
+    assert tok.sequence_length == 1600 and tok.vocab_size == 1000
+    x = synth(6, 10, 32, seed=5)
+    ids, pd, mp = tok.encode(x, return_mp_tokens=True)
+    o = OracleBPE.from_strings(tok.bpe_tokenizer.get_vocab(), [f"{a} {b}" for a, b in tok.bpe_tokenizer.merge_strings()])
+    for i in range(6):
+        assert ids[i] == o.encode(mp[i].cpu().numpy() - tok.bpe_min_token)
+    assert torch.equal(tok.bpe_to_mp_tokens(ids), mp)
+    corpus = torch.cat([tok.encode_to_mp_tokens(b["actions"])[0] for b in
+                        __import__("beast_tokenizer_b200.synth", fromlist=["SyntheticLoader"]).SyntheticLoader(12, 32, 10, 32, seed0=0)])
+    o2 = OracleBPE.train(corpus.cpu().numpy(), 2048)
+    assert tok.bpe_tokenizer.merges_txt() == o2.merges_txt()
