@@ -139,10 +139,10 @@ class GpuBpeEngine:
 
             # plain stream launches: ~60 us of host enqueue per merge, never a sync (capturing the
             # iteration into a CUDA graph costs more to instantiate than 1 700 replays save)
+            self.work[:4].zero_()
             for _ in range(max_merges):
-                step(0)
+                step(0)                                 # fold previous delta + arg-max + select, scan, rewrite
                 coll.reduce_(self.delta, "sum")
-                step(1)
             ctl_h = ctl.cpu().tolist()
             n = ctl_h[5]
             return log[:4 * n].cpu().view(-1, 4).tolist()

@@ -43,7 +43,7 @@ struct BpeCtl {
     int n_tokens;           // vocabulary size so far (= next new id)
     int n_merges;           // merges logged
     int done;               // sticky: no pair reached min_frequency, or the vocabulary is full
-    int pad;
+    int has_delta;          // the delta block of merge (a, b, c) still has to be folded into the histogram
 };
 
 
@@ -292,25 +292,32 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
         const int nch_max = warp_max_i(nch);
         int q0 = -1;
         unsigned int carry = 0;                               // bit 15: previous chunk ended with `a`
-        for (int ci = 0; ci < nch_max; ++ci) {
-            if (ci < nch && q0 < 0) {
-                const uint4 w = __ldg(&sym4[(long long)ci * n_stride + row0]);
-                const unsigned int wd[4] = {w.x, w.y, w.z, w.w};
-                unsigned int fa[4];                           // bit 15 / 31: half-word has id == a
+        auto test_chunk = [&](const uint4& w, int ci) {
+            const unsigned int wd[4] = {w.x, w.y, w.z, w.w};
+            unsigned int fa[4];                               // bit 15 / 31: half-word has id == a
 #pragma unroll
-                for (int k = 0; k < 4; ++k) fa[k] = ~(((wd[k] ^ A2) & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
-                if (carry | fa[0] | fa[1] | fa[2] | fa[3]) {
+            for (int k = 0; k < 4; ++k) fa[k] = ~(((wd[k] ^ A2) & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+            if (carry | fa[0] | fa[1] | fa[2] | fa[3]) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned int y = wd[k] ^ B2;        // fb: half-word == b exactly
-                        const unsigned int fb = ~((((y & 0x7fff7fffu) + 0x7fff7fffu)) | y) & 0x80008000u;
-                        const unsigned int h = ((fa[k] << 16) | (k ? fa[k - 1] >> 16 : carry)) & fb;
-                        if (h && q0 < 0) q0 = ci * kChunk + 2 * k + ((h & 0x8000u) ? 0 : 1) - 1;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned int y = wd[k] ^ B2;            // fb: half-word == b exactly
+                    const unsigned int fb = ~((((y & 0x7fff7fffu) + 0x7fff7fffu)) | y) & 0x80008000u;
+                    const unsigned int h = ((fa[k] << 16) | (k ? fa[k - 1] >> 16 : carry)) & fb;
+                    if (h && q0 < 0) q0 = ci * kChunk + 2 * k + ((h & 0x8000u) ? 0 : 1) - 1;
                 }
-                carry = fa[3] >> 16;
             }
-            if (__all_sync(0xffffffffu, q0 >= 0 || ci + 1 >= nch)) break;
+            carry = fa[3] >> 16;
+        };
+        for (int ci = 0; ci < nch_max; ci += 2) {             // two independent 128-bit loads in flight per lane
+            if (ci < nch && q0 < 0) {
+                // streaming (evict-first) loads: the corpus pass must not push the V x V histogram out of L2
+                const uint4 w0 = __ldcs(&sym4[(long long)ci * n_stride + row0]);
+                uint4 w1 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                if (ci + 1 < nch) w1 = __ldcs(&sym4[(long long)(ci + 1) * n_stride + row0]);
+                test_chunk(w0, ci);
+                if (q0 < 0) test_chunk(w1, ci + 1);
+            }
+            if (__all_sync(0xffffffffu, q0 >= 0 || ci + 2 >= nch)) break;
         }
         const unsigned int hits = __ballot_sync(0xffffffffu, q0 >= 0);
         if (hits) {
@@ -376,8 +383,10 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
         prev_new = id;
         push(x);
     };
+    uint4 w_next = sym4[(long long)cs * n_stride + seq];
     for (int ci = cs; ci < nch; ++ci) {
-        const uint4 w = sym4[(long long)ci * n_stride + seq];
+        const uint4 w = w_next;
+        if (ci + 1 < nch) w_next = sym4[(long long)(ci + 1) * n_stride + seq];   // next chunk in flight while this one is processed
 #pragma unroll
         for (int j = 0; j < kChunk; ++j) {
             if (ci * kChunk + j >= n) break;
@@ -450,6 +459,93 @@ __global__ void bpe_select_kernel(unsigned long long* __restrict__ result, BpeCt
     ctl->b = (int)(flat % (unsigned int)V);
     ctl->c = ctl->n_tokens++;
     ctl->count = count;
+    int* e = log + 4 * ctl->n_merges++;
+    e[0] = ctl->a; e[1] = ctl->b; e[2] = ctl->c; e[3] = count;
+}
+
+// Fused iteration head of the sync-free loop: fold the (all-reduced) delta block of the previous merge
+// into the histogram, find the arg-max of the updated table in the same pass, and let the last block
+// apply BpeTrainer's stop rules, assign the next id and log the merge.  Every delta entry belongs to
+// exactly one histogram entry (column a: (x, a); row b: (b, y); column c: (x, c); row c: (c, y)), so
+// the thread that owns that entry consumes and clears it.
+__global__ void __launch_bounds__(256)
+bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int* __restrict__ delta,
+                   unsigned long long* __restrict__ result, unsigned int* __restrict__ ticket, int* __restrict__ log,
+                   int vocab_size, int min_frequency, int max_merges, int* __restrict__ work_count) {
+    if (ctl->done) return;
+    const int n_active = ctl->n_tokens;
+    const bool fold = ctl->has_delta != 0;
+    const int pa = ctl->a, pb = ctl->b, pc = ctl->c;
+    unsigned long long best = 0;
+    // rows are walked by warps, columns by lanes, four entries per lane and step (128-bit loads when the
+    // row pitch allows): no integer division, coalesced rows, several independent loads in flight
+    const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = (V & 3) == 0;
+    auto visit = [&](int* row, int x, int y, int v) {
+        if (fold) {
+            int d = 0;
+            bool touched = false;
+            if (y == pa) { d += delta[x]; delta[x] = 0; touched = true; }
+            if (x == pb) { d += delta[V + y]; delta[V + y] = 0; touched = true; }
+            if (y == pc) { d += delta[2 * V + x]; delta[2 * V + x] = 0; touched = true; }
+            if (x == pc) { d += delta[3 * V + y]; delta[3 * V + y] = 0; touched = true; }
+            if (x == pa && y == pb) { v = 0; d = 0; touched = true; }          // the merged pair is gone for good
+            if (touched) { v += d; row[y] = v; }
+        }
+        if (v > 0) {
+            const unsigned int flat = (unsigned int)x * (unsigned int)V + (unsigned int)y;
+            const unsigned long long key = ((unsigned long long)(unsigned int)v << 32) | (0xffffffffu - flat);
+            best = key > best ? key : best;
+        }
+    };
+    for (int x = blockIdx.x * warps_per_block + (threadIdx.x >> 5); x < n_active; x += gridDim.x * warps_per_block) {
+        int* row = hist + (long long)x * V;
+        if (vec) {
+            for (int y0 = lane * 4; y0 < n_active; y0 += 128) {
+                const int4 q = *(const int4*)(row + y0);                         // y0 + 3 < V: inside the row
+                visit(row, x, y0, q.x);
+                if (y0 + 1 < n_active) visit(row, x, y0 + 1, q.y);
+                if (y0 + 2 < n_active) visit(row, x, y0 + 2, q.z);
+                if (y0 + 3 < n_active) visit(row, x, y0 + 3, q.w);
+            }
+        } else {
+            for (int y = lane; y < n_active; y += 32) visit(row, x, y, row[y]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long s_best[8];
+    __shared__ bool s_last;
+    if (lane == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < warps_per_block; ++w) best = s_best[w] > best ? s_best[w] : best;
+        if (best) atomicMax(result, best);
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    // ---- last block: select
+    __threadfence();
+    const unsigned long long key = *(volatile unsigned long long*)result;
+    *result = 0;
+    *ticket = 0;
+    *work_count = 0;
+    ctl->has_delta = 0;
+    const int count = (int)(key >> 32);
+    if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges) {
+        ctl->done = 1;
+        return;
+    }
+    const unsigned int flat = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
+    ctl->a = (int)(flat / (unsigned int)V);
+    ctl->b = (int)(flat % (unsigned int)V);
+    ctl->c = ctl->n_tokens++;
+    ctl->count = count;
+    ctl->has_delta = 1;
     int* e = log + 4 * ctl->n_merges++;
     e[0] = ctl->a; e[1] = ctl->b; e[2] = ctl->c; e[3] = count;
 }
@@ -750,12 +846,7 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
     if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (phase == 1) {
-        bpe_apply_delta_kernel<<<1, 1024, 0, st>>>(hist, delta, 0, 0, 0, V, (const BpeCtl*)ctl);
-        count_launch();
-        BEAST_CHECK_LAUNCH();
-        return BEAST_OK;
-    }
+    if (phase == 1) return BEAST_OK;          // the delta is folded by the next iteration's first kernel
     const size_t smem = (size_t)4 * V * sizeof(int);
     int rc = rewrite_smem_attr(smem);
     if (rc != BEAST_OK) return rc;
@@ -764,11 +855,11 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     int* work_count = work;                  // work = {count, pad[3], seq[N], q0[N]}
     int* work_seq = work + 4;
     int* work_q0 = work + 4 + N;
-    // the arg-max grid is sized for the full table: n_active lives on the device
-    bpe_argmax_kernel<<<sms * 4, 256, 0, st>>>(hist, V, V, (const BpeCtl*)ctl, (unsigned long long*)result);
-    bpe_select_kernel<<<1, 1, 0, st>>>((unsigned long long*)result, (BpeCtl*)ctl, log, V, vocab_size, min_frequency,
-                                      max_merges, work_count);
-    count_launch(2);
+    // one launch folds the previous delta, finds the arg-max and selects the merge (n_active lives on the device)
+    unsigned int* ticket = (unsigned int*)(work + 1);
+    bpe_iterate_kernel<<<sms * 8, 256, 0, st>>>(hist, V, (BpeCtl*)ctl, delta, (unsigned long long*)result, ticket, log,
+                                               vocab_size, min_frequency, max_merges, work_count);
+    count_launch(1);
     if (N > 0) {
         const int grid = merge_grid(N);
         bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count, work_seq, work_q0);

@@ -187,10 +187,11 @@ int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* resul
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
                     int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream);
 int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
-/* Sync-free training loop: one iteration = phase 0 (arg-max, select with BpeTrainer's stop rules —
- * vocabulary full / count < min_frequency —, merge into delta) [+ all-reduce(delta) when sharded] + phase 1
- * (hist += delta).  ctl: 8 x int32 device block {a, b, c, count, n_tokens, n_merges, done, pad}, caller sets
- * n_tokens = alphabet size and zeroes the rest; log: int32 [4 * max_merges] receives (a, b, new_id, count) per
+/* Sync-free training loop: one iteration = phase 0 — three launches: (1) fold the previous merge's delta
+ * into the histogram, arg-max, select with BpeTrainer's stop rules (vocabulary full / count < min_frequency),
+ * (2) scan for the pair, (3) rewrite the listed sequences into delta — [+ all-reduce(delta) when sharded].
+ * phase 1 is a no-op kept for symmetry.  ctl: 8 x int32 device block {a, b, c, count, n_tokens, n_merges, done,
+ * has_delta}, caller sets n_tokens = alphabet size and zeroes the rest; work: int32 [4 + 2*N] zeroed by the caller; log: int32 [4 * max_merges] receives (a, b, new_id, count) per
  * merge; result: the arg-max scratch word (zeroed by the caller once).  Nothing is read back until the end. */
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                    int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
