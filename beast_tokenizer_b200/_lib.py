@@ -31,6 +31,7 @@ class PlanDesc(C.Structure):
         ("proj_joint_h", C.POINTER(C.c_float)), ("proj_grip_h", C.POINTER(C.c_float)),
         ("phi_joint_h", C.POINTER(C.c_float)), ("phi_grip_h", C.POINTER(C.c_float)),
         ("knots_joint_h", C.POINTER(C.c_float)), ("knots_grip_h", C.POINTER(C.c_float)),
+        ("init_cond_order", C.c_int32), ("end_cond_order", C.c_int32),
     ]
 
 
@@ -47,6 +48,8 @@ _SIGNATURES = {
                                          C.c_int32, c_f32p, C.c_void_p]),
     "beast_dequantize_f32": (C.c_int, [C.c_void_p, c_i64p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     "beast_eval_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int32, c_f32p, C.c_void_p]),
+    "beast_reconstruct_bc_f32": (C.c_int, [C.c_void_p, c_i64p, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, c_f32p,
+                                           C.c_int32, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "beast_fit_minmax_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int32, C.c_void_p]),
     "beast_minmax_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int32, c_f32p, c_f32p, C.c_int32, C.c_void_p]),
     "beast_bounds_expand_f32": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_float, C.c_void_p]),

@@ -18,7 +18,8 @@ def make_times(duration: float, seq_len: int) -> torch.Tensor:
 
 
 def knot_vector(num_basis: int, degree_p: int) -> torch.Tensor:
-    """Clamped uniform knots with init/end condition order 0 (uni_bspline_basis.py:40-55)."""
+    """Clamped uniform knots for `num_basis` control points (uni_bspline_basis.py:40-55; with
+    init/end condition orders the caller passes num_ctrlp = num_basis + init + end)."""
     inner = num_basis + 1 - degree_p
     if inner < 1:
         raise ValueError(f"num_basis={num_basis} too small for degree_p={degree_p}")
@@ -76,6 +77,47 @@ def ridge_projector(phi: torch.Tensor, reg: float = 1e-9) -> torch.Tensor:
     return torch.linalg.solve(a, f.T).to(torch.float32).contiguous()
 
 
+def ridge_projector64(phi: torch.Tensor, reg: float = 1e-9) -> torch.Tensor:
+    f = phi.to(torch.float64)
+    a = f.T @ f + reg * torch.eye(f.shape[1], dtype=torch.float64)
+    return torch.linalg.solve(a, f.T)
+
+
+def conditioned_projector(times: torch.Tensor, tau: float, phi_full: torch.Tensor, knots: torch.Tensor,
+                          num_basis: int, degree_p: int, init_order: int, end_order: int) -> torch.Tensor:
+    """Projector for init/end condition orders 1 and 2 (mp/uni_bspline.py:500-586).
+
+    The reference pins the first `init_order` / last `end_order` control points to the boundary
+    position and finite-difference velocity it reads off the trajectory itself
+    (init_pos = y[0], init_vel = (y[1]-y[0])/dt, end_pos = y[-1] (- y[0]), end_vel =
+    (y[-1]-y[-2])/dt; control points per uni_bspline_basis.py:192-274), subtracts their
+    contribution (+ init_pos) from y and ridge-fits the remaining columns.  Every step is linear
+    in y, so it is still w = P_eff . y with P_eff = P_learn (I - M): one [nb, T] table, fp64."""
+    T = phi_full.shape[0]
+    nc = num_basis + init_order + end_order
+    f = phi_full.to(torch.float64)
+    k = knots.to(torch.float64)
+    t = times.to(torch.float64)
+    tau64 = float(torch.tensor(tau, dtype=torch.float32))
+    dt = float(t[1] - t[0])
+    e = torch.eye(T, dtype=torch.float64)
+    m = torch.zeros(T, T, dtype=torch.float64)
+    if init_order != 0:
+        m += torch.ones(T, 1, dtype=torch.float64) @ e[0:1]          # + init_pos on every sample
+        if init_order == 2:                                           # ctrl 1 = init_vel*tau*dk/p (+0)
+            dk = float(k[1 + degree_p] - k[1])
+            m += f[:, 1:2] @ ((e[1:2] - e[0:1]) / dt * tau64 * dk / degree_p)
+    if end_order != 0:
+        end_pos = e[T - 1:T] - (e[0:1] if init_order != 0 else 0.0)  # relative when init_pos is pinned
+        m += f[:, nc - 1:nc] @ end_pos
+        if end_order == 2:
+            dk = float(k[nc - 1 + degree_p] - k[nc - 1])
+            end_vel = (e[T - 1:T] - e[T - 2:T - 1]) / dt
+            m += f[:, nc - 2:nc - 1] @ (end_pos - end_vel * tau64 * dk / degree_p)
+    p_learn = ridge_projector64(phi_full[:, init_order:nc - end_order])
+    return (p_learn @ (e - m)).to(torch.float32).contiguous()
+
+
 @dataclass
 class SplineConstants:
     seq_len: int
@@ -86,12 +128,14 @@ class SplineConstants:
     joint_indices: List[int]
     gripper_indices: List[int]
     times: torch.Tensor            # [T] fp32 (CPU)
-    phi_joint: torch.Tensor        # [T, nb]
+    phi_joint: torch.Tensor        # [T, nb + init_order + end_order] (all control points)
     proj_joint: torch.Tensor       # [nb, T]
     knots_joint: torch.Tensor
     phi_grip: Optional[torch.Tensor]
     proj_grip: Optional[torch.Tensor]
     knots_grip: Optional[torch.Tensor]
+    init_order: int = 0
+    end_order: int = 0
 
     @property
     def slot_to_dof(self) -> List[int]:
@@ -99,15 +143,22 @@ class SplineConstants:
 
 
 def build_constants(times: torch.Tensor, duration: float, num_basis: int, degree_p: int,
-                    joint_indices, gripper_indices) -> SplineConstants:
+                    joint_indices, gripper_indices, init_order: int = 0, end_order: int = 0) -> SplineConstants:
     times = times.detach().to("cpu", torch.float32).reshape(-1).contiguous()
-    phi_j = bspline_basis(times, duration, num_basis, degree_p)
+    nc = num_basis + init_order + end_order
+    phi_j = bspline_basis(times, duration, nc, degree_p)
+    knots_j = knot_vector(nc, degree_p)
+    if init_order or end_order:
+        proj_j = conditioned_projector(times, duration, phi_j, knots_j, num_basis, degree_p, init_order, end_order)
+    else:
+        proj_j = ridge_projector(phi_j)
     has_grip = len(gripper_indices) > 0
     phi_g = bspline_basis(times, duration, num_basis, 0) if has_grip else None
     return SplineConstants(
         seq_len=int(times.numel()), num_dof=len(joint_indices) + len(gripper_indices), num_basis=num_basis,
         degree_p=degree_p, tau=float(torch.tensor(duration, dtype=torch.float32)),
         joint_indices=list(joint_indices), gripper_indices=list(gripper_indices), times=times,
-        phi_joint=phi_j, proj_joint=ridge_projector(phi_j), knots_joint=knot_vector(num_basis, degree_p),
+        phi_joint=phi_j, proj_joint=proj_j, knots_joint=knots_j,
         phi_grip=phi_g, proj_grip=ridge_projector(phi_g) if has_grip else None,
-        knots_grip=knot_vector(num_basis, 0) if has_grip else None)
+        knots_grip=knot_vector(num_basis, 0) if has_grip else None,
+        init_order=init_order, end_order=end_order)

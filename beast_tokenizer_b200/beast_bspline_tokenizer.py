@@ -48,7 +48,8 @@ class _Plan:
             tau=consts.tau, slot_to_dof_h=slots,
             proj_joint_h=fptr(consts.proj_joint), proj_grip_h=fptr(consts.proj_grip),
             phi_joint_h=fptr(consts.phi_joint), phi_grip_h=fptr(consts.phi_grip),
-            knots_joint_h=fptr(consts.knots_joint), knots_grip_h=fptr(consts.knots_grip))
+            knots_joint_h=fptr(consts.knots_joint), knots_grip_h=fptr(consts.knots_grip),
+            init_cond_order=consts.init_order, end_cond_order=consts.end_order)
         handle = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(lib.beast_plan_create(C.byref(desc), C.byref(handle)), "beast_plan_create")
@@ -71,9 +72,16 @@ class BEASTBsplineTokenizer(TokenizerBase):
                  init_cond_order=0, end_cond_order=0, init_pos=True,
                  use_bpe=False, device="cuda", llm_vocab_size: Optional[int] = None):
         super().__init__()
-        if init_cond_order != 0 or end_cond_order != 0:
-            # boundary-condition splines are outside the B200 hot path
-            raise NotImplementedError("init_cond_order / end_cond_order != 0 are not supported by the B200 path")
+        if init_cond_order not in (0, 1, 2) or end_cond_order not in (0, 1, 2):
+            # the reference's end order -1 / goal basis variants are not reachable from its own tokenizer config
+            raise NotImplementedError("init_cond_order / end_cond_order must be 0, 1 or 2")
+        if (init_cond_order == 2 or end_cond_order == 2) and degree_p < 1:
+            raise NotImplementedError("velocity conditions need degree_p >= 1")
+        self.init_cond_order = int(init_cond_order)
+        self.end_cond_order = int(end_cond_order)
+        # The reference's joint MP keeps the pinned boundary control points of its LAST fit as object
+        # state and reconstruct_traj silently uses them (mp/uni_bspline.py:68-104, 126-136); same here.
+        self._boundary = None
 
         self.dt = 0.01
         # gripper handling exactly as the reference (:55-70): indices are dropped unless zero-order
@@ -143,7 +151,8 @@ class BEASTBsplineTokenizer(TokenizerBase):
         key = (dev, self.times.data_ptr(), int(self.times.numel()), int(self.vocab_size))
         if self._plan_cache is None or self._plan_cache[0] != key:
             consts = build_constants(self.times, self.duration, self.num_basis, self.degree_p,
-                                     self.joint_indices, self.gripper_indices)
+                                     self.joint_indices, self.gripper_indices,
+                                     self.init_cond_order, self.end_cond_order)
             self._plan_cache = (key, _Plan(consts, self.vocab_size, dev), self.times)
         return self._plan_cache[1]
 
@@ -178,12 +187,68 @@ class BEASTBsplineTokenizer(TokenizerBase):
             _lib.check(plan._lib.beast_encode_f32(plan.handle, _lib.ptr(x), B, _lib.ptr(lo), _lib.ptr(hi),
                                                   int(offset), _lib.ptr(params), _lib.ptr(tokens),
                                                   _lib.stream_ptr(dev)), "beast_encode_f32")
+        self._remember_boundary(x, plan)
         return tokens, params
 
-    @staticmethod
-    def _params_dict(params):
+    @property
+    def _has_conditions(self) -> bool:
+        return (self.init_cond_order != 0 or self.end_cond_order != 0) and self.joint_dof > 0
+
+    def _remember_boundary(self, x, plan):
+        """Boundary state of a fit with non-zero condition orders (mp/uni_bspline.py:500-531,
+        basis_gn/uni_bspline_basis.py:192-274): the pinned control points are functions of the four
+        boundary samples y[0], y[1], y[-2], y[-1] only — O(B*D) elementwise work next to the fit."""
+        if not self._has_conditions:
+            return
+        io, eo, p = self.init_cond_order, self.end_cond_order, self.degree_p
+        c = plan.consts
+        nc = self.num_basis + io + eo
+        t = c.times
+        inv_dt = float(torch.tensor(1.0) / (t[1] - t[0]))
+        tau = c.tau
+        ji = torch.as_tensor(self.joint_indices, device=x.device)
+        y0, y1, ym2, ym1 = (x[:, i, :].index_select(1, ji) for i in (0, 1, -2, -1))
+        st = {"init_pos": None, "init_vel": None, "end_pos": None, "end_vel": None}
+        parts = []
+        if io != 0:
+            st["init_pos"] = y0
+            st["init_vel"] = (y1 - y0) * inv_dt
+            parts.append(torch.zeros_like(y0))
+            if io == 2:
+                dk = float(c.knots_joint[1 + p] - c.knots_joint[1])
+                parts.append(st["init_vel"] * tau * dk / p + 0.0)
+        if eo != 0:
+            end_pos = ym1 - y0 if io != 0 else ym1
+            st["end_vel"] = (ym1 - ym2) * inv_dt
+            if eo == 2:
+                dk = float(c.knots_joint[nc - 1 + p] - c.knots_joint[nc - 1])
+                parts.append(end_pos - st["end_vel"] * tau * dk / p)
+            parts.append(end_pos)
+            st["end_pos"] = end_pos + y0 if io != 0 else end_pos       # returned absolute (:600)
+        st["bc"] = torch.stack(parts, dim=-1).contiguous()             # [B, n_joint, io + eo]
+        st["bias"] = y0.contiguous() if io != 0 else None
+        self._boundary = st
+
+    def _params_dict(self, params):
         # keys of UniformBSpline.learn_mp_params_from_trajs (mp/uni_bspline.py:597-602)
-        return {"params": params, "init_pos": None, "init_vel": None, "end_pos": None, "end_vel": None}
+        st = self._boundary if self._has_conditions else None
+        if st is None:
+            return {"params": params, "init_pos": None, "init_vel": None, "end_pos": None, "end_vel": None}
+        return {"params": params, "init_pos": st["init_pos"], "init_vel": st["init_vel"],
+                "end_pos": st["end_pos"], "end_vel": st["end_vel"]}
+
+    def _pinned(self, batch):
+        """(bc, bias) of the last fit for a reconstruct of `batch` trajectories."""
+        if not self._has_conditions:
+            return None, None
+        st = self._boundary
+        if st is None:
+            raise RuntimeError("init_cond_order / end_cond_order != 0: reconstruct needs the boundary conditions "
+                               "of a previous encode (the reference keeps them as state of its MP object)")
+        if st["bc"].shape[0] != batch:
+            raise RuntimeError(f"boundary conditions were fitted for a batch of {st['bc'].shape[0]}, "
+                               f"cannot reconstruct a batch of {batch}")
+        return st["bc"], st["bias"]
 
     # ------------------------------------------------------------------ preparation
     def set_llm_vocab_size(self, llm_vocab_size: Optional[int]):
@@ -349,6 +414,7 @@ class BEASTBsplineTokenizer(TokenizerBase):
         with torch.cuda.device(dev):
             _lib.check(plan._lib.beast_fit_minmax_f32(plan.handle, _lib.ptr(x), x.shape[0], _lib.ptr(lo), _lib.ptr(hi), 0,
                                                       _lib.stream_ptr(dev)), "beast_fit_minmax_f32")
+        self._remember_boundary(x, plan)
         self.w_min.copy_(lo.to(self.w_min.device))
         self.w_max.copy_(hi.to(self.w_max.device))
 
@@ -506,8 +572,20 @@ class BEASTBsplineTokenizer(TokenizerBase):
         B = tokens.shape[0]
         lo, hi = self._bounds(dev)
         init_p = self._init_p(kwargs, dev, B)
+        bc, bias = self._pinned(B)
         with torch.cuda.device(dev):
-            if times is None:
+            if bc is not None:
+                tq = 0
+                if times is not None:
+                    times = self._check_times(times, dev, B)
+                    tq = times.shape[1]
+                out = torch.empty((B, tq if times is not None else plan.consts.seq_len, self.num_dof), device=dev,
+                                  dtype=torch.float32)
+                _lib.check(plan._lib.beast_reconstruct_bc_f32(
+                    plan.handle, _lib.ptr(tokens), None, B, _lib.ptr(lo), _lib.ptr(hi), int(offset), _lib.ptr(init_p),
+                    _lib.ptr(times), tq, _lib.ptr(bc), _lib.ptr(bias), _lib.ptr(out), _lib.stream_ptr(dev)),
+                    "beast_reconstruct_bc_f32")
+            elif times is None:
                 out = torch.empty((B, plan.consts.seq_len, self.num_dof), device=dev, dtype=torch.float32)
                 _lib.check(plan._lib.beast_decode_f32(plan.handle, _lib.ptr(tokens), B, _lib.ptr(lo), _lib.ptr(hi),
                                                       int(offset), _lib.ptr(init_p), _lib.ptr(out),
@@ -545,9 +623,16 @@ class BEASTBsplineTokenizer(TokenizerBase):
             tq = times.shape[1]
         out = torch.empty((B, tq if times is not None else plan.consts.seq_len, self.num_dof), device=dev,
                           dtype=torch.float32)
+        bc, bias = self._pinned(B)
         with torch.cuda.device(dev):
-            _lib.check(plan._lib.beast_eval_f32(plan.handle, _lib.ptr(params), B, _lib.ptr(init_p), _lib.ptr(times),
-                                                tq, _lib.ptr(out), _lib.stream_ptr(dev)), "beast_eval_f32")
+            if bc is not None:
+                _lib.check(plan._lib.beast_reconstruct_bc_f32(
+                    plan.handle, None, _lib.ptr(params), B, None, None, 0, _lib.ptr(init_p), _lib.ptr(times), tq,
+                    _lib.ptr(bc), _lib.ptr(bias), _lib.ptr(out), _lib.stream_ptr(dev)), "beast_reconstruct_bc_f32")
+            else:
+                _lib.check(plan._lib.beast_eval_f32(plan.handle, _lib.ptr(params), B, _lib.ptr(init_p),
+                                                    _lib.ptr(times), tq, _lib.ptr(out), _lib.stream_ptr(dev)),
+                           "beast_eval_f32")
         return out
 
     # ------------------------------------------------------------------ evaluation

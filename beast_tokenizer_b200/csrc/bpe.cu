@@ -745,12 +745,8 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
     const int rows = stage_rows_per_block(L);
     if (rows < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = stage_smem(L, rows);
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(bpe_symbolize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
-    }
+    static size_t granted[kMaxDevices] = {};
+    if (int rc = opt_in_smem(bpe_symbolize_kernel, smem, granted)) return rc;
     const long long grid = (N + rows - 1) / rows;
     bpe_symbolize_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
         (const long long*)bins, N, L, min_token, byte_to_id, cls_tab, sym, len, n_stride, err, rows);
@@ -794,13 +790,8 @@ static int merge_grid(long long n) {
 
 static int rewrite_smem_attr(size_t smem) {
     if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(bpe_rewrite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
-    }
-    return BEAST_OK;
+    static size_t granted[kMaxDevices] = {};
+    return opt_in_smem(bpe_rewrite_kernel, smem, granted);
 }
 
 extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
@@ -884,13 +875,9 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     if (rows < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = stage_smem(L, rows);
     const bool lng = mult * L > kMaxWord;
-    static size_t attr[2] = {48 * 1024, 48 * 1024};
-    if (smem > attr[lng]) {
-        cudaError_t e = lng ? cudaFuncSetAttribute(bpe_encode_kernel<kMaxWordLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(bpe_encode_kernel<kMaxWord>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr[lng] = smem;
-    }
+    static size_t granted[2][kMaxDevices] = {};
+    if (int rc = lng ? opt_in_smem(bpe_encode_kernel<kMaxWordLong>, smem, granted[1])
+                     : opt_in_smem(bpe_encode_kernel<kMaxWord>, smem, granted[0])) return rc;
     const long long grid = (N + rows - 1) / rows;
     if (lng)
         bpe_encode_kernel<kMaxWordLong><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
@@ -925,12 +912,8 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
     const int rows = stage_rows_per_block(L);
     if (rows < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)rows * (L + 1) * 2;
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(bpe_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
-    }
+    static size_t granted[kMaxDevices] = {};
+    if (int rc = opt_in_smem(bpe_decode_kernel, smem, granted)) return rc;
     const long long grid = (N + rows - 1) / rows;
     bpe_decode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
         flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out, status_out,

@@ -15,12 +15,13 @@ namespace beast {
 // ---------------------------------------------------------------- plan
 struct Plan {
     int T, D, nb, n_joint, degree_p, V;
+    int ico, eco, nc;      // pinned leading / trailing joint control points; nc = nb + ico + eco
     float tau;
     int slot_to_dof[BEAST_MAX_SLOTS];
     // host copies
     float* proj_joint_h;   // [nb*T]  [k][t]
     float* proj_grip_h;    // [nb*T] or nullptr
-    float* phi_joint_h;    // [T*nb]  [t][k]
+    float* phi_joint_h;    // [T*nc]  [t][c]
     float* phi_grip_h;
     // device copies (one allocation)
     float* dev_block;
@@ -28,7 +29,7 @@ struct Plan {
     float* proj_grip_d;
     float* phi_joint_d;
     float* phi_grip_d;
-    float* knots_joint_d;  // [nb+degree_p+1]
+    float* knots_joint_d;  // [nc+degree_p+1]
     float* knots_grip_d;   // [nb+1]
     int* slot_to_dof_d;
     int num_sms;
@@ -209,6 +210,25 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// Opt-in to more than 48 KB of dynamic shared memory. The attribute is per (kernel, device), so the
+// granted size is remembered per device: a process that drives several GPUs sets it on each.
+constexpr int kMaxDevices = 64;
+template <typename F>
+static inline int opt_in_smem(F kernel, size_t smem, size_t (&granted)[kMaxDevices]) {
+    if (smem <= 48 * 1024) return BEAST_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= kMaxDevices) return BEAST_E_UNSUPPORTED;
+    if (smem > granted[dev]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        granted[dev] = smem;
+    }
+    return BEAST_OK;
+}
+
 
 }  // namespace beast
 

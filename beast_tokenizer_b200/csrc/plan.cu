@@ -24,6 +24,8 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
     *out = nullptr;
     if (d->seq_len < 1 || d->num_basis < 1 || d->num_dof < 1 || d->num_dof > BEAST_MAX_DOF) return BEAST_E_SHAPE;
     if (d->n_joint < 0 || d->n_joint > d->num_dof || d->vocab_size < 2 || d->degree_p < 0) return BEAST_E_SHAPE;
+    if (d->init_cond_order < 0 || d->init_cond_order > 2 || d->end_cond_order < 0 || d->end_cond_order > 2)
+        return BEAST_E_UNSUPPORTED;
     if (!d->slot_to_dof_h || !d->proj_joint_h || !d->phi_joint_h || !d->knots_joint_h) return BEAST_E_NULL;
     const bool has_grip = d->n_joint < d->num_dof;
     if (has_grip && (!d->proj_grip_h || !d->phi_grip_h || !d->knots_grip_h)) return BEAST_E_NULL;
@@ -35,11 +37,12 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
     memset(p, 0, sizeof(Plan));
     p->T = d->seq_len; p->D = d->num_dof; p->nb = d->num_basis; p->n_joint = d->n_joint;
     p->degree_p = d->degree_p; p->V = d->vocab_size; p->tau = d->tau;
+    p->ico = d->init_cond_order; p->eco = d->end_cond_order; p->nc = p->nb + p->ico + p->eco;
     for (int i = 0; i < p->D; ++i) p->slot_to_dof[i] = d->slot_to_dof_h[i];
-    const size_t nt = (size_t)p->nb * p->T;
-    const size_t nkj = (size_t)p->nb + p->degree_p + 1, nkg = (size_t)p->nb + 1;
+    const size_t nt = (size_t)p->nb * p->T, ntc = (size_t)p->nc * p->T;
+    const size_t nkj = (size_t)p->nc + p->degree_p + 1, nkg = (size_t)p->nb + 1;
     p->proj_joint_h = dup_h(d->proj_joint_h, nt);
-    p->phi_joint_h = dup_h(d->phi_joint_h, nt);
+    p->phi_joint_h = dup_h(d->phi_joint_h, ntc);
     p->proj_grip_h = has_grip ? dup_h(d->proj_grip_h, nt) : nullptr;
     p->phi_grip_h = has_grip ? dup_h(d->phi_grip_h, nt) : nullptr;
 
@@ -48,7 +51,7 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     // one device block: 4 tables + 2 knot vectors + slot map (all 4-byte elements)
-    const size_t total = 4 * nt + nkj + nkg + BEAST_MAX_SLOTS;
+    const size_t total = 3 * nt + ntc + nkj + nkg + BEAST_MAX_SLOTS;
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->dev_block, total * sizeof(float));
     if (e != cudaSuccess) { beast_plan_destroy((beast_plan_t*)p); return (int)e; }
     float* host = (float*)calloc(total, sizeof(float));
@@ -61,7 +64,7 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
     };
     put(d->proj_joint_h, nt, &p->proj_joint_d);
     put(has_grip ? d->proj_grip_h : nullptr, nt, &p->proj_grip_d);
-    put(d->phi_joint_h, nt, &p->phi_joint_d);
+    put(d->phi_joint_h, ntc, &p->phi_joint_d);
     put(has_grip ? d->phi_grip_h : nullptr, nt, &p->phi_grip_d);
     put(d->knots_joint_h, nkj, &p->knots_joint_d);
     put(has_grip ? d->knots_grip_h : nullptr, nkg, &p->knots_grip_d);

@@ -192,7 +192,12 @@ decode_generic_kernel(const long long* __restrict__ tokens, const float* __restr
                       const float* __restrict__ times, const float* __restrict__ knots_j,
                       const float* __restrict__ knots_g, float tau, const float* __restrict__ w_min,
                       const float* __restrict__ w_max, float vm1, long long offset,
-                      const float* __restrict__ init_p, float* __restrict__ out) {
+                      const float* __restrict__ init_p, int ico, int eco, const float* __restrict__ bc,
+                      const float* __restrict__ bias, float* __restrict__ out) {
+    // Pinned control points (init/end condition orders, mp/uni_bspline.py:126-166): joint slot s of
+    // trajectory b evaluates cat[bc[b,s,:ico], c[0..nb), bc[b,s,ico:]] against the nc-column basis and
+    // adds bias[b,s] (the trajectory's init_pos).
+    const int nc = nb + ico + eco, nbc = ico + eco;
     float Nj[kMaxEvalKnots];
     float Ng[kMaxEvalKnots];
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_rows;
@@ -204,19 +209,23 @@ decode_generic_kernel(const long long* __restrict__ tokens, const float* __restr
         if (times) {
             // linear_phase.py:22-23 with delay = 0: clip(t / tau, 0, 1)
             const float u = clampf(__fdiv_rn(__fsub_rn(times[idx], 0.0f), tau), 0.0f, 1.0f);
-            deboor_basis(knots_j, nb, degree_p, u, Nj);
+            deboor_basis(knots_j, nc, degree_p, u, Nj);
             rj = Nj;
             if (n_joint < D) deboor_basis(knots_g, nb, 0, u, Ng);
             rg = Ng;
         } else {
-            rj = phi_j + (long long)t * nb;
+            rj = phi_j + (long long)t * nc;
             rg = phi_g + (long long)t * nb;
         }
         const long long row = (long long)D * nb;
         for (int slot = 0; slot < D; ++slot) {
             const int dof = slot_to_dof[slot];
-            const float* r = slot < n_joint ? rj : rg;
+            const bool pinned = nbc > 0 && slot < n_joint;
+            const float* r = slot < n_joint ? rj + ico : rg;
+            const float* pin = pinned ? bc + (b * n_joint + slot) * nbc : nullptr;
             float acc = 0.0f;
+            if (pinned)
+                for (int c = 0; c < ico; ++c) acc = fmaf(rj[c], pin[c], acc);
             for (int k = 0; k < nb; ++k) {
                 float c;
                 if (FROM_TOKENS) {
@@ -227,6 +236,10 @@ decode_generic_kernel(const long long* __restrict__ tokens, const float* __restr
                 }
                 if (k == 0 && init_p && slot < n_joint) c = init_p[b * D + dof];
                 acc = fmaf(r[k], c, acc);
+            }
+            if (pinned) {
+                for (int c = 0; c < eco; ++c) acc = fmaf(rj[ico + nb + c], pin[ico + c], acc);
+                if (bias) acc = __fadd_rn(acc, bias[b * n_joint + slot]);
             }
             out[idx * D + dof] = acc;
         }
@@ -306,13 +319,8 @@ static int launch_dec_fast(const Plan* p, const long long* tokens, long long n_t
     static_assert(8 * NB + 4 <= 4 * T, "token tile (+ init_p) must fit under the output tile");
     const size_t smem = (size_t)kDecStages * ((((size_t)S * T * p->D * 4u) + 127u) & ~(size_t)127u);
     if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<T, NB, DT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_smem = smem;
-    }
+    static size_t granted[kMaxDevices] = {};
+    if (int rc = opt_in_smem(decode_fast_kernel<T, NB, DT>, smem, granted)) return rc;
     const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
     decode_fast_kernel<T, NB, DT><<<grid, kDecThreads, smem, st>>>(tab, a);
     count_launch();
@@ -322,20 +330,23 @@ static int launch_dec_fast(const Plan* p, const long long* tokens, long long n_t
 
 static int launch_generic(const Plan* p, const long long* tokens, const float* params, long long B, int Tq,
                           const float* times, const float* w_min, const float* w_max, long long offset,
-                          const float* init_p, float* out, cudaStream_t st) {
-    if (times && p->nb + p->degree_p + 1 > kMaxEvalKnots) return BEAST_E_UNSUPPORTED;
+                          const float* init_p, const float* bc, const float* bias, float* out, cudaStream_t st) {
+    if (times && p->nc + p->degree_p + 1 > kMaxEvalKnots) return BEAST_E_UNSUPPORTED;
+    if ((p->ico + p->eco > 0) && p->n_joint > 0 && !bc) return BEAST_E_NULL;   // pinned points are required
     const long long n_rows = B * Tq;
     const int grid = dec_grid_for(n_rows, 128, p->num_sms);
     if (tokens)
         decode_generic_kernel<true><<<grid, 128, 0, st>>>(tokens, nullptr, n_rows, Tq, p->D, p->nb, p->n_joint,
                                                           p->degree_p, p->slot_to_dof_d, p->phi_joint_d, p->phi_grip_d,
                                                           times, p->knots_joint_d, p->knots_grip_d, p->tau, w_min,
-                                                          w_max, (float)(p->V - 1), offset, init_p, out);
+                                                          w_max, (float)(p->V - 1), offset, init_p, p->ico, p->eco,
+                                                          bc, bias, out);
     else
         decode_generic_kernel<false><<<grid, 128, 0, st>>>(nullptr, params, n_rows, Tq, p->D, p->nb, p->n_joint,
                                                            p->degree_p, p->slot_to_dof_d, p->phi_joint_d,
                                                            p->phi_grip_d, times, p->knots_joint_d, p->knots_grip_d,
-                                                           p->tau, nullptr, nullptr, 0.0f, 0, init_p, out);
+                                                           p->tau, nullptr, nullptr, 0.0f, 0, init_p, p->ico, p->eco,
+                                                           bc, bias, out);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -356,7 +367,7 @@ extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens,
     cudaStream_t st = (cudaStream_t)stream;
     const int T = p->T, D = p->D, nb = p->nb;
     long long done = 0;
-    if (T == 50 && nb == 10 && !dec_fast_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
+    if (T == 50 && nb == 10 && p->nc == nb && !dec_fast_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
         (!init_p || dec_aligned16(init_p))) {
         const int S = (kDecColumns / D) & ~3;
         if (S >= 4 && B >= S) {
@@ -374,7 +385,7 @@ extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens,
     }
     if (done < B)
         return launch_generic(p, (const long long*)tokens + done * (long long)D * nb, nullptr, B - done, T, nullptr,
-                              w_min, w_max, offset, init_p ? init_p + done * D : nullptr,
+                              w_min, w_max, offset, init_p ? init_p + done * D : nullptr, nullptr, nullptr,
                               traj_out + done * (long long)T * D, st);
     return BEAST_OK;
 }
@@ -386,8 +397,8 @@ extern "C" int beast_decode_times_f32(const beast_plan_t* plan, const int64_t* t
     if (!p || !w_min || !w_max || (B > 0 && (!tokens || !traj_out || !times))) return BEAST_E_NULL;
     if (B < 0 || Tq < 0) return BEAST_E_SHAPE;
     if (B == 0 || Tq == 0) return BEAST_OK;
-    return launch_generic(p, (const long long*)tokens, nullptr, B, Tq, times, w_min, w_max, offset, init_p, traj_out,
-                          (cudaStream_t)stream);
+    return launch_generic(p, (const long long*)tokens, nullptr, B, Tq, times, w_min, w_max, offset, init_p, nullptr,
+                          nullptr, traj_out, (cudaStream_t)stream);
 }
 
 extern "C" int beast_eval_f32(const beast_plan_t* plan, const float* params, int64_t B, const float* init_p,
@@ -398,8 +409,24 @@ extern "C" int beast_eval_f32(const beast_plan_t* plan, const float* params, int
     if (B == 0) return BEAST_OK;
     const int tq = times ? Tq : p->T;
     if (tq == 0) return BEAST_OK;
-    return launch_generic(p, nullptr, params, B, tq, times, nullptr, nullptr, 0, init_p, traj_out,
+    return launch_generic(p, nullptr, params, B, tq, times, nullptr, nullptr, 0, init_p, nullptr, nullptr, traj_out,
                           (cudaStream_t)stream);
+}
+
+extern "C" int beast_reconstruct_bc_f32(const beast_plan_t* plan, const int64_t* tokens, const float* params,
+                                        int64_t B, const float* w_min, const float* w_max, int64_t offset,
+                                        const float* init_p, const float* times, int32_t Tq, const float* bc,
+                                        const float* bias, float* traj_out, void* stream) {
+    const Plan* p = (const Plan*)plan;
+    if (!p || (B > 0 && (!traj_out || (!tokens && !params)))) return BEAST_E_NULL;
+    if (tokens && params) return BEAST_E_SHAPE;
+    if (tokens && (!w_min || !w_max)) return BEAST_E_NULL;
+    if (B < 0 || Tq < 0) return BEAST_E_SHAPE;
+    if (B == 0) return BEAST_OK;
+    const int tq = times ? Tq : p->T;
+    if (tq == 0) return BEAST_OK;
+    return launch_generic(p, (const long long*)tokens, params, B, tq, times, w_min, w_max, offset, init_p, bc, bias,
+                          traj_out, (cudaStream_t)stream);
 }
 
 extern "C" int beast_dequantize_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B, const float* w_min,

@@ -346,13 +346,8 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
     const size_t smem = (size_t)kEncStages * ((((size_t)S * T * p->D * 4u) + 127u) & ~(size_t)127u);
     static_assert(12 * NB <= 4 * T, "staged outputs must fit over the input tile");
     if ((int)smem > p->max_smem_optin) return BEAST_E_UNSUPPORTED;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(encode_fast_kernel<T, NB, DT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_smem = smem;
-    }
+    static size_t granted[kMaxDevices] = {};
+    if (int rc = opt_in_smem(encode_fast_kernel<T, NB, DT>, smem, granted)) return rc;
     const int grid = (int)(n_tiles < p->num_sms ? n_tiles : p->num_sms);
     encode_fast_kernel<T, NB, DT><<<grid, kEncThreads, smem, st>>>(tab, a);
     count_launch();

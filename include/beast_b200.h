@@ -43,10 +43,16 @@ enum {
  *   proj_joint_h [num_basis*seq_len] row-major [k][t] : P = (Phi^T Phi + 1e-9 I)^-1 Phi^T, the
  *        closed form of the ridge solve at MP_lite_PyTorch/mp_pytorch/mp/uni_bspline.py:559-586
  *   proj_grip_h  same for the degree-0 gripper spline (NULL when n_joint == num_dof)
- *   phi_joint_h  [seq_len*num_basis] row-major [t][k] : basis at the tokenizer's own times
- *        (basis_gn/uni_bspline_basis.py:59-113); phi_grip_h likewise (NULL if no grippers)
- *   knots_joint_h [num_basis+degree_p+1], knots_grip_h [num_basis+1] : knot vectors (:48-55),
- *        used when the caller supplies its own evaluation times. */
+ *   phi_joint_h  [seq_len*num_ctrlp] row-major [t][c] : basis at the tokenizer's own times
+ *        (basis_gn/uni_bspline_basis.py:59-113), num_ctrlp = num_basis + init_cond_order +
+ *        end_cond_order (:40); phi_grip_h [seq_len*num_basis] likewise (NULL if no grippers)
+ *   knots_joint_h [num_ctrlp+degree_p+1], knots_grip_h [num_basis+1] : knot vectors (:48-55),
+ *        used when the caller supplies its own evaluation times.
+ *   init_cond_order / end_cond_order (0, 1 or 2): how many leading / trailing control points of
+ *        every JOINT spline are pinned by boundary conditions instead of being tokens
+ *        (mp/uni_bspline.py:500-537).  proj_joint_h then already folds the conditions in
+ *        (they are linear in the trajectory); decode takes the pinned points per trajectory
+ *        through beast_reconstruct_bc_f32. */
 typedef struct beast_plan_desc {
     int32_t seq_len;
     int32_t num_dof;
@@ -62,6 +68,8 @@ typedef struct beast_plan_desc {
     const float* phi_grip_h;
     const float* knots_joint_h;
     const float* knots_grip_h;
+    int32_t init_cond_order;
+    int32_t end_cond_order;
 } beast_plan_desc_t;
 
 typedef struct beast_plan beast_plan_t;
@@ -109,6 +117,22 @@ int beast_decode_times_f32(const beast_plan_t* plan, const int64_t* tokens, int6
                            const float* w_min, const float* w_max, int64_t offset,
                            const float* init_p, const float* times, int32_t Tq,
                            float* traj_out, void* stream);
+
+/* ---- K3 with pinned control points (init/end condition orders 1, 2).  Replaces
+ * UniformBSpline.get_traj_pos when `params_init` / `params_end` are set
+ * (MP_lite_PyTorch/mp_pytorch/mp/uni_bspline.py:126-166, as reached from reconstruct_traj /
+ * reconstruct_traj_continuous, beast/beast_bspline_tokenizer.py:498-582):
+ *   exactly one of tokens [B, nb*D] int64 / params [B, D*nb] fp32 ('(d t)') is non-NULL
+ *   bc   [B, n_joint, init_cond_order + end_cond_order] fp32: the pinned control points of every
+ *        joint slot (leading ones first), as the reference's MP object holds them after a fit
+ *   bias [B, n_joint] fp32 (nullable): added to every sample (the fit's init_pos)
+ *   times [B, Tq] (nullable: the plan's own times, Tq ignored)
+ * A plan with both orders 0 accepts bc = bias = NULL and then equals beast_decode_times_f32 /
+ * beast_eval_f32. */
+int beast_reconstruct_bc_f32(const beast_plan_t* plan, const int64_t* tokens, const float* params, int64_t B,
+                             const float* w_min, const float* w_max, int64_t offset, const float* init_p,
+                             const float* times, int32_t Tq, const float* bc, const float* bias,
+                             float* traj_out, void* stream);
 
 /* decode() alone (:483-496, utils.py:20-26): tokens -> coefficients [B, D*nb] '(d t)'. */
 int beast_dequantize_f32(const beast_plan_t* plan, const int64_t* tokens, int64_t B,

@@ -306,6 +306,156 @@ def reconstruct_traj(tokens, times, tau, num_basis, degree_p, joint_idx, grip_id
 
 
 # --------------------------------------------------------------------------
+# init / end condition orders 1 and 2 (joint spline only; goal basis and
+# end order -1 are not reachable through BEASTBsplineTokenizer)
+# --------------------------------------------------------------------------
+def boundary_state(trajs_joint, times, init_order: int, end_order: int) -> dict:
+    """Boundary position / finite-difference velocity the reference reads off
+    the trajectory itself (mp/uni_bspline.py:507-531): init_pos = y[0],
+    init_vel = (y[1]-y[0]) * (1/dt), end_pos = y[-1] (made RELATIVE to
+    init_pos when init_order != 0, :90-91), end_vel = (y[-1]-y[-2]) * (1/dt),
+    dt = times[1]-times[0]."""
+    y = np.asarray(trajs_joint, dtype=F32)
+    t = np.asarray(times, dtype=F32)
+    if t.ndim == 1:
+        t = np.broadcast_to(t, (y.shape[0], t.shape[0]))
+    inv_dt = (F32(1) / (t[:, 1] - t[:, 0]).astype(F32)).astype(F32)[:, None]
+    st = {"init_pos": None, "init_vel": None, "end_pos": None, "end_vel": None}
+    if init_order != 0:
+        st["init_pos"] = y[:, 0, :].copy()
+        st["init_vel"] = ((y[:, 1, :] - y[:, 0, :]).astype(F32) * inv_dt).astype(F32)
+    if end_order != 0:
+        end_pos = y[:, -1, :].copy()
+        if st["init_pos"] is not None:
+            end_pos = (end_pos - st["init_pos"]).astype(F32)
+        st["end_pos"] = end_pos
+        st["end_vel"] = ((y[:, -1, :] - y[:, -2, :]).astype(F32) * inv_dt).astype(F32)
+    return st
+
+
+def boundary_ctrl_points(st: dict, tau: float, knots: np.ndarray, degree_p: int, num_ctrlp: int,
+                         init_order: int, end_order: int):
+    """Pinned control points (basis_gn/uni_bspline_basis.py:192-229 with
+    init_pos = 0 as passed at mp/uni_bspline.py:76-78, and :231-274):
+      init: [0, ((init_vel*tau) * (k[1+p]-k[1])) / p + 0]
+      end : [end_pos - ((end_vel*tau) * (k[nc-1+p]-k[nc-1])) / p, end_pos]
+    each [B, d, order]; None for order 0."""
+    p_init = p_end = None
+    if init_order != 0:
+        zero = np.zeros_like(st["init_pos"], dtype=F32)
+        p_init = zero[..., None]
+        if init_order == 2:
+            dk = F32(knots[1 + degree_p] - knots[1])
+            v = ((((st["init_vel"] * F32(tau)).astype(F32) * dk).astype(F32) / F32(degree_p)).astype(F32)
+                 + zero).astype(F32)
+            p_init = np.concatenate([p_init, v[..., None]], axis=-1)
+    if end_order != 0:
+        ep = st["end_pos"]
+        p_end = ep[..., None]
+        if end_order == 2:
+            dk = F32(knots[num_ctrlp - 1 + degree_p] - knots[num_ctrlp - 1])
+            v = (ep - (((st["end_vel"] * F32(tau)).astype(F32) * dk).astype(F32) / F32(degree_p)).astype(F32)
+                 ).astype(F32)
+            p_end = np.concatenate([v[..., None], p_end], axis=-1)
+    return p_init, p_end
+
+
+def fit_joint_with_conditions(trajs_joint, times, tau, num_basis, degree_p, init_order, end_order,
+                              reg: float = 1e-9):
+    """learn_mp_params_from_trajs with pinned boundary control points
+    (mp/uni_bspline.py:471-602): subtract the pinned points' contribution
+    (and init_pos) from the trajectory, ridge-fit the remaining num_basis
+    columns of the [T, num_ctrlp] basis.  Returns (params [B, d*nb], state)
+    where state carries what the reference's MP object keeps for the next
+    reconstruct: init_pos, ctrl_init, ctrl_end (+ the returned dict entries)."""
+    y = np.asarray(trajs_joint, dtype=F32)
+    Bn, T, d = y.shape
+    nc = num_basis + init_order + end_order
+    knots = knot_vector(nc, degree_p)
+    phi_full = bspline_basis(times, tau, nc, degree_p)                    # [T, nc]
+    st = boundary_state(y, times, init_order, end_order)
+    p_init, p_end = boundary_ctrl_points(st, tau, knots, degree_p, nc, init_order, end_order)
+    parts = []
+    if p_init is not None:
+        parts.append(p_init)
+    parts.append(np.zeros((Bn, d, num_basis), dtype=F32))
+    if p_end is not None:
+        parts.append(p_end)
+    dummy = np.concatenate(parts, axis=-1)                                # [B, d, nc]
+    pos_det = np.einsum('tk,bdk->btd', phi_full, dummy).astype(F32)
+    if init_order != 0:
+        pos_det = (pos_det + st["init_pos"][:, None, :]).astype(F32)
+    pos_w = (y - pos_det).astype(F32)
+    phi_learn = phi_full[:, init_order:nc - end_order]
+    params = fit_mp(phi_learn, pos_w, reg)
+    state = dict(st)
+    state["ctrl_init"], state["ctrl_end"] = p_init, p_end
+    # the dict learn_mp_params_from_trajs returns (:597-602): end_pos made absolute again
+    state["ret_end_pos"] = ((st["end_pos"] + st["init_pos"]).astype(F32)
+                            if st["end_pos"] is not None and st["init_pos"] is not None else st["end_pos"])
+    return params, state
+
+
+def eval_joint_with_conditions(params_joint, state, times, tau, num_basis, degree_p, init_order, end_order):
+    """get_traj_pos with pinned control points (mp/uni_bspline.py:126-166):
+    cat[ctrl_init, params, ctrl_end] against the full basis, + init_pos.
+    params_joint [B, d, nb] -> [B, T', d]."""
+    nc = num_basis + init_order + end_order
+    parts = []
+    if state.get("ctrl_init") is not None:
+        parts.append(state["ctrl_init"])
+    parts.append(np.asarray(params_joint, dtype=F32))
+    if state.get("ctrl_end") is not None:
+        parts.append(state["ctrl_end"])
+    full = np.concatenate(parts, axis=-1)
+    phi = bspline_basis(np.asarray(times, dtype=F32), tau, nc, degree_p)
+    sub = 'tk,bdk->btd' if phi.ndim == 2 else 'btk,bdk->btd'
+    pos = np.einsum(sub, phi, full).astype(F32)
+    if state.get("init_pos") is not None:
+        pos = (pos + state["init_pos"][:, None, :]).astype(F32)
+    return pos
+
+
+def compute_weights_cond(trajs, times, tau, num_basis, degree_p, joint_idx, grip_idx, init_order, end_order):
+    """compute_weights / the fit half of encode for non-zero condition orders:
+    conditions apply to the joint MP only (beast_bspline_tokenizer.py:79-96)."""
+    trajs = np.asarray(trajs, dtype=F32)
+    w, state = fit_joint_with_conditions(trajs[..., joint_idx], times, tau, num_basis, degree_p,
+                                         init_order, end_order)
+    if len(grip_idx) > 0:
+        wg = fit_mp(bspline_basis(times, tau, num_basis, 0), trajs[..., grip_idx])
+        w = np.concatenate([w, wg], axis=-1)
+    return w.astype(F32), state
+
+
+def reconstruct_from_params_cond(params, state, times, tau, num_basis, degree_p, joint_idx, grip_idx,
+                                 init_order, end_order, init_p=None, use_init_pos=True):
+    """reconstruct_traj after decode (beast_bspline_tokenizer.py:503-536) when the joint MP
+    carries pinned control points from its last fit (`state`)."""
+    params = np.array(params, dtype=F32, copy=True)
+    Bn = params.shape[0]
+    nj, ng = len(joint_idx), len(grip_idx)
+    D = nj + ng
+    p3 = params.reshape(Bn, D, num_basis)
+    if use_init_pos and init_p is not None:
+        init_p = np.asarray(init_p, dtype=F32)
+        for i, j in enumerate(joint_idx):
+            p3[:, i, 0] = init_p[:, j]
+    joint_pos = eval_joint_with_conditions(p3[:, :nj], state, times, tau, num_basis, degree_p,
+                                           init_order, end_order)
+    pos = np.zeros((Bn, joint_pos.shape[1], D), dtype=F32)
+    for i, j in enumerate(joint_idx):
+        pos[..., j] = joint_pos[..., i]
+    if ng > 0:
+        phi_g = bspline_basis(np.asarray(times, dtype=F32), tau, num_basis, 0)
+        sub = 'tk,bdk->btd' if phi_g.ndim == 2 else 'btk,bdk->btd'
+        gp = np.einsum(sub, phi_g, p3[:, nj:]).astype(F32)
+        for i, j in enumerate(grip_idx):
+            pos[..., j] = gp[..., i]
+    return pos
+
+
+# --------------------------------------------------------------------------
 # bounds
 # --------------------------------------------------------------------------
 def bounds_minmax(params):

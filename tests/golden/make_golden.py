@@ -149,9 +149,59 @@ def bpe_case(ref, name, *, bpe_vocab_size, fit_batches, fit_seed0, max_sequences
     print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+COND_ORDERS = [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)]
+
+
+def cond_case(ref, name, *, batch=16, seed=31, custom_T=37):
+    """Non-zero init/end condition orders (MP_lite_PyTorch/mp_pytorch/mp/uni_bspline.py:500-537):
+    the first/last control points of every JOINT spline are pinned to the trajectory's boundary
+    position (order 1) and velocity (order 2).  The reference keeps those boundary control points
+    as state of its MP object, so reconstruct_traj uses the ones of the LAST fit — recorded here
+    with a second encode on other data in between ("stale" outputs)."""
+    cfg = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
+               gripper_indices=[6, 13], device="cpu")
+    x = synth(batch, 50, 14, seed)
+    x2 = synth(batch, 50, 14, seed + 1)
+    g = torch.Generator().manual_seed(seed + 99)
+    out = {"trajs": npy(x), "trajs_other": npy(x2),
+           "orders": np.asarray(COND_ORDERS, dtype=np.int64)}
+    for io, eo in COND_ORDERS:
+        tok = ref.BEASTBsplineTokenizer(init_cond_order=io, end_cond_order=eo, **cfg)
+        k = f"o{io}{eo}_"
+        out[k + "phi_joint"] = npy(tok.mp.basis_gn.basis(tok.times))
+        out[k + "knots_joint"] = npy(tok.mp.basis_gn.knots_vec)
+        tok.update_weights_bounds(x)
+        out[k + "w_min"], out[k + "w_max"] = npy(tok.w_min).copy(), npy(tok.w_max).copy()
+        toks, pd = tok.encode(x)
+        out[k + "tokens"], out[k + "params"] = npy(toks), npy(pd["params"])
+        for key in ("init_pos", "init_vel", "end_pos", "end_vel"):
+            if pd[key] is not None:
+                out[k + key] = npy(pd[key])
+        out[k + "recon"] = npy(tok.reconstruct_traj(toks))
+        init_p = x[:, 0, :] + 0.001
+        out[k + "recon_initp"] = npy(tok.reconstruct_traj(toks, init_p=init_p))
+        tt = torch.sort(torch.rand(batch, custom_T, generator=g) * float(tok.duration), dim=1)[0]
+        tt[:, 0] = 0.0
+        tt[:, -1] = float(tok.times[-1])
+        out[k + "custom_times"] = npy(tt)
+        out[k + "recon_custom_times"] = npy(tok.reconstruct_traj(toks, times=tt))
+        ctoks, _ = tok.encode_continuous(x)
+        out[k + "cont_tokens"] = npy(ctoks)
+        tok.encode(x2)                                    # boundary state now belongs to x2
+        out[k + "recon_stale"] = npy(tok.reconstruct_traj(toks))
+        l2, l1 = (float(v) for v in tok.compute_reconstruction_error(x))
+        out[k + "recon_err"] = np.asarray([l2, l1], dtype=np.float64)
+    out["init_p"] = npy(x[:, 0, :] + 0.001)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 def main():
     ref = import_reference()
     import tokenizers
+    if "--only-cond" in sys.argv:                         # add the newest case without touching the others
+        cond_case(ref, "cond_orders")
+        return
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:
         json.dump({"torch": torch.__version__, "numpy": np.__version__,
                    "tokenizers": tokenizers.__version__,
@@ -175,6 +225,8 @@ def main():
     bpe_case(ref, "bpe_d14_small", bpe_vocab_size=400, fit_batches=8, fit_seed0=2000, max_sequences=200)
     # a 1000-bin tokenizer (the CLI default vocab): shifted bins are codepoints up to U+03E7 (2-byte UTF-8)
     bpe_case(ref, "bpe_v1000", bpe_vocab_size=1600, fit_batches=24, fit_seed0=3000, vocab_size=1000)
+    # init/end condition orders 1 and 2 on the bimanual config
+    cond_case(ref, "cond_orders")
 
 
 if __name__ == "__main__":

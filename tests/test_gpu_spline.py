@@ -323,3 +323,85 @@ def test_clamped_and_extreme_bounds():
     ora = O.reconstruct_from_params(coeff, tok.times.numpy(), 2 * math.pi, 10, 4, joint, grip)
     fin = np.isfinite(ora) & (np.abs(ora) < 1e20)
     assert np.abs(rec[fin] - ora[fin]).max() <= 1e-5 * np.abs(ora[fin]).max()
+
+
+# ---------------------------------------------------------------- init / end condition orders
+COND_CFG = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, degree_p=4,
+                gripper_zero_order=True, gripper_indices=[6, 13], llm_vocab_size=None)
+
+
+@pytest.mark.parametrize("orders", [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)])
+def test_condition_orders_vs_golden(orders):
+    """Pinned boundary control points (mp/uni_bspline.py:500-537, 126-166): same K1 with the
+    conditions folded into the projector, K3 with the pinned points of the last fit — compared with
+    the live reference's outputs, including its stateful ("stale") reconstruct."""
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    io, eo = orders
+    g = load_golden("cond_orders")
+    k = f"o{io}{eo}_"
+    tok = BEASTBsplineTokenizer(device="cuda", init_cond_order=io, end_cond_order=eo, **COND_CFG)
+    x, x2 = torch.from_numpy(g["trajs"]), torch.from_numpy(g["trajs_other"])
+    with pytest.raises(RuntimeError):
+        tok.reconstruct_traj(torch.from_numpy(g[k + "tokens"]))       # no fit yet: no boundary state
+    tok.update_weights_bounds(x)
+    assert rel_err(tok.w_min.cpu().numpy(), g[k + "w_min"]) <= TOL
+    assert rel_err(tok.w_max.cpu().numpy(), g[k + "w_max"]) <= TOL
+    tok.w_min.copy_(torch.from_numpy(g[k + "w_min"]))
+    tok.w_max.copy_(torch.from_numpy(g[k + "w_max"]))
+    tokens, pd = tok.encode(x)
+    params = pd["params"].cpu().numpy()
+    assert rel_err(params, g[k + "params"]) <= TOL
+    flips = check_flips(tokens.cpu().numpy(), g[k + "tokens"], g[k + "params"], g[k + "w_min"], g[k + "w_max"],
+                        COND_CFG)
+    print(f"orders {orders}: {len(flips)} / {tokens.numel()} bin flips vs reference: {flips[:5]}")
+    assert np.array_equal(tok._quantize(torch.from_numpy(g[k + "params"])).cpu().numpy(), g[k + "tokens"])
+    for key in ("init_pos", "init_vel", "end_pos", "end_vel"):
+        if k + key in g:
+            assert rel_err(pd[key].cpu().numpy(), g[k + key]) <= 1e-6, key
+        else:
+            assert pd[key] is None
+    ref_tokens = torch.from_numpy(g[k + "tokens"])
+    assert rel_err(tok.reconstruct_traj(ref_tokens).cpu().numpy(), g[k + "recon"]) <= TOL
+    init_p = torch.from_numpy(g["init_p"])
+    assert rel_err(tok.reconstruct_traj(ref_tokens, init_p=init_p).cpu().numpy(), g[k + "recon_initp"]) <= TOL
+    tt = torch.from_numpy(g[k + "custom_times"])
+    assert rel_err(tok.reconstruct_traj(ref_tokens, times=tt).cpu().numpy(), g[k + "recon_custom_times"]) <= TOL
+    ctoks, _ = tok.encode_continuous(x)
+    n = tok._normalize(torch.from_numpy(g[k + "params"])).cpu().numpy()
+    assert np.array_equal(n, g[k + "cont_tokens"])                    # bit-exact given the reference coefficients
+    assert np.abs(ctoks.cpu().numpy() - g[k + "cont_tokens"]).max() <= 2.0 * TOL * np.abs(g[k + "params"]).max() / \
+        max(float((g[k + "w_max"] - g[k + "w_min"]).min()), 1e-8) + 1e-6
+    rc = tok.reconstruct_traj_continuous(ctoks).cpu().numpy()
+    # the oracle evaluates the same coefficients with the same pinned points
+    joint, grip = layout(COND_CFG)
+    times = O.linspace_f32(0, 2 * math.pi, 50)
+    _, st = O.compute_weights_cond(g["trajs"], times, 2 * math.pi, 10, 4, joint, grip, io, eo)
+    ro = O.reconstruct_from_params_cond(params, st, times, 2 * math.pi, 10, 4, joint, grip, io, eo)
+    assert rel_err(rc, ro) <= 5e-5                                    # normalise/denormalise round trip in between
+    # state semantics: after fitting other data the same tokens reconstruct with THAT boundary state
+    tok.encode(x2)
+    assert rel_err(tok.reconstruct_traj(ref_tokens).cpu().numpy(), g[k + "recon_stale"]) <= TOL
+    with pytest.raises(RuntimeError):
+        tok.reconstruct_traj(ref_tokens[:5])                          # batch no longer matches the state
+    l2, l1 = tok.compute_reconstruction_error(x)
+    assert abs(float(l2) - g[k + "recon_err"][0]) <= 1e-5 * max(1.0, abs(g[k + "recon_err"][0])) + 1e-9
+
+
+def test_condition_orders_large_batch_matches_oracle():
+    """Orders (2, 2) on a batch that exercises the fast K1 tiles + ragged tail."""
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    from beast_tokenizer_b200.synth import synth
+    tok = BEASTBsplineTokenizer(device="cuda", init_cond_order=2, end_cond_order=2, **COND_CFG)
+    x = synth(32 * 37 + 11, 50, 14, seed=77)
+    tok.update_weights_bounds(x)
+    tokens, pd = tok.encode(x)
+    joint, grip = layout(COND_CFG)
+    times = O.linspace_f32(0, 2 * math.pi, 50)
+    w, st = O.compute_weights_cond(x.numpy(), times, 2 * math.pi, 10, 4, joint, grip, 2, 2)
+    params = pd["params"].cpu().numpy()
+    assert rel_err(params, w) <= TOL
+    lo, hi = tok.w_min.cpu().numpy(), tok.w_max.cpu().numpy()
+    assert np.array_equal(tokens.cpu().numpy(), O.tokens_from_params(params, lo, hi, 256, 14, 10))
+    dec = O.decode(tokens.cpu().numpy(), lo, hi, 256, 14, 10)
+    ro = O.reconstruct_from_params_cond(dec, st, times, 2 * math.pi, 10, 4, joint, grip, 2, 2)
+    assert rel_err(tok.reconstruct_traj(tokens).cpu().numpy(), ro) <= TOL

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, GOLDEN_CASES, ROOT, load_golden
+from conftest import GOLDEN, GOLDEN_CASES, ROOT, load_golden, rel_err
 
 
 def test_host_constants_match_reference_basis(golden_case):
@@ -156,3 +156,32 @@ def test_synth_is_deterministic():
     assert np.array_equal(synth(96, 50, 14, 2).numpy(), g["trajs"])
     batches = list(SyntheticLoader(2, 32, 50, 14, seed0=1))
     assert len(batches) == 2 and batches[0]["actions"].shape == (32, 50, 14)
+
+
+@pytest.mark.parametrize("orders", [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)])
+def test_conditioned_projector_matches_reference(orders):
+    """Non-zero init/end condition orders stay one linear map per joint: w = P_eff . y with the
+    boundary terms folded in (basis.conditioned_projector) reproduces the reference's coefficients."""
+    import torch
+    from beast_tokenizer_b200.basis import build_constants, make_times
+    io, eo = orders
+    g = load_golden("cond_orders")
+    k = f"o{io}{eo}_"
+    joint = [i for i in range(14) if i not in (6, 13)]
+    c = build_constants(make_times(2 * math.pi, 50), 2 * math.pi, 10, 4, joint, [6, 13], io, eo)
+    assert np.array_equal(c.phi_joint.numpy(), g[k + "phi_joint"])
+    assert np.array_equal(c.knots_joint.numpy(), g[k + "knots_joint"])
+    assert tuple(c.proj_joint.shape) == (10, 50)
+    x = torch.from_numpy(g["trajs"]).double()
+    w = torch.einsum("kt,btd->bdk", c.proj_joint.double(), x[..., joint]).reshape(x.shape[0], -1).numpy()
+    assert rel_err(w, g[k + "params"][:, :120]) <= 1e-5
+
+
+def test_condition_order_ctor_errors():
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    with pytest.raises(NotImplementedError):
+        BEASTBsplineTokenizer(num_dof=2, end_cond_order=-1, device="cpu")
+    with pytest.raises(NotImplementedError):
+        BEASTBsplineTokenizer(num_dof=2, init_cond_order=3, device="cpu")
+    tok = BEASTBsplineTokenizer(num_dof=2, init_cond_order=2, end_cond_order=1, device="cpu")
+    assert tok._config["init_cond_order"] == 2 and tok._config["end_cond_order"] == 1

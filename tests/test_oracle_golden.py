@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import beast_oracle as O
-from conftest import rel_err
+from conftest import load_golden, rel_err
 
 TOL = 1e-5          # north-star tolerance for coefficients / trajectories
 
@@ -143,3 +143,51 @@ def test_torch_reference_port_matches_golden(golden_case):
     assert rel_err(rec.numpy(), g["recon_fit"]) <= 1e-6
     rec = port.reconstruct_traj(torch.from_numpy(g["tokens_fit"]), init_p=torch.from_numpy(g["init_p"]))
     assert rel_err(rec.numpy(), g["recon_fit_initp"]) <= 1e-6
+
+
+# ---------------------------------------------------------------- init / end condition orders
+COND_CFG = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, degree_p=4,
+                gripper_zero_order=True, gripper_indices=[6, 13])
+
+
+def _cond_orders():
+    return [tuple(int(v) for v in row) for row in load_golden("cond_orders")["orders"]]
+
+
+@pytest.mark.parametrize("orders", [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)])
+def test_condition_orders_oracle_matches_reference(orders):
+    """Pins the restatement of mp/uni_bspline.py:500-537 + 126-166 (pinned boundary control points)
+    against outputs of the live reference, including its stateful reconstruct."""
+    io, eo = orders
+    assert orders in _cond_orders()
+    g = load_golden("cond_orders")
+    k = f"o{io}{eo}_"
+    tau = 2 * math.pi
+    times = O.linspace_f32(0, tau, 50)
+    joint, grip = O.slot_layout(14, True, [6, 13])
+    nc = 10 + io + eo
+    assert np.array_equal(O.knot_vector(nc, 4), g[k + "knots_joint"])
+    assert np.array_equal(O.bspline_basis(times, tau, nc, 4), g[k + "phi_joint"])
+    w, st = O.compute_weights_cond(g["trajs"], times, tau, 10, 4, joint, grip, io, eo)
+    assert rel_err(w, g[k + "params"]) <= 1e-5
+    for key, have in (("init_pos", st["init_pos"]), ("init_vel", st["init_vel"]),
+                      ("end_pos", st["ret_end_pos"]), ("end_vel", st["end_vel"])):
+        if k + key in g:
+            assert np.array_equal(have, g[k + key]), key          # plain fp32 elementwise: bit-exact
+        else:
+            assert have is None
+    lo, hi = g[k + "w_min"], g[k + "w_max"]
+    assert rel_err(w.min(0), lo) <= 1e-5 and rel_err(w.max(0), hi) <= 1e-5
+    assert np.array_equal(O.tokens_from_params(g[k + "params"], lo, hi, 256, 14, 10), g[k + "tokens"])
+    dec = O.decode(g[k + "tokens"], lo, hi, 256, 14, 10)
+    args = (times, tau, 10, 4, joint, grip, io, eo)
+    assert rel_err(O.reconstruct_from_params_cond(dec, st, *args), g[k + "recon"]) <= 1e-5
+    assert rel_err(O.reconstruct_from_params_cond(dec, st, *args, init_p=g["init_p"]), g[k + "recon_initp"]) <= 1e-5
+    r = O.reconstruct_from_params_cond(dec, st, g[k + "custom_times"], tau, 10, 4, joint, grip, io, eo)
+    assert rel_err(r, g[k + "recon_custom_times"]) <= 1e-5
+    # the reference reconstructs with the boundary state of its LAST fit
+    _, st_other = O.compute_weights_cond(g["trajs_other"], times, tau, 10, 4, joint, grip, io, eo)
+    assert rel_err(O.reconstruct_from_params_cond(dec, st_other, *args), g[k + "recon_stale"]) <= 1e-5
+    assert rel_err(O.reconstruct_from_params_cond(dec, st, *args), g[k + "recon_stale"]) > 1e-3
+    cont = O.normalize_tensor(w, lo, hi).reshape(-1, 14, 10).transpose(0, 2, 1).reshape(-1, 140)
+    assert np.abs(cont - g[k + "cont_tokens"]).max() <= 2e-5
