@@ -24,8 +24,7 @@ namespace beast {
 constexpr int kBpeBlock = 128;
 constexpr uint16_t kWordStart = 0x8000u;
 constexpr uint16_t kIdMask = 0x7fffu;
-constexpr int kMaxWord = 512;            // longest pre-token (in byte-level symbols) of the common encode kernel
-constexpr int kMaxWordLong = 8192;       // long-sequence variant (e.g. 1600 bins x 2 bytes)
+constexpr int kMaxWordLong = 8192;       // longest pre-token (in symbols) of the thread-per-sequence encode kernel
 
 // Corpus layout ("chunk-major"): the symbols of sequence `seq` live in 16-byte chunks of 8,
 // chunk c of all sequences contiguous:  sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)].
@@ -73,7 +72,8 @@ __device__ __forceinline__ int utf8_encode(int c, int (&b)[3]) {
 }
 
 // Length of the pre-token starting at codepoint i of cp[0..n) (shared memory).
-__device__ __forceinline__ int pretoken_len(const uint16_t* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
+template <typename CP>
+__device__ __forceinline__ int pretoken_len(const CP* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
     const int c = cp[i];
     if (c == 39 && i + 1 < n) {                              // 's|'t|'re|'ve|'m|'ll|'d
         const int d = cp[i + 1];
@@ -98,18 +98,21 @@ __device__ __forceinline__ int pretoken_len(const uint16_t* cp, int i, int n, co
     return 1;                                                // \s+
 }
 
-// Cooperative load of kBpeBlock rows of bins into shared memory as shifted 16-bit codepoints.
+// Cooperative load of rows of bins into shared memory as shifted codepoints (CP = uint8_t when every
+// valid shifted bin is below 256 — half the footprint, twice the resident sequences — else uint16_t).
 // status: bit 0 = a value below min_token, bit 1 = a value above max_token (per sequence).
+template <typename CP>
 __device__ __forceinline__ void stage_rows(const long long* __restrict__ bins, long long base, long long N, int L,
-                                           long long min_token, long long max_shift, uint16_t* s_cp, int LP,
+                                           long long min_token, long long max_shift, CP* s_cp, int LP,
                                            int* s_status, int rows_per_block) {
+    constexpr long long kCpMax = sizeof(CP) == 1 ? 0xFF : 0xD7FF;
     const long long rows = (N - base) < rows_per_block ? (N - base) : rows_per_block;
     for (long long idx = threadIdx.x; idx < rows * L; idx += blockDim.x) {
         const int r = (int)(idx / L), p = (int)(idx - (long long)r * L);
         const long long v = bins[(base + r) * L + p] - min_token;
         if (v < 0) atomicOr(&s_status[r], 1);
         else if (v > max_shift) atomicOr(&s_status[r], 2);
-        s_cp[r * LP + p] = (uint16_t)(v < 0 ? 0 : (v > 0xD7FF ? 0xD7FF : v));
+        s_cp[r * LP + p] = (CP)(v < 0 ? 0 : (v > kCpMax ? kCpMax : v));
     }
 }
 
@@ -161,7 +164,7 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
     for (int i = threadIdx.x; i < rows; i += blockDim.x) s_status[i] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * rows;
-    stage_rows(bins, base, N, L, min_token, 0xD7FF, s_cp, LP, s_status, rows);
+    stage_rows<uint16_t>(bins, base, N, L, min_token, 0xD7FF, s_cp, LP, s_status, rows);
     __syncthreads();
     const long long seq = base + threadIdx.x;
     if (threadIdx.x >= rows || seq >= N) return;
@@ -573,7 +576,7 @@ bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, i
 // ---------------------------------------------------------------- encode (K5a)
 // rank_tab[a*V + b] = rank << 16 | new_id, or 0xffffffff.  One thread per sequence; the word being
 // merged lives in local memory with its pair keys cached, so a merge costs one scan + two lookups.
-template <int MAXW>
+template <int MAXW, typename CP>
 __global__ void __launch_bounds__(kBpeBlock)
 bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token, long long max_shift,
                   const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
@@ -581,20 +584,20 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
                   int* __restrict__ len_out, int* __restrict__ status_out, int rows) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
-    uint16_t* s_cp = (uint16_t*)s_raw;
-    int* s_status = (int*)(s_raw + (((size_t)rows * LP * 2 + 3) & ~(size_t)3));
+    CP* s_cp = (CP*)s_raw;
+    int* s_status = (int*)(s_raw + (((size_t)rows * LP * sizeof(CP) + 3) & ~(size_t)3));
     __shared__ short s_b2i[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
     for (int i = threadIdx.x; i < rows; i += blockDim.x) s_status[i] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * rows;
-    stage_rows(bins, base, N, L, min_token, max_shift, s_cp, LP, s_status, rows);
+    stage_rows<CP>(bins, base, N, L, min_token, max_shift, s_cp, LP, s_status, rows);
     __syncthreads();
     const long long seq = base + threadIdx.x;
     if (threadIdx.x >= rows || seq >= N) return;
     status_out[seq] = s_status[threadIdx.x];
     if (s_status[threadIdx.x]) { len_out[seq] = 0; return; }
-    const uint16_t* cp = s_cp + threadIdx.x * LP;
+    const CP* cp = s_cp + threadIdx.x * LP;
     uint16_t* out = ids_out + seq * (long long)out_stride;
     uint16_t w[MAXW];
     unsigned int key[MAXW];
@@ -629,6 +632,179 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
         for (int q = 0; q < wl; ++q) out[m++] = w[q];
     }
     len_out[seq] = m;
+}
+
+// ---------------------------------------------------------------- encode (K5a), one warp per sequence
+// The GPT-2 pre-tokeniser is a left-to-right regex, but its token starts are a LOCAL function of the
+// codepoints: a class run starts where the class changes (a single U+0020 before a non-space run joins
+// it), the last blank of a longer whitespace run splits off when text follows, and an apostrophe that
+// starts a token and is followed by s/t/m/d/re/ve/ll swallows those letters and forces a restart after
+// them.  (Checked against the sequential matcher on adversarial strings, tests/test_bpe_oracle.py.)
+__device__ __forceinline__ bool base_start(const uint16_t* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
+    if (i == 0) return true;
+    const int k = cp_class(cp[i], cls_tab), kp = cp_class(cp[i - 1], cls_tab);
+    if (k != CLS_S) {
+        if (kp == k) return false;
+        if (kp == CLS_S) return cp[i - 1] != 32;             // " ?" prefix: the blank belongs to this token
+        return true;
+    }
+    if (kp != CLS_S) return true;
+    return i + 1 < n && cp_class(cp[i + 1], cls_tab) != CLS_S;  // \s+(?!\S) leaves the last blank
+}
+__device__ __forceinline__ int contraction_len(const uint16_t* cp, int i, int n) {
+    if (i + 1 < n) {
+        const int d = cp[i + 1];
+        if (d == 's' || d == 't' || d == 'm' || d == 'd') return 2;
+        if (i + 2 < n) {
+            const int e = cp[i + 2];
+            if ((d == 'r' && e == 'e') || (d == 'v' && e == 'e') || (d == 'l' && e == 'l')) return 3;
+        }
+    }
+    return 0;
+}
+__device__ __forceinline__ bool token_start(const uint16_t* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
+    for (int back = 1; back <= 3 && back <= i; ++back) {
+        const int j = i - back;
+        if (cp[j] == 39) {
+            const int len = contraction_len(cp, j, n);
+            if (len > 0 && base_start(cp, j, n, cls_tab)) {
+                if (back < len) return false;                // inside 's / 're ...
+                if (back == len) return true;                // the matcher restarts right after it
+            }
+        }
+    }
+    return base_start(cp, i, n, cls_tab);
+}
+
+// Per warp in shared memory: key u32[M], sym u16[M], wid u16[M], cp u16[L], wbeg u16[L+2]  (M = symbols max).
+// A: stage the row (coalesced), B: every lane expands its slice of codepoints into byte-level symbols
+// tagged with their word number (one packed warp scan gives symbol and word offsets), C: pair ranks for
+// all adjacent symbols in parallel + ordered word list, D: one lane per word applies the merges lowest
+// rank first inside its own segment, E: scan of the final word lengths, ids written in order.
+__global__ void __launch_bounds__(256)
+bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token,
+                       long long max_shift, const short* __restrict__ byte_to_id,
+                       const uint8_t* __restrict__ cls_tab, const unsigned int* __restrict__ rank_tab, int V,
+                       uint16_t* __restrict__ ids_out, int out_stride, int* __restrict__ len_out,
+                       int* __restrict__ status_out, int M, int warp_bytes) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ short s_b2i[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint8_t* mine = s_raw + (size_t)warp * warp_bytes;
+    unsigned int* key = (unsigned int*)mine;
+    uint16_t* sym = (uint16_t*)(key + M);
+    uint16_t* wid = sym + M;
+    uint16_t* cp = wid + M;
+    uint16_t* wbeg = cp + ((L + 1) & ~1);
+    const int P = (L + 31) >> 5;
+    const unsigned int FULL = 0xffffffffu, NONE = 0xffffffffu;
+    for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
+        // ---- A
+        int st = 0;
+        const long long* row = bins + seq * L;
+        for (int i = lane; i < L; i += 32) {
+            const long long v = row[i] - min_token;
+            if (v < 0) st |= 1;
+            else if (v > max_shift) st |= 2;
+            cp[i] = (uint16_t)(v < 0 ? 0 : (v > 0xD7FF ? 0xD7FF : v));
+        }
+        st = __reduce_or_sync(FULL, st);
+        __syncwarp();
+        if (st) {
+            if (lane == 0) { status_out[seq] = st; len_out[seq] = 0; }
+            continue;
+        }
+        // ---- B
+        const int p0 = lane * P, p1 = min(L, p0 + P);
+        int ns = 0, nst = 0;
+        unsigned int smask = 0;
+        for (int i = p0; i < p1; ++i) {
+            int bt[3];
+            const int nbt = utf8_encode(cp[i], bt);
+            for (int r = 0; r < nbt; ++r) ns += s_b2i[bt[r]] >= 0;
+            const bool t = token_start(cp, i, L, cls_tab);
+            nst += t;
+            if (t && i - p0 < 32) smask |= 1u << (i - p0);
+        }
+        const unsigned int packed = ((unsigned int)ns << 16) | (unsigned int)nst;
+        unsigned int inc = packed;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int total = (int)(__shfl_sync(FULL, inc, 31) >> 16);
+        int off = (int)((inc - packed) >> 16), w = (int)((inc - packed) & 0xffffu);
+        for (int i = p0; i < p1; ++i) {
+            const bool t = i - p0 < 32 ? ((smask >> (i - p0)) & 1u) != 0 : token_start(cp, i, L, cls_tab);
+            w += t;
+            int bt[3];
+            const int nbt = utf8_encode(cp[i], bt);
+            for (int r = 0; r < nbt; ++r) {
+                const int id = s_b2i[bt[r]];
+                if (id >= 0) { sym[off] = (uint16_t)id; wid[off] = (uint16_t)w; ++off; }
+            }
+        }
+        __syncwarp();
+        // ---- C
+        int nwords = 0;
+        for (int s0 = 0; s0 < total; s0 += 32) {
+            const int s = s0 + lane;
+            bool isb = false;
+            if (s < total) {
+                isb = s == 0 || wid[s] != wid[s - 1];
+                key[s] = (s + 1 < total && wid[s + 1] == wid[s])
+                             ? __ldg(&rank_tab[(size_t)sym[s] * V + sym[s + 1]]) : NONE;
+            }
+            const unsigned int m = __ballot_sync(FULL, isb);
+            if (isb) wbeg[nwords + __popc(m & ((1u << lane) - 1u))] = (uint16_t)s;
+            nwords += __popc(m);
+        }
+        if (lane == 0) wbeg[nwords] = (uint16_t)total;
+        __syncwarp();
+        // ---- D
+        for (int wq = lane; wq < nwords; wq += 32) {
+            const int b = wbeg[wq];
+            int wl = wbeg[wq + 1] - b;
+            uint16_t* ws = sym + b;
+            unsigned int* wk = key + b;
+            while (wl >= 2) {
+                unsigned int best = NONE, best_rank = NONE;
+                int bp = -1;
+                for (int q = 0; q + 1 < wl; ++q) {           // lowest rank, leftmost first
+                    const unsigned int kq = wk[q];
+                    if (kq != NONE && (kq >> 16) < best_rank) { best = kq; best_rank = kq >> 16; bp = q; }
+                }
+                if (bp < 0) break;
+                ws[bp] = (uint16_t)(best & 0xffffu);
+                for (int q = bp + 1; q + 1 < wl; ++q) { ws[q] = ws[q + 1]; wk[q] = wk[q + 1]; }
+                --wl;
+                if (bp > 0) wk[bp - 1] = __ldg(&rank_tab[(size_t)ws[bp - 1] * V + ws[bp]]);
+                if (bp + 1 < wl) wk[bp] = __ldg(&rank_tab[(size_t)ws[bp] * V + ws[bp + 1]]);
+            }
+            wid[b] = (uint16_t)wl;                           // final length, kept in the word's own segment
+        }
+        __syncwarp();
+        // ---- E
+        uint16_t* out = ids_out + seq * (long long)out_stride;
+        int done = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int wq = w0 + lane;
+            int b = 0, wl = 0;
+            if (wq < nwords) { b = wbeg[wq]; wl = wid[b]; }
+            int run = wl;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, run, o);
+                if (lane >= o) run += t;
+            }
+            const int o0 = done + run - wl;
+            for (int q = 0; q < wl; ++q) out[o0 + q] = sym[b + q];
+            done += __shfl_sync(FULL, run, 31);
+        }
+        if (lane == 0) { len_out[seq] = done; status_out[seq] = 0; }
+        __syncwarp();
+    }
 }
 
 // padded rows -> CSR (offsets are an exclusive scan of len, computed by the caller)
@@ -708,12 +884,14 @@ static int bpe_grid(long long n, int block) {
 }
 
 // rows of bins staged per block: as many as fit in ~180 KB of shared memory, at most one per thread
-static int stage_rows_per_block(int L) {
-    long long r = (180 * 1024) / ((long long)(L + 1) * 2 + 4);
+static int stage_rows_per_block(int L, int cp_bytes = 2) {
+    long long r = (180 * 1024) / ((long long)(L + 1) * cp_bytes + 4);
     if (r > kBpeBlock) r = kBpeBlock;
     return (int)r;
 }
-static size_t stage_smem(int L, int rows) { return (((size_t)rows * (L + 1) * 2 + 3) & ~(size_t)3) + (size_t)rows * sizeof(int); }
+static size_t stage_smem(int L, int rows, int cp_bytes = 2) {
+    return (((size_t)rows * (L + 1) * cp_bytes + 3) & ~(size_t)3) + (size_t)rows * sizeof(int);
+}
 
 }  // namespace beast
 
@@ -871,22 +1049,42 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     const int mult = max_shift < 0x80 ? 1 : (max_shift < 0x800 ? 2 : 3);       // UTF-8 bytes per bin
     if (N < 0 || L < 1 || mult * L > kMaxWordLong || out_stride < mult * L || V < 1 || V > 65535 || max_shift > 0xD7FF)
         return BEAST_E_SHAPE;
+    const int M = mult * L;
+    if (M > 65535) return BEAST_E_SHAPE;
+    // one warp per sequence, working arrays in shared memory; sequences too long for that (or
+    // BEAST_B200_BPE_THREAD_ENCODE=1) take the one-thread-per-sequence kernel
+    const size_t warp_bytes = ((size_t)8 * M + 2 * (size_t)((L + 1) & ~1) + 2 * (size_t)(L + 2) + 15) & ~(size_t)15;
+    int warps = (int)((200 * 1024) / warp_bytes);
+    if (warps > 8) warps = 8;
+    const char* env = getenv("BEAST_B200_BPE_THREAD_ENCODE");
+    if (warps >= 1 && !(env && env[0] == '1')) {
+        const size_t smem = warp_bytes * warps;
+        static size_t granted[kMaxDevices] = {};
+        if (int rc = opt_in_smem(bpe_encode_warp_kernel, smem, granted)) return rc;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
+        if (per_sm > 2048 / (warps * 32)) per_sm = 2048 / (warps * 32);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (N + warps - 1) / warps;
+        if (grid > sms * per_sm) grid = sms * per_sm;
+        bpe_encode_warp_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
+            (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
+            len_out, status_out, M, (int)warp_bytes);
+        count_launch();
+        BEAST_CHECK_LAUNCH();
+        return BEAST_OK;
+    }
     const int rows = stage_rows_per_block(L);
     if (rows < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = stage_smem(L, rows);
-    const bool lng = mult * L > kMaxWord;
-    static size_t granted[2][kMaxDevices] = {};
-    if (int rc = lng ? opt_in_smem(bpe_encode_kernel<kMaxWordLong>, smem, granted[1])
-                     : opt_in_smem(bpe_encode_kernel<kMaxWord>, smem, granted[0])) return rc;
+    static size_t granted[kMaxDevices] = {};
+    if (int rc = opt_in_smem(bpe_encode_kernel<kMaxWordLong, uint16_t>, smem, granted)) return rc;
     const long long grid = (N + rows - 1) / rows;
-    if (lng)
-        bpe_encode_kernel<kMaxWordLong><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-            (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
-            len_out, status_out, rows);
-    else
-        bpe_encode_kernel<kMaxWord><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-            (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
-            len_out, status_out, rows);
+    bpe_encode_kernel<kMaxWordLong, uint16_t><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+        (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
+        len_out, status_out, rows);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;

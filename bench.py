@@ -191,7 +191,11 @@ def hf_train_cpu(bins_np, vocab):
         return {"engine": "oracle/bpe_oracle.c (1 thread)", "seconds": time.perf_counter() - t0, "merges": len(o.merges),
                 "merges_txt": o.merges_txt()}
     t0 = time.perf_counter()
-    strings = ["".join(map(chr, (row - mn).astype(int))) for row in bins_np]
+    # chr(bin - min) per symbol (beast/beast_bpe_trainer.py:86-92), built with one UTF-32 decode
+    flat = (bins_np - mn).astype("<u4")
+    text = flat.tobytes().decode("utf-32-le")
+    L = bins_np.shape[1]
+    strings = [text[i * L:(i + 1) * L] for i in range(bins_np.shape[0])]
     t1 = time.perf_counter()
     hf = ByteLevelBPETokenizer()
     trainer = BpeTrainer(vocab_size=vocab, min_frequency=2, show_progress=False, special_tokens=[],
@@ -206,7 +210,7 @@ def hf_train_cpu(bins_np, vocab):
             "merges_txt": "#version: 0.2\n" + "".join(m + "\n" for m in merges)}
 
 
-def bpe_legs(tok, dev, rank, world, dist, with_cpu):
+def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
     """BPE-train merges/s on the 1.6 M-sequence corpus sharded over the ranks (strong scaling), and
     BPE encode / decode sequences/s on 1 M trajectories (rank 0's GPU)."""
     import torch
@@ -250,6 +254,15 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu):
                                "sample": f"{BPE_CPU_SAMPLE} of the 1.6 M sequences (trainer cost is ~linear in the corpus)",
                                "gpu_same_sample": {"seconds": g_secs, "merges_per_s": len(st_s.tokenizer.merges) / g_secs},
                                "merge_table_identical": cpu["merges_txt"] == st_s.tokenizer.merges_txt()}
+        if cpu_full and world == 1:
+            # --bpe-cpu-full: the reference trainer on the WHOLE 1.6 M-sequence corpus (minutes of host time)
+            full = hf_train_cpu(bins.cpu().numpy(), BPE_VOCAB)
+            out["cpu_baseline"]["full_corpus"] = {
+                "sequences": int(bins.shape[0]), "seconds": full["seconds"],
+                "string_build_seconds": full.get("string_build_seconds"),
+                "merges_per_s": full["merges"] / full["seconds"], "gpu_seconds": secs,
+                "speedup_1gpu": full["seconds"] / secs,
+                "merge_table_identical": full["merges_txt"] == state.tokenizer.merges_txt()}
     # BPE encode + reconstruct (configs[4]) on device-resident CSR
     btok = BEASTBsplineBPETokenizer.from_beast(tok, bpe_vocab_size=BPE_VOCAB, device=str(dev))
     btok.set_llm_vocab_size(None)
@@ -335,6 +348,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpe", action="store_true", help="skip the BPE-train / BPE-apply legs")
+    ap.add_argument("--bpe-cpu-full", action="store_true",
+                    help="also run the reference BPE trainer on the full 1.6 M-sequence corpus (minutes of host time)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -494,7 +509,8 @@ def main():
     if not args.no_bpe:
         del xs, toks, pars, outs, xh
         torch.cuda.empty_cache()
-        bpe_train, bpe_apply = bpe_legs(tok, dev, rank, world, dist, world == 1 and not args.no_cpu_baseline)
+        bpe_train, bpe_apply = bpe_legs(tok, dev, rank, world, dist, world == 1 and not args.no_cpu_baseline,
+                                        cpu_full=args.bpe_cpu_full)
 
     if world > 1:
         t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms], device=dev, dtype=torch.float64)

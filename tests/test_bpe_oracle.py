@@ -90,3 +90,60 @@ def test_against_live_library():
         assert o.merges_lines() == hf_merges
         for r in bins[:50]:
             assert o.encode(r - mn) == hf.encode("".join(map(chr, r - mn)), add_special_tokens=False).ids
+
+
+def test_pretoken_starts_are_a_local_rule():
+    """The warp-per-sequence encode kernel (csrc/bpe.cu: base_start / token_start) finds token starts
+    with a rule that looks at most three codepoints back and one ahead.  Restated here and checked
+    against the sequential matcher of the oracle on adversarial strings."""
+    from oracle.bpe_oracle import pretokenize, unicode_classes
+    cls = unicode_classes(0x3000)
+    S = 3
+
+    def base_start(c, i):
+        n = len(c)
+        if i == 0:
+            return True
+        k, kp = cls[c[i]], cls[c[i - 1]]
+        if k != S:
+            if kp == k:
+                return False
+            if kp == S:
+                return c[i - 1] != 32
+            return True
+        if kp != S:
+            return True
+        return i + 1 < n and cls[c[i + 1]] != S
+
+    def contraction_len(c, i):
+        n = len(c)
+        if i + 1 < n:
+            d = chr(c[i + 1])
+            if d in "stmd":
+                return 2
+            if i + 2 < n and d + chr(c[i + 2]) in ("re", "ve", "ll"):
+                return 3
+        return 0
+
+    def token_start(c, i):
+        for back in range(1, min(3, i) + 1):
+            j = i - back
+            if c[j] == 39:
+                ln = contraction_len(c, j)
+                if ln > 0 and base_start(c, j):
+                    if back < ln:
+                        return False
+                    if back == ln:
+                        return True
+        return base_start(c, i)
+
+    rng = np.random.default_rng(0)
+    alphabet = [39, 39, 39, 32, 32, 9, 10, 160] + [ord(ch) for ch in "stmdrevla12!?"] + [200, 178, 0x3b1, 0x660, 0x2003]
+    for _ in range(20000):
+        c = [int(v) for v in rng.choice(alphabet, int(rng.integers(1, 14)))]
+        want = pretokenize(np.asarray(c, dtype=np.uint16)).astype(bool).tolist()
+        assert [token_start(c, i) for i in range(len(c))] == want, c
+    for _ in range(300):
+        c = [int(v) for v in rng.integers(0, 256, 140)]
+        want = pretokenize(np.asarray(c, dtype=np.uint16)).astype(bool).tolist()
+        assert [token_start(c, i) for i in range(len(c))] == want
