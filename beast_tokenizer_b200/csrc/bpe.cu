@@ -640,16 +640,20 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
 // it), the last blank of a longer whitespace run splits off when text follows, and an apostrophe that
 // starts a token and is followed by s/t/m/d/re/ve/ll swallows those letters and forces a restart after
 // them.  (Checked against the sequential matcher on adversarial strings, tests/test_bpe_oracle.py.)
-__device__ __forceinline__ bool base_start(const uint16_t* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
+// class of a codepoint: Latin-1 from a 256-entry shared-memory copy, the rest from the host-built table
+__device__ __forceinline__ int cls_of(int c, const uint8_t* s_cls, const uint8_t* __restrict__ cls_tab) {
+    return c < 256 ? (int)s_cls[c] : (int)__ldg(cls_tab + c);
+}
+__device__ __forceinline__ bool base_start(const uint16_t* cp, int i, int n, const uint8_t* s_cls, const uint8_t* __restrict__ cls_tab) {
     if (i == 0) return true;
-    const int k = cp_class(cp[i], cls_tab), kp = cp_class(cp[i - 1], cls_tab);
+    const int k = cls_of(cp[i], s_cls, cls_tab), kp = cls_of(cp[i - 1], s_cls, cls_tab);
     if (k != CLS_S) {
         if (kp == k) return false;
         if (kp == CLS_S) return cp[i - 1] != 32;             // " ?" prefix: the blank belongs to this token
         return true;
     }
     if (kp != CLS_S) return true;
-    return i + 1 < n && cp_class(cp[i + 1], cls_tab) != CLS_S;  // \s+(?!\S) leaves the last blank
+    return i + 1 < n && cls_of(cp[i + 1], s_cls, cls_tab) != CLS_S;  // \s+(?!\S) leaves the last blank
 }
 __device__ __forceinline__ int contraction_len(const uint16_t* cp, int i, int n) {
     if (i + 1 < n) {
@@ -662,25 +666,26 @@ __device__ __forceinline__ int contraction_len(const uint16_t* cp, int i, int n)
     }
     return 0;
 }
-__device__ __forceinline__ bool token_start(const uint16_t* cp, int i, int n, const uint8_t* __restrict__ cls_tab) {
+__device__ __forceinline__ bool token_start(const uint16_t* cp, int i, int n, const uint8_t* s_cls, const uint8_t* __restrict__ cls_tab) {
     for (int back = 1; back <= 3 && back <= i; ++back) {
         const int j = i - back;
         if (cp[j] == 39) {
             const int len = contraction_len(cp, j, n);
-            if (len > 0 && base_start(cp, j, n, cls_tab)) {
+            if (len > 0 && base_start(cp, j, n, s_cls, cls_tab)) {
                 if (back < len) return false;                // inside 's / 're ...
                 if (back == len) return true;                // the matcher restarts right after it
             }
         }
     }
-    return base_start(cp, i, n, cls_tab);
+    return base_start(cp, i, n, s_cls, cls_tab);
 }
 
 // Per warp in shared memory: key u32[M], sym u16[M], wid u16[M], cp u16[L], wbeg u16[L+2]  (M = symbols max).
 // A: stage the row (coalesced), B: every lane expands its slice of codepoints into byte-level symbols
 // tagged with their word number (one packed warp scan gives symbol and word offsets), C: pair ranks for
-// all adjacent symbols in parallel + ordered word list, D: one lane per word applies the merges lowest
-// rank first inside its own segment, E: scan of the final word lengths, ids written in order.
+// all adjacent symbols in parallel (slot = rank << 16 | symbol) + ordered word list, D: one lane per word
+// applies the merges lowest rank first inside its own segment, E: scan of the final word lengths, ids
+// written in order.
 __global__ void __launch_bounds__(256)
 bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token,
                        long long max_shift, const short* __restrict__ byte_to_id,
@@ -689,7 +694,8 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                        int* __restrict__ status_out, int M, int warp_bytes) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ short s_b2i[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_b2i[i] = byte_to_id[i];
+    __shared__ uint8_t s_cls[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_b2i[i] = byte_to_id[i]; s_cls[i] = (uint8_t)cp_class_latin1(i); }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint8_t* mine = s_raw + (size_t)warp * warp_bytes;
@@ -724,7 +730,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
             int bt[3];
             const int nbt = utf8_encode(cp[i], bt);
             for (int r = 0; r < nbt; ++r) ns += s_b2i[bt[r]] >= 0;
-            const bool t = token_start(cp, i, L, cls_tab);
+            const bool t = token_start(cp, i, L, s_cls, cls_tab);
             nst += t;
             if (t && i - p0 < 32) smask |= 1u << (i - p0);
         }
@@ -737,7 +743,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
         const int total = (int)(__shfl_sync(FULL, inc, 31) >> 16);
         int off = (int)((inc - packed) >> 16), w = (int)((inc - packed) & 0xffffu);
         for (int i = p0; i < p1; ++i) {
-            const bool t = i - p0 < 32 ? ((smask >> (i - p0)) & 1u) != 0 : token_start(cp, i, L, cls_tab);
+            const bool t = i - p0 < 32 ? ((smask >> (i - p0)) & 1u) != 0 : token_start(cp, i, L, s_cls, cls_tab);
             w += t;
             int bt[3];
             const int nbt = utf8_encode(cp[i], bt);
@@ -754,8 +760,11 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
             bool isb = false;
             if (s < total) {
                 isb = s == 0 || wid[s] != wid[s - 1];
-                key[s] = (s + 1 < total && wid[s + 1] == wid[s])
-                             ? __ldg(&rank_tab[(size_t)sym[s] * V + sym[s + 1]]) : NONE;
+                // slot = rank of the pair (s, s+1) in the high half (0xffff: none), symbol s in the low half
+                const unsigned int me = sym[s];
+                const unsigned int r = (s + 1 < total && wid[s + 1] == wid[s])
+                                           ? __ldg(&rank_tab[(size_t)me * V + sym[s + 1]]) : NONE;
+                key[s] = (r & 0xffff0000u) | me;
             }
             const unsigned int m = __ballot_sync(FULL, isb);
             if (isb) wbeg[nwords + __popc(m & ((1u << lane) - 1u))] = (uint16_t)s;
@@ -763,25 +772,32 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
         }
         if (lane == 0) wbeg[nwords] = (uint16_t)total;
         __syncwarp();
-        // ---- D
+        // ---- D: one lane per word; a word's slots are only touched by its lane
         for (int wq = lane; wq < nwords; wq += 32) {
             const int b = wbeg[wq];
             int wl = wbeg[wq + 1] - b;
-            uint16_t* ws = sym + b;
             unsigned int* wk = key + b;
             while (wl >= 2) {
-                unsigned int best = NONE, best_rank = NONE;
+                // lowest rank, leftmost first: equal ranks mean the same pair, hence equal slots, and the
+                // strict compare keeps the first
+                unsigned int best = 0xffff0000u;
                 int bp = -1;
-                for (int q = 0; q + 1 < wl; ++q) {           // lowest rank, leftmost first
-                    const unsigned int kq = wk[q];
-                    if (kq != NONE && (kq >> 16) < best_rank) { best = kq; best_rank = kq >> 16; bp = q; }
+                for (int q = 0; q + 1 < wl; ++q) {
+                    const unsigned int v = wk[q];
+                    if (v < best) { best = v; bp = q; }
                 }
                 if (bp < 0) break;
-                ws[bp] = (uint16_t)(best & 0xffffu);
-                for (int q = bp + 1; q + 1 < wl; ++q) { ws[q] = ws[q + 1]; wk[q] = wk[q + 1]; }
+                const unsigned int left = best & 0xffffu, right = wk[bp + 1] & 0xffffu;
+                const unsigned int nid = __ldg(&rank_tab[(size_t)left * V + right]) & 0xffffu;
+                for (int q = bp + 1; q + 1 < wl; ++q) wk[q] = wk[q + 1];
                 --wl;
-                if (bp > 0) wk[bp - 1] = __ldg(&rank_tab[(size_t)ws[bp - 1] * V + ws[bp]]);
-                if (bp + 1 < wl) wk[bp] = __ldg(&rank_tab[(size_t)ws[bp] * V + ws[bp + 1]]);
+                unsigned int r = 0xffff0000u;
+                if (bp + 1 < wl) r = __ldg(&rank_tab[(size_t)nid * V + (wk[bp + 1] & 0xffffu)]) & 0xffff0000u;
+                wk[bp] = r | nid;
+                if (bp > 0) {
+                    const unsigned int ls = wk[bp - 1] & 0xffffu;
+                    wk[bp - 1] = (__ldg(&rank_tab[(size_t)ls * V + nid]) & 0xffff0000u) | ls;
+                }
             }
             wid[b] = (uint16_t)wl;                           // final length, kept in the word's own segment
         }
@@ -799,7 +815,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                 if (lane >= o) run += t;
             }
             const int o0 = done + run - wl;
-            for (int q = 0; q < wl; ++q) out[o0 + q] = sym[b + q];
+            for (int q = 0; q < wl; ++q) out[o0 + q] = (uint16_t)(key[b + q] & 0xffffu);
             done += __shfl_sync(FULL, run, 31);
         }
         if (lane == 0) { len_out[seq] = done; status_out[seq] = 0; }
