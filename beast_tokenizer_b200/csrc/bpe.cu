@@ -639,7 +639,7 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
 // codepoints: a class run starts where the class changes (a single U+0020 before a non-space run joins
 // it), the last blank of a longer whitespace run splits off when text follows, and an apostrophe that
 // starts a token and is followed by s/t/m/d/re/ve/ll swallows those letters and forces a restart after
-// them.  (Checked against the sequential matcher on adversarial strings, tests/test_bpe_oracle.py.)
+// them.  (Checked against the sequential matcher on adversarial strings by the CPU test suite.)
 // class of a codepoint: Latin-1 from a 256-entry shared-memory copy, the rest from the host-built table
 __device__ __forceinline__ int cls_of(int c, const uint8_t* s_cls, const uint8_t* __restrict__ cls_tab) {
     return c < 256 ? (int)s_cls[c] : (int)__ldg(cls_tab + c);
