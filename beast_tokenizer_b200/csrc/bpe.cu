@@ -36,6 +36,16 @@ __device__ __forceinline__ long long sym_index(int p, long long seq, long long n
     return ((long long)(p >> 3) * n_stride + seq) * kChunk + (p & 7);
 }
 
+// Pair signatures: kSigBits bits per sequence, bit hash(a, b) set for every in-word adjacent pair the
+// sequence holds or ever held (bits are only added, so the set is a superset).  Stored word-major
+// (sig[word * n_stride + seq]) so that the scan for one pair reads a single 4-byte column.
+constexpr int kScanTile = 2048;          // sequences filtered per block and step by the signature scan
+constexpr int kSigWords = 64;
+constexpr int kSigBits = kSigWords * 32;
+__device__ __forceinline__ unsigned int sig_hash(unsigned int a, unsigned int b) {
+    return ((a * 0x9E3779B1u + b * 0x85EBCA77u) >> 15) & (unsigned int)(kSigBits - 1);
+}
+
 // Device-side control block of the sync-free training loop (bpe_train_step).
 struct BpeCtl {
     int a, b, c, count;     // the merge selected for this iteration
@@ -205,6 +215,80 @@ bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, 
     }
 }
 
+// Same count with a block-private [A x A] histogram in shared memory, A = number of DISTINCT ids in the
+// corpus (the byte-level symbols before any merge: 194 for a 256-bin tokenizer, 150 KB; their ids are
+// sparse in [0, n_ids), so they are renumbered through `used_ids`): the ~200 pair increments per
+// sequence become shared-memory atomics, one global atomic per non-zero cell and block at the end.
+// 128-bit chunk loads, one thread per sequence.
+__global__ void __launch_bounds__(1024)
+bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
+                      int V, int n_ids, const short* __restrict__ used_ids, int A, int* __restrict__ hist) {
+    extern __shared__ int s_hist[];                          // [A*A] counters, then u16 inverse map [n_ids]
+    const int cells = A * A;
+    unsigned short* s_inv = (unsigned short*)(s_hist + cells);
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < n_ids; i += blockDim.x) s_inv[i] = 0xffffu;
+    __syncthreads();
+    for (int i = threadIdx.x; i < A; i += blockDim.x) s_inv[used_ids[i]] = (unsigned short)i;
+    __syncthreads();
+    for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
+         seq += (long long)gridDim.x * blockDim.x) {
+        const int n = len[seq];
+        unsigned int prev = 0xffffu;
+        for (int c = 0; c * kChunk < n; ++c) {
+            const int4 q = __ldcs((const int4*)(sym + ((long long)c * n_stride + seq) * kChunk));
+            const unsigned int w[4] = {(unsigned int)q.x, (unsigned int)q.y, (unsigned int)q.z, (unsigned int)q.w};
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                if (c * kChunk + j >= n) break;
+                const unsigned int cur = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                const unsigned int id = cur & kIdMask;
+                const unsigned int ci = id < (unsigned int)n_ids ? s_inv[id] : 0xffffu;
+                if (prev != 0xffffu && ci != 0xffffu && !(cur & kWordStart)) atomicAdd(&s_hist[prev * A + ci], 1);
+                prev = ci;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        const int v = s_hist[i];
+        if (v) atomicAdd(&hist[(long long)used_ids[i / A] * V + used_ids[i % A]], v);
+    }
+}
+
+// Build the pair signatures of every sequence: thread-private bit sets in shared memory (word-major, so
+// neither the updates nor the final coalesced column writes conflict), 128-bit chunk loads.
+constexpr int kSigBlock = 128;
+__global__ void __launch_bounds__(kSigBlock)
+bpe_signature_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
+                     unsigned int* __restrict__ sig) {
+    __shared__ unsigned int s_sig[kSigWords * kSigBlock];
+    for (long long base = (long long)blockIdx.x * kSigBlock; base < N; base += (long long)gridDim.x * kSigBlock) {
+        for (int wd = 0; wd < kSigWords; ++wd) s_sig[wd * kSigBlock + threadIdx.x] = 0;
+        const long long seq = base + threadIdx.x;
+        if (seq < N) {
+            const int n = len[seq];
+            unsigned int prev = 0;
+            for (int c = 0; c * kChunk < n; ++c) {
+                const int4 q = __ldcs((const int4*)(sym + ((long long)c * n_stride + seq) * kChunk));
+                const unsigned int w[4] = {(unsigned int)q.x, (unsigned int)q.y, (unsigned int)q.z, (unsigned int)q.w};
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    if (c * kChunk + j >= n) break;
+                    const unsigned int cur = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                    const unsigned int id = cur & kIdMask;
+                    if ((c | j) && !(cur & kWordStart)) {
+                        const unsigned int h = sig_hash(prev, id);
+                        s_sig[(h >> 5) * kSigBlock + threadIdx.x] |= 1u << (h & 31u);
+                    }
+                    prev = id;
+                }
+            }
+            for (int wd = 0; wd < kSigWords; ++wd) sig[(long long)wd * n_stride + seq] = s_sig[wd * kSigBlock + threadIdx.x];
+        }
+    }
+}
+
 // ---------------------------------------------------------------- arg-max with the trainer's tie-break
 // key = count << 32 | ~flat: the largest key is the largest count and, among equals, the smallest
 // flat index a*V + b, i.e. the lexicographically smallest (a, b).
@@ -276,19 +360,21 @@ __device__ __forceinline__ uint16_t chunk_get(const uint4& w, int j) {        //
 __global__ void __launch_bounds__(256)
 bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
                 int a, int b, const BpeCtl* __restrict__ ctl, int* __restrict__ work_count, int* __restrict__ work_seq,
-                int* __restrict__ work_q0) {
+                int* __restrict__ work_q0, const unsigned int* __restrict__ sig) {
     if (ctl) {
         if (ctl->done) return;
         a = ctl->a; b = ctl->b;
     }
+    // signature column of this pair: sequences whose bit is clear cannot contain (a, b) and are never read
+    const unsigned int sh = sig_hash((unsigned int)a, (unsigned int)b);
+    const unsigned int* sig_col = sig ? sig + (long long)(sh >> 5) * n_stride : nullptr;
+    const unsigned int sig_bit = 1u << (sh & 31u);
     const uint4* sym4 = (const uint4*)sym;
     const int lane = threadIdx.x & 31;
     const unsigned int A2 = (unsigned int)a | ((unsigned int)a << 16);
     const unsigned int B2 = (unsigned int)b | ((unsigned int)b << 16);
-    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N;
-         base += (long long)gridDim.x * blockDim.x) {
-        const long long seq = base + lane;
-        const bool valid = seq < N;
+    // one warp, 32 sequences (`valid` lanes), chunks walked in lock step; hits go to the work list
+    auto scan_warp = [&](long long seq, bool valid) {
         const int n = valid ? len[seq] : 0;
         const int nch = (n + kChunk - 1) >> 3;
         const long long row0 = valid ? seq : 0;
@@ -333,6 +419,40 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
                 work_q0[slot] = q0;
             }
         }
+    };
+    if (!sig_col) {
+        for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N;
+             base += (long long)gridDim.x * blockDim.x)
+            scan_warp(base + lane, base + lane < N);
+        return;
+    }
+    // With signatures: a block filters a tile of kScanTile sequences down to the ones whose bit is set
+    // (one coalesced 4-byte column read), compacts them in shared memory, and only those are walked —
+    // by full warps, so the number of chunk walks drops with the pass rate, not just the bytes.
+    __shared__ int s_list[kScanTile];
+    __shared__ int s_n;
+    for (long long tile = (long long)blockIdx.x * kScanTile; tile < N; tile += (long long)gridDim.x * kScanTile) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < kScanTile; k += blockDim.x) {
+            const long long seq = tile + k;
+            const bool pass = seq < N && (__ldg(sig_col + seq) & sig_bit);
+            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+            }
+        }
+        __syncthreads();
+        const int n_pass = s_n;
+        for (int i0 = threadIdx.x & ~31; i0 < n_pass; i0 += blockDim.x) {
+            const int i = i0 + lane;
+            const bool valid = i < n_pass;
+            scan_warp(valid ? tile + s_list[i] : 0, valid);
+        }
+        __syncthreads();
     }
 }
 
@@ -343,7 +463,13 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
 // stored before the first merge.  Count changes go to the block-private delta block.
 __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int* __restrict__ len, long long seq,
                                                  int q0, long long n_stride, int a, int b, int c, int V,
-                                                 int* s_delta) {
+                                                 int* s_delta, unsigned int* __restrict__ sig) {
+    auto sig_add = [&](int x, int y) {                        // the rewritten sequence now holds the pair (x, y)
+        if (sig) {
+            const unsigned int h = sig_hash((unsigned int)x, (unsigned int)y);
+            sig[(long long)(h >> 5) * n_stride + seq] |= 1u << (h & 31u);     // this thread owns the sequence
+        }
+    };
     int* col_a = s_delta;
     int* row_b = s_delta + V;
     int* col_c = s_delta + 2 * V;
@@ -380,6 +506,7 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
         if (prev_merged && !(x & kWordStart)) {              // right neighbour of a merge
             atomicAdd(&row_b[id], -1);                       // (b, y) disappears
             atomicAdd(&row_c[id], 1);                        // (c, y) appears
+            sig_add(c, id);
         }
         prev_merged = false;
         prev_old = id;
@@ -400,6 +527,7 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
                     if (!(pend_sym & kWordStart)) {          // the pair with the left neighbour changes
                         atomicAdd(&col_a[prev_old], -1);     // (old left, a) disappears
                         atomicAdd(&col_c[prev_new], 1);      // (new left, c) appears
+                        sig_add(prev_new, c);
                     }
                     dirty = true;
                     prev_merged = true;
@@ -423,7 +551,8 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
 __global__ void __launch_bounds__(256)
 bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int a, int b, int c, int V,
                    const BpeCtl* __restrict__ ctl, const int* __restrict__ work_count,
-                   const int* __restrict__ work_seq, const int* __restrict__ work_q0, int* __restrict__ delta) {
+                   const int* __restrict__ work_seq, const int* __restrict__ work_q0, int* __restrict__ delta,
+                   unsigned int* __restrict__ sig) {
     extern __shared__ int s_delta[];
     if (ctl) {
         if (ctl->done) return;
@@ -435,7 +564,7 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_work;
          i += (long long)gridDim.x * blockDim.x)
-        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta);
+        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta, sig);
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
         const int d = s_delta[i];
@@ -950,10 +1079,25 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
 }
 
 extern "C" int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
-                               int32_t* hist, void* stream) {
+                               int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist, void* stream) {
     if (N == 0) return BEAST_OK;
     if (!sym || !len || !hist) return BEAST_E_NULL;
-    if (N < 0 || V < 1 || V > 32767) return BEAST_E_SHAPE;
+    if (N < 0 || V < 1 || V > 32767 || n_ids < 0 || n_ids > V || n_used < 0 || n_used > n_ids) return BEAST_E_SHAPE;
+    const size_t smem = (size_t)n_used * n_used * sizeof(int) + (((size_t)n_ids * 2 + 15) & ~(size_t)15);
+    if (used_ids && n_used > 0 && smem <= 200 * 1024 && ((uintptr_t)sym & 15u) == 0) {
+        static size_t granted[kMaxDevices] = {};
+        if (int rc = opt_in_smem(bpe_count_smem_kernel, smem, granted)) return rc;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        long long grid = (N + 1023) / 1024;
+        if (grid > sms) grid = sms;
+        bpe_count_smem_kernel<<<(unsigned)grid, 1024, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, n_ids,
+                                                                                   used_ids, n_used, hist);
+        count_launch();
+        BEAST_CHECK_LAUNCH();
+        return BEAST_OK;
+    }
     bpe_count_kernel<<<bpe_grid(N, 256), 256, 0, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, hist);
     count_launch();
     BEAST_CHECK_LAUNCH();
@@ -1004,8 +1148,9 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
     cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     const int grid = merge_grid(N);
-    bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0);
-    bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta);
+    bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0, nullptr);
+    bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta,
+                                                nullptr);
     count_launch(2);
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -1020,13 +1165,27 @@ extern "C" int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t
     return BEAST_OK;
 }
 
+extern "C" int32_t bpe_signature_words(void) { return kSigWords; }
+
+extern "C" int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint32_t* sig,
+                                    void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (!sym || !len || !sig) return BEAST_E_NULL;
+    if (N < 0 || n_stride < N) return BEAST_E_SHAPE;
+    if ((uintptr_t)sym & 15u) return BEAST_E_ALIGN;
+    bpe_signature_kernel<<<bpe_grid(N, kSigBlock), kSigBlock, 0, (cudaStream_t)stream>>>(sym, len, N, n_stride, sig);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
 // One iteration of the sync-free training loop.  phase 0: arg-max -> select -> merge (fills delta);
 // phase 1: hist += delta.  The caller runs [phase 0, all-reduce(delta) when sharded, phase 1] up to
 // (vocab_size - alphabet) times without reading anything back; ctl / log are read once at the end.
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                               int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
                               int32_t vocab_size, int32_t min_frequency, int32_t max_merges, int32_t phase,
-                              void* stream) {
+                              uint32_t* sig, void* stream) {
     if (!hist || !delta || !ctl || !log || !result || !work) return BEAST_E_NULL;
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
     if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
@@ -1047,9 +1206,10 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     count_launch(1);
     if (N > 0) {
         const int grid = merge_grid(N);
-        bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count, work_seq, work_q0);
+        bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count, work_seq, work_q0,
+                                              sig);
         bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, work_count,
-                                                    work_seq, work_q0, delta);
+                                                    work_seq, work_q0, delta, sig);
         count_launch(2);
     }
     BEAST_CHECK_LAUNCH();

@@ -185,7 +185,10 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  * bpe_symbolize  bins [N, L] int64 -> sym / len through the GPT-2 pre-tokeniser (A.2) and the byte-level
  *                expansion (A.3); byte_to_id[256] int16 (-1 = not in the vocabulary: dropped); cls_tab[max
  *                shifted bin + 1] uint8: character class of every codepoint >= 256 (0 other, 1 \p{L}, 2 \p{N}, 3 \s).
- * bpe_count_pairs  hist[a*V + b] += #adjacent (a, b) inside pre-tokens (int32, V x V).
+ * bpe_count_pairs  hist[a*V + b] += #adjacent (a, b) inside pre-tokens (int32, V x V).  Optional hint:
+ *                used_ids[n_used] = the distinct ids that can occur in sym (ascending, all < n_ids: the
+ *                byte-level symbols before any merge) — when n_used^2 counters fit in shared memory the
+ *                count runs on block-private histograms; NULL / 0 = global atomics.
  * bpe_argmax     result = count << 32 | (0xffffffff - (a*V + b)) of the best pair (0 if none): maximum
  *                count, ties -> smallest (a, b) (BpeTrainer's heap order).
  * bpe_apply_merge  replace (a, b) by c left to right, non-overlapping, compacting in place; the count
@@ -206,7 +209,7 @@ int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, 
                   const uint8_t* cls_tab, uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err,
                   void* stream);
 int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
-                    int32_t* hist, void* stream);
+                    int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist, void* stream);
 int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream);
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
                     int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream);
@@ -219,7 +222,14 @@ int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t
  * merge; result: the arg-max scratch word (zeroed by the caller once).  Nothing is read back until the end. */
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                    int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
-                   int32_t min_frequency, int32_t max_merges, int32_t phase, void* stream);
+                   int32_t min_frequency, int32_t max_merges, int32_t phase, uint32_t* sig, void* stream);
+/* Pair signatures for bpe_train_step (optional, sig = NULL scans every sequence): uint32
+ * [bpe_signature_words()][n_stride], bit hash(a, b) of sequence s set when s holds (or ever held) the
+ * in-word pair (a, b).  The scan for a merge reads one 4-byte column and skips the sequences whose bit
+ * is clear; the rewrite adds the bits of the pairs it creates.  Build once after bpe_symbolize. */
+int32_t bpe_signature_words(void);
+int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint32_t* sig,
+                         void* stream);
 int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
                const int16_t* byte_to_id, const uint8_t* cls_tab, const uint32_t* rank_tab, int32_t V,
                uint16_t* ids_padded, int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream);

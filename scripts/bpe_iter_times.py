@@ -19,12 +19,19 @@ lib = eng.lib
 ctl = torch.zeros(8, device=dev, dtype=torch.int32); ctl[4] = len(tokens)
 mm = 2048 - len(tokens)
 log = torch.zeros(4 * mm, device=dev, dtype=torch.int32); eng.result.zero_()
+SIG = None
+USE_SIG = os.environ.get("NOSIG") != "1"
+sig_t = torch.empty((int(lib.bpe_signature_words()), eng.stride), device=dev, dtype=torch.int32)
+def build_sig():
+    _lib.check(lib.bpe_build_signatures(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, _lib.ptr(sig_t), _lib.stream_ptr(dev)), "sig")
 def step(ph):
     _lib.check(lib.bpe_train_step(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, eng.V, _lib.ptr(eng.hist), _lib.ptr(eng.delta),
-                                  _lib.ptr(ctl), _lib.ptr(log), _lib.ptr(eng.result), _lib.ptr(eng.work), 2048, 2, mm, ph, _lib.stream_ptr(dev)), "s")
+                                  _lib.ptr(ctl), _lib.ptr(log), _lib.ptr(eng.result), _lib.ptr(eng.work), 2048, 2, mm, ph, SIG, _lib.stream_ptr(dev)), "s")
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(mm + 1)]
 evs[0].record()
 for i in range(mm):
+    if USE_SIG and i >= 64 and (i - 64) % 256 == 0:
+        build_sig(); SIG = _lib.ptr(sig_t)
     step(0); step(1); evs[i + 1].record()
 torch.cuda.synchronize()
 ts = [evs[i].elapsed_time(evs[i + 1]) for i in range(mm)]
