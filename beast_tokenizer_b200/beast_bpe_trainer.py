@@ -80,7 +80,7 @@ class GpuBpeEngine:
             self.len = torch.zeros(self.stride, device=self.dev, dtype=torch.int32)
             self.hist = torch.zeros((V, V), device=self.dev, dtype=torch.int32)
             self.delta = torch.zeros(4 * V, device=self.dev, dtype=torch.int32)
-            self.result = torch.zeros(1, device=self.dev, dtype=torch.int64)
+            self.result = torch.zeros(256, device=self.dev, dtype=torch.int64)   # arg-max scratch (per-block maxima)
             self.work = torch.zeros(4 + 2 * self.stride, device=self.dev, dtype=torch.int32)   # scan -> rewrite work list
             err = torch.zeros(1, device=self.dev, dtype=torch.int32)
             b2i = torch.from_numpy(byte_to_id).to(self.dev)
@@ -101,7 +101,7 @@ class GpuBpeEngine:
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.bpe_argmax(_lib.ptr(self.hist), self.V, n_active, _lib.ptr(self.result),
                                            _lib.stream_ptr(self.dev)), "bpe_argmax")
-        key = int(self.result.item()) & 0xFFFFFFFFFFFFFFFF
+        key = int(self.result[0].item()) & 0xFFFFFFFFFFFFFFFF
         if key == 0:
             return 0, -1, -1
         flat = 0xFFFFFFFF - (key & 0xFFFFFFFF)
@@ -142,22 +142,31 @@ class GpuBpeEngine:
                 _lib.check(self.lib.bpe_build_signatures(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride,
                                                          _lib.ptr(sig), _lib.stream_ptr(dev)), "bpe_build_signatures")
 
-            def step(phase, use_sig):
+            def step(phase, use_sig, iters=1):
                 _lib.check(self.lib.bpe_train_step(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, self.V,
                                                    _lib.ptr(self.hist), _lib.ptr(self.delta), _lib.ptr(ctl),
                                                    _lib.ptr(log), _lib.ptr(self.result), _lib.ptr(self.work),
                                                    int(vocab_size), int(min_frequency), max_merges, phase,
-                                                   _lib.ptr(sig) if use_sig else None, _lib.stream_ptr(dev)),
+                                                   _lib.ptr(sig) if use_sig else None, int(iters),
+                                                   _lib.stream_ptr(dev)),
                            "bpe_train_step")
 
             # plain stream launches: ~60 us of host enqueue per merge, never a sync (capturing the
             # iteration into a CUDA graph costs more to instantiate than 1 700 replays save)
             self.work[:4].zero_()
-            for i in range(max_merges):
+            i = 0
+            while i < max_merges:
                 if i >= sig_start and (i - sig_start) % sig_rebuild == 0:
                     build_sig()
-                step(0, i >= sig_start)                 # fold previous delta + arg-max + select, scan, rewrite
-                coll.reduce_(self.delta, "sum")
+                if coll.on:
+                    step(0, i >= sig_start)             # fold previous delta + arg-max + select, scan, rewrite
+                    coll.reduce_(self.delta, "sum")
+                    i += 1
+                else:                                   # unsharded: enqueue up to the next signature rebuild in one call
+                    nxt = sig_start if i < sig_start else i + sig_rebuild - (i - sig_start) % sig_rebuild
+                    n = min(nxt, max_merges) - i
+                    step(0, i >= sig_start, n)
+                    i += n
             ctl_h = ctl.cpu().tolist()
             n = ctl_h[5]
             return log[:4 * n].cpu().view(-1, 4).tolist()

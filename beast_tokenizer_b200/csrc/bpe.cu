@@ -360,7 +360,7 @@ __device__ __forceinline__ uint16_t chunk_get(const uint4& w, int j) {        //
 __global__ void __launch_bounds__(256)
 bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
                 int a, int b, const BpeCtl* __restrict__ ctl, int* __restrict__ work_count, int* __restrict__ work_seq,
-                int* __restrict__ work_q0, const unsigned int* __restrict__ sig) {
+                int* __restrict__ work_q0, const unsigned int* __restrict__ sig, int tile_size) {
     if (ctl) {
         if (ctl->done) return;
         a = ctl->a; b = ctl->b;
@@ -431,10 +431,10 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
     // by full warps, so the number of chunk walks drops with the pass rate, not just the bytes.
     __shared__ int s_list[kScanTile];
     __shared__ int s_n;
-    for (long long tile = (long long)blockIdx.x * kScanTile; tile < N; tile += (long long)gridDim.x * kScanTile) {
+    for (long long tile = (long long)blockIdx.x * tile_size; tile < N; tile += (long long)gridDim.x * tile_size) {
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        for (int k = threadIdx.x; k < kScanTile; k += blockDim.x) {
+        for (int k = threadIdx.x; k < tile_size; k += blockDim.x) {
             const long long seq = tile + k;
             const bool pass = seq < N && (__ldg(sig_col + seq) & sig_bit);
             const unsigned int m = __ballot_sync(0xffffffffu, pass);
@@ -595,52 +595,90 @@ __global__ void bpe_select_kernel(unsigned long long* __restrict__ result, BpeCt
     e[0] = ctl->a; e[1] = ctl->b; e[2] = ctl->c; e[3] = count;
 }
 
-// Fused iteration head of the sync-free loop: fold the (all-reduced) delta block of the previous merge
-// into the histogram, find the arg-max of the updated table in the same pass, and let the last block
-// apply BpeTrainer's stop rules, assign the next id and log the merge.  Every delta entry belongs to
-// exactly one histogram entry (column a: (x, a); row b: (b, y); column c: (x, c); row c: (c, y)), so
-// the thread that owns that entry consumes and clears it.
-__global__ void __launch_bounds__(256)
-bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int* __restrict__ delta,
-                   unsigned long long* __restrict__ result, unsigned int* __restrict__ ticket, int* __restrict__ log,
-                   int vocab_size, int min_frequency, int max_merges, int* __restrict__ work_count) {
+// Iteration head of the sync-free loop: fold the (all-reduced) delta block of the previous merge into the
+// histogram and find the arg-max of the updated table in the same launch.  The delta touches only column a,
+// row b, column c and row c of the previous merge (a, b) -> c.
+// (One block of 1024 threads per SM writes its maximum to partial[block]; bpe_pick_kernel finishes.)
+__global__ void __launch_bounds__(1024)
+bpe_iterate_kernel(int* __restrict__ hist, int V, const BpeCtl* __restrict__ ctl, int* __restrict__ delta,
+                   unsigned long long* __restrict__ partial) {
     if (ctl->done) return;
     const int n_active = ctl->n_tokens;
     const bool fold = ctl->has_delta != 0;
     const int pa = ctl->a, pb = ctl->b, pc = ctl->c;
     unsigned long long best = 0;
-    // rows are walked by warps, columns by lanes, four entries per lane and step (128-bit loads when the
-    // row pitch allows): no integer division, coalesced rows, several independent loads in flight
     const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
     const bool vec = (V & 3) == 0;
-    auto visit = [&](int* row, int x, int y, int v) {
-        if (fold) {
-            int d = 0;
-            bool touched = false;
-            if (y == pa) { d += delta[x]; delta[x] = 0; touched = true; }
-            if (x == pb) { d += delta[V + y]; delta[V + y] = 0; touched = true; }
-            if (y == pc) { d += delta[2 * V + x]; delta[2 * V + x] = 0; touched = true; }
-            if (x == pc) { d += delta[3 * V + y]; delta[3 * V + y] = 0; touched = true; }
-            if (x == pa && y == pb) { v = 0; d = 0; touched = true; }          // the merged pair is gone for good
-            if (touched) { v += d; row[y] = v; }
-        }
+    auto consider = [&](int x, int y, int v) {
         if (v > 0) {
             const unsigned int flat = (unsigned int)x * (unsigned int)V + (unsigned int)y;
             const unsigned long long key = ((unsigned long long)(unsigned int)v << 32) | (0xffffffffu - flat);
             best = key > best ? key : best;
         }
     };
-    for (int x = blockIdx.x * warps_per_block + (threadIdx.x >> 5); x < n_active; x += gridDim.x * warps_per_block) {
-        int* row = hist + (long long)x * V;
-        if (vec) {
-            for (int y0 = lane * 4; y0 < n_active; y0 += 128) {
-                const int4 q = *(const int4*)(row + y0);                         // y0 + 3 < V: inside the row
-                visit(row, x, y0, q.x);
-                if (y0 + 1 < n_active) visit(row, x, y0 + 1, q.y);
-                if (y0 + 2 < n_active) visit(row, x, y0 + 2, q.z);
-                if (y0 + 3 < n_active) visit(row, x, y0 + 3, q.w);
+    // Entries of column a / row b / column c / row c carry a pending delta: the bulk pass skips them (four
+    // compares, no memory traffic) and the short pass below folds and weighs them; the merged pair (a, b)
+    // is gone for good.
+    auto visit = [&](int* row, int x, int y, int v) {
+        if (fold) {
+            if (y == pa || x == pb || y == pc || x == pc) return;
+            if (x == pa && y == pb) { row[y] = 0; return; }
+        }
+        consider(x, y, v);
+    };
+    if (fold) {
+        // 4 x n_active special entries, one per thread: which = 0 column a (j, a), 1 row b (b, j), 2 column c
+        // (j, c), 3 row c (c, j).  An entry on two of the lines belongs to the first one in that order and takes
+        // both deltas; the delta block itself is cleared afterwards by bpe_pick_kernel.
+        const unsigned int nthreads = gridDim.x * blockDim.x;
+        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * (unsigned int)n_active; i += nthreads) {
+            const int which = (int)(i / (unsigned int)n_active), j = (int)(i - (unsigned int)which * n_active);
+            const int x = which == 0 ? j : (which == 1 ? pb : (which == 2 ? j : pc));
+            const int y = which == 0 ? pa : (which == 1 ? j : (which == 2 ? pc : j));
+            const bool on0 = y == pa, on1 = x == pb, on2 = y == pc;
+            if ((which == 1 && on0) || (which == 2 && (on0 || on1)) || (which == 3 && (on0 || on1 || on2))) continue;
+            int d = 0;
+            if (on0) d += delta[x];
+            if (on1) d += delta[V + y];
+            if (on2) d += delta[2 * V + x];
+            if (x == pc) d += delta[3 * V + y];
+            int* cell = hist + (long long)x * V + y;
+            int v = *cell + d;
+            if (x == pa && y == pb) v = 0;
+            if (d != 0 || v == 0) *cell = v;
+            consider(x, y, v);
+        }
+    }
+    if (vec) {
+        // the live n_active x n_active corner as a flat list of 128-bit units, dealt round-robin to ALL
+        // threads (a warp reads 512 contiguous bytes), four independent loads in flight per thread
+        const unsigned int n4 = (unsigned int)(n_active + 3) >> 2;
+        const unsigned int total = (unsigned int)n_active * n4;
+        const unsigned int nthreads = gridDim.x * blockDim.x;
+        for (unsigned int u0 = blockIdx.x * blockDim.x + threadIdx.x; u0 < total; u0 += 4u * nthreads) {
+            int4 q[4];
+            unsigned int xs[4], ys[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int u = u0 + (unsigned int)k * nthreads;
+                xs[k] = u / n4;
+                ys[k] = (u - xs[k] * n4) * 4u;
+                if (u < total) q[k] = *(const int4*)(hist + (long long)xs[k] * V + ys[k]);
             }
-        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (u0 + (unsigned int)k * nthreads >= total) break;
+                int* row = hist + (long long)xs[k] * V;
+                const int x = (int)xs[k], y0 = (int)ys[k];
+                visit(row, x, y0, q[k].x);
+                if (y0 + 1 < n_active) visit(row, x, y0 + 1, q[k].y);
+                if (y0 + 2 < n_active) visit(row, x, y0 + 2, q[k].z);
+                if (y0 + 3 < n_active) visit(row, x, y0 + 3, q[k].w);
+            }
+        }
+    } else {
+        for (int x = blockIdx.x * warps_per_block + (threadIdx.x >> 5); x < n_active; x += gridDim.x * warps_per_block) {
+            int* row = hist + (long long)x * V;
             for (int y = lane; y < n_active; y += 32) visit(row, x, y, row[y]);
         }
     }
@@ -648,23 +686,38 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int*
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other > best ? other : best;
     }
-    __shared__ unsigned long long s_best[8];
-    __shared__ bool s_last;
+    __shared__ unsigned long long s_best[32];
     if (lane == 0) s_best[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < warps_per_block; ++w) best = s_best[w] > best ? s_best[w] : best;
-        if (best) atomicMax(result, best);
-        __threadfence();
-        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        partial[blockIdx.x] = best;                          // plain store: bpe_pick_kernel runs after this grid
     }
+}
+
+// Second half of the iteration head: reduce the per-block maxima, apply BpeTrainer's stop rules (vocabulary
+// full, count < min_frequency), assign the next id, log the merge.  One small block; keeping it a separate
+// launch costs ~2 us, whereas a last-block-done ticket inside the arg-max grid costs ten times that in
+// same-address atomics, fences and barrier waits.
+__global__ void __launch_bounds__(256)
+bpe_pick_kernel(const unsigned long long* __restrict__ partial, int n_partial, BpeCtl* __restrict__ ctl,
+                int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges,
+                int* __restrict__ work_count, int* __restrict__ delta) {
+    if (ctl->done) return;
+    if (ctl->has_delta)                                      // consumed by bpe_iterate_kernel just before
+        for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) delta[i] = 0;
+    unsigned long long best = 0;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) best = partial[i] > best ? partial[i] : best;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long s_best[8];
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
-    // ---- last block: select
-    __threadfence();
-    const unsigned long long key = *(volatile unsigned long long*)result;
-    *result = 0;
-    *ticket = 0;
+    if (threadIdx.x != 0) return;
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_best[w] > best ? s_best[w] : best;
+    const unsigned long long key = best;
     *work_count = 0;
     ctl->has_delta = 0;
     const int count = (int)(key >> 32);
@@ -1148,7 +1201,7 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
     cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     const int grid = merge_grid(N);
-    bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0, nullptr);
+    bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0, nullptr, 0);
     bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta,
                                                 nullptr);
     count_launch(2);
@@ -1185,7 +1238,7 @@ extern "C" int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                               int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
                               int32_t vocab_size, int32_t min_frequency, int32_t max_merges, int32_t phase,
-                              uint32_t* sig, void* stream) {
+                              uint32_t* sig, int32_t iters, void* stream) {
     if (!hist || !delta || !ctl || !log || !result || !work) return BEAST_E_NULL;
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
     if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
@@ -1199,18 +1252,27 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     int* work_count = work;                  // work = {count, pad[3], seq[N], q0[N]}
     int* work_seq = work + 4;
     int* work_q0 = work + 4 + N;
-    // one launch folds the previous delta, finds the arg-max and selects the merge (n_active lives on the device)
-    unsigned int* ticket = (unsigned int*)(work + 1);
-    bpe_iterate_kernel<<<sms * 8, 256, 0, st>>>(hist, V, (BpeCtl*)ctl, delta, (unsigned long long*)result, ticket, log,
-                                               vocab_size, min_frequency, max_merges, work_count);
-    count_launch(1);
-    if (N > 0) {
-        const int grid = merge_grid(N);
-        bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count, work_seq, work_q0,
-                                              sig);
-        bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, work_count,
-                                                    work_seq, work_q0, delta, sig);
+    // tile of the signature scan: large enough to fill warps with survivors, small enough to use every SM
+    // (a multiple of the block size, so every thread takes part in the ballots)
+    long long tile = ((N / ((long long)sms * 2) + 255) / 256) * 256;
+    if (tile < 256) tile = 256;
+    if (tile > kScanTile) tile = kScanTile;
+    const int grid = merge_grid(N > 0 ? N : 1);
+    // `iters` iterations back to back (unsharded training: nothing happens between them on the host)
+    for (int it = 0; it < (iters < 1 ? 1 : iters); ++it) {
+        // one launch folds the previous delta, finds the arg-max and selects the merge (n_active lives on the device)
+        const int n_part = sms < 256 ? sms : 256;             // `result` holds 256 words
+        bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, (const BpeCtl*)ctl, delta, (unsigned long long*)result);
+        bpe_pick_kernel<<<1, 256, 0, st>>>((const unsigned long long*)result, n_part, (BpeCtl*)ctl, log, V, vocab_size,
+                                           min_frequency, max_merges, work_count, delta);
         count_launch(2);
+        if (N > 0) {
+            bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count, work_seq,
+                                                  work_q0, sig, (int)tile);
+            bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, work_count,
+                                                        work_seq, work_q0, delta, sig);
+            count_launch(2);
+        }
     }
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;

@@ -214,15 +214,18 @@ int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* resul
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
                     int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream);
 int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
-/* Sync-free training loop: one iteration = phase 0 — three launches: (1) fold the previous merge's delta
- * into the histogram, arg-max, select with BpeTrainer's stop rules (vocabulary full / count < min_frequency),
- * (2) scan for the pair, (3) rewrite the listed sequences into delta — [+ all-reduce(delta) when sharded].
+/* Sync-free training loop: one iteration = phase 0 — four launches: (1) fold the previous merge's delta
+ * into the histogram and arg-max it, (2) pick: BpeTrainer's stop rules (vocabulary full / count < min_frequency),
+ * next id, merge log, (3) scan for the pair, (4) rewrite the listed sequences into delta — [+ all-reduce(delta)
+ * when sharded].
  * phase 1 is a no-op kept for symmetry.  ctl: 8 x int32 device block {a, b, c, count, n_tokens, n_merges, done,
  * has_delta}, caller sets n_tokens = alphabet size and zeroes the rest; work: int32 [4 + 2*N] zeroed by the caller; log: int32 [4 * max_merges] receives (a, b, new_id, count) per
- * merge; result: the arg-max scratch word (zeroed by the caller once).  Nothing is read back until the end. */
+ * merge; result: arg-max scratch, 256 x uint64 (per-block maxima).  Nothing is read back until the end.
+ * iters: iterations enqueued by this call (> 1 only when no all-reduce has to run between them). */
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                    int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
-                   int32_t min_frequency, int32_t max_merges, int32_t phase, uint32_t* sig, void* stream);
+                   int32_t min_frequency, int32_t max_merges, int32_t phase, uint32_t* sig, int32_t iters,
+                   void* stream);
 /* Pair signatures for bpe_train_step (optional, sig = NULL scans every sequence): uint32
  * [bpe_signature_words()][n_stride], bit hash(a, b) of sequence s set when s holds (or ever held) the
  * in-word pair (a, b).  The scan for a merge reads one 4-byte column and skips the sequences whose bit

@@ -20,7 +20,7 @@ for N in (65536, 400000):
         SIG = None
 def step(ph):
             _lib.check(lib.bpe_train_step(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, eng.V, _lib.ptr(eng.hist), _lib.ptr(eng.delta),
-                                          _lib.ptr(ctl), _lib.ptr(log), _lib.ptr(eng.result), _lib.ptr(eng.work), 2048, 2, mm, ph, SIG, _lib.stream_ptr(dev)), "s")
+                                          _lib.ptr(ctl), _lib.ptr(log), _lib.ptr(eng.result), _lib.ptr(eng.work), 2048, 2, mm, ph, SIG, 1, _lib.stream_ptr(dev)), "s")
         torch.cuda.synchronize(); t0 = time.perf_counter()
         if mode == "plain":
             for _ in range(mm): step(0); step(1)

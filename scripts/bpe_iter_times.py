@@ -26,7 +26,7 @@ def build_sig():
     _lib.check(lib.bpe_build_signatures(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, _lib.ptr(sig_t), _lib.stream_ptr(dev)), "sig")
 def step(ph):
     _lib.check(lib.bpe_train_step(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, eng.V, _lib.ptr(eng.hist), _lib.ptr(eng.delta),
-                                  _lib.ptr(ctl), _lib.ptr(log), _lib.ptr(eng.result), _lib.ptr(eng.work), 2048, 2, mm, ph, SIG, _lib.stream_ptr(dev)), "s")
+                                  _lib.ptr(ctl), _lib.ptr(log), _lib.ptr(eng.result), _lib.ptr(eng.work), 2048, 2, mm, ph, SIG, 1, _lib.stream_ptr(dev)), "s")
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(mm + 1)]
 evs[0].record()
 for i in range(mm):
