@@ -40,10 +40,16 @@ __device__ __forceinline__ long long sym_index(int p, long long seq, long long n
 // sequence holds or ever held (bits are only added, so the set is a superset).  Stored word-major
 // (sig[word * n_stride + seq]) so that the scan for one pair reads a single 4-byte column.
 constexpr int kScanTile = 2048;          // sequences filtered per block and step by the signature scan
+constexpr int kDirectDeltaWork = 1 << 14; // rewrite: work lists up to this size update the global delta directly
 constexpr int kSigWords = 64;
 constexpr int kSigBits = kSigWords * 32;
+// Two independent hash positions per pair (a Bloom filter with k = 2): a sequence passes the scan's
+// filter only if both bits are set, which squares the false-positive rate for one more 4-byte column.
 __device__ __forceinline__ unsigned int sig_hash(unsigned int a, unsigned int b) {
     return ((a * 0x9E3779B1u + b * 0x85EBCA77u) >> 15) & (unsigned int)(kSigBits - 1);
+}
+__device__ __forceinline__ unsigned int sig_hash2(unsigned int a, unsigned int b) {
+    return ((a * 0xC2B2AE3Du + b * 0x27D4EB2Fu + 0x165667B1u) >> 13) & (unsigned int)(kSigBits - 1);
 }
 
 // Device-side control block of the sync-free training loop (bpe_train_step).
@@ -278,8 +284,9 @@ bpe_signature_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ l
                     const unsigned int cur = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
                     const unsigned int id = cur & kIdMask;
                     if ((c | j) && !(cur & kWordStart)) {
-                        const unsigned int h = sig_hash(prev, id);
+                        const unsigned int h = sig_hash(prev, id), h2 = sig_hash2(prev, id);
                         s_sig[(h >> 5) * kSigBlock + threadIdx.x] |= 1u << (h & 31u);
+                        s_sig[(h2 >> 5) * kSigBlock + threadIdx.x] |= 1u << (h2 & 31u);
                     }
                     prev = id;
                 }
@@ -366,9 +373,10 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
         a = ctl->a; b = ctl->b;
     }
     // signature column of this pair: sequences whose bit is clear cannot contain (a, b) and are never read
-    const unsigned int sh = sig_hash((unsigned int)a, (unsigned int)b);
+    const unsigned int sh = sig_hash((unsigned int)a, (unsigned int)b), sh2 = sig_hash2((unsigned int)a, (unsigned int)b);
     const unsigned int* sig_col = sig ? sig + (long long)(sh >> 5) * n_stride : nullptr;
-    const unsigned int sig_bit = 1u << (sh & 31u);
+    const unsigned int* sig_col2 = sig ? sig + (long long)(sh2 >> 5) * n_stride : nullptr;
+    const unsigned int sig_bit = 1u << (sh & 31u), sig_bit2 = 1u << (sh2 & 31u);
     const uint4* sym4 = (const uint4*)sym;
     const int lane = threadIdx.x & 31;
     const unsigned int A2 = (unsigned int)a | ((unsigned int)a << 16);
@@ -436,7 +444,7 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
         __syncthreads();
         for (int k = threadIdx.x; k < tile_size; k += blockDim.x) {
             const long long seq = tile + k;
-            const bool pass = seq < N && (__ldg(sig_col + seq) & sig_bit);
+            const bool pass = seq < N && (__ldg(sig_col + seq) & sig_bit) && (__ldg(sig_col2 + seq) & sig_bit2);
             const unsigned int m = __ballot_sync(0xffffffffu, pass);
             if (m) {
                 int base = 0;
@@ -466,10 +474,13 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
                                                  int* s_delta, unsigned int* __restrict__ sig) {
     auto sig_add = [&](int x, int y) {                        // the rewritten sequence now holds the pair (x, y)
         if (sig) {
-            const unsigned int h = sig_hash((unsigned int)x, (unsigned int)y);
-            sig[(long long)(h >> 5) * n_stride + seq] |= 1u << (h & 31u);     // this thread owns the sequence
+            const unsigned int h = sig_hash((unsigned int)x, (unsigned int)y), h2 = sig_hash2((unsigned int)x, (unsigned int)y);
+            atomicOr(&sig[(long long)(h >> 5) * n_stride + seq], 1u << (h & 31u));   // no return value: fire and forget
+            atomicOr(&sig[(long long)(h2 >> 5) * n_stride + seq], 1u << (h2 & 31u));
         }
     };
+    // s_delta: block-private counters in shared memory (long work lists) or the global delta block itself
+    // (short lists: the few changes go out as fire-and-forget reductions); inlined per call site
     int* col_a = s_delta;
     int* row_b = s_delta + V;
     int* col_c = s_delta + 2 * V;
@@ -513,10 +524,17 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
         prev_new = id;
         push(x);
     };
+    // the chunks of one sequence are n_stride * 16 bytes apart: pull the next few towards L1 ahead of the
+    // one-deep register pipeline (reads run ahead of the in-place writes, which never pass chunk ci)
+    auto prefetch_chunk = [&](int ci) {
+        if (ci < nch) asm volatile("prefetch.global.L1 [%0];" ::"l"(&sym4[(long long)ci * n_stride + seq]));
+    };
     uint4 w_next = sym4[(long long)cs * n_stride + seq];
+    prefetch_chunk(cs + 1); prefetch_chunk(cs + 2); prefetch_chunk(cs + 3); prefetch_chunk(cs + 4);
     for (int ci = cs; ci < nch; ++ci) {
         const uint4 w = w_next;
         if (ci + 1 < nch) w_next = sym4[(long long)(ci + 1) * n_stride + seq];   // next chunk in flight while this one is processed
+        prefetch_chunk(ci + 5);
 #pragma unroll
         for (int j = 0; j < kChunk; ++j) {
             if (ci * kChunk + j >= n) break;
@@ -560,6 +578,13 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
     }
     const int n_work = *work_count;
     if ((long long)blockIdx.x * blockDim.x >= n_work) return;       // nothing for this block
+    if (n_work <= kDirectDeltaWork) {
+        // short work list (the steady state after the first ~100 merges): the few count changes go straight
+        // to the global delta block as fire-and-forget reductions, no 4 x V block-private counters to zero and flush
+        const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n_work) rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, delta, sig);
+        return;
+    }
     for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_work;
