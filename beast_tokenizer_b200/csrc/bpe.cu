@@ -1095,6 +1095,138 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
     }
 }
 
+// ---------------------------------------------------------------- decode (K5b), one warp per sequence
+// Lanes read the ids (coalesced), a warp scan of the token byte lengths places every token's bytes in
+// shared memory, then UTF-8 is decoded in parallel: a byte that is not a continuation byte starts a
+// character whose index is the number of such bytes before it (ballot + popcount).  Errors follow the
+// sequential decoder's order: the byte stream ends at the first id out of range; an invalid byte before
+// that point gives status 2, else the bad id gives 1, else an unfinished character at the end gives 2,
+// else a character count != L gives 3 (the reference's length ValueError, bpe_tokenizer.py:241-244).
+__device__ __forceinline__ int utf8_lead_len(int b) {
+    return b < 0x80 ? 1 : ((b & 0xE0) == 0xC0 ? 2 : ((b & 0xF0) == 0xE0 ? 3 : ((b & 0xF8) == 0xF0 ? 4 : 0)));
+}
+
+__global__ void __launch_bounds__(256)
+bpe_decode_warp_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
+                       long long min_token, const int* __restrict__ tok_off, const uint8_t* __restrict__ tok_bytes,
+                       int n_vocab, long long* __restrict__ bins_out, int* __restrict__ status_out,
+                       int* __restrict__ declen_out, int cap, int warp_bytes) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint8_t* s_b = s_raw + (size_t)warp * warp_bytes;
+    uint16_t* s_cp = (uint16_t*)(s_b + ((cap + 15) & ~15));
+    const unsigned int FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
+        const long long p0 = offsets[seq], p1 = offsets[seq + 1];
+        int B = 0, status = 0, cnt = 0;
+        bool bad_tok = false, overflow = false;
+        for (long long q0 = p0; q0 < p1; q0 += 32) {
+            const long long q = q0 + lane;
+            const int id = q < p1 ? flat[q] : 0;
+            const bool isbad = q < p1 && (id < 0 || id >= n_vocab);
+            const unsigned int badm = __ballot_sync(FULL, isbad);
+            const int nvalid = badm ? __ffs(badm) - 1 : 32;
+            int b0 = 0, len = 0;
+            if (q < p1 && lane < nvalid) { b0 = tok_off[id]; len = tok_off[id + 1] - b0; }
+            int inc = len;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int total = __shfl_sync(FULL, inc, 31);
+            if (B + total > cap) { overflow = true; break; }
+            const int at = B + inc - len;
+            for (int k = 0; k < len; ++k) s_b[at + k] = tok_bytes[b0 + k];
+            B += total;
+            if (badm) { bad_tok = true; break; }
+        }
+        __syncwarp();
+        if (overflow) {
+            // more bytes than any valid sequence can have: the sequential state machine decides which error
+            // comes first (rare; one lane, straight from global memory)
+            if (lane == 0) {
+                int pending = 0, acc = 0;
+                for (long long p = p0; p < p1 && !status; ++p) {
+                    const int id = flat[p];
+                    if (id < 0 || id >= n_vocab) { status = 1; break; }
+                    for (int q = tok_off[id]; q < tok_off[id + 1]; ++q) {
+                        const int bt = tok_bytes[q];
+                        int out_c = -1;
+                        if (pending) {
+                            if ((bt & 0xC0) != 0x80) { status = 2; break; }
+                            acc = (acc << 6) | (bt & 0x3F);
+                            if (--pending == 0) out_c = acc;
+                        } else if (bt < 0x80) out_c = bt;
+                        else if (utf8_lead_len(bt) >= 2) { pending = utf8_lead_len(bt) - 1; acc = bt & (0x3F >> pending); }
+                        else { status = 2; break; }
+                        if (out_c >= 0) {
+                            if (out_c > 0xFFFF) { status = 2; break; }
+                            if (cnt < L) s_cp[cnt] = (uint16_t)out_c;
+                            ++cnt;
+                        }
+                    }
+                }
+                if (!status && pending) status = 2;
+                if (!status && cnt != L) status = 3;
+            }
+            status = __shfl_sync(FULL, status, 0);
+            cnt = __shfl_sync(FULL, cnt, 0);
+        } else {
+            int first_err = 0x7fffffff, n_start = 0;
+            bool pend_end = false;
+            for (int i0 = 0; i0 < B; i0 += 32) {
+                const int i = i0 + lane;
+                const bool valid = i < B;
+                const int b = valid ? s_b[i] : 0;
+                const bool cont = valid && (b & 0xC0) == 0x80;
+                const bool start = valid && !cont;
+                int err = 0x7fffffff, cpv = -1;
+                if (start) {
+                    const int n = utf8_lead_len(b);
+                    if (n == 0) err = i;                      // 0xF8..0xFF
+                    else {
+                        int acc = n == 1 ? b : (b & (0x7F >> n));
+                        bool complete = true;
+                        for (int k = 1; k < n; ++k) {
+                            if (i + k >= B) { pend_end = true; complete = false; break; }
+                            const int c = s_b[i + k];
+                            if ((c & 0xC0) != 0x80) { err = i + k; complete = false; break; }
+                            acc = (acc << 6) | (c & 0x3F);
+                        }
+                        if (complete) {
+                            if (acc > 0xFFFF) err = i + n - 1;
+                            else cpv = acc;
+                        }
+                    }
+                } else if (cont) {                            // must lie inside the span of the lead before it
+                    bool covered = false;
+                    for (int k = 1; k <= 3 && k <= i; ++k) {
+                        const int c = s_b[i - k];
+                        if ((c & 0xC0) != 0x80) { covered = utf8_lead_len(c) > k; break; }
+                    }
+                    if (!covered) err = i;
+                }
+                const unsigned int sm = __ballot_sync(FULL, start);
+                const int idx = n_start + __popc(sm & lt);
+                if (cpv >= 0 && idx < L) s_cp[idx] = (uint16_t)cpv;
+                n_start += __popc(sm);
+                first_err = min(first_err, __reduce_min_sync(FULL, err));
+            }
+            pend_end = __any_sync(FULL, pend_end);
+            cnt = n_start - (pend_end ? 1 : 0);
+            if (first_err != 0x7fffffff) status = 2;
+            else if (bad_tok) status = 1;
+            else if (pend_end) status = 2;
+            else if (cnt != L) status = 3;
+        }
+        __syncwarp();
+        if (lane == 0) { status_out[seq] = status; declen_out[seq] = cnt; }
+        long long* out = bins_out + seq * L;
+        for (int i = lane; i < L; i += 32) out[i] = (long long)s_cp[i] + min_token;
+        __syncwarp();
+    }
+}
+
 static int bpe_grid(long long n, int block) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1370,6 +1502,33 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
     if (N == 0) return BEAST_OK;
     if (!offsets || !tok_off || !tok_bytes || !bins_out || !status_out || !declen_out) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_vocab < 1) return BEAST_E_SHAPE;
+    {   // one warp per sequence; BEAST_B200_BPE_THREAD_DECODE=1 (or rows too long for shared memory) takes the
+        // one-thread-per-sequence kernel
+        const int cap = 4 * L + 64;                          // a valid sequence has at most 3 L bytes
+        const size_t warp_bytes = (((size_t)cap + 15) & ~(size_t)15) + (((size_t)L * 2 + 15) & ~(size_t)15);
+        int warps = (int)((200 * 1024) / warp_bytes);
+        if (warps > 8) warps = 8;
+        const char* env = getenv("BEAST_B200_BPE_THREAD_DECODE");
+        if (warps >= 1 && !(env && env[0] == '1')) {
+            const size_t smem = warp_bytes * warps;
+            static size_t granted_w[kMaxDevices] = {};
+            if (int rc = opt_in_smem(bpe_decode_warp_kernel, smem, granted_w)) return rc;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
+            if (per_sm > 2048 / (warps * 32)) per_sm = 2048 / (warps * 32);
+            if (per_sm < 1) per_sm = 1;
+            long long grid = (N + warps - 1) / warps;
+            if (grid > sms * per_sm) grid = sms * per_sm;
+            bpe_decode_warp_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
+                flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out,
+                status_out, declen_out, cap, (int)warp_bytes);
+            count_launch();
+            BEAST_CHECK_LAUNCH();
+            return BEAST_OK;
+        }
+    }
     const int rows = stage_rows_per_block(L);
     if (rows < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)rows * (L + 1) * 2;

@@ -227,3 +227,46 @@ def test_train_cli_flow_reference_defaults(tmp_path):
                         __import__("beast_tokenizer_b200.synth", fromlist=["SyntheticLoader"]).SyntheticLoader(12, 32, 10, 32, seed0=0)])
     o2 = OracleBPE.train(corpus.cpu().numpy(), 2048)
     assert tok.bpe_tokenizer.merges_txt() == o2.merges_txt()
+
+
+def test_decode_kernels_agree_on_garbage(monkeypatch):
+    """The warp-per-sequence decode and the one-thread-per-sequence decode (the sequential UTF-8 state
+    machine) must report the same status for arbitrary id streams: random ids give stray continuation
+    bytes, truncated characters, ids out of range, wrong lengths — and a few valid rows."""
+    from beast_tokenizer_b200 import FIGBPE
+    rng = np.random.default_rng(11)
+    bins = np.clip(rng.normal(500, 150, (3000, 60)).round(), 0, 999).astype(np.int64)     # 2-byte UTF-8 symbols
+    state = FIGBPE(vocab_size=1500, show_progress=False).fit_from_bins(torch.from_numpy(bins).cuda())
+    tk = state.tokenizer
+    n_vocab = len(tk.tokens)
+    good, goff, st = tk.encode_bins(torch.from_numpy(bins[:200]).cuda(), state.min_token, state.max_token)
+    good, goff = good.cpu().numpy(), goff.cpu().numpy()
+    rows = [good[goff[i]:goff[i + 1]] for i in range(200)]                                # valid rows
+    for i in range(600):
+        kind = i % 6
+        if kind == 0:                                                                       # random ids, random length
+            rows.append(rng.integers(0, n_vocab, int(rng.integers(0, 140))))
+        elif kind == 1:                                                                     # a valid row with one id replaced
+            r = rows[i % 200].copy(); r[rng.integers(0, len(r))] = rng.integers(0, n_vocab); rows.append(r)
+        elif kind == 2:                                                                     # id out of range somewhere
+            r = rows[i % 200].copy(); r[rng.integers(0, len(r))] = n_vocab + int(rng.integers(0, 5)); rows.append(r)
+        elif kind == 3:                                                                     # negative id after garbage
+            r = rng.integers(0, n_vocab, 20); r[rng.integers(0, 20)] = -1; rows.append(r)
+        elif kind == 4:                                                                     # truncated / extended valid rows
+            r = rows[i % 200]; rows.append(np.concatenate([r[:len(r) // 2], r[:int(rng.integers(0, 4))]]))
+        else:                                                                               # far too long: overflow path
+            rows.append(rng.integers(0, n_vocab, 400))
+    flat = torch.from_numpy(np.concatenate(rows).astype(np.int32)).cuda()
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)).cuda()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BEAST_B200_BPE_THREAD_DECODE", mode)
+        dec, stt, ln = tk.decode_ids(flat, offs, 60, state.min_token)
+        out[mode] = (dec.cpu().numpy(), stt.cpu().numpy(), ln.cpu().numpy())
+    (d0, s0, l0), (d1, s1, l1) = out["0"], out["1"]
+    assert np.array_equal(s0, s1), np.flatnonzero(s0 != s1)[:10]
+    assert set(np.unique(s0)) >= {0, 1, 2, 3}
+    ok = s0 == 0
+    assert ok[:200].all() and np.array_equal(d0[ok], d1[ok]) and np.array_equal(d0[:200], bins[:200])
+    len_known = (s0 == 0) | (s0 == 3)
+    assert np.array_equal(l0[len_known], l1[len_known])
