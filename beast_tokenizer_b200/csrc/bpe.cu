@@ -40,7 +40,8 @@ __device__ __forceinline__ long long sym_index(int p, long long seq, long long n
 // sequence holds or ever held (bits are only added, so the set is a superset).  Stored word-major
 // (sig[word * n_stride + seq]) so that the scan for one pair reads a single 4-byte column.
 constexpr int kScanTile = 2048;          // sequences filtered per block and step by the signature scan
-constexpr int kDirectDeltaWork = 1 << 14; // rewrite: work lists up to this size update the global delta directly
+constexpr int kDirectDeltaWork = 1 << 17; // rewrite: work lists up to this size are rewritten one warp per sequence
+constexpr int kGlobalDeltaWork = 1 << 14; // ... and up to this size their count changes go straight to the global delta block // rewrite: work lists up to this size update the global delta directly
 constexpr int kSigWords = 64;
 constexpr int kSigBits = kSigWords * 32;
 // Two independent hash positions per pair (a Bloom filter with k = 2): a sequence passes the scan's
@@ -566,6 +567,133 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
     len[seq] = n_new;
 }
 
+// Warp-cooperative rewrite of ONE sequence (short work lists: the steady state of training, where the
+// latency of a single divergent thread per sequence is the cost).  Lane l owns chunk cs + l (eight
+// symbols in registers); the caller guarantees at most 32 chunks from cs on.
+//   cand[p]  = id[p] == a and the next symbol is exactly b (same pre-token)
+//   match[p] = cand[p] and not match[p-1]          (left-to-right, non-overlapping; matters only for a == b)
+// The recurrence is a composition of one-bit functions, so each lane evaluates its chunk for both possible
+// inputs and a warp scan of the compositions yields every lane's true input.  Symbol p+1 of a match is
+// dropped, symbol p becomes c; output positions are a prefix sum of the kept counts; count changes of
+// the neighbours go to the global delta block (and the signature) as fire-and-forget reductions.
+__device__ __forceinline__ void rewrite_sequence_warp(uint16_t* __restrict__ sym, int* __restrict__ len, long long seq,
+                                                      int q0, int n, long long n_stride, int a, int b, int c, int V,
+                                                      int* __restrict__ delta, unsigned int* __restrict__ sig,
+                                                      uint16_t* s_out) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint4* sym4 = (uint4*)sym;
+    const int nch = (n + kChunk - 1) >> 3;
+    const int cs = q0 >> 3;
+    const int ci = cs + lane;
+    const uint16_t bsym = (uint16_t)b;
+    uint4 w = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (ci < nch) w = sym4[(long long)ci * n_stride + seq];
+    unsigned int s[kChunk];
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) s[j] = chunk_get(w, j);
+    // neighbours across lanes: two symbols ahead, one behind
+    unsigned int nx0 = __shfl_down_sync(FULL, s[0], 1), nx1 = __shfl_down_sync(FULL, s[1], 1);
+    unsigned int pv7 = __shfl_up_sync(FULL, s[7], 1);
+    if (lane == 31) { nx0 = kPad; nx1 = kPad; }
+    if (lane == 0) {
+        pv7 = kPad;
+        if (cs > 0) pv7 = (sym4[(long long)(cs - 1) * n_stride + seq].w >> 16) & 0xffffu;
+    }
+    const int p0 = ci * kChunk;                               // position of s[0]
+    auto at = [&](int j) -> unsigned int { return j < 0 ? pv7 : (j < kChunk ? s[j < 0 ? 0 : (j > 7 ? 7 : j)] : (j == 8 ? nx0 : nx1)); };
+    unsigned int cand = 0;
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+        const unsigned int nxt = j + 1 < kChunk ? s[j + 1 < kChunk ? j + 1 : 7] : nx0;
+        if (p0 + j + 1 < n && (s[j] & kIdMask) == (unsigned int)a && nxt == bsym) cand |= 1u << j;
+    }
+    // match bits for incoming 0 / 1, then the lane's true input by a scan over function compositions
+    auto run = [&](unsigned int m_in) {
+        unsigned int m = 0, prev = m_in;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            const unsigned int mj = ((cand >> j) & 1u) & (prev ^ 1u);
+            m |= mj << j;
+            prev = mj;
+        }
+        return m;
+    };
+    const unsigned int m_if0 = run(0u), m_if1 = run(1u);
+    unsigned int f = ((m_if0 >> 7) & 1u) | (((m_if1 >> 7) & 1u) << 1);     // bit x = output for input x
+    for (int o = 1; o < 32; o <<= 1) {                        // inclusive scan: F_l = f_l o F_{l-o}
+        const unsigned int g = __shfl_up_sync(FULL, f, o);
+        if (lane >= o) f = ((f >> (g & 1u)) & 1u) | (((f >> ((g >> 1) & 1u)) & 1u) << 1);
+    }
+    unsigned int m_in = __shfl_up_sync(FULL, f & 1u, 1);      // the sequence enters chunk cs with input 0
+    if (lane == 0) m_in = 0;
+    const unsigned int match = m_in ? m_if1 : m_if0;
+    const unsigned int match_prev = __shfl_up_sync(FULL, match, 1), match_next = __shfl_down_sync(FULL, match, 1);
+    auto is_match = [&](int j) -> bool {                      // j in [-2, 9]
+        if (j < 0) return lane > 0 && ((match_prev >> (j + kChunk)) & 1u);
+        if (j < kChunk) return (match >> j) & 1u;
+        return lane < 31 && ((match_next >> (j - kChunk)) & 1u);
+    };
+    auto sig_add = [&](int x, int y) {
+        if (sig) {
+            const unsigned int h = sig_hash((unsigned int)x, (unsigned int)y), h2 = sig_hash2((unsigned int)x, (unsigned int)y);
+            atomicOr(&sig[(long long)(h >> 5) * n_stride + seq], 1u << (h & 31u));
+            atomicOr(&sig[(long long)(h2 >> 5) * n_stride + seq], 1u << (h2 & 31u));
+        }
+    };
+    // kept symbols of this lane and their values
+    int kept = 0;
+    unsigned int outv[kChunk];
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+        const bool valid = p0 + j < n;
+        const bool dropped = j == 0 ? (m_in != 0) : ((match >> (j - 1)) & 1u);
+        outv[j] = 0xffffffffu;                                // not kept
+        if (valid && !dropped) {
+            outv[j] = ((match >> j) & 1u) ? ((unsigned int)c | (s[j] & kWordStart)) : s[j];
+            ++kept;
+        }
+        if ((match >> j) & 1u) {                              // neighbour counts of the merge at p0 + j
+            if (!(s[j] & kWordStart)) {                       // a left neighbour inside the pre-token
+                const bool left_merged = is_match(j - 2);
+                const int prev_old = left_merged ? b : (int)(at(j - 1) & kIdMask);
+                const int prev_new = left_merged ? c : prev_old;
+                atomicAdd(&delta[prev_old], -1);              // (old left, a) disappears
+                atomicAdd(&delta[2 * V + prev_new], 1);       // (new left, c) appears
+                sig_add(prev_new, c);
+            }
+            const unsigned int r = at(j + 2);
+            if (p0 + j + 2 < n && !(r & kWordStart) && !is_match(j + 2)) {
+                const int id = (int)(r & kIdMask);
+                atomicAdd(&delta[V + id], -1);                // (b, y) disappears
+                atomicAdd(&delta[3 * V + id], 1);             // (c, y) appears
+                sig_add(c, id);
+            }
+        }
+    }
+    int inc = kept;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int total = __shfl_sync(FULL, inc, 31);
+    int o = inc - kept;
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j)
+        if (outv[j] != 0xffffffffu) s_out[o++] = (uint16_t)outv[j];
+    const int padded = (total + kChunk - 1) & ~(kChunk - 1);
+    for (int i = total + lane; i < padded; i += 32) s_out[i] = kPad;
+    __syncwarp();
+    if (lane * kChunk < padded) {
+        const uint16_t* src = s_out + lane * kChunk;
+        sym4[(long long)(cs + lane) * n_stride + seq] =
+            make_uint4((unsigned int)src[0] | ((unsigned int)src[1] << 16), (unsigned int)src[2] | ((unsigned int)src[3] << 16),
+                       (unsigned int)src[4] | ((unsigned int)src[5] << 16), (unsigned int)src[6] | ((unsigned int)src[7] << 16));
+    }
+    if (lane == 0) len[seq] = cs * kChunk + total;
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(256)
 bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int a, int b, int c, int V,
                    const BpeCtl* __restrict__ ctl, const int* __restrict__ work_count,
@@ -577,12 +705,57 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
         a = ctl->a; b = ctl->b; c = ctl->c;
     }
     const int n_work = *work_count;
-    if ((long long)blockIdx.x * blockDim.x >= n_work) return;       // nothing for this block
+    if (n_work > kDirectDeltaWork && (long long)blockIdx.x * blockDim.x >= n_work) return;       // nothing for this block
     if (n_work <= kDirectDeltaWork) {
         // short work list (the steady state after the first ~100 merges): the few count changes go straight
-        // to the global delta block as fire-and-forget reductions, no 4 x V block-private counters to zero and flush
-        const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < n_work) rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, delta, sig);
+        // to the global delta block as fire-and-forget reductions, no 4 x V block-private counters to zero and
+        // flush; one WARP per sequence (entries with more than 32 chunks left take the one-thread state machine)
+        __shared__ uint16_t s_out[8][32 * kChunk + kChunk];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        // a warp's entries are e0 + k * stride: the lanes fetch the (sequence, position, length) triples of up to
+        // 32 of them at once, so that dependent-load chain is paid once per batch; the chunks of entry k + 1 are
+        // pulled towards L1 while entry k is rewritten
+        const long long stride = (long long)gridDim.x * nw;
+        const uint4* sym4 = (const uint4*)sym;
+        const bool use_smem = n_work > kGlobalDeltaWork;
+        if (use_smem) {
+            if ((long long)blockIdx.x * nw >= n_work) return;        // no entry for this block
+            for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
+            __syncthreads();
+        }
+        for (long long e0 = (long long)blockIdx.x * nw + warp; e0 < n_work; e0 += 32 * stride) {
+            const long long my_e = e0 + lane * stride;
+            const bool have = my_e < n_work;
+            const int my_seq = have ? work_seq[my_e] : 0, my_q0 = have ? work_q0[my_e] : 0;
+            const int my_n = have ? len[my_seq] : 0;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, have));
+            for (int k = 0; k < cnt; ++k) {
+                const long long seq = __shfl_sync(0xffffffffu, my_seq, k);
+                const int q0 = __shfl_sync(0xffffffffu, my_q0, k), n = __shfl_sync(0xffffffffu, my_n, k);
+                if (k + 1 < cnt) {
+                    const long long seq2 = __shfl_sync(0xffffffffu, my_seq, k + 1);
+                    const int ci2 = (__shfl_sync(0xffffffffu, my_q0, k + 1) >> 3) + lane;
+                    const int nch2 = (__shfl_sync(0xffffffffu, my_n, k + 1) + kChunk - 1) >> 3;
+                    if (ci2 < nch2) asm volatile("prefetch.global.L1 [%0];" ::"l"(&sym4[(long long)ci2 * n_stride + seq2]));
+                }
+                const int chunks_left = ((n + kChunk - 1) >> 3) - (q0 >> 3);
+                if (use_smem) {                               // block-private counters: hot neighbours would serialise in L2
+                    if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, s_delta, sig, s_out[warp]);
+                    else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, s_delta, sig);
+                } else {
+                    if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, delta, sig, s_out[warp]);
+                    else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, delta, sig);
+                }
+                __syncwarp();
+            }
+        }
+        if (use_smem) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
+                const int d = s_delta[i];
+                if (d) atomicAdd(&delta[i], d);
+            }
+        }
         return;
     }
     for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
