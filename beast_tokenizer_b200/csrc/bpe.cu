@@ -5,18 +5,24 @@
 // kernels implement the same algorithm on integer symbols:
 //
 //   symbolise   bins -> GPT-2 pre-tokenisation -> UTF-8 bytes -> symbol ids, word-start flag in bit 15
-//   count       adjacent-pair histogram, dense V x V int32 (L2-resident: 16 MB at V = 2048)
-//   argmax      max count, ties -> smallest (a, b)  ==  smallest flat index a*V + b
-//   merge       per sequence, left to right, non-overlapping, in-place compaction; the count changes
-//               are confined to column a, row b, column c, row c of the histogram and are collected
-//               in a 4 x V delta block (summed over GPUs with one small all-reduce when sharded)
-//   encode      per word: repeatedly merge the lowest-rank pair, leftmost first
-//   decode      ids -> token bytes -> UTF-8 -> codepoints + min_token
+//   count       adjacent-pair histogram, dense V x V int32 (L2-resident: 16 MB at V = 2048), counted in
+//               block-private shared-memory histograms over the distinct byte-level symbols
+//   iterate     fold the previous merge's 4 x V delta block, arg-max: max count, ties -> smallest (a, b)
+//   pick        BpeTrainer's stop rules, next id, merge log (all on the device: the loop never syncs)
+//   scan        which sequences hold (a, b): per-sequence 2048-bit pair signatures (Bloom filter, word-major)
+//               filter the corpus down to the survivors, which are walked in lock step; hits -> work list
+//   rewrite     left to right, non-overlapping, in-place compaction — one warp per sequence (short lists)
+//               or one thread per sequence (long lists); the count changes are confined to column a, row b,
+//               column c, row c of the histogram and are collected in the 4 x V delta block (summed over
+//               GPUs with one small all-reduce when sharded)
+//   encode      one warp per sequence: token starts by a local rule, per word repeatedly merge the
+//               lowest-rank pair, leftmost first
+//   decode      one warp per sequence: ids -> token bytes -> UTF-8 -> codepoints + min_token
 //
 // Corpus layout: CHUNK-MAJOR — 8 consecutive symbols (16 bytes) of one sequence form a chunk and chunk c
-// of all sequences is contiguous: sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)] (uint16).  One thread
-// owns one sequence; a warp reads / writes chunk c of its 32 sequences as 512 contiguous bytes, one
-// 128-bit access per lane, so the serial per-sequence state machines run at full coalescing.
+// of all sequences is contiguous: sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)] (uint16).  A warp that
+// walks 32 sequences reads / writes chunk c of all of them as 512 contiguous bytes, one 128-bit access
+// per lane.
 #include "common.cuh"
 
 namespace beast {
@@ -768,29 +774,6 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
         const int d = s_delta[i];
         if (d) atomicAdd(&delta[i], d);
     }
-}
-
-// Decode the arg-max key, apply the stop rules of BpeTrainer (vocabulary full, count < min_frequency),
-// assign the next id, log the merge.  One thread; also re-arms the arg-max result.
-__global__ void bpe_select_kernel(unsigned long long* __restrict__ result, BpeCtl* __restrict__ ctl,
-                                  int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges,
-                                  int* __restrict__ work_count) {
-    const unsigned long long key = *result;
-    *result = 0;
-    *work_count = 0;
-    if (ctl->done) return;
-    const int count = (int)(key >> 32);
-    if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges) {
-        ctl->done = 1;
-        return;
-    }
-    const unsigned int flat = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
-    ctl->a = (int)(flat / (unsigned int)V);
-    ctl->b = (int)(flat % (unsigned int)V);
-    ctl->c = ctl->n_tokens++;
-    ctl->count = count;
-    int* e = log + 4 * ctl->n_merges++;
-    e[0] = ctl->a; e[1] = ctl->b; e[2] = ctl->c; e[3] = count;
 }
 
 // Iteration head of the sync-free loop: fold the (all-reduced) delta block of the previous merge into the
