@@ -296,10 +296,52 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
              "encode_seq_per_s": nb / (ev[0].elapsed_time(ev[1]) * 1e-3),
              "decode_seq_per_s": nb / (ev[1].elapsed_time(ev[2]) * 1e-3),
              "ids_per_sequence": float(flat.numel()) / nb, "round_trip_exact": bool(torch.equal(back, mp))}
+    if with_cpu:
+        ref = bpe_apply_cpu_reference(btok, mp[:4096].cpu())
+        if ref is not None:
+            ids_gpu = btok._discrete_to_bpe(mp[:64])
+            hf = btok.bpe_tokenizer.to_hf()
+            ref["ids_identical_to_gpu"] = ids_gpu == [hf.encode("".join(map(chr, r))).ids
+                                                      for r in (mp[:64].cpu() - btok.bpe_min_token).tolist()]
+            apply["cpu_reference"] = ref
     return out, apply
 
 
-def bounds_leg(tok, dev):
+def bounds_cpu_reference(n=4096):
+    """fit_parameters as the reference runs it (beast_bspline_tokenizer.py:181-220): per batch of 32 the fit on the
+    host, weights concatenated, np.quantile(1 %, 99 %) — bounded sample, linear in the trajectory count."""
+    import numpy as np
+    import torch
+    from beast_tokenizer_b200.synth import synth
+    port = make_port()
+    x = synth(n, T, D, seed=7)
+    port.compute_weights(x[:32])
+    t0 = time.perf_counter()
+    w = torch.cat([port.compute_weights(x[i:i + 32]) for i in range(0, n, 32)]).numpy()
+    np.quantile(w, 0.01, axis=0), np.quantile(w, 0.99, axis=0)
+    dt = time.perf_counter() - t0
+    return {"traj_per_s": n / dt, "seconds": dt, "sample": f"{n} trajectories in batches of 32, torch-CPU port + np.quantile, "
+            f"{cpu_threads()} threads"}
+
+
+def bpe_apply_cpu_reference(btok, mp_tokens_cpu, n=4096):
+    """_discrete_to_bpe / _bpe_to_discrete as the reference runs them (beast_bspline_bpe_tokenizer.py:175-247): a Python
+    loop over rows around HF tokenizer.encode / decode."""
+    try:
+        hf = btok.bpe_tokenizer.to_hf()
+    except ImportError:
+        return None
+    rows = (mp_tokens_cpu[:n] - btok.bpe_min_token).tolist()
+    t0 = time.perf_counter()
+    ids = [hf.encode("".join(map(chr, r))).ids for r in rows]
+    t1 = time.perf_counter()
+    back = [[ord(ch) + btok.bpe_min_token for ch in hf.decode(i)] for i in ids]
+    t2 = time.perf_counter()
+    return {"batch": n, "encode_seq_per_s": n / (t1 - t0), "decode_seq_per_s": n / (t2 - t1),
+            "round_trip_exact": back == mp_tokens_cpu[:n].tolist(), "engine": "tokenizers (per-row Python loop, as the reference)"}
+
+
+def bounds_leg(tok, dev, with_cpu=False):
     """BASELINE configs[2]: weight bounds over 100 000 trajectories — the fused min/max reduction
     (update_weights_bounds) and the reference-faithful quantile fit (fit_parameters)."""
     import torch
@@ -331,6 +373,8 @@ def bounds_leg(tok, dev):
         out.setdefault("fit_parameters", {})[label] = {"seconds": dt, "traj_per_s": n / dt}
     tok.w_min.copy_(saved[0])
     tok.w_max.copy_(saved[1])
+    if with_cpu:
+        out["cpu_reference"] = bounds_cpu_reference()
     return out
 
 
@@ -504,7 +548,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
-    bounds = bounds_leg(tok, dev) if rank == 0 else None
+    bounds = bounds_leg(tok, dev, with_cpu=world == 1 and not args.no_cpu_baseline) if rank == 0 else None
     bpe_train = bpe_apply = None
     if not args.no_bpe:
         del xs, toks, pars, outs, xh
