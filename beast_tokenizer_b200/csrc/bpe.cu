@@ -728,6 +728,25 @@ __device__ __forceinline__ void rewrite_sequence_warp(uint16_t* __restrict__ sym
     __syncwarp();
 }
 
+// Block-private 4 x V delta counters in (dynamic, 16-byte aligned) shared memory: zero / flush with
+// 128-bit accesses; only non-zero counters reach the global delta block.
+__device__ __forceinline__ void zero_delta_block(int* s_delta, int V) {
+    int4* p = (int4*)s_delta;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) p[i] = make_int4(0, 0, 0, 0);      // 4 V ints = V int4
+}
+__device__ __forceinline__ void flush_delta_block(const int* s_delta, int* __restrict__ delta, int V) {
+    const int4* p = (const int4*)s_delta;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const int4 d = p[i];
+        if (d.x | d.y | d.z | d.w) {
+            if (d.x) atomicAdd(&delta[4 * i], d.x);
+            if (d.y) atomicAdd(&delta[4 * i + 1], d.y);
+            if (d.z) atomicAdd(&delta[4 * i + 2], d.z);
+            if (d.w) atomicAdd(&delta[4 * i + 3], d.w);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int a, int b, int c, int V,
                    const BpeCtl* __restrict__ ctl, const int* __restrict__ work_count,
@@ -754,7 +773,7 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
         const bool use_smem = n_work > kGlobalDeltaWork;
         if (use_smem) {
             if ((long long)blockIdx.x * nw >= n_work) return;        // no entry for this block
-            for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
+            zero_delta_block(s_delta, V);
             __syncthreads();
         }
         for (long long e0 = (long long)blockIdx.x * nw + warp; e0 < n_work; e0 += 32 * stride) {
@@ -785,23 +804,17 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
         }
         if (use_smem) {
             __syncthreads();
-            for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
-                const int d = s_delta[i];
-                if (d) atomicAdd(&delta[i], d);
-            }
+            flush_delta_block(s_delta, delta, V);
         }
         return;
     }
-    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) s_delta[i] = 0;
+    zero_delta_block(s_delta, V);
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_work;
          i += (long long)gridDim.x * blockDim.x)
         rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta, sig);
     __syncthreads();
-    for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) {
-        const int d = s_delta[i];
-        if (d) atomicAdd(&delta[i], d);
-    }
+    flush_delta_block(s_delta, delta, V);
 }
 
 // Iteration head of the sync-free loop: fold the (all-reduced) delta block of the previous merge into the
