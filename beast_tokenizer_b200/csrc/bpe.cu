@@ -1109,7 +1109,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
     uint16_t* cp = wid + M;
     uint16_t* wbeg = cp + ((L + 1) & ~1);
     const int P = (L + 31) >> 5;
-    const unsigned int FULL = 0xffffffffu, NONE = 0xffffffffu;
+    const unsigned int FULL = 0xffffffffu, NONE = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
         // ---- A
         int st = 0;
@@ -1176,8 +1176,25 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
         }
         if (lane == 0) wbeg[nwords] = (uint16_t)total;
         __syncwarp();
-        // ---- D: one lane per word; a word's slots are only touched by its lane
-        for (int wq = lane; wq < nwords; wq += 32) {
+        // ---- D: one lane per word; a word's slots are only touched by its lane.  Lanes that sit in different
+        // loops of the merge code serialise, so words are handed out longest class first (>= 7 symbols, 3-6, 2; finer classes cost more in ballots than they save):
+        // the lanes of one round then run words of similar length.  Single symbols need no work at all.
+        // (`sym` is free after phase C and holds the order list.)
+        int n_order = 0;
+        for (int cls = 0; cls < 3; ++cls) {
+            for (int w0 = 0; w0 < nwords; w0 += 32) {
+                const int wq = w0 + lane;
+                const int wl = wq < nwords ? wbeg[wq + 1] - wbeg[wq] : 0;
+                const bool in = cls == 0 ? wl >= 7 : (cls == 1 ? (wl >= 3 && wl <= 6) : wl == 2);
+                const unsigned int m = __ballot_sync(FULL, in);
+                if (in) sym[n_order + __popc(m & lt_mask)] = (uint16_t)wq;
+                n_order += __popc(m);
+                if (cls == 0 && wl == 1) wid[wbeg[wq]] = 1;
+            }
+        }
+        __syncwarp();
+        for (int oi = lane; oi < n_order; oi += 32) {
+            const int wq = sym[oi];
             const int b = wbeg[wq];
             int wl = wbeg[wq + 1] - b;
             unsigned int* wk = key + b;
