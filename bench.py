@@ -226,16 +226,20 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    state = fig.fit_from_bins(bins)
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    secs = float(dt.item())
+    runs = []
+    for _ in range(2):                                # the first full-size fit also pays the allocator's cudaMallocs (~1 GB of buffers)
+        t0 = time.perf_counter()
+        state = fig.fit_from_bins(bins)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        runs.append(float(dt.item()))
+    secs = min(runs)
     n_merges = len(state.tokenizer.merges)
     out = {"metric": "BPE-train merges/sec", "value": n_merges / secs, "unit": "merges/s", "seconds": secs,
-           "merges": n_merges, "vocab": BPE_VOCAB, "sequences": BPE_BATCHES * BPE_BATCH, "n_gpus": world,
+           "runs_seconds": runs, "merges": n_merges, "vocab": BPE_VOCAB, "sequences": BPE_BATCHES * BPE_BATCH, "n_gpus": world,
            "scaling": "strong", "sharding": f"{BPE_CHUNKS} chunks of {per_chunk} sequences round-robin over ranks; "
            "min/max, seen bytes, histogram and per-merge 4xV deltas all-reduced (NCCL)"}
     if rank != 0:
