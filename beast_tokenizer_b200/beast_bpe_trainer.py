@@ -159,7 +159,7 @@ class GpuBpeEngine:
                 if i >= sig_start and (i - sig_start) % sig_rebuild == 0:
                     build_sig()
                 if coll.on:
-                    step(0, i >= sig_start)             # fold previous delta + arg-max + select, scan, rewrite
+                    step(0, i >= sig_start)             # fold previous delta + arg-max, pick, scan, rewrite
                     coll.reduce_(self.delta, "sum")
                     i += 1
                 else:                                   # unsharded: enqueue up to the next signature rebuild in one call

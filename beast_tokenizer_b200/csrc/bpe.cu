@@ -1603,9 +1603,11 @@ extern "C" int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int
     return BEAST_OK;
 }
 
-// One iteration of the sync-free training loop.  phase 0: arg-max -> select -> merge (fills delta);
-// phase 1: hist += delta.  The caller runs [phase 0, all-reduce(delta) when sharded, phase 1] up to
-// (vocab_size - alphabet) times without reading anything back; ctl / log are read once at the end.
+// `iters` iterations of the sync-free training loop, each: iterate (fold the previous merge's delta, arg-max)
+// -> pick (stop rules, next id, log) -> scan (work list) -> rewrite (fills delta).  The caller runs
+// [one iteration, all-reduce(delta)] when sharded, or blocks of iterations when not, up to
+// (vocab_size - alphabet) merges without reading anything back; ctl / log are read once at the end.
+// (phase 1, once a separate hist += delta pass, is a no-op kept so that older callers still work.)
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                               int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
                               int32_t vocab_size, int32_t min_frequency, int32_t max_merges, int32_t phase,
@@ -1634,7 +1636,7 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     const int deep_walk = N <= (1 << 19) ? 1 : 0;
     // `iters` iterations back to back (unsharded training: nothing happens between them on the host)
     for (int it = 0; it < (iters < 1 ? 1 : iters); ++it) {
-        // one launch folds the previous delta, finds the arg-max and selects the merge (n_active lives on the device)
+        // fold the previous delta + arg-max, then pick the merge (n_active lives on the device)
         const int n_part = sms < 256 ? sms : 256;             // `result` holds 256 words
         bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, (const BpeCtl*)ctl, delta, (unsigned long long*)result);
         bpe_pick_kernel<<<1, 256, 0, st>>>((const unsigned long long*)result, n_part, (BpeCtl*)ctl, log, V, vocab_size,
