@@ -9,6 +9,7 @@ as device CSR tensors without the host round trip.
 from __future__ import annotations
 
 import json
+import itertools
 import numbers
 from pathlib import Path
 from typing import Iterable, List, Optional, Sequence, Union
@@ -198,16 +199,22 @@ class BEASTBsplineBPETokenizer(BEASTBsplineTokenizer):
             token_sequences = [tokens]
         else:
             token_sequences = tokens
-        arrays = []
-        for token in token_sequences:
-            if isinstance(token, torch.Tensor):
-                arrays.append(token.detach().cpu().numpy().astype(np.int64).reshape(-1))
-            else:
-                arrays.append(np.asarray([int(t) for t in token], dtype=np.int64).reshape(-1))
-        lens = np.asarray([a.size for a in arrays], dtype=np.int64)
-        offsets = np.zeros(len(arrays) + 1, dtype=np.int64)
+        if isinstance(token_sequences, (list, tuple)) and token_sequences and \
+                all(type(t) in (list, tuple) for t in token_sequences):
+            # the ragged List[List[int]] that encode() returns: one C-level pass instead of an int() call per id
+            lens = np.fromiter(map(len, token_sequences), dtype=np.int64, count=len(token_sequences))
+            flat = np.fromiter(itertools.chain.from_iterable(token_sequences), dtype=np.int64, count=int(lens.sum()))
+        else:
+            arrays = []
+            for token in token_sequences:
+                if isinstance(token, torch.Tensor):
+                    arrays.append(token.detach().cpu().numpy().astype(np.int64).reshape(-1))
+                else:
+                    arrays.append(np.asarray([int(t) for t in token], dtype=np.int64).reshape(-1))
+            lens = np.asarray([a.size for a in arrays], dtype=np.int64)
+            flat = np.concatenate(arrays) if arrays else np.zeros(0, dtype=np.int64)
+        offsets = np.zeros(len(lens) + 1, dtype=np.int64)
         np.cumsum(lens, out=offsets[1:])
-        flat = np.concatenate(arrays) if arrays else np.zeros(0, dtype=np.int64)
         if flat.size and (flat.min() < -2 ** 31 or flat.max() >= 2 ** 31):
             raise ValueError("BPE token id out of range")
         return torch.from_numpy(flat.astype(np.int32)).to(dev), torch.from_numpy(offsets).to(dev)

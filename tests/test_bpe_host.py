@@ -197,3 +197,24 @@ def test_sharded_training_two_ranks_gloo():
     for _, merges_txt, vocab_json, mn, mx in results:
         assert merges_txt == o.merges_txt() and vocab_json == o.vocab_json()
         assert (mn, mx) == (int(bins.min()), int(bins.max()))
+
+
+def test_ids_to_csr_accepts_every_container():
+    """bpe_to_mp_tokens / reconstruct_traj take the ragged List[List[int]] that encode() returns, and also
+    tuples, numpy rows, tensors, a single flat list: all must flatten to the same CSR (host logic, no GPU)."""
+    from beast_tokenizer_b200.beast_bspline_bpe_tokenizer import BEASTBsplineBPETokenizer as T
+    obj = T.__new__(T)
+    rows = [[1, 2, 3], [4], [], [5, 6, 2047]]
+    flat, off = T._ids_to_csr(obj, rows, "cpu")
+    assert flat.dtype == torch.int32 and off.dtype == torch.int64
+    assert flat.tolist() == [1, 2, 3, 4, 5, 6, 2047] and off.tolist() == [0, 3, 4, 4, 7]
+    for variant in (tuple(tuple(r) for r in rows), [np.asarray(r, dtype=np.int64) for r in rows],
+                    [torch.tensor(r, dtype=torch.long) for r in rows], [[np.int32(v) for v in r] for r in rows]):
+        f2, o2 = T._ids_to_csr(obj, variant, "cpu")
+        assert torch.equal(f2, flat) and torch.equal(o2, off)
+    f3, o3 = T._ids_to_csr(obj, [7, 8, 9], "cpu")                     # one sequence given as a flat list
+    assert f3.tolist() == [7, 8, 9] and o3.tolist() == [0, 3]
+    f4, o4 = T._ids_to_csr(obj, torch.tensor([[1, 2], [3, 4]]), "cpu")
+    assert f4.tolist() == [1, 2, 3, 4] and o4.tolist() == [0, 2, 4]
+    with pytest.raises(ValueError):
+        T._ids_to_csr(obj, [[2 ** 40]], "cpu")
