@@ -287,16 +287,39 @@ class BEASTBsplineTokenizer(TokenizerBase):
             except Exception:
                 iterator = dataloader
         sample_count = 0
+        # The reference fits batch by batch; the coefficients of a trajectory do not depend on its position in a
+        # batch, so small loader batches (32 in the reference's training script) are gathered on the device and
+        # fitted ~4 096 at a time: one K1 launch per chunk instead of one per batch.
+        dev = self._cuda()
+        pending, pending_rows = [], 0
+
+        def flush():
+            nonlocal pending_rows
+            if pending:
+                params.append(self.compute_weights(pending[0] if len(pending) == 1 else torch.cat(pending, dim=0)))
+                pending.clear()
+                pending_rows = 0
+
         for batch in iterator:
             if "actions" not in batch:
                 raise KeyError("Expected batch to contain an 'actions' entry.")
             act_chunks = batch["actions"][..., : self.num_dof]
-            params.append(self.compute_weights(act_chunks))
+            gather = (torch.is_tensor(act_chunks) and act_chunks.dim() == 3 and act_chunks.shape[1] == self.times.numel()
+                      and act_chunks.shape[2] == self.num_dof and not self._has_conditions)
+            if gather:
+                pending.append(act_chunks.to(dev, torch.float32))
+                pending_rows += act_chunks.shape[0]
+                if pending_rows >= 4096:
+                    flush()
+            else:                                   # odd shapes raise here, as they would per batch; boundary-condition
+                flush()                             # tokenizers keep the reference's "state of the last batch" semantics
+                params.append(self.compute_weights(act_chunks))
             sample_count += 1
             if sample_count >= sample_limit:
                 if verbose:
                     print("Precomputed enough samples for weight normalizer of MP")
                 break
+        flush()
         if not params:
             raise RuntimeError("No parameters were gathered from the dataloader.")
         params = torch.cat(params, dim=0)

@@ -203,3 +203,35 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_fit_parameters_gathers_small_batches():
+    """fit_parameters fits the loader's small batches ~4 096 trajectories at a time (host logic only: the fit and
+    the quantile select are stubbed)."""
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    tok = BEASTBsplineTokenizer(num_dof=3, num_basis=4, seq_len=10, vocab_size=16, device="cpu")
+    calls = []
+    tok._cuda = lambda: torch.device("cpu")
+
+    def fake_fit(x):
+        calls.append(tuple(x.shape))
+        return x.reshape(x.shape[0], -1)[:, :12].float()
+
+    tok.compute_weights = fake_fit
+    tok._column_quantiles = lambda p, qs: (p.min(0).values, p.max(0).values)
+    batches = [{"actions": torch.randn(32, 10, 5)} for _ in range(300)]
+    tok.fit_parameters(batches, verbose=False)
+    assert calls == [(4096, 10, 3), (4096, 10, 3), (1408, 10, 3)]
+    want_lo = torch.cat([b["actions"][..., :3] for b in batches]).reshape(9600, -1)[:, :12].min(0).values
+    assert torch.equal(tok.w_min, want_lo)
+    calls.clear()
+    tok.fit_parameters(batches, max_samples=5, verbose=False)
+    assert calls == [(160, 10, 3)]
+    calls.clear()
+    odd = [{"actions": torch.randn(32, 10, 5)}, {"actions": torch.randn(4, 7, 5)}, {"actions": torch.randn(8, 10, 5)}]
+    tok.fit_parameters(odd, verbose=False)                       # an odd-shaped batch is passed through on its own
+    assert calls == [(32, 10, 3), (4, 7, 3), (8, 10, 3)]
+    with pytest.raises(KeyError):
+        tok.fit_parameters([{"x": 1}], verbose=False)
+    with pytest.raises(RuntimeError):
+        tok.fit_parameters([], verbose=False)
