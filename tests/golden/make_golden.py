@@ -150,22 +150,25 @@ def bpe_case(ref, name, *, bpe_vocab_size, fit_batches, fit_seed0, max_sequences
 
 
 COND_ORDERS = [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)]
+COND_ODD = dict(cfg=dict(num_dof=5, num_basis=8, seq_len=33, vocab_size=1000, degree_p=3, gripper_zero_order=True,
+                         gripper_indices=[0]), orders=[(2, 1), (1, 2)], batch=9, seed=41, custom_T=11)
 
 
-def cond_case(ref, name, *, batch=16, seed=31, custom_T=37):
+def cond_case(ref, name, *, batch=16, seed=31, custom_T=37, cfg=None, orders=None):
     """Non-zero init/end condition orders (MP_lite_PyTorch/mp_pytorch/mp/uni_bspline.py:500-537):
     the first/last control points of every JOINT spline are pinned to the trajectory's boundary
     position (order 1) and velocity (order 2).  The reference keeps those boundary control points
     as state of its MP object, so reconstruct_traj uses the ones of the LAST fit — recorded here
     with a second encode on other data in between ("stale" outputs)."""
-    cfg = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
-               gripper_indices=[6, 13], device="cpu")
-    x = synth(batch, 50, 14, seed)
-    x2 = synth(batch, 50, 14, seed + 1)
+    cfg = dict(cfg or dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
+                           gripper_indices=[6, 13]), device="cpu")
+    orders = orders or COND_ORDERS
+    x = synth(batch, cfg["seq_len"], cfg["num_dof"], seed)
+    x2 = synth(batch, cfg["seq_len"], cfg["num_dof"], seed + 1)
     g = torch.Generator().manual_seed(seed + 99)
     out = {"trajs": npy(x), "trajs_other": npy(x2),
-           "orders": np.asarray(COND_ORDERS, dtype=np.int64)}
-    for io, eo in COND_ORDERS:
+           "orders": np.asarray(orders, dtype=np.int64)}
+    for io, eo in orders:
         tok = ref.BEASTBsplineTokenizer(init_cond_order=io, end_cond_order=eo, **cfg)
         k = f"o{io}{eo}_"
         out[k + "phi_joint"] = npy(tok.mp.basis_gn.basis(tok.times))
@@ -199,8 +202,9 @@ def cond_case(ref, name, *, batch=16, seed=31, custom_T=37):
 def main():
     ref = import_reference()
     import tokenizers
-    if "--only-cond" in sys.argv:                         # add the newest case without touching the others
+    if "--only-cond" in sys.argv:                         # add the newest cases without touching the others
         cond_case(ref, "cond_orders")
+        cond_case(ref, "cond_odd", **COND_ODD)
         return
     with open(os.path.join(HERE, "VERSIONS.json"), "w") as f:
         json.dump({"torch": torch.__version__, "numpy": np.__version__,
@@ -227,6 +231,8 @@ def main():
     bpe_case(ref, "bpe_v1000", bpe_vocab_size=1600, fit_batches=24, fit_seed0=3000, vocab_size=1000)
     # init/end condition orders 1 and 2 on the bimanual config
     cond_case(ref, "cond_orders")
+    # ... and on an odd geometry (cubic, gripper first, 1000 bins, T = 33): generic kernels on the GPU side
+    cond_case(ref, "cond_odd", **COND_ODD)
 
 
 if __name__ == "__main__":

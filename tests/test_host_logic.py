@@ -158,23 +158,33 @@ def test_synth_is_deterministic():
     assert len(batches) == 2 and batches[0]["actions"].shape == (32, 50, 14)
 
 
-@pytest.mark.parametrize("orders", [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)])
-def test_conditioned_projector_matches_reference(orders):
+COND_CASES = {
+    "cond_orders": dict(num_dof=14, num_basis=10, seq_len=50, degree_p=4, gripper_indices=[6, 13]),
+    "cond_odd": dict(num_dof=5, num_basis=8, seq_len=33, degree_p=3, gripper_indices=[0]),
+}
+
+
+@pytest.mark.parametrize("case,orders", [("cond_orders", o) for o in [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)]] +
+                         [("cond_odd", o) for o in [(2, 1), (1, 2)]])
+def test_conditioned_projector_matches_reference(case, orders):
     """Non-zero init/end condition orders stay one linear map per joint: w = P_eff . y with the
     boundary terms folded in (basis.conditioned_projector) reproduces the reference's coefficients."""
     import torch
     from beast_tokenizer_b200.basis import build_constants, make_times
     io, eo = orders
-    g = load_golden("cond_orders")
+    cfg = COND_CASES[case]
+    g = load_golden(case)
     k = f"o{io}{eo}_"
-    joint = [i for i in range(14) if i not in (6, 13)]
-    c = build_constants(make_times(2 * math.pi, 50), 2 * math.pi, 10, 4, joint, [6, 13], io, eo)
+    D, nb, T, p = cfg["num_dof"], cfg["num_basis"], cfg["seq_len"], cfg["degree_p"]
+    grip = cfg["gripper_indices"]
+    joint = [i for i in range(D) if i not in grip]
+    c = build_constants(make_times(2 * math.pi, T), 2 * math.pi, nb, p, joint, grip, io, eo)
     assert np.array_equal(c.phi_joint.numpy(), g[k + "phi_joint"])
     assert np.array_equal(c.knots_joint.numpy(), g[k + "knots_joint"])
-    assert tuple(c.proj_joint.shape) == (10, 50)
+    assert tuple(c.proj_joint.shape) == (nb, T)
     x = torch.from_numpy(g["trajs"]).double()
     w = torch.einsum("kt,btd->bdk", c.proj_joint.double(), x[..., joint]).reshape(x.shape[0], -1).numpy()
-    assert rel_err(w, g[k + "params"][:, :120]) <= 1e-5
+    assert rel_err(w, g[k + "params"][:, :len(joint) * nb]) <= 1e-5
 
 
 def test_condition_order_ctor_errors():

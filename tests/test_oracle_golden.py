@@ -146,29 +146,31 @@ def test_torch_reference_port_matches_golden(golden_case):
 
 
 # ---------------------------------------------------------------- init / end condition orders
-COND_CFG = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, degree_p=4,
-                gripper_zero_order=True, gripper_indices=[6, 13])
+COND_CASES = {
+    "cond_orders": dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, degree_p=4, gripper_indices=[6, 13]),
+    "cond_odd": dict(num_dof=5, num_basis=8, seq_len=33, vocab_size=1000, degree_p=3, gripper_indices=[0]),
+}
+COND_PARAMS = [("cond_orders", o) for o in [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)]] + \
+              [("cond_odd", o) for o in [(2, 1), (1, 2)]]
 
 
-def _cond_orders():
-    return [tuple(int(v) for v in row) for row in load_golden("cond_orders")["orders"]]
-
-
-@pytest.mark.parametrize("orders", [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)])
-def test_condition_orders_oracle_matches_reference(orders):
+@pytest.mark.parametrize("case,orders", COND_PARAMS)
+def test_condition_orders_oracle_matches_reference(case, orders):
     """Pins the restatement of mp/uni_bspline.py:500-537 + 126-166 (pinned boundary control points)
     against outputs of the live reference, including its stateful reconstruct."""
     io, eo = orders
-    assert orders in _cond_orders()
-    g = load_golden("cond_orders")
+    cfg = COND_CASES[case]
+    g = load_golden(case)
+    assert list(orders) in g["orders"].tolist()
     k = f"o{io}{eo}_"
+    D, nb, T, V, p = cfg["num_dof"], cfg["num_basis"], cfg["seq_len"], cfg["vocab_size"], cfg["degree_p"]
     tau = 2 * math.pi
-    times = O.linspace_f32(0, tau, 50)
-    joint, grip = O.slot_layout(14, True, [6, 13])
-    nc = 10 + io + eo
-    assert np.array_equal(O.knot_vector(nc, 4), g[k + "knots_joint"])
-    assert np.array_equal(O.bspline_basis(times, tau, nc, 4), g[k + "phi_joint"])
-    w, st = O.compute_weights_cond(g["trajs"], times, tau, 10, 4, joint, grip, io, eo)
+    times = O.linspace_f32(0, tau, T)
+    joint, grip = O.slot_layout(D, True, cfg["gripper_indices"])
+    nc = nb + io + eo
+    assert np.array_equal(O.knot_vector(nc, p), g[k + "knots_joint"])
+    assert np.array_equal(O.bspline_basis(times, tau, nc, p), g[k + "phi_joint"])
+    w, st = O.compute_weights_cond(g["trajs"], times, tau, nb, p, joint, grip, io, eo)
     assert rel_err(w, g[k + "params"]) <= 1e-5
     for key, have in (("init_pos", st["init_pos"]), ("init_vel", st["init_vel"]),
                       ("end_pos", st["ret_end_pos"]), ("end_vel", st["end_vel"])):
@@ -178,16 +180,17 @@ def test_condition_orders_oracle_matches_reference(orders):
             assert have is None
     lo, hi = g[k + "w_min"], g[k + "w_max"]
     assert rel_err(w.min(0), lo) <= 1e-5 and rel_err(w.max(0), hi) <= 1e-5
-    assert np.array_equal(O.tokens_from_params(g[k + "params"], lo, hi, 256, 14, 10), g[k + "tokens"])
-    dec = O.decode(g[k + "tokens"], lo, hi, 256, 14, 10)
-    args = (times, tau, 10, 4, joint, grip, io, eo)
+    assert np.array_equal(O.tokens_from_params(g[k + "params"], lo, hi, V, D, nb), g[k + "tokens"])
+    dec = O.decode(g[k + "tokens"], lo, hi, V, D, nb)
+    args = (times, tau, nb, p, joint, grip, io, eo)
     assert rel_err(O.reconstruct_from_params_cond(dec, st, *args), g[k + "recon"]) <= 1e-5
     assert rel_err(O.reconstruct_from_params_cond(dec, st, *args, init_p=g["init_p"]), g[k + "recon_initp"]) <= 1e-5
-    r = O.reconstruct_from_params_cond(dec, st, g[k + "custom_times"], tau, 10, 4, joint, grip, io, eo)
+    r = O.reconstruct_from_params_cond(dec, st, g[k + "custom_times"], tau, nb, p, joint, grip, io, eo)
     assert rel_err(r, g[k + "recon_custom_times"]) <= 1e-5
     # the reference reconstructs with the boundary state of its LAST fit
-    _, st_other = O.compute_weights_cond(g["trajs_other"], times, tau, 10, 4, joint, grip, io, eo)
+    _, st_other = O.compute_weights_cond(g["trajs_other"], times, tau, nb, p, joint, grip, io, eo)
     assert rel_err(O.reconstruct_from_params_cond(dec, st_other, *args), g[k + "recon_stale"]) <= 1e-5
     assert rel_err(O.reconstruct_from_params_cond(dec, st, *args), g[k + "recon_stale"]) > 1e-3
-    cont = O.normalize_tensor(w, lo, hi).reshape(-1, 14, 10).transpose(0, 2, 1).reshape(-1, 140)
-    assert np.abs(cont - g[k + "cont_tokens"]).max() <= 2e-5
+    cont = O.normalize_tensor(w, lo, hi).reshape(-1, D, nb).transpose(0, 2, 1).reshape(-1, D * nb)
+    assert np.abs(cont - g[k + "cont_tokens"]).max() <= 2.0 * 1e-5 * np.abs(g[k + "params"]).max() / \
+        max(float((hi - lo).min()), 1e-8) + 1e-6
