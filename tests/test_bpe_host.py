@@ -218,3 +218,43 @@ def test_ids_to_csr_accepts_every_container():
     assert f4.tolist() == [1, 2, 3, 4] and o4.tolist() == [0, 2, 4]
     with pytest.raises(ValueError):
         T._ids_to_csr(obj, [[2 ** 40]], "cpu")
+
+
+def test_match_resolution_by_function_composition():
+    """The warp-per-sequence rewrite (csrc/bpe.cu: rewrite_sequence_warp) resolves the greedy left-to-right rule
+    match[p] = cand[p] and not match[p-1] without a serial pass: every lane evaluates its 8-symbol chunk for both
+    possible incoming values, the two results form a one-bit function, and an inclusive scan over function
+    compositions gives each lane its true input.  Restated here lane by lane and compared with the serial rule."""
+    rng = np.random.default_rng(5)
+
+    def serial(cand):
+        out, prev = [], 0
+        for c in cand:
+            prev = c & (prev ^ 1)
+            out.append(prev)
+        return out
+
+    def run_chunk(bits, m_in):
+        out, prev = [], m_in
+        for c in bits:
+            prev = c & (prev ^ 1)
+            out.append(prev)
+        return out
+
+    for trial in range(400):
+        n_lanes = 32
+        p_run = rng.choice([0.05, 0.3, 0.7, 0.95])
+        cand = (rng.random(n_lanes * 8) < p_run).astype(int).tolist()        # long runs exercise the (a, a) case
+        chunks = [cand[8 * lane:8 * lane + 8] for lane in range(n_lanes)]
+        f = []                                                               # bit x of f = chunk output for input x
+        for ch in chunks:
+            f.append(run_chunk(ch, 0)[-1] | (run_chunk(ch, 1)[-1] << 1))
+        o = 1
+        while o < n_lanes:                                                   # Hillis-Steele scan, F_l = f_l o F_{l-o}
+            g = [f[lane - o] if lane >= o else None for lane in range(n_lanes)]
+            f = [((f[lane] >> (g[lane] & 1)) & 1) | (((f[lane] >> ((g[lane] >> 1) & 1)) & 1) << 1)
+                 if g[lane] is not None else f[lane] for lane in range(n_lanes)]
+            o <<= 1
+        m_in = [0] + [f[lane - 1] & 1 for lane in range(1, n_lanes)]
+        got = [b for lane in range(n_lanes) for b in run_chunk(chunks[lane], m_in[lane])]
+        assert got == serial(cand)
