@@ -258,3 +258,105 @@ def test_match_resolution_by_function_composition():
         m_in = [0] + [f[lane - 1] & 1 for lane in range(1, n_lanes)]
         got = [b for lane in range(n_lanes) for b in run_chunk(chunks[lane], m_in[lane])]
         assert got == serial(cand)
+
+
+def test_parallel_utf8_decode_rules_match_the_state_machine():
+    """The warp-per-sequence BPE decode (csrc/bpe.cu: bpe_decode_warp_kernel) classifies every byte on its own:
+    a non-continuation byte starts a character (index = number of such bytes before it), a continuation byte
+    must lie inside the span of the lead before it.  Restated here and compared with the sequential decoder
+    (status 2 = invalid UTF-8, 3 = wrong length, character count) on random byte streams."""
+    rng = np.random.default_rng(9)
+
+    def lead_len(b):
+        return 1 if b < 0x80 else 2 if (b & 0xE0) == 0xC0 else 3 if (b & 0xF0) == 0xE0 else 4 if (b & 0xF8) == 0xF0 else 0
+
+    def sequential(bs, L):
+        status = cnt = pending = acc = 0
+        out = []
+        for bt in bs:
+            c = -1
+            if pending:
+                if (bt & 0xC0) != 0x80:
+                    return 2, cnt, out
+                acc = (acc << 6) | (bt & 0x3F)
+                pending -= 1
+                if pending == 0:
+                    c = acc
+            elif bt < 0x80:
+                c = bt
+            elif lead_len(bt) >= 2:
+                pending = lead_len(bt) - 1
+                acc = bt & (0x3F >> pending)
+            else:
+                return 2, cnt, out
+            if c >= 0:
+                if c > 0xFFFF:
+                    return 2, cnt, out
+                if cnt < L:
+                    out.append(c)
+                cnt += 1
+        if pending:
+            return 2, cnt, out
+        return (3 if cnt != L else 0), cnt, out
+
+    def parallel(bs, L):
+        B = len(bs)
+        first_err, pend_end, n_start, out = None, False, 0, {}
+        for i, b in enumerate(bs):                      # every i is an independent lane
+            cont = (b & 0xC0) == 0x80
+            err = None
+            if not cont:
+                n = lead_len(b)
+                idx = sum(1 for j in range(i) if (bs[j] & 0xC0) != 0x80)
+                if n == 0:
+                    err = i
+                else:
+                    acc, complete = (b if n == 1 else b & (0x7F >> n)), True
+                    for k in range(1, n):
+                        if i + k >= B:
+                            pend_end, complete = True, False
+                            break
+                        c = bs[i + k]
+                        if (c & 0xC0) != 0x80:
+                            err, complete = i + k, False
+                            break
+                        acc = (acc << 6) | (c & 0x3F)
+                    if complete:
+                        if acc > 0xFFFF:
+                            err = i + n - 1
+                        elif idx < L:
+                            out[idx] = acc
+                n_start += 1
+            else:
+                covered = False
+                for k in range(1, min(3, i) + 1):
+                    c = bs[i - k]
+                    if (c & 0xC0) != 0x80:
+                        covered = lead_len(c) > k
+                        break
+                if not covered:
+                    err = i
+            if err is not None and (first_err is None or err < first_err):
+                first_err = err
+        cnt = n_start - (1 if pend_end else 0)
+        if first_err is not None:
+            return 2, None, None
+        if pend_end:
+            return 2, None, None
+        return (3 if cnt != L else 0), cnt, [out[i] for i in range(min(cnt, L))]
+
+    pool = [0x41, 0x7A, 0xC3, 0xA9, 0x80, 0xBF, 0xE2, 0x82, 0xAC, 0xF0, 0x9F, 0x98, 0xF8, 0xFF, 0xC2]
+    for trial in range(3000):
+        if trial % 3 == 0:                              # valid text with a few mutations
+            text = "".join(chr(int(v)) for v in rng.integers(1, 0x2FFF, int(rng.integers(0, 12))))
+            bs = list(text.encode("utf-8"))
+            if bs and trial % 6 == 0:
+                bs[int(rng.integers(0, len(bs)))] = int(rng.choice(pool))
+        else:
+            bs = [int(v) for v in rng.choice(pool, int(rng.integers(0, 14)))]
+        L = int(rng.integers(0, 8))
+        s1, c1, o1 = sequential(bs, L)
+        s2, c2, o2 = parallel(bs, L)
+        assert s1 == s2, (bs, L, s1, s2)
+        if s1 in (0, 3):
+            assert c1 == c2 and o1 == o2, (bs, L)
