@@ -35,6 +35,15 @@ class PlanDesc(C.Structure):
     ]
 
 
+BPE_MAX_PEERS = 16
+
+
+class BpePeers(C.Structure):
+    """bpe_peers_t (include/beast_b200.h): the ranks' delta blocks / flag arrays as device pointers."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grid_blocks", C.c_int32), ("epoch_base", C.c_int32),
+                ("delta", C.c_void_p * BPE_MAX_PEERS), ("flags", C.c_void_p * BPE_MAX_PEERS)]
+
+
 _SIGNATURES = {
     "beast_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
     "beast_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -64,8 +73,12 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "bpe_apply_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bpe_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                                 C.c_int32, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_int32, C.POINTER(BpePeers), C.c_void_p]),
+    "beast_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "beast_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "beast_peer_close": (C.c_int, [C.c_void_p]),
+    "beast_peer_free": (C.c_int, [C.c_void_p]),
     "bpe_signature_words": (C.c_int32, []),
     "bpe_build_signatures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bpe_encode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

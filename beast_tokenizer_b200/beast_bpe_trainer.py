@@ -13,6 +13,7 @@ ends with the same vocabulary.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence, Union
 
@@ -82,6 +83,7 @@ class GpuBpeEngine:
             self.delta = torch.zeros(4 * V, device=self.dev, dtype=torch.int32)
             self.result = torch.zeros(256, device=self.dev, dtype=torch.int64)   # arg-max scratch (per-block maxima)
             self.work = torch.zeros(4 + 2 * self.stride, device=self.dev, dtype=torch.int32)   # scan -> rewrite work list
+            self.mode = "single GPU"
             err = torch.zeros(1, device=self.dev, dtype=torch.int32)
             b2i = torch.from_numpy(byte_to_id).to(self.dev)
             st = _lib.stream_ptr(self.dev)
@@ -118,58 +120,184 @@ class GpuBpeEngine:
             _lib.check(self.lib.bpe_apply_delta(_lib.ptr(self.hist), _lib.ptr(self.delta), a, b, c, self.V,
                                                 _lib.stream_ptr(self.dev)), "bpe_apply_delta")
 
-    def run_fast(self, coll: "_Collective", n_tokens: int, vocab_size: int, min_frequency: int):
-        """Sync-free merge loop: arg-max, stop rules, id assignment and the merge log all stay on the
-        device (bpe_train_step); the host only enqueues iterations (plus the NCCL all-reduce of the
-        delta block when sharded) and reads the log once.  Returns [(a, b, new_id, count)] assuming every merge creates a NEW token string; the
-        caller verifies that and falls back to the exact host-driven loop otherwise."""
-        max_merges = int(vocab_size) - int(n_tokens)
-        if max_merges <= 0:
+    def start_run(self, n_tokens: int, vocab_size: int, min_frequency: int, peers: Optional["_lib.BpePeers"] = None,
+                  delta: Optional[torch.Tensor] = None) -> "_FastRun":
+        return _FastRun(self, n_tokens, vocab_size, min_frequency, peers, delta)
+
+    def run_fast(self, coll: "_Collective", n_tokens: int, vocab_size: int, min_frequency: int, progress=None):
+        """Sync-free merge loop: arg-max, stop rules, id assignment and the merge log all stay on the device
+        (bpe_train_step); the host only enqueues iterations and reads the log once (or once per 256-merge block
+        when a progress bar is shown).  Sharded: the per-merge all-reduce of the 4 x V deltas is part of the
+        iteration-head kernel (peer loads over NVLink, see _PeerBlock), so nothing runs on the host between
+        merges either; without peer access the deltas go through one NCCL all-reduce per merge instead.
+        Returns [(a, b, new_id, count)] assuming every merge creates a NEW token string; the caller verifies
+        that and falls back to the exact host-driven loop otherwise."""
+        if int(vocab_size) - int(n_tokens) <= 0:
             return []
-        dev = self.dev
+        peers = delta = None
+        if coll.on:
+            block = _PeerBlock.get(self.dev, self.V, coll)
+            if block is not None:
+                peers, delta = block.begin_run(coll), block.delta_view
+            self.mode = "peer-fused (NVLink loads inside bpe_iterate_kernel)" if block is not None else \
+                "nccl all-reduce per merge (no peer access)"
+        run = self.start_run(n_tokens, vocab_size, min_frequency, peers, delta)
+        while not run.finished:
+            if coll.on and peers is None:
+                run.enqueue(limit=1)
+                coll.reduce_(run.delta_half(run.enqueued - 1), "sum")
+            else:
+                run.enqueue()
+            if progress is not None:
+                progress(run.merges_done())
+        return run.finish()
+
+
+class _FastRun:
+    """One pass of the device-driven merge loop over an engine: owns ctl / log / signatures, enqueues
+    iterations in blocks that end at the signature (re)build points."""
+    SIG_START, SIG_REBUILD = 64, 256
+
+    def __init__(self, eng: GpuBpeEngine, n_tokens, vocab_size, min_frequency, peers=None, delta=None):
+        self.eng, self.peers = eng, peers
+        self.vocab_size, self.min_frequency = int(vocab_size), int(min_frequency)
+        self.max_merges = max(int(vocab_size) - int(n_tokens), 0)
+        self.enqueued = 0
+        dev = eng.dev
         with torch.cuda.device(dev):
-            ctl = torch.zeros(8, device=dev, dtype=torch.int32)
-            ctl[4] = n_tokens
-            log = torch.zeros(4 * max_merges, device=dev, dtype=torch.int32)
-            self.result.zero_()
-            # Pair signatures (one 4-byte column read per merge tells which sequences can hold the pair).  The
-            # first merges touch most sequences anyway, so the signatures are built after kSigStart merges and
-            # rebuilt from the current corpus every kSigRebuild merges (0.6 ms at 1.6 M sequences) to drop stale bits.
-            sig = torch.empty((int(self.lib.bpe_signature_words()), self.stride), device=dev, dtype=torch.int32)
-            sig_start, sig_rebuild = 64, 256
+            self.ctl = torch.zeros(16, device=dev, dtype=torch.int32)
+            self.ctl[4] = n_tokens
+            self.log = torch.zeros(4 * max(self.max_merges, 1), device=dev, dtype=torch.int32)
+            eng.result.zero_()
+            eng.work[:4].zero_()
+            # count deltas, double-buffered by merge parity: the peers' copy when sharded over NVLink
+            self.delta = delta if delta is not None else torch.zeros(8 * eng.V, device=dev, dtype=torch.int32)
+            # Pair signatures (two 4-byte column reads per merge tell which sequences can hold the pair).  The
+            # first merges touch most sequences anyway, so the signatures are built after SIG_START merges and
+            # rebuilt from the current corpus every SIG_REBUILD merges (0.6 ms at 1.6 M sequences) to drop stale bits.
+            self.sig = torch.empty((int(eng.lib.bpe_signature_words()), eng.stride), device=dev, dtype=torch.int32)
 
-            def build_sig():
-                _lib.check(self.lib.bpe_build_signatures(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride,
-                                                         _lib.ptr(sig), _lib.stream_ptr(dev)), "bpe_build_signatures")
+    @property
+    def finished(self) -> bool:
+        return self.enqueued >= self.max_merges
 
-            def step(phase, use_sig, iters=1):
-                _lib.check(self.lib.bpe_train_step(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, self.V,
-                                                   _lib.ptr(self.hist), _lib.ptr(self.delta), _lib.ptr(ctl),
-                                                   _lib.ptr(log), _lib.ptr(self.result), _lib.ptr(self.work),
-                                                   int(vocab_size), int(min_frequency), max_merges, phase,
-                                                   _lib.ptr(sig) if use_sig else None, int(iters),
-                                                   _lib.stream_ptr(dev)),
-                           "bpe_train_step")
+    def delta_half(self, merge: int) -> torch.Tensor:
+        V = self.eng.V
+        return self.delta[(merge & 1) * 4 * V:((merge & 1) + 1) * 4 * V]
 
-            # plain stream launches: ~60 us of host enqueue per merge, never a sync (capturing the
-            # iteration into a CUDA graph costs more to instantiate than 1 700 replays save)
-            self.work[:4].zero_()
-            i = 0
-            while i < max_merges:
-                if i >= sig_start and (i - sig_start) % sig_rebuild == 0:
-                    build_sig()
-                if coll.on:
-                    step(0, i >= sig_start)             # fold previous delta + arg-max, pick, scan, rewrite
-                    coll.reduce_(self.delta, "sum")
-                    i += 1
-                else:                                   # unsharded: enqueue up to the next signature rebuild in one call
-                    nxt = sig_start if i < sig_start else i + sig_rebuild - (i - sig_start) % sig_rebuild
-                    n = min(nxt, max_merges) - i
-                    step(0, i >= sig_start, n)
-                    i += n
-            ctl_h = ctl.cpu().tolist()
-            n = ctl_h[5]
-            return log[:4 * n].cpu().view(-1, 4).tolist()
+    def enqueue(self, limit: Optional[int] = None) -> int:
+        """Enqueue the next block of iterations on the current stream (never synchronises)."""
+        eng, i = self.eng, self.enqueued
+        if i >= self.max_merges:
+            return 0
+        dev = eng.dev
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            if i >= self.SIG_START and (i - self.SIG_START) % self.SIG_REBUILD == 0:
+                _lib.check(eng.lib.bpe_build_signatures(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride,
+                                                        _lib.ptr(self.sig), st), "bpe_build_signatures")
+            nxt = self.SIG_START if i < self.SIG_START else i + self.SIG_REBUILD - (i - self.SIG_START) % self.SIG_REBUILD
+            n = min(nxt, self.max_merges) - i
+            if limit is not None:
+                n = min(n, int(limit))
+            _lib.check(eng.lib.bpe_train_step(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, eng.V,
+                                              _lib.ptr(eng.hist), _lib.ptr(self.delta), _lib.ptr(self.ctl),
+                                              _lib.ptr(self.log), _lib.ptr(eng.result), _lib.ptr(eng.work),
+                                              self.vocab_size, self.min_frequency, self.max_merges,
+                                              _lib.ptr(self.sig) if i >= self.SIG_START else None, int(n),
+                                              C.byref(self.peers) if self.peers is not None else None, st),
+                       "bpe_train_step")
+        self.enqueued += n
+        return n
+
+    def merges_done(self) -> int:
+        return int(self.ctl[5].item())                      # synchronises: progress display only
+
+    def finish(self):
+        ctl_h = self.ctl.cpu().tolist()
+        if ctl_h[8]:
+            raise _lib.BeastB200Error("sharded BPE training: a peer GPU did not publish its merge epoch within 5 s "
+                                      "(ranks out of step or peer memory not reachable)")
+        n = ctl_h[5]
+        return self.log[:4 * n].cpu().view(-1, 4).tolist()
+
+
+class _PeerBlock:
+    """Peer-visible memory of one rank for the sharded trainer: int32 [2][4*V] count deltas + BPE_MAX_PEERS flags,
+    allocated with cudaMalloc, exported over CUDA IPC and mapped by every other rank of the group (one process
+    per GPU on one NVLink / NVSwitch node).  Cached per (device, V, group) for the life of the process."""
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, dev, V, coll: "_Collective"):
+        import os
+        if os.environ.get("BEAST_B200_BPE_NO_PEER") == "1":
+            return None
+        key = (str(dev), int(V), id(coll.group))
+        if key not in cls._cache:
+            cls._cache[key] = cls._create(dev, V, coll)
+        return cls._cache[key]
+
+    @classmethod
+    def _create(cls, dev, V, coll):
+        dist, lib = coll.dist, _lib.load()
+        world, rank = dist.get_world_size(coll.group), dist.get_rank(coll.group)
+        if world > _lib.BPE_MAX_PEERS:
+            return None
+        self = cls()
+        self.V, self.dev, self.world, self.rank = int(V), dev, world, rank
+        n_delta = 8 * self.V
+        nbytes = 4 * (n_delta + _lib.BPE_MAX_PEERS)
+        own, handle, ok = C.c_void_p(), C.create_string_buffer(64), 1
+        with torch.cuda.device(dev):
+            if lib.beast_peer_alloc(nbytes, C.byref(own), handle) != 0:
+                ok, own = 0, C.c_void_p()
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (ok, bytes(handle.raw)), group=coll.group)
+            ptrs = [None] * world
+            ok = int(all(g[0] for g in gathered))
+            if ok:
+                for r, (_, h) in enumerate(gathered):
+                    if r == rank:
+                        ptrs[r] = own.value
+                        continue
+                    mapped = C.c_void_p()
+                    if lib.beast_peer_open(C.create_string_buffer(h, 64), C.byref(mapped)) != 0:
+                        ok = 0
+                        break
+                    ptrs[r] = mapped.value
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            coll.reduce_(flag, "min")                       # every rank must have mapped every peer
+            if not int(flag.item()):
+                return None
+        self.ptrs = ptrs
+        # torch view of this rank's delta halves (reduced by NCCL only on the fallback path; otherwise just a pointer)
+        self.delta_view = _wrap_device_int32(own.value, n_delta, dev)
+        self.flags_view = _wrap_device_int32(own.value + 4 * n_delta, _lib.BPE_MAX_PEERS, dev)
+        return self
+
+    def begin_run(self, coll) -> "_lib.BpePeers":
+        """Run boundary: no rank may touch peer memory for the new run while another still reads it for the old
+        one, and no rank may publish an epoch before every rank has cleared its flags.  Two tiny all-reduces
+        are those barriers (stream-ordered on every rank, no host synchronisation)."""
+        t = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        coll.reduce_(t, "sum")
+        self.flags_view.zero_()
+        coll.reduce_(t, "sum")
+        peers = _lib.BpePeers()
+        peers.world, peers.rank, peers.grid_blocks, peers.epoch_base = self.world, self.rank, 0, 0
+        for r in range(self.world):
+            peers.delta[r] = self.ptrs[r]
+            peers.flags[r] = self.ptrs[r] + 4 * 8 * self.V
+        return peers
+
+
+def _wrap_device_int32(ptr: int, n: int, dev) -> torch.Tensor:
+    """A torch tensor over memory this library allocated (CUDA array interface; never freed by torch)."""
+    class _Mem:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 3,
+                                    "strides": None}
+    return torch.as_tensor(_Mem(), device=dev)
 
 
 def scan_bins_gpu(bins: torch.Tensor, coll: _Collective):
@@ -216,8 +344,12 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
     coll.reduce_(eng.hist, "sum")                       # replicated global histogram
     index = {t: i for i, t in enumerate(tokens)}
     merges: List[tuple] = []
-    if hasattr(eng, "run_fast") and not show_progress:
-        log = eng.run_fast(coll, len(tokens), vocab_size, min_frequency)
+    if hasattr(eng, "run_fast"):
+        bar = tqdm(total=max(vocab_size - len(tokens), 0), desc="BPE merges", leave=False) if (show_progress and tqdm) else None
+        log = eng.run_fast(coll, len(tokens), vocab_size, min_frequency,
+                           progress=(lambda n: bar.update(n - bar.n)) if bar is not None else None)
+        if bar is not None:
+            bar.close()
         fast_tokens, fast_index, ok = list(tokens), dict(index), True
         for a, b, c, _count in log:
             new = fast_tokens[a] + fast_tokens[b]
@@ -227,7 +359,9 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
             fast_index[new] = c
             fast_tokens.append(new)
         if ok:
-            return B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log]), min_token, max_token
+            model = B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log])
+            model.trainer_mode = getattr(eng, "mode", "single GPU")
+            return model, min_token, max_token
         eng = make_engine()
         coll.reduce_(eng.hist, "sum")
     bar = tqdm(total=max(vocab_size - len(tokens), 0), desc="BPE merges", leave=False) if (show_progress and tqdm) else None
@@ -310,17 +444,39 @@ class FIGBPE:
             raise NotImplementedError("the B200 BPE trainer expects equal-length sequences (BEAST tokens are)")
         return self.fit_from_bins(torch.from_numpy(np.stack(processed)))
 
+    GATHER_ROWS = 4096      # loader batches are gathered on the device and fitted this many trajectories at a time
+
     def fit_from_trajectories(self, tokenizer: BEASTBsplineTokenizer, trajectories: Iterable[Union[ArrayLike, dict]], *,
                               update_bounds: bool = False, batch_key: str = "actions",
                               max_sequences: Optional[int] = None) -> FIGBPEState:
+        """Reference :100-151: encode every loader batch to MP tokens, train on them.  The tokens of a trajectory
+        do not depend on its batch (fixed bounds), so small loader batches (32 in the reference's script) are
+        copied into a device staging block and fitted GATHER_ROWS at a time — one K1 launch per ~4 096
+        trajectories instead of one per batch; the token chunks never leave the GPU."""
         chunks: List[torch.Tensor] = []
         collected = 0
         encode_fn = getattr(tokenizer, "encode_to_mp_tokens", None)
+        offset = 0
         if encode_fn is None:
             encode_fn = tokenizer.encode
+            offset = None                                # encode() adds the LLM offset when one is configured
         progress_bar = None
         if self.show_progress and tqdm is not None:
             progress_bar = tqdm(total=max_sequences, desc="Collecting BEAST sequences for BPE", unit="seq", leave=False)
+        # gathering needs per-batch independence: fixed bounds, no boundary-condition state of "the last batch"
+        can_gather = (not update_bounds and isinstance(tokenizer, BEASTBsplineTokenizer)
+                      and not tokenizer._has_conditions and torch.cuda.is_available())
+        staging, filled = None, 0
+        T, D = (tokenizer.times.numel(), tokenizer.num_dof) if can_gather else (0, 0)
+
+        def flush():
+            nonlocal filled
+            if filled:
+                off = offset if offset is not None else (
+                    tokenizer._llm_vocab_offset() if tokenizer.llm_vocab_size is not None else 0)
+                chunks.append(tokenizer._fit(staging[:filled], want_tokens=True, offset=off)[0])
+                filled = 0
+
         for batch in trajectories:
             if isinstance(batch, dict):
                 if batch_key not in batch:
@@ -330,20 +486,36 @@ class FIGBPE:
                 data = batch
             if not torch.is_tensor(data):
                 data = torch.as_tensor(data)
-            tokens, _ = encode_fn(data, update_bounds=update_bounds)       # stays on the GPU
-            if max_sequences is not None and collected + tokens.shape[0] > max_sequences:
-                tokens = tokens[: max_sequences - collected]
-            chunks.append(tokens)
-            collected += tokens.shape[0]
+            n_new = None
+            if (can_gather and data.dim() == 3 and data.shape[1] == T and data.shape[2] >= D
+                    and 0 < data.shape[0] <= self.GATHER_ROWS):
+                if max_sequences is not None and collected + data.shape[0] > max_sequences:
+                    data = data[: max_sequences - collected]
+                if staging is None:
+                    staging = torch.empty((self.GATHER_ROWS, T, D), device=tokenizer._cuda(), dtype=torch.float32)
+                if filled + data.shape[0] > self.GATHER_ROWS:
+                    flush()
+                staging[filled:filled + data.shape[0]].copy_(data[..., :D], non_blocking=True)
+                filled += data.shape[0]
+                n_new = data.shape[0]
+            else:
+                flush()                                  # keep the loader's order
+                tokens, _ = encode_fn(data, update_bounds=update_bounds)       # stays on the GPU
+                if max_sequences is not None and collected + tokens.shape[0] > max_sequences:
+                    tokens = tokens[: max_sequences - collected]
+                chunks.append(tokens)
+                n_new = tokens.shape[0]
+            collected += n_new
             if progress_bar is not None:
-                progress_bar.update(tokens.shape[0])
+                progress_bar.update(n_new)
             if max_sequences is not None and collected >= max_sequences:
                 break
+        flush()
         if progress_bar is not None:
             progress_bar.close()
         if not chunks or collected == 0:
             raise ValueError("No non-empty sequences provided for BPE training.")
-        return self.fit_from_bins(torch.cat(chunks, 0))
+        return self.fit_from_bins(chunks[0] if len(chunks) == 1 else torch.cat(chunks, 0))
 
     def get_state(self) -> FIGBPEState:
         if self.tokenizer is None or self.min_token is None or self.max_token is None:

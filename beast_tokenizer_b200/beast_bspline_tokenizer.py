@@ -21,7 +21,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _dist, _lib
 from .base_tokenizer import TokenizerBase
 from .basis import SplineConstants, build_constants, make_times
 
@@ -273,10 +273,13 @@ class BEASTBsplineTokenizer(TokenizerBase):
         return self.llm_vocab_size - self.vocab_size
 
     @torch.no_grad()
-    def fit_parameters(self, dataloader, max_samples=None, verbose=True):
+    def fit_parameters(self, dataloader, max_samples=None, verbose=True, process_group=None):
         """1 % / 99 % per-column quantiles of the fitted coefficients (reference :181-220).
         Coefficients stay on the GPU; the order statistics np.quantile needs are selected
-        exactly by beast_colselect_f32 and interpolated with numpy's own lerp."""
+        exactly by beast_colselect_f32 and interpolated with numpy's own lerp.
+        Sharded (torch.distributed initialised, one process per GPU, every rank iterates ITS shard of the
+        loader): the ranks' coefficient rows are all-gathered (56 MB per 100 k trajectories) before the exact
+        selection, so every rank ends with the quantiles of the whole data set; process_group=False = local."""
         params = []
         sample_limit = max_samples if max_samples is not None else float("inf")
         iterator = dataloader
@@ -320,9 +323,15 @@ class BEASTBsplineTokenizer(TokenizerBase):
                     print("Precomputed enough samples for weight normalizer of MP")
                 break
         flush()
-        if not params:
+        dist, group = _dist.resolve(process_group)
+        if not params and dist is None:
             raise RuntimeError("No parameters were gathered from the dataloader.")
-        params = torch.cat(params, dim=0)
+        params = (torch.cat(params, dim=0) if params else
+                  torch.empty((0, self.num_dof * self.num_basis), device=dev, dtype=torch.float32))
+        if dist is not None:
+            params = _dist.gather_rows(params, group)
+            if params.shape[0] == 0:
+                raise RuntimeError("No parameters were gathered from the dataloader.")
         lo, hi = self._column_quantiles(params, (0.01, 0.99))
         self.w_min.copy_(lo.to(self.w_min.device))
         self.w_max.copy_(hi.to(self.w_max.device))
@@ -425,9 +434,10 @@ class BEASTBsplineTokenizer(TokenizerBase):
         return self._fit(demos, want_tokens=False)[1]
 
     @torch.no_grad()
-    def update_weights_bounds(self, demos):
+    def update_weights_bounds(self, demos, process_group=None):
         """Global per-column min / max of the coefficients (reference :362-378): one fused launch,
-        the coefficients are reduced in registers and never written."""
+        the coefficients are reduced in registers and never written.  Sharded (torch.distributed initialised,
+        every rank passes its shard of the trajectories): one MIN and one MAX all-reduce of the D*nb vectors."""
         plan = self._plan()
         dev = plan.device
         x = self._prep_trajs(demos, dev)
@@ -438,6 +448,7 @@ class BEASTBsplineTokenizer(TokenizerBase):
             _lib.check(plan._lib.beast_fit_minmax_f32(plan.handle, _lib.ptr(x), x.shape[0], _lib.ptr(lo), _lib.ptr(hi), 0,
                                                       _lib.stream_ptr(dev)), "beast_fit_minmax_f32")
         self._remember_boundary(x, plan)
+        _dist.allreduce_minmax(lo, hi, process_group)
         self.w_min.copy_(lo.to(self.w_min.device))
         self.w_max.copy_(hi.to(self.w_max.device))
 
@@ -453,11 +464,14 @@ class BEASTBsplineTokenizer(TokenizerBase):
         return lo, hi
 
     @torch.no_grad()
-    def update_weights_bounds_per_batch(self, weights):
-        """Monotone expansion with 1e-4 hysteresis (reference :379-389)."""
+    def update_weights_bounds_per_batch(self, weights, process_group=None):
+        """Monotone expansion with 1e-4 hysteresis (reference :379-389).  Local by default (it runs inside
+        encode(update_bounds=True), which ranks call independently); pass a process group (or "world") to
+        all-reduce the batch min / max first, so that every rank expands identically."""
         dev = self._cuda()
         weights = weights.to(dev, torch.float32).reshape(-1, self.num_dof * self.num_basis).contiguous()
         lo, hi = self._minmax(weights)
+        _dist.allreduce_minmax(lo, hi, process_group, implicit=False)
         on_dev = self.w_min.device == dev and self.w_max.device == dev
         w_min = self.w_min if on_dev else self.w_min.to(dev)
         w_max = self.w_max if on_dev else self.w_max.to(dev)

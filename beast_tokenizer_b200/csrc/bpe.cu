@@ -23,6 +23,7 @@
 // of all sequences is contiguous: sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)] (uint16).  A warp that
 // walks 32 sequences reads / writes chunk c of all of them as 512 contiguous bytes, one 128-bit access
 // per lane.
+#include <cstring>
 #include "common.cuh"
 
 namespace beast {
@@ -66,7 +67,35 @@ struct BpeCtl {
     int n_merges;           // merges logged
     int done;               // sticky: no pair reached min_frequency, or the vocabulary is full
     int has_delta;          // the delta block of merge (a, b, c) still has to be folded into the histogram
+    int err;                // sticky: 1 = a peer did not publish its epoch in time (sharded runs)
+    int pad[7];
 };
+
+// Sharded training: the ranks' delta blocks and flag arrays as seen from this GPU (bpe_peers_t of the C ABI).
+struct BpePeersDev {
+    int world, rank, epoch_base;
+    int* delta[BPE_MAX_PEERS];
+    int* flags[BPE_MAX_PEERS];
+};
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kPeerWaitNs = 5000000000ull;     // a peer that stays silent for 5 s is reported, not waited for
 
 
 // GPT-2 pre-tokeniser character classes for codepoints 0..255
@@ -756,6 +785,7 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
     if (ctl) {
         if (ctl->done) return;
         a = ctl->a; b = ctl->b; c = ctl->c;
+        delta += ((ctl->n_merges - 1) & 1) * 4 * V;           // double-buffered by merge parity (peers may still read the other half)
     }
     const int n_work = *work_count;
     if (n_work > kDirectDeltaWork && (long long)blockIdx.x * blockDim.x >= n_work) return;       // nothing for this block
@@ -817,17 +847,28 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
     flush_delta_block(s_delta, delta, V);
 }
 
-// Iteration head of the sync-free loop: fold the (all-reduced) delta block of the previous merge into the
-// histogram and find the arg-max of the updated table in the same launch.  The delta touches only column a,
-// row b, column c and row c of the previous merge (a, b) -> c.
+// Iteration head of the sync-free loop: arg-max of the histogram, folding the delta block of the previous merge
+// on the way.  The delta touches only column a, row b, column c and row c of the previous merge (a, b) -> c: the
+// bulk pass skips those entries (four compares), a short second pass folds and weighs them.
+// Sharded runs: the per-merge all-reduce of the 4 x V deltas lives HERE.  Block 0 publishes "my rewrite of merge
+// m - 1 is complete" into every peer's flag array (release, system scope) as soon as the kernel starts; the bulk
+// pass — which needs nothing from the peers — hides the NVLink round trip; then every block waits for its own
+// flags and the fold pass sums the ranks' delta blocks with peer loads.  The histogram replicas stay identical, so
+// every rank picks the same merge without a broadcast.
 // (One block of 1024 threads per SM writes its maximum to partial[block]; bpe_pick_kernel finishes.)
 __global__ void __launch_bounds__(1024)
-bpe_iterate_kernel(int* __restrict__ hist, int V, const BpeCtl* __restrict__ ctl, int* __restrict__ delta,
-                   unsigned long long* __restrict__ partial) {
+bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int* __restrict__ delta,
+                   unsigned long long* __restrict__ partial, const __grid_constant__ BpePeersDev peers) {
     if (ctl->done) return;
     const int n_active = ctl->n_tokens;
     const bool fold = ctl->has_delta != 0;
     const int pa = ctl->a, pb = ctl->b, pc = ctl->c;
+    const int epoch = peers.epoch_base + ctl->n_merges;
+    const int world = peers.world;
+    if (world > 1 && blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peers.flags[threadIdx.x] + peers.rank, epoch);
+    }
     unsigned long long best = 0;
     const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
     const bool vec = (V & 3) == 0;
@@ -838,9 +879,6 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, const BpeCtl* __restrict__ ctl
             best = key > best ? key : best;
         }
     };
-    // Entries of column a / row b / column c / row c carry a pending delta: the bulk pass skips them (four
-    // compares, no memory traffic) and the short pass below folds and weighs them; the merged pair (a, b)
-    // is gone for good.
     auto visit = [&](int* row, int x, int y, int v) {
         if (fold) {
             if (y == pa || x == pb || y == pc || x == pc) return;
@@ -848,29 +886,6 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, const BpeCtl* __restrict__ ctl
         }
         consider(x, y, v);
     };
-    if (fold) {
-        // 4 x n_active special entries, one per thread: which = 0 column a (j, a), 1 row b (b, j), 2 column c
-        // (j, c), 3 row c (c, j).  An entry on two of the lines belongs to the first one in that order and takes
-        // both deltas; the delta block itself is cleared afterwards by bpe_pick_kernel.
-        const unsigned int nthreads = gridDim.x * blockDim.x;
-        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * (unsigned int)n_active; i += nthreads) {
-            const int which = (int)(i / (unsigned int)n_active), j = (int)(i - (unsigned int)which * n_active);
-            const int x = which == 0 ? j : (which == 1 ? pb : (which == 2 ? j : pc));
-            const int y = which == 0 ? pa : (which == 1 ? j : (which == 2 ? pc : j));
-            const bool on0 = y == pa, on1 = x == pb, on2 = y == pc;
-            if ((which == 1 && on0) || (which == 2 && (on0 || on1)) || (which == 3 && (on0 || on1 || on2))) continue;
-            int d = 0;
-            if (on0) d += delta[x];
-            if (on1) d += delta[V + y];
-            if (on2) d += delta[2 * V + x];
-            if (x == pc) d += delta[3 * V + y];
-            int* cell = hist + (long long)x * V + y;
-            int v = *cell + d;
-            if (x == pa && y == pb) v = 0;
-            if (d != 0 || v == 0) *cell = v;
-            consider(x, y, v);
-        }
-    }
     if (vec) {
         // the live n_active x n_active corner as a flat list of 128-bit units, dealt round-robin to ALL
         // threads (a warp reads 512 contiguous bytes), four independent loads in flight per thread
@@ -904,6 +919,57 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, const BpeCtl* __restrict__ ctl
             for (int y = lane; y < n_active; y += 32) visit(row, x, y, row[y]);
         }
     }
+    if (fold) {
+        const int* dloc = delta + ((ctl->n_merges - 1) & 1) * 4 * V;      // this rank's half for merge m - 1
+        if (world > 1) {
+            // every peer has finished the rewrite of merge m - 1 once its epoch shows up in OUR flag array
+            if (threadIdx.x < world && !ctl->err) {
+                const int* f = peers.flags[peers.rank] + threadIdx.x;
+                if (ld_acquire_sys(f) < epoch) {
+                    const unsigned long long t0 = global_ns();
+                    while (ld_acquire_sys(f) < epoch) {
+                        __nanosleep(64);
+                        if (global_ns() - t0 > kPeerWaitNs) { atomicExch(&ctl->err, 1); break; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int boff = ((ctl->n_merges - 1) & 1) * 4 * V;
+        auto dsum = [&](int idx) {
+            int acc = dloc[idx];
+            if (world > 1) {
+                int v[BPE_MAX_PEERS];
+#pragma unroll
+                for (int r = 0; r < BPE_MAX_PEERS; ++r)
+                    v[r] = (r < world && r != peers.rank) ? ld_relaxed_sys(peers.delta[r] + boff + idx) : 0;
+#pragma unroll
+                for (int r = 0; r < BPE_MAX_PEERS; ++r) acc += v[r];
+            }
+            return acc;
+        };
+        // 4 x n_active special entries, one per thread: which = 0 column a (j, a), 1 row b (b, j), 2 column c
+        // (j, c), 3 row c (c, j).  An entry on two of the lines belongs to the first one in that order and takes
+        // both deltas; the delta half itself is cleared by bpe_pick_kernel before it is written again.
+        const unsigned int nthreads = gridDim.x * blockDim.x;
+        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * (unsigned int)n_active; i += nthreads) {
+            const int which = (int)(i / (unsigned int)n_active), j = (int)(i - (unsigned int)which * n_active);
+            const int x = which == 0 ? j : (which == 1 ? pb : (which == 2 ? j : pc));
+            const int y = which == 0 ? pa : (which == 1 ? j : (which == 2 ? pc : j));
+            const bool on0 = y == pa, on1 = x == pb, on2 = y == pc;
+            if ((which == 1 && on0) || (which == 2 && (on0 || on1)) || (which == 3 && (on0 || on1 || on2))) continue;
+            int d = 0;
+            if (on0) d += dsum(x);
+            if (on1) d += dsum(V + y);
+            if (on2) d += dsum(2 * V + x);
+            if (x == pc) d += dsum(3 * V + y);
+            int* cell = hist + (long long)x * V + y;
+            int v = *cell + d;
+            if (x == pa && y == pb) v = 0;
+            if (d != 0 || v == 0) *cell = v;
+            consider(x, y, v);
+        }
+    }
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other > best ? other : best;
@@ -926,8 +992,11 @@ bpe_pick_kernel(const unsigned long long* __restrict__ partial, int n_partial, B
                 int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges,
                 int* __restrict__ work_count, int* __restrict__ delta) {
     if (ctl->done) return;
-    if (ctl->has_delta)                                      // consumed by bpe_iterate_kernel just before
-        for (int i = threadIdx.x; i < 4 * V; i += blockDim.x) delta[i] = 0;
+    {   // the half that the rewrite of THIS merge fills: it held merge m - 2, which every rank (peers included:
+        // they published epoch m after their fold of m - 2) has consumed
+        int4* d4 = (int4*)(delta + (ctl->n_merges & 1) * 4 * V);
+        for (int i = threadIdx.x; i < V; i += blockDim.x) d4[i] = make_int4(0, 0, 0, 0);
+    }
     unsigned long long best = 0;
     for (int i = threadIdx.x; i < n_partial; i += blockDim.x) best = partial[i] > best ? partial[i] : best;
     for (int o = 16; o > 0; o >>= 1) {
@@ -943,7 +1012,8 @@ bpe_pick_kernel(const unsigned long long* __restrict__ partial, int n_partial, B
     *work_count = 0;
     ctl->has_delta = 0;
     const int count = (int)(key >> 32);
-    if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges) {
+    if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges ||
+        ctl->err) {
         ctl->done = 1;
         return;
     }
@@ -1603,25 +1673,39 @@ extern "C" int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int
     return BEAST_OK;
 }
 
-// `iters` iterations of the sync-free training loop, each: iterate (fold the previous merge's delta, arg-max)
-// -> pick (stop rules, next id, log) -> scan (work list) -> rewrite (fills delta).  The caller runs
-// [one iteration, all-reduce(delta)] when sharded, or blocks of iterations when not, up to
-// (vocab_size - alphabet) merges without reading anything back; ctl / log are read once at the end.
-// (phase 1, once a separate hist += delta pass, is a no-op kept so that older callers still work.)
+// `iters` iterations of the sync-free training loop, each: iterate (arg-max + fold of the previous merge's delta,
+// summed over the peers' blocks when sharded) -> pick (stop rules, next id, log) -> scan (work list) -> rewrite
+// (fills delta[merge & 1]).  The caller enqueues up to (vocab_size - alphabet) iterations without reading anything
+// back; ctl / log are read once at the end.
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                               int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
-                              int32_t vocab_size, int32_t min_frequency, int32_t max_merges, int32_t phase,
-                              uint32_t* sig, int32_t iters, void* stream) {
+                              int32_t vocab_size, int32_t min_frequency, int32_t max_merges, uint32_t* sig,
+                              int32_t iters, const bpe_peers_t* peers_h, void* stream) {
     if (!hist || !delta || !ctl || !log || !result || !work) return BEAST_E_NULL;
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
     if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
+    if ((uintptr_t)delta & 15u) return BEAST_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    if (phase == 1) return BEAST_OK;          // the delta is folded by the next iteration's first kernel
     const size_t smem = (size_t)4 * V * sizeof(int);
     int rc = rewrite_smem_attr(smem);
     if (rc != BEAST_OK) return rc;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    BpePeersDev peers;
+    memset(&peers, 0, sizeof(peers));
+    peers.world = 1;
+    int n_part = sms < 256 ? sms : 256;                       // `result` holds 256 words
+    if (peers_h && peers_h->world > 1) {
+        if (peers_h->world > BPE_MAX_PEERS || peers_h->rank < 0 || peers_h->rank >= peers_h->world) return BEAST_E_SHAPE;
+        peers.world = peers_h->world; peers.rank = peers_h->rank; peers.epoch_base = peers_h->epoch_base;
+        for (int r = 0; r < peers.world; ++r) {
+            if (!peers_h->delta[r] || !peers_h->flags[r]) return BEAST_E_NULL;
+            peers.delta[r] = peers_h->delta[r];
+            peers.flags[r] = peers_h->flags[r];
+        }
+        if (peers.delta[peers.rank] != delta) return BEAST_E_SHAPE;
+    }
+    if (peers_h && peers_h->grid_blocks > 0 && peers_h->grid_blocks < n_part) n_part = peers_h->grid_blocks;
     int* work_count = work;                  // work = {count, pad[3], seq[N], q0[N]}
     int* work_seq = work + 4;
     int* work_q0 = work + 4 + N;
@@ -1634,11 +1718,9 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     // small shards are latency-bound (few tiles per SM): walk the survivors with four loads in flight; large
     // ones are better off with two (measured: 65 k sequences 0.056 -> 0.053 s, 1.6 M sequences 0.214 -> 0.228 s)
     const int deep_walk = N <= (1 << 19) ? 1 : 0;
-    // `iters` iterations back to back (unsharded training: nothing happens between them on the host)
+    // `iters` iterations back to back (nothing happens between them on the host, sharded or not)
     for (int it = 0; it < (iters < 1 ? 1 : iters); ++it) {
-        // fold the previous delta + arg-max, then pick the merge (n_active lives on the device)
-        const int n_part = sms < 256 ? sms : 256;             // `result` holds 256 words
-        bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, (const BpeCtl*)ctl, delta, (unsigned long long*)result);
+        bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, (BpeCtl*)ctl, delta, (unsigned long long*)result, peers);
         bpe_pick_kernel<<<1, 256, 0, st>>>((const unsigned long long*)result, n_part, (BpeCtl*)ctl, log, V, vocab_size,
                                            min_frequency, max_merges, work_count, delta);
         count_launch(2);
@@ -1655,6 +1737,46 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
         }
     }
     BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+// Peer-visible device memory (CUDA IPC) for the sharded trainer's delta blocks and flags.
+extern "C" int beast_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out_h) {
+    if (!ptr_out || !handle_out_h) return BEAST_E_NULL;
+    if (bytes < 1) return BEAST_E_SHAPE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size is part of the C ABI");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return (int)e; }
+    memcpy(handle_out_h, &h, sizeof(h));
+    *ptr_out = p;
+    return BEAST_OK;
+}
+extern "C" int beast_peer_open(const void* handle_h, void** ptr_out) {
+    if (!handle_h || !ptr_out) return BEAST_E_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_h, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    *ptr_out = p;
+    return BEAST_OK;
+}
+extern "C" int beast_peer_close(void* ptr) {
+    if (!ptr) return BEAST_E_NULL;
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return BEAST_OK;
+}
+extern "C" int beast_peer_free(void* ptr) {
+    if (!ptr) return BEAST_E_NULL;
+    cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     return BEAST_OK;
 }
 

@@ -90,13 +90,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-CPU_CHUNK = 2048
+CPU_CHUNK = 8192          # the reference needs ~300 KB of scratch per trajectory, 8 192 fit comfortably
 
 
 def make_port():
     """oracle/reference_port_torch.py: the reference's own sequence of torch CPU ops (basis rebuilt
-    per call, dense block-diagonal basis, one 120x120 LU per trajectory — mp/uni_bspline.py:539-586),
-    bit-identical to the live reference on the golden vectors."""
+    per call, dense block-diagonal basis, one 120x120 LU per trajectory — mp/uni_bspline.py:539-586);
+    pinned to the live reference's golden vectors (coefficients within 1e-6 normwise, tokens equal up to
+    the listed edge flips: tests/test_oracle_golden.py)."""
     from oracle.reference_port_torch import ReferencePort
     return ReferencePort(num_dof=D, num_basis=NB, seq_len=T, vocab_size=V, degree_p=4, gripper_zero_order=True,
                          gripper_indices=GRIP, llm_vocab_size=LLM_VOCAB)
@@ -112,8 +113,23 @@ def cpu_threads():
     return int(torch.get_num_threads())
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms must use the box's cores.  Call before the
+    first `import torch` of the process when possible (the env var is read at import), and set the count anyway."""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(k, None)
+    import torch
+    n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    os.environ.setdefault("RAYON_NUM_THREADS", str(n))
+    os.environ.setdefault("TOKENIZERS_PARALLELISM", "true")
+    return n
+
+
 def cpu_baseline(budget_s=12.0):
     """Bounded sample of the same workload on the host cores (rank 0, N=1)."""
+    use_all_host_threads()
     from beast_tokenizer_b200.synth import synth
     port = make_port()
     x = synth(CPU_CHUNK, T, D, seed=2)
@@ -134,6 +150,7 @@ def run_reference(args, rank):
     """--impl reference: the reference's CPU algorithm (torch-CPU port) on this box's host cores."""
     if rank != 0:
         return
+    use_all_host_threads()
     from beast_tokenizer_b200.synth import synth
     port = make_port()
     x = synth(CPU_CHUNK, T, D, seed=2)
@@ -238,12 +255,38 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
         runs.append(float(dt.item()))
     secs = min(runs)
     n_merges = len(state.tokenizer.merges)
+    import hashlib
+    table = state.tokenizer.merges_txt() + state.tokenizer.vocab_json()
+    sha = hashlib.sha256(table.encode("utf-8")).hexdigest()
     out = {"metric": "BPE-train merges/sec", "value": n_merges / secs, "unit": "merges/s", "seconds": secs,
+           "us_per_merge": 1e6 * secs / max(n_merges, 1),
            "runs_seconds": runs, "merges": n_merges, "vocab": BPE_VOCAB, "sequences": BPE_BATCHES * BPE_BATCH, "n_gpus": world,
-           "scaling": "strong", "sharding": f"{BPE_CHUNKS} chunks of {per_chunk} sequences round-robin over ranks; "
-           "min/max, seen bytes, histogram and per-merge 4xV deltas all-reduced (NCCL)"}
+           "scaling": "strong", "merge_table_sha256": sha,
+           "delta_reduction": getattr(state.tokenizer, "trainer_mode", "single GPU"),
+           "sharding": f"{BPE_CHUNKS} chunks of {per_chunk} sequences round-robin over ranks; min/max, seen bytes and the "
+           "initial histogram all-reduced once (NCCL); per-merge 4xV deltas summed inside bpe_iterate_kernel over peer memory"}
+    if world > 1:
+        # every rank must hold the same table, and it must be the table of the unsharded corpus
+        shas = [None] * world
+        dist.all_gather_object(shas, sha)
+        out["ranks_agree"] = all(h == sha for h in shas)
+        if rank == 0:
+            full = torch.cat([tok.encode(synth_device(per_chunk, T, D, 1000 + c, dev), respect_llm_vocab_size=False)[0]
+                              for c in range(BPE_CHUNKS)])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref = FIGBPE(vocab_size=BPE_VOCAB, show_progress=False, device=str(dev), process_group=False).fit_from_bins(full)
+            torch.cuda.synchronize()
+            ref_secs = time.perf_counter() - t0
+            ref_table = ref.tokenizer.merges_txt() + ref.tokenizer.vocab_json()
+            out["identical_to_unsharded"] = ref_table == table
+            out["unsharded_same_gpu"] = {"seconds": ref_secs, "merge_table_sha256": hashlib.sha256(ref_table.encode("utf-8")).hexdigest()}
+            del full
+        dist.barrier()
     if rank != 0:
         return out, None
+    if world == 1:
+        out["e2e_fit_from_trajectories"] = bpe_e2e_leg(tok, dev, with_cpu)
     if with_cpu:
         # the reference trainer on the same bins, bounded sample; the GPU trainer on that sample must agree
         sample = synth_bins_sample(tok, dev)
@@ -259,7 +302,7 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
                                "gpu_same_sample": {"seconds": g_secs, "merges_per_s": len(st_s.tokenizer.merges) / g_secs},
                                "merge_table_identical": cpu["merges_txt"] == st_s.tokenizer.merges_txt()}
         if cpu_full and world == 1:
-            # --bpe-cpu-full: the reference trainer on the WHOLE 1.6 M-sequence corpus (minutes of host time)
+            # the reference trainer on the WHOLE 1.6 M-sequence corpus (about a minute of host time; --no-bpe-cpu-full skips it)
             full = hf_train_cpu(bins.cpu().numpy(), BPE_VOCAB)
             out["cpu_baseline"]["full_corpus"] = {
                 "sequences": int(bins.shape[0]), "seconds": full["seconds"],
@@ -309,6 +352,65 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
                                                       for r in (mp[:64].cpu() - btok.bpe_min_token).tolist()]
             apply["cpu_reference"] = ref
     return out, apply
+
+
+def bpe_e2e_leg(tok, dev, with_cpu):
+    """BASELINE configs[3] end to end through the public API: BEASTBsplineBPETokenizer.fit_from_trajectories over a
+    loader of 50 000 HOST batches x 32 trajectories (wall clock: H2D of every batch, K1, symbolise, count, merge loop,
+    vocabulary).  Beside it the reference flow (beast/beast_bpe_trainer.py:100-151: per-batch encode, D2H, chr strings,
+    HF BpeTrainer) timed on a stated subset of the same loader."""
+    import torch
+    from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
+    from beast_tokenizer_b200.synth import synth_device
+    n_batches, bs = BPE_BATCHES, BPE_BATCH
+    # the loader's batches as views of host blocks (generated on the GPU, copied out once: 4.5 GB of host memory)
+    blocks = []
+    per = BPE_BATCHES * BPE_BATCH // BPE_CHUNKS
+    for c in range(BPE_CHUNKS):
+        blocks.append(synth_device(per, T, D, 1000 + c, dev).cpu())
+    loader = [{"actions": blk[i:i + bs]} for blk in blocks for i in range(0, per, bs)]
+    assert len(loader) == n_batches
+    btok = BEASTBsplineBPETokenizer.from_beast(tok, bpe_vocab_size=BPE_VOCAB, device=str(dev))
+    btok.set_llm_vocab_size(None)
+    btok.fit_from_trajectories(loader[:64], show_progress=False)            # warm-up
+    torch.cuda.synchronize()
+    runs = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        state = btok.fit_from_trajectories(loader, show_progress=False)
+        torch.cuda.synchronize()
+        runs.append(time.perf_counter() - t0)
+    secs = min(runs)
+    import hashlib
+    out = {"workload": f"{n_batches} host batches x {bs} trajectories [32, 50, 14] fp32 (pageable host memory), "
+                       f"bpe_vocab_size {BPE_VOCAB}", "seconds": secs, "runs_seconds": runs,
+           "merges": len(state.tokenizer.merges), "sequences_per_s": n_batches * bs / secs,
+           "merge_table_sha256": hashlib.sha256((state.tokenizer.merges_txt() + state.tokenizer.vocab_json()).encode("utf-8")).hexdigest(),
+           "h2d_bytes": 4 * T * D * n_batches * bs, "timer": "host clock, device synchronised"}
+    if with_cpu:
+        # the reference's flow on the first `nb_cpu` batches: torch-CPU port encode per batch + HF trainer
+        nb_cpu = 128
+        port = make_port()
+        port.offset = 0                                            # BPE works on MP tokens (encode_to_mp_tokens)
+        lo, hi = tok._bounds(dev)
+        port.w_min, port.w_max = lo.cpu(), hi.cpu()
+        t0 = time.perf_counter()
+        rows = []
+        for b in loader[:nb_cpu]:
+            tokens, _ = port.encode(b["actions"])
+            rows.append(tokens.numpy())
+        import numpy as np
+        bins_cpu = np.concatenate(rows)
+        t1 = time.perf_counter()
+        cpu = hf_train_cpu(bins_cpu, BPE_VOCAB)
+        t2 = time.perf_counter()
+        enc_s = t1 - t0
+        out["cpu_reference"] = {
+            "kind": "port + tokenizers", "batches": nb_cpu, "encode_seconds": enc_s, "train_seconds": t2 - t1,
+            "encode_seconds_extrapolated_full": enc_s * n_batches / nb_cpu,
+            "note": f"reference flow on the first {nb_cpu} of {n_batches} batches: per-batch encode on the host ({cpu_threads()} "
+                    "threads) scales linearly with the batch count; the trainer time on the full corpus is bpe_train.cpu_baseline.full_corpus"}
+    return out
 
 
 def bounds_cpu_reference(n=4096):
@@ -396,8 +498,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bpe", action="store_true", help="skip the BPE-train / BPE-apply legs")
-    ap.add_argument("--bpe-cpu-full", action="store_true",
-                    help="also run the reference BPE trainer on the full 1.6 M-sequence corpus (minutes of host time)")
+    ap.add_argument("--no-bpe-cpu-full", action="store_true",
+                    help="skip the reference BPE trainer on the full 1.6 M-sequence corpus (about a minute of host time)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -425,7 +527,7 @@ def main():
     B = args.batch
     tok = BEASTBsplineTokenizer(num_dof=D, num_basis=NB, seq_len=T, vocab_size=V, gripper_zero_order=True,
                                 gripper_indices=GRIP, device=f"cuda:{local_rank}", llm_vocab_size=LLM_VOCAB)
-    tok.fit_parameters(SyntheticLoader(100, 32, T, D, seed0=1), verbose=False)
+    tok.fit_parameters(SyntheticLoader(100, 32, T, D, seed0=1), verbose=False, process_group=False)   # same loader on every rank
     plan = tok._plan()
     lib = plan._lib
     lo, hi = tok._bounds(dev)
@@ -546,6 +648,35 @@ def main():
     e2e_sync()
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - w0)      # host clock around fully synchronised work on 3 streams
+    # copy-only ceiling of the same leg: the same pinned buffers, chunks and streams, no kernels — what the host
+    # side (PCIe root, host DRAM) can move; e2e is to be read as a fraction of this
+    dx = torch.empty((cb + n_chunks, T, D), device=dev, dtype=torch.float32)
+    dtok = torch.empty((cb + n_chunks, NB * D), device=dev, dtype=torch.int64)
+    drec = torch.empty((cb + n_chunks, T, D), device=dev, dtype=torch.float32)
+
+    def copy_only_step(i):
+        src = xh[i % 2]
+        for c in range(n_chunks):
+            st = streams[c % n_streams]
+            with torch.cuda.stream(st):
+                sl = slice(c * cb, (c + 1) * cb if c < n_chunks - 1 else B)
+                n = sl.stop - sl.start
+                dx[:n].copy_(src[sl], non_blocking=True)
+                tok_h[sl].copy_(dtok[:n], non_blocking=True)
+                rec_h[sl].copy_(drec[:n], non_blocking=True)
+
+    copy_only_step(0)
+    e2e_sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    c0 = time.perf_counter()
+    for i in range(Ke):
+        copy_only_step(i)
+    e2e_sync()
+    torch.cuda.synchronize()
+    copy_ms = 1e3 * (time.perf_counter() - c0)
+    del dx, dtok, drec
     # spot-check the pipelined results against a plain single-stream call
     chk_t, _ = tok.encode(xh[(Ke - 1) % 2][:cb])
     assert torch.equal(chk_t.cpu(), tok_h[:cb]), "pipelined e2e tokens differ"
@@ -558,12 +689,12 @@ def main():
         del xs, toks, pars, outs, xh
         torch.cuda.empty_cache()
         bpe_train, bpe_apply = bpe_legs(tok, dev, rank, world, dist, world == 1 and not args.no_cpu_baseline,
-                                        cpu_full=args.bpe_cpu_full)
+                                        cpu_full=not args.no_bpe_cpu_full)
 
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms, copy_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, enc_ms, dec_ms = [float(v) for v in t.tolist()]
+        ms_total, e2e_ms, enc_ms, dec_ms, copy_ms = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -580,7 +711,8 @@ def main():
                              "decode reads tokens written two steps earlier"},
             "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "trajectories/s",
                     "h2d_bytes_per_step": 4 * T * D * B, "d2h_bytes_per_step": (8 * NB * D + 4 * T * D) * B,
-                    "steps": Ke, "ms_per_step": e2e_ms / Ke,
+                    "steps": Ke, "ms_per_step": e2e_ms / Ke, "copy_only_ms": copy_ms / Ke,
+                    "frac_of_copy_only": copy_ms / e2e_ms,
                     "path": "BEASTBsplineTokenizer.encode(pinned host) -> reconstruct_traj -> tokens+trajectories to pinned host; "
                             "8 chunks over 3 CUDA streams (H2D / kernels / D2H overlapped)", "timer": "host clock, all streams synchronised"},
             "gpu_launches": int(launches),

@@ -214,18 +214,46 @@ int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* resul
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
                     int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream);
 int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
-/* Sync-free training loop: one iteration = phase 0 — four launches: (1) fold the previous merge's delta
- * into the histogram and arg-max it, (2) pick: BpeTrainer's stop rules (vocabulary full / count < min_frequency),
- * next id, merge log, (3) scan for the pair, (4) rewrite the listed sequences into delta — [+ all-reduce(delta)
- * when sharded].
- * phase 1 is a no-op kept for symmetry.  ctl: 8 x int32 device block {a, b, c, count, n_tokens, n_merges, done,
- * has_delta}, caller sets n_tokens = alphabet size and zeroes the rest; work: int32 [4 + 2*N] zeroed by the caller; log: int32 [4 * max_merges] receives (a, b, new_id, count) per
- * merge; result: arg-max scratch, 256 x uint64 (per-block maxima).  Nothing is read back until the end.
- * iters: iterations enqueued by this call (> 1 only when no all-reduce has to run between them). */
+/* Peers of a sharded training run (one process per GPU, sequences sharded, V x V histogram replicated).
+ * delta[r] / flags[r] are rank r's count-delta block (int32 [2][4*V], double-buffered by merge parity) and
+ * flag array (int32 [BPE_MAX_PEERS]) as DEVICE pointers valid on the calling rank's GPU: its own allocation for
+ * r == rank, a peer mapping (beast_peer_open) otherwise.  The per-merge SUM all-reduce of the 4 x V deltas is
+ * folded into the iteration head: every rank publishes "rewrite of merge m done" by storing the epoch into
+ * flags[p][rank] of every peer p (release, system scope), waits for its own flags, then sums the ranks' delta
+ * blocks with peer loads over NVLink while it folds them into its histogram replica.  No host round, no NCCL call
+ * between merges.  grid_blocks: blocks of the iteration-head kernel (0 = one per SM); tests that run several
+ * ranks on ONE GPU pass a smaller grid so that all ranks' (spinning) kernels are co-resident. */
+#define BPE_MAX_PEERS 16
+typedef struct bpe_peers {
+    int32_t world, rank;
+    int32_t grid_blocks;
+    int32_t epoch_base;      /* added to the merge index in the flags (lets a caller reuse flags without clearing) */
+    int32_t* delta[BPE_MAX_PEERS];
+    int32_t* flags[BPE_MAX_PEERS];
+} bpe_peers_t;
+
+/* Peer-visible device memory for bpe_peers_t: cudaMalloc + CUDA IPC.  beast_peer_alloc returns a zeroed
+ * allocation on the current device and its 64-byte IPC handle (handle_out_h, host); another PROCESS on the same
+ * node maps it with beast_peer_open (peer access is enabled lazily); beast_peer_close unmaps, beast_peer_free
+ * releases the owner's allocation.  These four calls synchronise / allocate (set-up, not the hot path). */
+int beast_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out_h);
+int beast_peer_open(const void* handle_h, void** ptr_out);
+int beast_peer_close(void* ptr);
+int beast_peer_free(void* ptr);
+
+/* Sync-free training loop: one iteration = four launches: (1) iterate: arg-max of the histogram, folding the
+ * previous merge's delta (summed over the peers when sharded) on the way, (2) pick: BpeTrainer's stop rules
+ * (vocabulary full / count < min_frequency), next id, merge log, (3) scan for the pair, (4) rewrite the listed
+ * sequences, count changes into delta[merge & 1].
+ * ctl: 8 x int32 device block {a, b, c, count, n_tokens, n_merges, done, has_delta}, caller sets n_tokens =
+ * alphabet size and zeroes the rest; delta: int32 [2][4*V] zeroed by the caller (== peers->delta[peers->rank]
+ * when sharded); work: int32 [4 + 2*N] zeroed by the caller; log: int32 [4 * max_merges] receives (a, b, new_id,
+ * count) per merge; result: arg-max scratch, 256 x uint64 (per-block maxima).  Nothing is read back until the end.
+ * iters: iterations enqueued by this call.  peers_h: NULL (or world == 1) = unsharded. */
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                    int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
-                   int32_t min_frequency, int32_t max_merges, int32_t phase, uint32_t* sig, int32_t iters,
-                   void* stream);
+                   int32_t min_frequency, int32_t max_merges, uint32_t* sig, int32_t iters,
+                   const bpe_peers_t* peers_h, void* stream);
 /* Pair signatures for bpe_train_step (optional, sig = NULL scans every sequence): uint32
  * [bpe_signature_words()][n_stride], bit hash(a, b) of sequence s set when s holds (or ever held) the
  * in-word pair (a, b).  The scan for a merge reads one 4-byte column and skips the sequences whose bit

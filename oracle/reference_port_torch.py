@@ -5,8 +5,9 @@ parity checker; this module exists because the reference's CPU path *is* a seque
 ops (einsum -> bmm, linalg.solve -> batched LU, elementwise clamp/round), so the honest CPU
 baseline for bench.py is the same sequence of torch ops on the same host cores — including the
 work the reference repeats on every call (basis rebuilt twice per fit, dense block-diagonal
-basis, one (D*nb)^2 LU per trajectory).  Pinned in tests/test_oracle_golden.py: tokens and
-coefficients equal the live reference's golden vectors bit for bit.
+basis, one (D*nb)^2 LU per trajectory).  Pinned in tests/test_oracle_golden.py against the live
+reference's golden vectors: basis bit-identical, coefficients / trajectories within 1e-6 normwise (the
+batched LU's thread schedule differs between runs), tokens equal on >= 99.9 % of the positions.
 
 Citations relative to /root/reference.
 """

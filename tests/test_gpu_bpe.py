@@ -270,3 +270,51 @@ def test_decode_kernels_agree_on_garbage(monkeypatch):
     assert ok[:200].all() and np.array_equal(d0[ok], d1[ok]) and np.array_equal(d0[:200], bins[:200])
     len_known = (s0 == 0) | (s0 == 3)
     assert np.array_equal(l0[len_known], l1[len_known])
+
+
+def test_peer_fused_delta_reduction_two_ranks_on_one_gpu():
+    """The sharded trainer's per-merge all-reduce lives inside bpe_iterate_kernel (peer loads of the other ranks'
+    delta blocks, epoch flags, no host round).  Here two 'ranks' share ONE GPU: two engines, two streams, each
+    rank's delta / flags are the other's peers; their iteration heads spin on each other's flags, so both grids
+    must be co-resident (grid_blocks = half the SMs).  Every rank must log exactly the merges of the unsharded run."""
+    import ctypes as C
+    from beast_tokenizer_b200 import _lib
+    from beast_tokenizer_b200.beast_bpe_trainer import GpuBpeEngine, _Collective, build_alphabet, scan_bins_gpu, train_bpe
+    rng = np.random.default_rng(21)
+    bins = np.clip(rng.normal(128, 30, (6000, 140)).round(), 0, 255).astype(np.int64)
+    bins[::3] = np.clip(bins[::3] + 40, 0, 255)
+    vocab = 700
+    dev = torch.device("cuda", torch.cuda.current_device())
+    full = torch.from_numpy(bins).to(dev)
+    ref, mn0, mx0 = train_bpe(full, vocab, 2, coll=_Collective(enabled=False))
+    mn, mx, seen = scan_bins_gpu(full, _Collective(enabled=False))
+    tokens, b2i = build_alphabet(mn, mx, seen)
+    world = 2
+    engs = [GpuBpeEngine(full[r::world].contiguous(), mn, b2i, vocab, mx - mn) for r in range(world)]
+    hist = sum(e.hist for e in engs)
+    for e in engs:
+        e.hist.copy_(hist)
+    deltas = [torch.zeros(8 * vocab, device=dev, dtype=torch.int32) for _ in range(world)]
+    flags = [torch.zeros(_lib.BPE_MAX_PEERS, device=dev, dtype=torch.int32) for _ in range(world)]
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    runs = []
+    for r in range(world):
+        p = _lib.BpePeers()
+        p.world, p.rank, p.grid_blocks, p.epoch_base = world, r, max(1, sms // 2 - 4), 0
+        for q in range(world):
+            p.delta[q] = deltas[q].data_ptr()
+            p.flags[q] = flags[q].data_ptr()
+        runs.append(engs[r].start_run(len(tokens), vocab, 2, peers=p, delta=deltas[r]))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    while not all(run.finished for run in runs):
+        for r in range(world):                            # one iteration per rank and turn: neither queue runs ahead
+            with torch.cuda.stream(streams[r]):
+                runs[r].enqueue(limit=1)
+    torch.cuda.synchronize()
+    logs = [run.finish() for run in runs]
+    assert logs[0] == logs[1]
+    assert [(a, b, c) for a, b, c, _ in logs[0]] == list(ref.merges)
+    assert len(logs[0]) == vocab - len(tokens)
+    for e in engs:                                        # replicas stayed identical
+        assert torch.equal(e.hist, engs[0].hist)

@@ -330,14 +330,21 @@ COND_CFG = dict(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, degree_p=4
                 gripper_zero_order=True, gripper_indices=[6, 13], llm_vocab_size=None)
 
 
-@pytest.mark.parametrize("orders", [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)])
-def test_condition_orders_vs_golden(orders):
+COND_ODD_CFG = dict(num_dof=5, num_basis=8, seq_len=33, vocab_size=1000, degree_p=3,
+                    gripper_zero_order=True, gripper_indices=[0])
+
+
+@pytest.mark.parametrize("case,orders", [("cond_orders", o) for o in [(1, 0), (2, 0), (0, 1), (0, 2), (1, 1), (2, 2)]] +
+                         [("cond_odd", o) for o in [(2, 1), (1, 2)]])
+def test_condition_orders_vs_golden(case, orders):
     """Pinned boundary control points (mp/uni_bspline.py:500-537, 126-166): same K1 with the
     conditions folded into the projector, K3 with the pinned points of the last fit — compared with
     the live reference's outputs, including its stateful ("stale") reconstruct."""
     from beast_tokenizer_b200 import BEASTBsplineTokenizer
     io, eo = orders
-    g = load_golden("cond_orders")
+    g = load_golden(case)
+    COND_CFG = COND_ODD_CFG if case == "cond_odd" else globals()["COND_CFG"]
+    nb, T, deg = COND_CFG["num_basis"], COND_CFG["seq_len"], COND_CFG["degree_p"]
     k = f"o{io}{eo}_"
     tok = BEASTBsplineTokenizer(device="cuda", init_cond_order=io, end_cond_order=eo, **COND_CFG)
     x, x2 = torch.from_numpy(g["trajs"]), torch.from_numpy(g["trajs_other"])
@@ -374,9 +381,9 @@ def test_condition_orders_vs_golden(orders):
     rc = tok.reconstruct_traj_continuous(ctoks).cpu().numpy()
     # the oracle evaluates the same coefficients with the same pinned points
     joint, grip = layout(COND_CFG)
-    times = O.linspace_f32(0, 2 * math.pi, 50)
-    _, st = O.compute_weights_cond(g["trajs"], times, 2 * math.pi, 10, 4, joint, grip, io, eo)
-    ro = O.reconstruct_from_params_cond(params, st, times, 2 * math.pi, 10, 4, joint, grip, io, eo)
+    times = O.linspace_f32(0, 2 * math.pi, T)
+    _, st = O.compute_weights_cond(g["trajs"], times, 2 * math.pi, nb, deg, joint, grip, io, eo)
+    ro = O.reconstruct_from_params_cond(params, st, times, 2 * math.pi, nb, deg, joint, grip, io, eo)
     assert rel_err(rc, ro) <= 5e-5                                    # normalise/denormalise round trip in between
     # state semantics: after fitting other data the same tokens reconstruct with THAT boundary state
     tok.encode(x2)
