@@ -31,6 +31,9 @@ except Exception:  # pragma: no cover
 
 ArrayLike = Union[Sequence[int], np.ndarray, torch.Tensor]
 
+# dense V x V histogram + 16*V bytes of shared-memory delta counters per block (csrc/bpe.cu: bpe_rewrite_kernel)
+MAX_TRAIN_VOCAB = 12800
+
 
 @dataclass
 class FIGBPEState:
@@ -56,11 +59,16 @@ class _Collective:
         return t
 
 
-def build_alphabet(min_token: int, max_token: int, seen_bytes: Sequence[int]):
-    """A.3: vocabulary = chr(0..max-min) U byte-level characters seen, ids by sorted codepoint."""
+def build_alphabet(min_token: int, max_token: int, seen_bytes: Sequence[int], special_tokens: Sequence[str] = ()):
+    """A.3: vocabulary = [special tokens, in order, duplicates skipped] + chr(0..max-min) U byte-level characters
+    seen, by sorted codepoint; a character that already is a (single-character) special token keeps that id."""
     chars = set(range(max_token - min_token + 1)) | {B2U[b] for b in range(256) if seen_bytes[b]}
-    tokens = [chr(c) for c in sorted(chars)]
-    index = {t: i for i, t in enumerate(tokens)}
+    tokens: List[str] = []
+    index: dict = {}
+    for t in list(special_tokens) + [chr(c) for c in sorted(chars)]:
+        if t not in index:
+            index[t] = len(tokens)
+            tokens.append(t)
     byte_to_id = np.array([index.get(chr(B2U[b]), -1) for b in range(256)], dtype=np.int16)
     return tokens, byte_to_id
 
@@ -68,7 +76,8 @@ def build_alphabet(min_token: int, max_token: int, seen_bytes: Sequence[int]):
 class GpuBpeEngine:
     """Device state of one shard: chunk-major symbols, lengths, replicated V x V histogram."""
 
-    def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int, max_shift: int = 255):
+    def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int, max_shift: int = 255,
+                 row_len: Optional[torch.Tensor] = None):
         self.lib = _lib.load()
         self.dev = bins.device
         self.N, self.L = bins.shape
@@ -89,7 +98,8 @@ class GpuBpeEngine:
             st = _lib.stream_ptr(self.dev)
             _lib.check(self.lib.bpe_symbolize(_lib.ptr(bins), self.N, self.L, int(min_token), _lib.ptr(b2i),
                                               _lib.ptr(class_table_device(self.dev)), _lib.ptr(self.sym),
-                                              _lib.ptr(self.len), self.stride, _lib.ptr(err), st), "bpe_symbolize")
+                                              _lib.ptr(self.len), self.stride, _lib.ptr(err), _lib.ptr(row_len), st),
+                       "bpe_symbolize")
             used = np.unique(byte_to_id[byte_to_id >= 0]).astype(np.int16)   # ids before any merge (byte-level symbols)
             used_d = torch.from_numpy(used).to(self.dev)
             n_ids = int(used[-1]) + 1 if used.size else 0
@@ -326,19 +336,25 @@ def scan_bins_gpu(bins: torch.Tensor, coll: _Collective):
 
 
 def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, engine_factory=None,
-              scan=None, coll: Optional[_Collective] = None, show_progress: bool = False):
+              scan=None, coll: Optional[_Collective] = None, show_progress: bool = False,
+              row_len: Optional[torch.Tensor] = None, special_tokens: Sequence[str] = ()):
     """The merge loop (A.4) over this rank's shard `bins` [N, L] int64.  Returns
     (B200ByteLevelBPE, min_token, max_token).  `engine_factory` / `scan` are injection points for the
-    CPU-only multi-process tests of the orchestration; production uses the GPU engine."""
+    CPU-only multi-process tests of the orchestration; production uses the GPU engine.
+    row_len [N] int32: sequences of unequal length, padded to L with an in-range value of the same row (so the
+    min / max / seen-byte scans need no mask).  special_tokens: BpeTrainer's, ids first."""
     coll = coll or _Collective()
     scan = scan or scan_bins_gpu
     engine_factory = engine_factory or GpuBpeEngine
     min_token, max_token, seen = scan(bins, coll)
-    tokens, byte_to_id = build_alphabet(min_token, max_token, seen)
+    tokens, byte_to_id = build_alphabet(min_token, max_token, seen, special_tokens)
     V = max(int(vocab_size), len(tokens))
-    if V > 32767:
-        raise NotImplementedError("bpe_vocab_size above 32767 is not supported")
-    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token)
+    if V > MAX_TRAIN_VOCAB:
+        raise NotImplementedError(
+            f"bpe_vocab_size {V} is above the trainer's limit of {MAX_TRAIN_VOCAB}: the merge loop keeps a dense "
+            f"V x V int32 pair histogram ({4 * V * V / 2**30:.1f} GiB here) and 16*V bytes of per-block shared-memory "
+            "counters (reference FIGBPE default is 1024; BASELINE config 2048)")
+    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token, row_len)
                            if engine_factory is GpuBpeEngine else engine_factory(bins, min_token, byte_to_id, V))
     eng = make_engine()
     coll.reduce_(eng.hist, "sum")                       # replicated global histogram
@@ -359,7 +375,7 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
             fast_index[new] = c
             fast_tokens.append(new)
         if ok:
-            model = B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log])
+            model = B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log], special_tokens=special_tokens)
             model.trainer_mode = getattr(eng, "mode", "single GPU")
             return model, min_token, max_token
         eng = make_engine()
@@ -383,7 +399,7 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
         eng.apply_delta(a, b, c)
     if bar is not None:
         bar.close()
-    return B200ByteLevelBPE(tokens, merges), min_token, max_token
+    return B200ByteLevelBPE(tokens, merges, special_tokens=special_tokens), min_token, max_token
 
 
 def _flatten_to_numpy(sequence: ArrayLike) -> np.ndarray:
@@ -404,8 +420,6 @@ class FIGBPE:
         self.vocab_size = vocab_size
         self.min_frequency = min_frequency
         self.special_tokens = list(special_tokens or [])
-        if self.special_tokens:
-            raise NotImplementedError("special tokens are not supported by the B200 BPE trainer")
         self.show_progress = show_progress
         self.max_token_length = max_token_length
         self.device = device
@@ -421,12 +435,16 @@ class FIGBPE:
             raise _lib.BeastB200Error("no CUDA device available: the BPE trainer has no CPU fallback")
         return torch.device("cuda", torch.cuda.current_device())
 
-    def fit_from_bins(self, bins: torch.Tensor) -> FIGBPEState:
-        """bins [N, L] int64 on the GPU (this rank's shard when sharded)."""
+    def fit_from_bins(self, bins: torch.Tensor, row_len: Optional[torch.Tensor] = None) -> FIGBPEState:
+        """bins [N, L] int64 on the GPU (this rank's shard when sharded); row_len [N]: see train_bpe."""
         # process_group=False forces a local (unsharded) fit even under torch.distributed
         coll = _Collective(enabled=False) if self.process_group is False else _Collective(self.process_group)
-        tok, mn, mx = train_bpe(bins.to(self._device(), torch.int64).contiguous(), self.vocab_size, self.min_frequency,
-                                coll=coll, show_progress=self.show_progress)
+        dev = self._device()
+        if row_len is not None:
+            row_len = row_len.to(dev, torch.int32).contiguous()
+        tok, mn, mx = train_bpe(bins.to(dev, torch.int64).contiguous(), self.vocab_size, self.min_frequency,
+                                coll=coll, show_progress=self.show_progress, row_len=row_len,
+                                special_tokens=self.special_tokens)
         self.tokenizer, self.min_token, self.max_token = tok, mn, mx
         return FIGBPEState(tokenizer=tok, min_token=mn, max_token=mx)
 
@@ -439,10 +457,16 @@ class FIGBPE:
             processed.append(arr)
         if not processed:
             raise ValueError("No non-empty sequences provided for BPE training.")
-        lengths = {a.size for a in processed}
-        if len(lengths) != 1:
-            raise NotImplementedError("the B200 BPE trainer expects equal-length sequences (BEAST tokens are)")
-        return self.fit_from_bins(torch.from_numpy(np.stack(processed)))
+        lengths = np.fromiter((a.size for a in processed), dtype=np.int64, count=len(processed))
+        if int(lengths.min()) == int(lengths.max()):
+            return self.fit_from_bins(torch.from_numpy(np.stack(processed)))
+        # unequal lengths (reference :76-98 takes any): pad every row with its own first value — in range, so
+        # min / max / the seen-byte set are those of the real data — and hand the true lengths to the symboliser
+        padded = np.empty((len(processed), int(lengths.max())), dtype=np.int64)
+        for i, a in enumerate(processed):
+            padded[i, :a.size] = a
+            padded[i, a.size:] = a[0]
+        return self.fit_from_bins(torch.from_numpy(padded), row_len=torch.from_numpy(lengths.astype(np.int32)))
 
     GATHER_ROWS = 4096      # loader batches are gathered on the device and fitted this many trajectories at a time
 

@@ -33,6 +33,7 @@ B2U = bytes_to_unicode()
 U2B = {c: b for b, c in enumerate(B2U)}
 
 MAX_SHIFT = 0xD7FF                      # shifted bins are codepoints below the surrogate range
+MAX_APPLY_VOCAB = 16384                 # dense V x V rank table of the encode kernel: 1 GiB at this size
 # letters added to Unicode after Python 3.12's tables (15.0) that the reference's regex engine already knows
 _NEWER_LETTERS = (7305, 7306, 42955, 42956, 42957, 42970, 42971, 42972)
 _WHITE_SPACE = {9, 10, 11, 12, 13, 32, 133, 160, 5760, 8232, 8233, 8239, 8287, 12288} | set(range(8192, 8203))
@@ -83,7 +84,12 @@ class Encoding:
 class B200ByteLevelBPE:
     """vocab: token strings (byte-level characters) in id order; merges: [(id_a, id_b, id_new)]."""
 
-    def __init__(self, vocab: Sequence[str], merges: Sequence[Tuple[int, int, int]]):
+    def __init__(self, vocab: Sequence[str], merges: Sequence[Tuple[int, int, int]],
+                 special_tokens: Sequence[str] = ()):
+        # BpeTrainer special tokens of THIS training run (HF registers them as added tokens on the trained object;
+        # a tokenizer reloaded from vocab.json / merges.txt — what the reference's from_pretrained does,
+        # beast_bspline_bpe_tokenizer.py:379-382 — no longer knows them, and neither does from_file here).
+        self.special_tokens: List[str] = list(dict.fromkeys(special_tokens))
         self.tokens: List[str] = list(vocab)
         self.merges: List[Tuple[int, int, int]] = [tuple(int(x) for x in m) for m in merges]
         self._vocab: Dict[str, int] = {t: i for i, t in enumerate(self.tokens)}
@@ -165,7 +171,10 @@ class B200ByteLevelBPE:
         bl = lambda prefix, trim: {"type": "ByteLevel", "add_prefix_space": prefix, "trim_offsets": trim,
                                    "use_regex": True}
         doc = {
-            "version": "1.0", "truncation": None, "padding": None, "added_tokens": [], "normalizer": None,
+            "version": "1.0", "truncation": None, "padding": None,
+            "added_tokens": [{"id": self._vocab[t], "content": t, "single_word": False, "lstrip": False, "rstrip": False,
+                              "normalized": False, "special": True} for t in self.special_tokens],
+            "normalizer": None,
             "pre_tokenizer": bl(False, True), "post_processor": bl(True, False), "decoder": bl(True, True),
             "model": {"type": "BPE", "dropout": None, "unk_token": None, "continuing_subword_prefix": None,
                       "end_of_word_suffix": None, "fuse_unk": False, "byte_fallback": False, "ignore_merges": False,
@@ -186,8 +195,10 @@ class B200ByteLevelBPE:
         if key in self._dev_tables:
             return self._dev_tables[key]
         V = len(self.tokens)
-        if V > 65535:
-            raise _lib.BeastB200Error("BPE vocabularies above 65535 entries are not supported")
+        if V > MAX_APPLY_VOCAB:
+            raise _lib.BeastB200Error(
+                f"BPE vocabulary of {V} entries: the encode kernel looks merge ranks up in a dense V x V uint32 table "
+                f"({4 * V * V / 2**30:.1f} GiB here); vocabularies up to {MAX_APPLY_VOCAB} entries (1 GiB) are supported")
         b2i = np.full(256, -1, dtype=np.int16)
         for b in range(256):
             b2i[b] = self._vocab.get(chr(B2U[b]), -1)
@@ -198,7 +209,12 @@ class B200ByteLevelBPE:
                 rank[k] = (r << 16) | c
         off = np.zeros(V + 1, dtype=np.int32)
         chunks = []
+        special_ids = {self._vocab[t] for t in self.special_tokens}
         for i in range(V):
+            if i in special_ids:                  # decode(skip_special_tokens=True), the library's default: no bytes
+                chunks.append(b"")
+                off[i + 1] = off[i]
+                continue
             # HF's ByteLevel decoder maps characters back to bytes; a token holding any other
             # character (the unused raw chr(i) alphabet entries) contributes its own UTF-8 bytes
             tok = self.tokens[i]
@@ -222,6 +238,7 @@ class B200ByteLevelBPE:
         t = self._tables(dev)
         bins = bins.to(torch.int64).contiguous()
         N, L = bins.shape
+        self._reject_special_text(bins, int(min_token))
         max_shift = MAX_SHIFT if max_token is None else int(max_token) - int(min_token)
         if max_shift > MAX_SHIFT:
             raise ValueError("BPE over more than 55 296 distinct bin values is not representable (surrogate range)")
@@ -241,6 +258,19 @@ class B200ByteLevelBPE:
             _lib.check(lib.bpe_compact(_lib.ptr(padded), stride, _lib.ptr(lens), _lib.ptr(offsets), N, _lib.ptr(flat),
                                        st), "bpe_compact")
         return flat[:total], offsets, status
+
+    def _reject_special_text(self, bins: torch.Tensor, min_token: int):
+        """The library matches special tokens in the TEXT before pre-tokenisation; a row whose chr() string
+        contains one would encode differently there.  Not implemented on the GPU: detected and refused."""
+        for t in self.special_tokens:
+            m = len(t)
+            if m == 0 or m > bins.shape[1] or bins.shape[0] == 0:
+                continue
+            pat = torch.tensor([ord(c) + min_token for c in t], device=bins.device, dtype=torch.int64)
+            if bool((bins.unfold(1, m, 1) == pat).all(-1).any()):
+                raise NotImplementedError(f"a sequence spells the special token {t!r}; the B200 encoder does not split "
+                                          "special tokens out of the text (train without special_tokens, or reload "
+                                          "the tokenizer from its files, which drops them as the reference does)")
 
     def decode_ids(self, flat: torch.Tensor, offsets: torch.Tensor, L: int, min_token: int):
         """CSR ids (CUDA) -> (bins int64 [N, L], status int32 [N], decoded length int32 [N])."""

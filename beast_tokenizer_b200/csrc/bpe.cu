@@ -206,7 +206,8 @@ bpe_seen_kernel(const long long* __restrict__ bins, long long n, long long min_t
 __global__ void __launch_bounds__(kBpeBlock)
 bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token,
                      const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
-                     uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int* err, int rows) {
+                     uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int* err, int rows,
+                     const int* __restrict__ row_len) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
     uint16_t* s_cp = (uint16_t*)s_raw;
@@ -223,8 +224,10 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
     if (s_status[threadIdx.x]) *err = 1;
     const uint16_t* cp = s_cp + threadIdx.x * LP;
     int m = 0, i = 0;
-    while (i < L) {
-        const int pl = pretoken_len(cp, i, L, cls_tab);
+    // sequences of unequal length arrive padded to L; the text of this one ends at row_len[seq]
+    const int Lr = row_len ? min(max(row_len[seq], 0), L) : L;
+    while (i < Lr) {
+        const int pl = pretoken_len(cp, i, Lr, cls_tab);
         uint16_t flag = kWordStart;
         for (int q = i; q < i + pl; ++q) {
             int bt[3];
@@ -1555,7 +1558,7 @@ extern "C" int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, 
 
 extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
                              const uint8_t* cls_tab, uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err,
-                             void* stream) {
+                             const int32_t* row_len, void* stream) {
     if (N == 0) return BEAST_OK;
     if (!bins || !byte_to_id || !cls_tab || !sym || !len || !err) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_stride < N || 3 * L > 32767) return BEAST_E_SHAPE;
@@ -1566,7 +1569,7 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
     if (int rc = opt_in_smem(bpe_symbolize_kernel, smem, granted)) return rc;
     const long long grid = (N + rows - 1) / rows;
     bpe_symbolize_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
-        (const long long*)bins, N, L, min_token, byte_to_id, cls_tab, sym, len, n_stride, err, rows);
+        (const long long*)bins, N, L, min_token, byte_to_id, cls_tab, sym, len, n_stride, err, rows, row_len);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;

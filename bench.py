@@ -648,6 +648,9 @@ def main():
     e2e_sync()
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - w0)      # host clock around fully synchronised work on 3 streams
+    # spot-check the pipelined results against a plain single-stream call
+    chk_t, _ = tok.encode(xh[(Ke - 1) % 2][:cb])
+    assert torch.equal(chk_t.cpu(), tok_h[:cb]), "pipelined e2e tokens differ"
     # copy-only ceiling of the same leg: the same pinned buffers, chunks and streams, no kernels — what the host
     # side (PCIe root, host DRAM) can move; e2e is to be read as a fraction of this
     dx = torch.empty((cb + n_chunks, T, D), device=dev, dtype=torch.float32)
@@ -677,9 +680,6 @@ def main():
     torch.cuda.synchronize()
     copy_ms = 1e3 * (time.perf_counter() - c0)
     del dx, dtok, drec
-    # spot-check the pipelined results against a plain single-stream call
-    chk_t, _ = tok.encode(xh[(Ke - 1) % 2][:cb])
-    assert torch.equal(chk_t.cpu(), tok_h[:cb]), "pipelined e2e tokens differ"
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 

@@ -185,6 +185,9 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  * bpe_symbolize  bins [N, L] int64 -> sym / len through the GPT-2 pre-tokeniser (A.2) and the byte-level
  *                expansion (A.3); byte_to_id[256] int16 (-1 = not in the vocabulary: dropped); cls_tab[max
  *                shifted bin + 1] uint8: character class of every codepoint >= 256 (0 other, 1 \p{L}, 2 \p{N}, 3 \s).
+ *                row_len [N] int32 (nullable): sequences of unequal length (FIGBPE.fit_from_sequences,
+ *                beast/beast_bpe_trainer.py:76-98) arrive padded to L with any in-range value; the text of
+ *                sequence s ends at row_len[s].
  * bpe_count_pairs  hist[a*V + b] += #adjacent (a, b) inside pre-tokens (int32, V x V).  Optional hint:
  *                used_ids[n_used] = the distinct ids that can occur in sym (ascending, all < n_ids: the
  *                byte-level symbols before any merge) — when n_used^2 counters fit in shared memory the
@@ -207,7 +210,7 @@ int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, int64_t* mi
                   int32_t* err, int32_t phase, void* stream);
 int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
                   const uint8_t* cls_tab, uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err,
-                  void* stream);
+                  const int32_t* row_len, void* stream);
 int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
                     int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist, void* stream);
 int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream);

@@ -150,15 +150,28 @@ static uint64_t hash_bytes(const uint8_t* p, int n) {
  *   merges [3 * vocab_size] : (id_a, id_b, id_new) in rank order
  * Returns 0 on success; *n_vocab_out, *n_merges_out set.  Negative on error.
  */
-int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_t min_token, int64_t max_token,
-                     int vocab_size, int min_frequency, int32_t* vocab_off, uint16_t* vocab_chars,
-                     int64_t vocab_chars_cap, int32_t* merges, int32_t* n_vocab_out, int32_t* n_merges_out) {
+/*
+ * bpe_oracle_train_ex adds what FIGBPE's other arguments reach in the library (beast/beast_bpe_trainer.py:46, 53, 76-98):
+ *   row_off [n_seq+1] (nullable): sequences of unequal length, sequence s = bins[row_off[s] .. row_off[s+1])
+ *   special tokens (n_special strings, UTF-16 code units in special_chars / special_off): BpeTrainer puts them
+ *   into the vocabulary FIRST, in order, duplicates skipped; the alphabet follows, skipping characters that
+ *   already are a (single-character) special token — such a character then carries the special token's id.
+ */
+int bpe_oracle_train_ex(const int64_t* bins, int64_t n_seq, int64_t seq_len, const int64_t* row_off, int64_t min_token,
+                        int64_t max_token, int vocab_size, int min_frequency, int n_special, const int32_t* special_off,
+                        const uint16_t* special_chars, int32_t* vocab_off, uint16_t* vocab_chars,
+                        int64_t vocab_chars_cap, int32_t* merges, int32_t* n_vocab_out, int32_t* n_merges_out) {
     init_tables();
     if (max_token - min_token > 0xD7FF || max_token < min_token) return -2;
     if (vocab_size < 1 || vocab_size > 8192) return -2;
-    if (max_token - min_token + 69 > 8192) return -2;          /* dense V x V counts */
+    if (max_token - min_token + 69 + n_special > 8192) return -2;          /* dense V x V counts */
     const int R = (int)(max_token - min_token);
-    const int L = (int)seq_len;
+    int L = (int)seq_len;
+    if (row_off) {
+        L = 1;
+        for (int64_t s = 0; s < n_seq; ++s) if (row_off[s + 1] - row_off[s] > L) L = (int)(row_off[s + 1] - row_off[s]);
+    }
+    const int Lmax = L;
 
     /* pass 1: pre-tokenise, expand, collect unique words with counts */
     uint16_t* cp = (uint16_t*)malloc(((size_t)L + 1) * 2);
@@ -175,8 +188,10 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     uint8_t seen[256];
     memset(seen, 0, sizeof(seen));
     for (int64_t s = 0; s < n_seq; ++s) {
+        const int64_t base = row_off ? row_off[s] : s * Lmax;
+        L = row_off ? (int)(row_off[s + 1] - row_off[s]) : Lmax;
         for (int i = 0; i < L; ++i) {
-            int64_t v = bins[s * L + i] - min_token;
+            int64_t v = bins[base + i] - min_token;
             if (v < 0 || v > 0xD7FF) { free(cp); free(ws); free(by); free(bws); free(pool); free(words); free(ht); return -3; }
             cp[i] = (uint16_t)v;
         }
@@ -228,9 +243,19 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     tk.n = 0; tk.off = vocab_off; tk.chars = vocab_chars; tk.cap_chars = (int)vocab_chars_cap;
     int* char_to_id = (int*)malloc(sizeof(int) * MAXCP);
     tk.off[0] = 0;
+    for (int i = 0; i < n_special; ++i) {                    /* special tokens first, duplicates skipped */
+        const int len = special_off[i + 1] - special_off[i];
+        if (tok_find(&tk, special_chars + special_off[i], len) >= 0) continue;
+        memcpy(tk.chars + tk.off[tk.n], special_chars + special_off[i], (size_t)len * 2);
+        tk.off[tk.n + 1] = tk.off[tk.n] + len;
+        tk.n++;
+    }
     for (int c = 0; c < MAXCP; ++c) {
         char_to_id[c] = -1;
         if (!in_alpha[c]) continue;
+        const uint16_t cc = (uint16_t)c;
+        const int have = tok_find(&tk, &cc, 1);              /* only a special token can already hold this string */
+        if (have >= 0) { char_to_id[c] = have; continue; }
         char_to_id[c] = tk.n;                                /* the whole alphabet is kept even if it exceeds vocab_size */
         tk.chars[tk.off[tk.n]] = (uint16_t)c;
         tk.off[tk.n + 1] = tk.off[tk.n] + 1;
@@ -295,6 +320,13 @@ int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_
     *n_vocab_out = tk.n;
     *n_merges_out = n_merges;
     return 0;
+}
+
+int bpe_oracle_train(const int64_t* bins, int64_t n_seq, int64_t seq_len, int64_t min_token, int64_t max_token,
+                     int vocab_size, int min_frequency, int32_t* vocab_off, uint16_t* vocab_chars,
+                     int64_t vocab_chars_cap, int32_t* merges, int32_t* n_vocab_out, int32_t* n_merges_out) {
+    return bpe_oracle_train_ex(bins, n_seq, seq_len, NULL, min_token, max_token, vocab_size, min_frequency, 0, NULL, NULL,
+                               vocab_off, vocab_chars, vocab_chars_cap, merges, n_vocab_out, n_merges_out);
 }
 
 /* ------------------------------------------------------------------ encode / decode */

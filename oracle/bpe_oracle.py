@@ -18,6 +18,10 @@ def lib():
         _lib.bpe_oracle_train.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int32),
                                           C.POINTER(C.c_int32)]
+        _lib.bpe_oracle_train_ex.restype = C.c_int
+        _lib.bpe_oracle_train_ex.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib.bpe_oracle_model_new.restype = C.c_void_p
         _lib.bpe_oracle_model_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib.bpe_oracle_model_free.argtypes = [C.c_void_p]
@@ -80,6 +84,37 @@ class OracleBPE:
                                     C.byref(nv), C.byref(nm))
         if rc != 0:
             raise RuntimeError(f"bpe_oracle_train failed: {rc}")
+        o = cls(off[:nv.value + 1].copy(), chars[:off[nv.value]].copy(), merges[:3 * nm.value].copy())
+        o.min_token, o.max_token = min_token, max_token
+        return o
+
+    @classmethod
+    def train_ragged(cls, sequences, vocab_size, min_frequency=2, special_tokens=()):
+        """FIGBPE.fit_from_sequences in full: sequences of unequal length, BpeTrainer special tokens."""
+        rows = [np.asarray(r, dtype=np.int64).reshape(-1) for r in sequences]
+        rows = [r for r in rows if r.size]
+        flat = np.ascontiguousarray(np.concatenate(rows))
+        row_off = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum([r.size for r in rows], out=row_off[1:])
+        min_token, max_token = int(flat.min()), int(flat.max())
+        sp_off = np.zeros(len(special_tokens) + 1, dtype=np.int32)
+        sp_chars = []
+        for i, t in enumerate(special_tokens):
+            sp_chars.extend(ord(c) for c in t)
+            sp_off[i + 1] = len(sp_chars)
+        sp_chars = np.asarray(sp_chars or [0], dtype=np.uint16)
+        cap_v = max(vocab_size, 512) + len(special_tokens)
+        off = np.zeros(cap_v + 1, dtype=np.int32)
+        cap = 4 * 1024 * 1024
+        chars = np.zeros(cap, dtype=np.uint16)
+        merges = np.zeros(3 * cap_v, dtype=np.int32)
+        nv, nm = C.c_int32(0), C.c_int32(0)
+        rc = lib().bpe_oracle_train_ex(flat.ctypes.data, len(rows), 0, row_off.ctypes.data, min_token, max_token,
+                                       vocab_size, min_frequency, len(special_tokens), sp_off.ctypes.data,
+                                       sp_chars.ctypes.data, off.ctypes.data, chars.ctypes.data, cap,
+                                       merges.ctypes.data, C.byref(nv), C.byref(nm))
+        if rc != 0:
+            raise RuntimeError(f"bpe_oracle_train_ex failed: {rc}")
         o = cls(off[:nv.value + 1].copy(), chars[:off[nv.value]].copy(), merges[:3 * nm.value].copy())
         o.min_token, o.max_token = min_token, max_token
         return o

@@ -92,6 +92,38 @@ def test_against_live_library():
             assert o.encode(r - mn) == hf.encode("".join(map(chr, r - mn)), add_special_tokens=False).ids
 
 
+def test_ragged_and_special_tokens_against_live_library():
+    """FIGBPE's remaining arguments (beast/beast_bpe_trainer.py:46, 53, 76-98): sequences of unequal length and
+    BpeTrainer special tokens (ids first, duplicates skipped, a single-character special token keeps its id when the
+    alphabet holds the same character) — oracle vs the library: vocabulary and merges."""
+    pytest.importorskip("tokenizers")
+    from tokenizers import ByteLevelBPETokenizer
+    from tokenizers.trainers import BpeTrainer
+    rng = np.random.default_rng(17)
+    cases = [
+        ([rng.integers(40, 100, int(rng.integers(1, 60))) for _ in range(300)], 300, []),
+        ([rng.integers(0, 256, int(rng.integers(5, 140))) for _ in range(400)], 600, ["<pad>", "<eos>", "<pad>"]),
+        ([rng.integers(30, 90, 50) for _ in range(200)], 330, ["<s>", chr(5), "ab"]),
+        ([rng.integers(0, 900, int(rng.integers(2, 80))) for _ in range(300)], 1300, ["<unk>"]),
+    ]
+    for rows, vs, special in cases:
+        mn = min(int(r.min()) for r in rows)
+        mx = max(int(r.max()) for r in rows)
+        hf = ByteLevelBPETokenizer()
+        trainer = BpeTrainer(vocab_size=vs, min_frequency=2, show_progress=False, special_tokens=special,
+                             initial_alphabet=[chr(i) for i in range(mx - mn + 1)], max_token_length=10000)
+        hf._tokenizer.train_from_iterator(["".join(map(chr, r - mn)) for r in rows], trainer=trainer)
+        o = OracleBPE.train_ragged(rows, vs, special_tokens=special)
+        assert (o.min_token, o.max_token) == (mn, mx)
+        assert o.vocab_dict() == hf.get_vocab()
+        model = json.loads(hf._tokenizer.to_str())["model"]
+        assert o.merges_lines() == [m if isinstance(m, str) else " ".join(m) for m in model["merges"]]
+    # equal-length input through the ragged entry point is the plain trainer
+    bins = rng.integers(0, 256, (200, 60))
+    a, b = OracleBPE.train(bins, 400), OracleBPE.train_ragged(list(bins), 400)
+    assert a.merges_txt() == b.merges_txt() and a.vocab_json() == b.vocab_json()
+
+
 def test_pretoken_starts_are_a_local_rule():
     """The warp-per-sequence encode kernel (csrc/bpe.cu: base_start / token_start) finds token starts
     with a rule that looks at most three codepoints back and one ahead.  Restated here and checked

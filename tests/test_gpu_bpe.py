@@ -318,3 +318,55 @@ def test_peer_fused_delta_reduction_two_ranks_on_one_gpu():
     assert len(logs[0]) == vocab - len(tokens)
     for e in engs:                                        # replicas stayed identical
         assert torch.equal(e.hist, engs[0].hist)
+
+
+def test_ragged_sequences_and_special_tokens_vs_oracle():
+    """FIGBPE.fit_from_sequences with sequences of unequal length and BpeTrainer special tokens (reference
+    beast/beast_bpe_trainer.py:46, 53, 76-98): vocabulary / merges identical to the oracle (itself pinned to the
+    library on such inputs); tokenizer.json lists the special tokens as added tokens; decode skips their ids."""
+    from beast_tokenizer_b200 import FIGBPE
+    rng = np.random.default_rng(23)
+    cases = [
+        ([rng.integers(40, 100, int(rng.integers(1, 60))) for _ in range(3000)], 300, []),
+        ([rng.integers(0, 256, int(rng.integers(5, 140))) for _ in range(4000)], 900, ["<pad>", "<eos>", "<pad>"]),
+        ([rng.integers(30, 90, 50) for _ in range(2000)], 330, ["<s>", chr(5), "ab"]),
+        ([rng.integers(0, 900, int(rng.integers(2, 80))) for _ in range(3000)], 1300, ["<unk>"]),
+    ]
+    for rows, vs, special in cases:
+        o = OracleBPE.train_ragged(rows, vs, special_tokens=special)
+        fig = FIGBPE(vocab_size=vs, show_progress=False, special_tokens=special)
+        st = fig.fit_from_sequences([torch.from_numpy(r) if i % 2 else r.tolist() for i, r in enumerate(rows)])
+        assert (st.min_token, st.max_token) == (o.min_token, o.max_token)
+        assert st.tokenizer.vocab_json() == o.vocab_json()
+        assert st.tokenizer.merges_txt() == o.merges_txt()
+        doc = json.loads(st.tokenizer.tokenizer_json())
+        uniq = list(dict.fromkeys(special))
+        assert [(t["id"], t["content"], t["special"]) for t in doc["added_tokens"]] == [(i, t, True) for i, t in enumerate(uniq)]
+    # encode / decode with a model that carries special tokens: ids follow the shifted vocabulary, special ids decode
+    # to nothing (skip_special_tokens), a row that spells a special token is refused
+    rows, vs, special = cases[1]
+    st = FIGBPE(vocab_size=vs, show_progress=False, special_tokens=special).fit_from_sequences(rows)
+    o = OracleBPE.train_ragged(rows, vs, special_tokens=special)
+    test = np.stack([r[:5] for r in rows[:64]])
+    flat, offs, status = st.tokenizer.encode_bins(torch.from_numpy(test).cuda(), st.min_token, st.max_token)
+    fl, of = flat.cpu().numpy(), offs.cpu().numpy()
+    for i in range(64):
+        assert fl[of[i]:of[i + 1]].tolist() == o.encode(test[i] - o.min_token)
+    with_special = torch.cat([torch.tensor([0, 1], dtype=torch.int32, device="cuda"), flat[of[0]:of[1]]])
+    dec, stt, ln = st.tokenizer.decode_ids(with_special, torch.tensor([0, with_special.numel()], device="cuda"), 5, st.min_token)
+    assert int(stt[0]) == 0 and np.array_equal(dec[0].cpu().numpy(), test[0])
+    spelled = test.copy()
+    spelled[3, :5] = np.array([ord(c) for c in "<pad>"]) + st.min_token
+    with pytest.raises(NotImplementedError):
+        st.tokenizer.encode_bins(torch.from_numpy(spelled).cuda(), st.min_token, st.max_token)
+    # the reloaded model (vocab.json + merges.txt, as the reference's from_pretrained) no longer knows them
+    from beast_tokenizer_b200 import B200ByteLevelBPE
+    re = B200ByteLevelBPE.from_vocab_merges(st.tokenizer.get_vocab(), st.tokenizer.merge_strings())
+    assert re.special_tokens == [] and re.encode_bins(torch.from_numpy(spelled).cuda(), st.min_token, st.max_token)[2].max() == 0
+
+
+def test_vocab_limits_are_reported_up_front():
+    from beast_tokenizer_b200 import FIGBPE
+    bins = torch.randint(0, 256, (64, 20), device="cuda")
+    with pytest.raises(NotImplementedError, match="trainer's limit"):
+        FIGBPE(vocab_size=20000, show_progress=False).fit_from_bins(bins)
