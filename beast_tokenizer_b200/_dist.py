@@ -3,7 +3,8 @@
 The reference has no distributed code; SURVEY.md §8(e) shards the path by rows: encode / decode need no
 collective, the bounds need a MIN / MAX all-reduce of two D*nb vectors (update_weights_bounds,
 beast/beast_bspline_tokenizer.py:362-378) and the exact quantile needs every rank's coefficient rows
-(fit_parameters, :181-220).  `process_group=False` forces a local call under an initialised group.
+(fit_parameters, :181-220).  A process group is "world" (the default group), a ProcessGroup, or False / None =
+local: the tokenizer opts in through set_process_group, it never communicates implicitly.
 """
 from typing import List, Optional
 

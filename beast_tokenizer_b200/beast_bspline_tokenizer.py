@@ -104,6 +104,9 @@ class BEASTBsplineTokenizer(TokenizerBase):
 
         self.times = make_times(duration, seq_len)
         self._plan_cache = None
+        # sharded fitting is opt-in (set_process_group): an implicit collective inside update_weights_bounds /
+        # fit_parameters would hang every caller that fits on one rank of an initialised job
+        self.process_group = False
         if self.gripper_dof > 0:
             print(f"Gripper MP initialized with {num_basis} basis functions for "
                   f"{self.gripper_dof} DOFs at indices {self.gripper_indices}")
@@ -264,6 +267,18 @@ class BEASTBsplineTokenizer(TokenizerBase):
         self.llm_vocab_size = llm_vocab_size
         self._config['llm_vocab_size'] = llm_vocab_size
 
+    def set_process_group(self, process_group="world"):
+        """Shard the FITTING calls over torch.distributed ranks (one process per GPU, every rank passes its shard of
+        the data): update_weights_bounds all-reduces MIN / MAX of the two D*nb vectors, fit_parameters all-gathers
+        the coefficient rows before the exact quantile selection, update_weights_bounds_per_batch all-reduces the
+        batch min / max.  "world" = the default group, a ProcessGroup = that group, False = local (the default).
+        encode / decode shard by rows and never communicate."""
+        self.process_group = process_group
+        return self
+
+    def _group(self, process_group):
+        return self.process_group if process_group is None else process_group
+
     def update_vlm_vocab_size(self, vlm_vocab_size):
         self.set_llm_vocab_size(vlm_vocab_size)
 
@@ -277,9 +292,9 @@ class BEASTBsplineTokenizer(TokenizerBase):
         """1 % / 99 % per-column quantiles of the fitted coefficients (reference :181-220).
         Coefficients stay on the GPU; the order statistics np.quantile needs are selected
         exactly by beast_colselect_f32 and interpolated with numpy's own lerp.
-        Sharded (torch.distributed initialised, one process per GPU, every rank iterates ITS shard of the
-        loader): the ranks' coefficient rows are all-gathered (56 MB per 100 k trajectories) before the exact
-        selection, so every rank ends with the quantiles of the whole data set; process_group=False = local."""
+        Sharded (set_process_group, or process_group= here; every rank iterates ITS shard of the loader): the
+        ranks' coefficient rows are all-gathered (56 MB per 100 k trajectories) before the exact selection, so
+        every rank ends with the quantiles of the whole data set."""
         params = []
         sample_limit = max_samples if max_samples is not None else float("inf")
         iterator = dataloader
@@ -323,13 +338,13 @@ class BEASTBsplineTokenizer(TokenizerBase):
                     print("Precomputed enough samples for weight normalizer of MP")
                 break
         flush()
-        dist, group = _dist.resolve(process_group)
+        dist, group = _dist.resolve(self._group(process_group), implicit=False)
         if not params and dist is None:
             raise RuntimeError("No parameters were gathered from the dataloader.")
         params = (torch.cat(params, dim=0) if params else
                   torch.empty((0, self.num_dof * self.num_basis), device=dev, dtype=torch.float32))
         if dist is not None:
-            params = _dist.gather_rows(params, group)
+            params = _dist.gather_rows(params, _dist.WORLD if group is None else group)
             if params.shape[0] == 0:
                 raise RuntimeError("No parameters were gathered from the dataloader.")
         lo, hi = self._column_quantiles(params, (0.01, 0.99))
@@ -436,8 +451,8 @@ class BEASTBsplineTokenizer(TokenizerBase):
     @torch.no_grad()
     def update_weights_bounds(self, demos, process_group=None):
         """Global per-column min / max of the coefficients (reference :362-378): one fused launch,
-        the coefficients are reduced in registers and never written.  Sharded (torch.distributed initialised,
-        every rank passes its shard of the trajectories): one MIN and one MAX all-reduce of the D*nb vectors."""
+        the coefficients are reduced in registers and never written.  Sharded (set_process_group, or
+        process_group= here; every rank passes its shard): one MIN and one MAX all-reduce of the D*nb vectors."""
         plan = self._plan()
         dev = plan.device
         x = self._prep_trajs(demos, dev)
@@ -448,7 +463,7 @@ class BEASTBsplineTokenizer(TokenizerBase):
             _lib.check(plan._lib.beast_fit_minmax_f32(plan.handle, _lib.ptr(x), x.shape[0], _lib.ptr(lo), _lib.ptr(hi), 0,
                                                       _lib.stream_ptr(dev)), "beast_fit_minmax_f32")
         self._remember_boundary(x, plan)
-        _dist.allreduce_minmax(lo, hi, process_group)
+        _dist.allreduce_minmax(lo, hi, self._group(process_group), implicit=False)
         self.w_min.copy_(lo.to(self.w_min.device))
         self.w_max.copy_(hi.to(self.w_max.device))
 
@@ -465,13 +480,12 @@ class BEASTBsplineTokenizer(TokenizerBase):
 
     @torch.no_grad()
     def update_weights_bounds_per_batch(self, weights, process_group=None):
-        """Monotone expansion with 1e-4 hysteresis (reference :379-389).  Local by default (it runs inside
-        encode(update_bounds=True), which ranks call independently); pass a process group (or "world") to
-        all-reduce the batch min / max first, so that every rank expands identically."""
+        """Monotone expansion with 1e-4 hysteresis (reference :379-389).  Sharded (set_process_group, or
+        process_group= here): the batch min / max are all-reduced first, so every rank expands identically."""
         dev = self._cuda()
         weights = weights.to(dev, torch.float32).reshape(-1, self.num_dof * self.num_basis).contiguous()
         lo, hi = self._minmax(weights)
-        _dist.allreduce_minmax(lo, hi, process_group, implicit=False)
+        _dist.allreduce_minmax(lo, hi, self._group(process_group), implicit=False)
         on_dev = self.w_min.device == dev and self.w_max.device == dev
         w_min = self.w_min if on_dev else self.w_min.to(dev)
         w_max = self.w_max if on_dev else self.w_max.to(dev)

@@ -527,7 +527,7 @@ def main():
     B = args.batch
     tok = BEASTBsplineTokenizer(num_dof=D, num_basis=NB, seq_len=T, vocab_size=V, gripper_zero_order=True,
                                 gripper_indices=GRIP, device=f"cuda:{local_rank}", llm_vocab_size=LLM_VOCAB)
-    tok.fit_parameters(SyntheticLoader(100, 32, T, D, seed0=1), verbose=False, process_group=False)   # same loader on every rank
+    tok.fit_parameters(SyntheticLoader(100, 32, T, D, seed0=1), verbose=False)
     plan = tok._plan()
     lib = plan._lib
     lo, hi = tok._bounds(dev)

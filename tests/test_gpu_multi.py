@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
         from beast_tokenizer_b200.synth import SyntheticLoader, synth_device
         tok = BEASTBsplineTokenizer(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
                                     gripper_indices=[6, 13], device=f"cuda:{rank}")
-        tok.fit_parameters(SyntheticLoader(20, 32, 50, 14, seed0=1), verbose=False, process_group=False)
+        tok.fit_parameters(SyntheticLoader(20, 32, 50, 14, seed0=1), verbose=False)      # local: never implicit
         n_chunks, per = 8, 5000
         chunk = lambda c: tok.encode(synth_device(per, 50, 14, 1000 + c, dev))[0]
         shard = torch.cat([chunk(c) for c in range(n_chunks) if c % world == rank])
@@ -44,6 +44,7 @@ def _worker(rank, world, port, q):
             out["ref"] = (ref.tokenizer.merges_txt(), ref.tokenizer.vocab_json(), ref.min_token, ref.max_token)
         # sharded bounds: every rank passes its shard of the trajectories
         xs = [synth_device(3000, 50, 14, 77 + c, dev) for c in range(world)]
+        tok.set_process_group("world")
         tok.update_weights_bounds(xs[rank])
         out["minmax"] = (tok.w_min.cpu().numpy(), tok.w_max.cpu().numpy())
         tok.fit_parameters([{"actions": xs[rank][i:i + 500]} for i in range(0, 3000, 500)], verbose=False)
@@ -52,9 +53,9 @@ def _worker(rank, world, port, q):
             allx = torch.cat([x.to(dev) for x in xs])
             t2 = BEASTBsplineTokenizer(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
                                        gripper_indices=[6, 13], device=f"cuda:{rank}")
-            t2.update_weights_bounds(allx, process_group=False)
+            t2.update_weights_bounds(allx)
             out["minmax_ref"] = (t2.w_min.cpu().numpy(), t2.w_max.cpu().numpy())
-            t2.fit_parameters([{"actions": allx}], verbose=False, process_group=False)
+            t2.fit_parameters([{"actions": allx}], verbose=False)
             out["quant_ref"] = (t2.w_min.cpu().numpy(), t2.w_max.cpu().numpy())
         q.put(out)
         dist.barrier()
