@@ -76,8 +76,12 @@ def build_alphabet(min_token: int, max_token: int, seen_bytes: Sequence[int], sp
 class GpuBpeEngine:
     """Device state of one shard: chunk-major symbols, lengths, replicated V x V histogram."""
 
+    DEDUP_SAMPLE = 65536          # "auto": distinct-word statistics are taken on this many sequences first
+    DEDUP_KEEP = 0.7              # ... and the corpus is de-duplicated when distinct symbols / symbols is below this
+    DEDUP_PACK = 256              # symbols per pseudo-sequence of packed distinct words (plus one straddling word)
+
     def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int, max_shift: int = 255,
-                 row_len: Optional[torch.Tensor] = None):
+                 row_len: Optional[torch.Tensor] = None, dedup="auto"):
         self.lib = _lib.load()
         self.dev = bins.device
         self.N, self.L = bins.shape
@@ -100,14 +104,98 @@ class GpuBpeEngine:
                                               _lib.ptr(class_table_device(self.dev)), _lib.ptr(self.sym),
                                               _lib.ptr(self.len), self.stride, _lib.ptr(err), _lib.ptr(row_len), st),
                        "bpe_symbolize")
+            if int(err.item()):
+                raise ValueError("discrete tokens outside the representable range after subtracting min_token")
+            self.weight = None
+            self.dedup_stats = None
+            if dedup and self.N > 0:
+                self._dedup_words(force=dedup is True)
             used = np.unique(byte_to_id[byte_to_id >= 0]).astype(np.int16)   # ids before any merge (byte-level symbols)
             used_d = torch.from_numpy(used).to(self.dev)
             n_ids = int(used[-1]) + 1 if used.size else 0
             _lib.check(self.lib.bpe_count_pairs(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, V,
-                                                n_ids, _lib.ptr(used_d), int(used.size), _lib.ptr(self.hist), st),
+                                                n_ids, _lib.ptr(used_d), int(used.size), _lib.ptr(self.hist),
+                                                _lib.ptr(self.weight), st),
                        "bpe_count_pairs")
-            if int(err.item()):
-                raise ValueError("discrete tokens outside the representable range after subtracting min_token")
+
+    # ------------------------------------------------------------------ word de-duplication
+    def _word_table(self, n_seq: int):
+        """Hash table over the words of the first n_seq sequences -> (rep locations, counts) of the distinct words,
+        or None on a hash collision (exactness is never traded: the caller keeps the plain corpus)."""
+        dev, lib = self.dev, self.lib
+        st = _lib.stream_ptr(dev)
+        totals = torch.zeros(2, device=dev, dtype=torch.int64)
+        _lib.check(lib.bpe_word_totals(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(totals), st),
+                   "bpe_word_totals")
+        words, symbols = (int(v) for v in totals.tolist())
+        if words == 0:
+            return None
+        size = 1 << max(10, (2 * words - 1).bit_length())
+        keys = torch.zeros(size, device=dev, dtype=torch.int64)
+        rep = torch.full((size,), -1, device=dev, dtype=torch.int64)          # 0xff..ff
+        count = torch.zeros(size, device=dev, dtype=torch.int32)
+        collision = torch.zeros(1, device=dev, dtype=torch.int32)
+        _lib.check(lib.bpe_word_table(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(keys),
+                                      _lib.ptr(rep), _lib.ptr(count), size, _lib.ptr(collision), st), "bpe_word_table")
+        slots = torch.nonzero(count, as_tuple=False).flatten()
+        if int(collision.item()):
+            return None
+        return rep[slots], count[slots], words, symbols
+
+    def _dedup_words(self, force: bool):
+        """Replace the symbolised corpus by its distinct words, packed into pseudo-sequences of equal-count words,
+        with one weight per pseudo-sequence.  "auto": only when a sample says the corpus is repetitive enough."""
+        dev, lib = self.dev, self.lib
+        if not force and self.N > 2 * self.DEDUP_SAMPLE:
+            probe = self._word_table(self.DEDUP_SAMPLE)
+            if probe is None:
+                return
+            rep, cnt, words, symbols = probe
+            ratio = float((rep & 0xFFFF).sum().item()) / max(symbols, 1)
+            self.dedup_stats = {"sampled_sequences": self.DEDUP_SAMPLE, "sample_distinct_symbol_ratio": ratio, "applied": False}
+            if ratio >= self.DEDUP_KEEP:
+                return
+        full = self._word_table(self.N)
+        if full is None:
+            self.dedup_stats = {"applied": False, "reason": "64-bit word hash collision: trained on the plain corpus"}
+            return
+        rep, cnt, words, symbols = full
+        lens = rep & 0xFFFF
+        distinct_symbols = int(lens.sum().item())
+        ratio = distinct_symbols / max(symbols, 1)
+        stats = {"words": words, "distinct_words": int(rep.numel()), "symbols": symbols,
+                 "distinct_symbols": distinct_symbols, "distinct_symbol_ratio": ratio, "applied": False}
+        self.dedup_stats = {**(self.dedup_stats or {}), **stats}
+        if not force and ratio >= self.DEDUP_KEEP:
+            return
+        # order by count (descending), pack words of equal count into pseudo-sequences of ~DEDUP_PACK symbols
+        cnt, order = torch.sort(cnt, descending=True, stable=True)
+        rep, lens = rep[order], lens[order]
+        U = int(rep.numel())
+        excl = torch.cumsum(lens, 0) - lens                                   # symbols before word i
+        new_group = torch.ones(U, device=dev, dtype=torch.bool)
+        new_group[1:] = cnt[1:] != cnt[:-1]
+        group_start = torch.cummax(torch.where(new_group, excl, torch.zeros_like(excl)), 0).values
+        bin_in_group = (excl - group_start) // self.DEDUP_PACK
+        new_bin = new_group.clone()
+        new_bin[1:] |= bin_in_group[1:] != bin_in_group[:-1]
+        pid = torch.cumsum(new_bin.to(torch.int64), 0) - 1                   # pseudo-sequence of word i
+        P = int(pid[-1].item()) + 1
+        first = torch.nonzero(new_bin, as_tuple=False).flatten()              # first word of every pseudo-sequence
+        off = excl - excl[first][pid]
+        plen = torch.zeros(P, device=dev, dtype=torch.int64).scatter_add_(0, pid, lens)
+        cap = int(plen.max().item())
+        if cap > 32767 or P > 0x7FFFFFFF:
+            return
+        sym2 = torch.empty(((cap + 7) // 8, P, 8), device=dev, dtype=torch.int16)
+        len2 = plen.to(torch.int32)
+        _lib.check(lib.bpe_word_pack(_lib.ptr(self.sym), self.stride, _lib.ptr(rep.contiguous()),
+                                     _lib.ptr(pid.to(torch.int32)), _lib.ptr(off.to(torch.int32)), U, _lib.ptr(sym2),
+                                     _lib.ptr(len2), P, P, _lib.stream_ptr(dev)), "bpe_word_pack")
+        self.sym, self.len, self.N, self.stride = sym2, len2, P, P
+        self.weight = cnt[first].to(torch.int32).contiguous()
+        self.work = torch.zeros(4 + 2 * P, device=dev, dtype=torch.int32)
+        self.dedup_stats.update(applied=True, pseudo_sequences=P, longest_pseudo_sequence=cap)
 
     def argmax(self, n_active: int):
         with torch.cuda.device(self.dev):
@@ -123,7 +211,7 @@ class GpuBpeEngine:
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.bpe_apply_merge(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, a, b, c,
                                                 self.V, _lib.ptr(self.delta), _lib.ptr(self.work),
-                                                _lib.stream_ptr(self.dev)), "bpe_apply_merge")
+                                                _lib.ptr(self.weight), _lib.stream_ptr(self.dev)), "bpe_apply_merge")
 
     def apply_delta(self, a: int, b: int, c: int):
         with torch.cuda.device(self.dev):
@@ -215,7 +303,8 @@ class _FastRun:
                                               _lib.ptr(self.log), _lib.ptr(eng.result), _lib.ptr(eng.work),
                                               self.vocab_size, self.min_frequency, self.max_merges,
                                               _lib.ptr(self.sig) if i >= self.SIG_START else None, int(n),
-                                              C.byref(self.peers) if self.peers is not None else None, st),
+                                              C.byref(self.peers) if self.peers is not None else None,
+                                              _lib.ptr(eng.weight), st),
                        "bpe_train_step")
         self.enqueued += n
         return n
@@ -337,12 +426,13 @@ def scan_bins_gpu(bins: torch.Tensor, coll: _Collective):
 
 def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, engine_factory=None,
               scan=None, coll: Optional[_Collective] = None, show_progress: bool = False,
-              row_len: Optional[torch.Tensor] = None, special_tokens: Sequence[str] = ()):
+              row_len: Optional[torch.Tensor] = None, special_tokens: Sequence[str] = (), dedup="auto"):
     """The merge loop (A.4) over this rank's shard `bins` [N, L] int64.  Returns
     (B200ByteLevelBPE, min_token, max_token).  `engine_factory` / `scan` are injection points for the
     CPU-only multi-process tests of the orchestration; production uses the GPU engine.
     row_len [N] int32: sequences of unequal length, padded to L with an in-range value of the same row (so the
-    min / max / seen-byte scans need no mask).  special_tokens: BpeTrainer's, ids first."""
+    min / max / seen-byte scans need no mask).  special_tokens: BpeTrainer's, ids first.  dedup: train on the
+    distinct pre-tokens with counts, as BpeTrainer does ("auto" = when a sample says it pays, True / False)."""
     coll = coll or _Collective()
     scan = scan or scan_bins_gpu
     engine_factory = engine_factory or GpuBpeEngine
@@ -354,7 +444,7 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
             f"bpe_vocab_size {V} is above the trainer's limit of {MAX_TRAIN_VOCAB}: the merge loop keeps a dense "
             f"V x V int32 pair histogram ({4 * V * V / 2**30:.1f} GiB here) and 16*V bytes of per-block shared-memory "
             "counters (reference FIGBPE default is 1024; BASELINE config 2048)")
-    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token, row_len)
+    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token, row_len, dedup)
                            if engine_factory is GpuBpeEngine else engine_factory(bins, min_token, byte_to_id, V))
     eng = make_engine()
     coll.reduce_(eng.hist, "sum")                       # replicated global histogram
@@ -377,6 +467,7 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
         if ok:
             model = B200ByteLevelBPE(fast_tokens, [(a, b, c) for a, b, c, _ in log], special_tokens=special_tokens)
             model.trainer_mode = getattr(eng, "mode", "single GPU")
+            model.dedup_stats = getattr(eng, "dedup_stats", None)
             return model, min_token, max_token
         eng = make_engine()
         coll.reduce_(eng.hist, "sum")
@@ -416,7 +507,8 @@ class FIGBPE:
     """Trainer for Byte Pair Encoding over discretised BEAST tokens (reference :39-160)."""
 
     def __init__(self, vocab_size: int = 1024, *, min_frequency: int = 2, special_tokens: Optional[Sequence[str]] = None,
-                 show_progress: bool = True, max_token_length: int = 10000, device=None, process_group=None) -> None:
+                 show_progress: bool = True, max_token_length: int = 10000, device=None, process_group=None,
+                 dedup="auto") -> None:
         self.vocab_size = vocab_size
         self.min_frequency = min_frequency
         self.special_tokens = list(special_tokens or [])
@@ -424,6 +516,7 @@ class FIGBPE:
         self.max_token_length = max_token_length
         self.device = device
         self.process_group = process_group
+        self.dedup = dedup
         self.tokenizer: Optional[B200ByteLevelBPE] = None
         self.min_token: Optional[int] = None
         self.max_token: Optional[int] = None
@@ -444,7 +537,7 @@ class FIGBPE:
             row_len = row_len.to(dev, torch.int32).contiguous()
         tok, mn, mx = train_bpe(bins.to(dev, torch.int64).contiguous(), self.vocab_size, self.min_frequency,
                                 coll=coll, show_progress=self.show_progress, row_len=row_len,
-                                special_tokens=self.special_tokens)
+                                special_tokens=self.special_tokens, dedup=self.dedup)
         self.tokenizer, self.min_token, self.max_token = tok, mn, mx
         return FIGBPEState(tokenizer=tok, min_token=mn, max_token=mx)
 

@@ -24,24 +24,9 @@
 // walks 32 sequences reads / writes chunk c of all of them as 512 contiguous bytes, one 128-bit access
 // per lane.
 #include <cstring>
-#include "common.cuh"
+#include "bpe_common.cuh"
 
 namespace beast {
-
-constexpr int kBpeBlock = 128;
-constexpr uint16_t kWordStart = 0x8000u;
-constexpr uint16_t kIdMask = 0x7fffu;
-constexpr int kMaxWordLong = 8192;       // longest pre-token (in symbols) of the thread-per-sequence encode kernel
-
-// Corpus layout ("chunk-major"): the symbols of sequence `seq` live in 16-byte chunks of 8,
-// chunk c of all sequences contiguous:  sym[((p >> 3) * n_stride + seq) * 8 + (p & 7)].
-// One thread owns one sequence; a warp reading chunk c of its 32 sequences touches 512 contiguous
-// bytes with one 128-bit load per lane.  Slots past len[seq] in the last chunk hold 0xffff.
-constexpr int kChunk = 8;
-constexpr uint16_t kPad = 0xffffu;
-__device__ __forceinline__ long long sym_index(int p, long long seq, long long n_stride) {
-    return ((long long)(p >> 3) * n_stride + seq) * kChunk + (p & 7);
-}
 
 // Pair signatures: kSigBits bits per sequence, bit hash(a, b) set for every in-word adjacent pair the
 // sequence holds or ever held (bits are only added, so the set is a superset).  Stored word-major
@@ -246,15 +231,16 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
 // ---------------------------------------------------------------- pair histogram
 __global__ void __launch_bounds__(256)
 bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
-                 int V, int* __restrict__ hist) {
+                 int V, int* __restrict__ hist, const int* __restrict__ weight) {
     for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
          seq += (long long)gridDim.x * blockDim.x) {
         const int n = len[seq];
         if (n < 2) continue;
+        const int wgt = weight ? weight[seq] : 1;
         int prev = sym[sym_index(0, seq, n_stride)] & kIdMask;
         for (int q = 1; q < n; ++q) {
             const uint16_t cur = sym[sym_index(q, seq, n_stride)];
-            if (!(cur & kWordStart)) atomicAdd(&hist[(long long)prev * V + (cur & kIdMask)], 1);
+            if (!(cur & kWordStart)) atomicAdd(&hist[(long long)prev * V + (cur & kIdMask)], wgt);
             prev = cur & kIdMask;
         }
     }
@@ -267,7 +253,8 @@ bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, 
 // 128-bit chunk loads, one thread per sequence.
 __global__ void __launch_bounds__(1024)
 bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
-                      int V, int n_ids, const short* __restrict__ used_ids, int A, int* __restrict__ hist) {
+                      int V, int n_ids, const short* __restrict__ used_ids, int A, int* __restrict__ hist,
+                      const int* __restrict__ weight) {
     extern __shared__ int s_hist[];                          // [A*A] counters, then u16 inverse map [n_ids]
     const int cells = A * A;
     unsigned short* s_inv = (unsigned short*)(s_hist + cells);
@@ -279,6 +266,7 @@ bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ 
     for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
          seq += (long long)gridDim.x * blockDim.x) {
         const int n = len[seq];
+        const int wgt = weight ? weight[seq] : 1;
         unsigned int prev = 0xffffu;
         for (int c = 0; c * kChunk < n; ++c) {
             const int4 q = __ldcs((const int4*)(sym + ((long long)c * n_stride + seq) * kChunk));
@@ -289,7 +277,7 @@ bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ 
                 const unsigned int cur = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
                 const unsigned int id = cur & kIdMask;
                 const unsigned int ci = id < (unsigned int)n_ids ? s_inv[id] : 0xffffu;
-                if (prev != 0xffffu && ci != 0xffffu && !(cur & kWordStart)) atomicAdd(&s_hist[prev * A + ci], 1);
+                if (prev != 0xffffu && ci != 0xffffu && !(cur & kWordStart)) atomicAdd(&s_hist[prev * A + ci], wgt);
                 prev = ci;
             }
         }
@@ -538,7 +526,7 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
 // stored before the first merge.  Count changes go to the block-private delta block.
 __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int* __restrict__ len, long long seq,
                                                  int q0, long long n_stride, int a, int b, int c, int V,
-                                                 int* s_delta, unsigned int* __restrict__ sig) {
+                                                 int* s_delta, unsigned int* __restrict__ sig, int wgt) {
     auto sig_add = [&](int x, int y) {                        // the rewritten sequence now holds the pair (x, y)
         if (sig) {
             const unsigned int h = sig_hash((unsigned int)x, (unsigned int)y), h2 = sig_hash2((unsigned int)x, (unsigned int)y);
@@ -582,8 +570,8 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
     auto emit_plain = [&](uint16_t x) {
         const int id = x & kIdMask;
         if (prev_merged && !(x & kWordStart)) {              // right neighbour of a merge
-            atomicAdd(&row_b[id], -1);                       // (b, y) disappears
-            atomicAdd(&row_c[id], 1);                        // (c, y) appears
+            atomicAdd(&row_b[id], -wgt);                     // (b, y) disappears
+            atomicAdd(&row_c[id], wgt);                      // (c, y) appears
             sig_add(c, id);
         }
         prev_merged = false;
@@ -610,8 +598,8 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
                 pend = false;
                 if (cur == bsym) {                           // merge (held a, b) -> c
                     if (!(pend_sym & kWordStart)) {          // the pair with the left neighbour changes
-                        atomicAdd(&col_a[prev_old], -1);     // (old left, a) disappears
-                        atomicAdd(&col_c[prev_new], 1);      // (new left, c) appears
+                        atomicAdd(&col_a[prev_old], -wgt);   // (old left, a) disappears
+                        atomicAdd(&col_c[prev_new], wgt);    // (new left, c) appears
                         sig_add(prev_new, c);
                     }
                     dirty = true;
@@ -645,7 +633,7 @@ __device__ __forceinline__ void rewrite_sequence(uint16_t* __restrict__ sym, int
 __device__ __forceinline__ void rewrite_sequence_warp(uint16_t* __restrict__ sym, int* __restrict__ len, long long seq,
                                                       int q0, int n, long long n_stride, int a, int b, int c, int V,
                                                       int* __restrict__ delta, unsigned int* __restrict__ sig,
-                                                      uint16_t* s_out) {
+                                                      uint16_t* s_out, int wgt) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     uint4* sym4 = (uint4*)sym;
@@ -724,15 +712,15 @@ __device__ __forceinline__ void rewrite_sequence_warp(uint16_t* __restrict__ sym
                 const bool left_merged = is_match(j - 2);
                 const int prev_old = left_merged ? b : (int)(at(j - 1) & kIdMask);
                 const int prev_new = left_merged ? c : prev_old;
-                atomicAdd(&delta[prev_old], -1);              // (old left, a) disappears
-                atomicAdd(&delta[2 * V + prev_new], 1);       // (new left, c) appears
+                atomicAdd(&delta[prev_old], -wgt);            // (old left, a) disappears
+                atomicAdd(&delta[2 * V + prev_new], wgt);     // (new left, c) appears
                 sig_add(prev_new, c);
             }
             const unsigned int r = at(j + 2);
             if (p0 + j + 2 < n && !(r & kWordStart) && !is_match(j + 2)) {
                 const int id = (int)(r & kIdMask);
-                atomicAdd(&delta[V + id], -1);                // (b, y) disappears
-                atomicAdd(&delta[3 * V + id], 1);             // (c, y) appears
+                atomicAdd(&delta[V + id], -wgt);              // (b, y) disappears
+                atomicAdd(&delta[3 * V + id], wgt);           // (c, y) appears
                 sig_add(c, id);
             }
         }
@@ -783,7 +771,7 @@ __global__ void __launch_bounds__(256)
 bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int a, int b, int c, int V,
                    const BpeCtl* __restrict__ ctl, const int* __restrict__ work_count,
                    const int* __restrict__ work_seq, const int* __restrict__ work_q0, int* __restrict__ delta,
-                   unsigned int* __restrict__ sig) {
+                   unsigned int* __restrict__ sig, const int* __restrict__ weight) {
     extern __shared__ int s_delta[];
     if (ctl) {
         if (ctl->done) return;
@@ -814,10 +802,12 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
             const bool have = my_e < n_work;
             const int my_seq = have ? work_seq[my_e] : 0, my_q0 = have ? work_q0[my_e] : 0;
             const int my_n = have ? len[my_seq] : 0;
+            const int my_w = (have && weight) ? weight[my_seq] : 1;
             const int cnt = __popc(__ballot_sync(0xffffffffu, have));
             for (int k = 0; k < cnt; ++k) {
                 const long long seq = __shfl_sync(0xffffffffu, my_seq, k);
                 const int q0 = __shfl_sync(0xffffffffu, my_q0, k), n = __shfl_sync(0xffffffffu, my_n, k);
+                const int wgt = __shfl_sync(0xffffffffu, my_w, k);
                 if (k + 1 < cnt) {
                     const long long seq2 = __shfl_sync(0xffffffffu, my_seq, k + 1);
                     const int ci2 = (__shfl_sync(0xffffffffu, my_q0, k + 1) >> 3) + lane;
@@ -826,11 +816,11 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
                 }
                 const int chunks_left = ((n + kChunk - 1) >> 3) - (q0 >> 3);
                 if (use_smem) {                               // block-private counters: hot neighbours would serialise in L2
-                    if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, s_delta, sig, s_out[warp]);
-                    else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, s_delta, sig);
+                    if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, s_delta, sig, s_out[warp], wgt);
+                    else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, s_delta, sig, wgt);
                 } else {
-                    if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, delta, sig, s_out[warp]);
-                    else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, delta, sig);
+                    if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, delta, sig, s_out[warp], wgt);
+                    else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, delta, sig, wgt);
                 }
                 __syncwarp();
             }
@@ -845,7 +835,8 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_work;
          i += (long long)gridDim.x * blockDim.x)
-        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta, sig);
+        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta, sig,
+                         weight ? weight[work_seq[i]] : 1);
     __syncthreads();
     flush_delta_block(s_delta, delta, V);
 }
@@ -1576,7 +1567,8 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
 }
 
 extern "C" int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
-                               int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist, void* stream) {
+                               int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist,
+                               const int32_t* weight, void* stream) {
     if (N == 0) return BEAST_OK;
     if (!sym || !len || !hist) return BEAST_E_NULL;
     if (N < 0 || V < 1 || V > 32767 || n_ids < 0 || n_ids > V || n_used < 0 || n_used > n_ids) return BEAST_E_SHAPE;
@@ -1590,12 +1582,12 @@ extern "C" int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t 
         long long grid = (N + 1023) / 1024;
         if (grid > sms) grid = sms;
         bpe_count_smem_kernel<<<(unsigned)grid, 1024, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, n_ids,
-                                                                                   used_ids, n_used, hist);
+                                                                                   used_ids, n_used, hist, weight);
         count_launch();
         BEAST_CHECK_LAUNCH();
         return BEAST_OK;
     }
-    bpe_count_kernel<<<bpe_grid(N, 256), 256, 0, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, hist);
+    bpe_count_kernel<<<bpe_grid(N, 256), 256, 0, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, hist, weight);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -1630,7 +1622,8 @@ static int rewrite_smem_attr(size_t smem) {
 }
 
 extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
-                               int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream) {
+                               int32_t c, int32_t V, int32_t* delta, int32_t* work, const int32_t* weight,
+                               void* stream) {
     if (!delta || !work) return BEAST_E_NULL;
     if (V < 1 || a < 0 || b < 0 || c < 0 || a >= V || b >= V || c >= V || c > 32766) return BEAST_E_SHAPE;
     if (N == 0) return BEAST_OK;
@@ -1647,7 +1640,7 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
     const int grid = merge_grid(N);
     bpe_scan_kernel<false><<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0, nullptr, 0);
     bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta,
-                                                nullptr);
+                                                nullptr, weight);
     count_launch(2);
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -1683,7 +1676,7 @@ extern "C" int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                               int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
                               int32_t vocab_size, int32_t min_frequency, int32_t max_merges, uint32_t* sig,
-                              int32_t iters, const bpe_peers_t* peers_h, void* stream) {
+                              int32_t iters, const bpe_peers_t* peers_h, const int32_t* weight, void* stream) {
     if (!hist || !delta || !ctl || !log || !result || !work) return BEAST_E_NULL;
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
     if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
@@ -1735,7 +1728,7 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
                 bpe_scan_kernel<false><<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count,
                                                              work_seq, work_q0, sig, (int)tile);
             bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, work_count,
-                                                        work_seq, work_q0, delta, sig);
+                                                        work_seq, work_q0, delta, sig, weight);
             count_launch(2);
         }
     }

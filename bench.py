@@ -285,7 +285,9 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
         dist.barrier()
     if rank != 0:
         return out, None
+    out["dedup"] = getattr(state.tokenizer, "dedup_stats", None)
     if world == 1:
+        out["repetitive_corpus"] = bpe_repetitive_leg(tok, dev, bins, with_cpu)
         out["e2e_fit_from_trajectories"] = bpe_e2e_leg(tok, dev, with_cpu)
     if with_cpu:
         # the reference trainer on the same bins, bounded sample; the GPU trainer on that sample must agree
@@ -352,6 +354,43 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
                                                       for r in (mp[:64].cpu() - btok.bpe_min_token).tolist()]
             apply["cpu_reference"] = ref
     return out, apply
+
+
+def bpe_repetitive_leg(tok, dev, bins, with_cpu):
+    """the trainer on a REPETITIVE corpus — 1.6 M sequences drawn from 20 000 distinct ones, the
+    regime of real robot data — with and without word de-duplication (distinct pre-tokens with counts, as HF's
+    BpeTrainer does); both must give the same table."""
+    import hashlib
+    import torch
+    from beast_tokenizer_b200 import FIGBPE
+    g = torch.Generator(device=dev).manual_seed(4)
+    pick = torch.randint(0, 20_000, (bins.shape[0],), generator=g, device=dev)
+    rep = bins[:20_000][pick].contiguous()
+    out = {"workload": f"{rep.shape[0]} sequences drawn from 20 000 distinct ones, vocab {BPE_VOCAB}"}
+    tables = {}
+    for mode in ("auto", False):
+        fig = FIGBPE(vocab_size=BPE_VOCAB, show_progress=False, device=str(dev), process_group=False, dedup=mode)
+        runs = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = fig.fit_from_bins(rep)
+            torch.cuda.synchronize()
+            runs.append(time.perf_counter() - t0)
+        tables[mode] = st.tokenizer.merges_txt() + st.tokenizer.vocab_json()
+        key = "dedup_auto" if mode == "auto" else "dedup_off"
+        out[key] = {"seconds": min(runs), "runs_seconds": runs, "merges": len(st.tokenizer.merges),
+                    "merges_per_s": len(st.tokenizer.merges) / min(runs), "stats": getattr(st.tokenizer, "dedup_stats", None)}
+    out["same_table"] = tables["auto"] == tables[False]
+    out["merge_table_sha256"] = hashlib.sha256(tables["auto"].encode("utf-8")).hexdigest()
+    out["speedup_from_dedup"] = out["dedup_off"]["seconds"] / out["dedup_auto"]["seconds"]
+    if with_cpu:
+        cpu = hf_train_cpu(rep.cpu().numpy(), BPE_VOCAB)
+        out["cpu_reference"] = {"engine": cpu["engine"], "seconds": cpu["seconds"], "string_build_seconds": cpu.get("string_build_seconds"),
+                                "merges_per_s": cpu["merges"] / cpu["seconds"],
+                                "merge_table_identical": cpu["merges_txt"] == st.tokenizer.merges_txt(),
+                                "speedup_1gpu": cpu["seconds"] / out["dedup_auto"]["seconds"]}
+    return out
 
 
 def bpe_e2e_leg(tok, dev, with_cpu):

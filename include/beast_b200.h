@@ -212,10 +212,11 @@ int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, 
                   const uint8_t* cls_tab, uint16_t* sym, int32_t* len, int64_t n_stride, int32_t* err,
                   const int32_t* row_len, void* stream);
 int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, int32_t V,
-                    int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist, void* stream);
+                    int32_t n_ids, const int16_t* used_ids, int32_t n_used, int32_t* hist, const int32_t* weight,
+                    void* stream);
 int bpe_argmax(const int32_t* hist, int32_t V, int32_t n_active, uint64_t* result, void* stream);
 int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t a, int32_t b,
-                    int32_t c, int32_t V, int32_t* delta, int32_t* work, void* stream);
+                    int32_t c, int32_t V, int32_t* delta, int32_t* work, const int32_t* weight, void* stream);
 int bpe_apply_delta(int32_t* hist, int32_t* delta, int32_t a, int32_t b, int32_t c, int32_t V, void* stream);
 /* Peers of a sharded training run (one process per GPU, sequences sharded, V x V histogram replicated).
  * delta[r] / flags[r] are rank r's count-delta block (int32 [2][4*V], double-buffered by merge parity) and
@@ -256,7 +257,30 @@ int beast_peer_free(void* ptr);
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
                    int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
                    int32_t min_frequency, int32_t max_merges, uint32_t* sig, int32_t iters,
-                   const bpe_peers_t* peers_h, void* stream);
+                   const bpe_peers_t* peers_h, const int32_t* weight, void* stream);
+/* Word de-duplication in front of the merge loop (what BpeTrainer does with the strings FIGBPE hands it,
+ * beast/beast_bpe_trainer.py:61-74: distinct pre-tokens with counts).  csrc/bpe_dedup.cu.
+ * bpe_word_totals  totals[0] = pre-tokens, totals[1] = symbols of the symbolised corpus (device, 2 x uint64).
+ * bpe_word_table   open-addressing table over the words: keys / rep uint64 [table_size], count int32 [table_size];
+ *                  table_size a power of two >= 2 x words; the caller zeroes keys and count and fills rep with
+ *                  0xff..ff.  After the call every occupied slot holds the location of its representative word
+ *                  (sequence << 32 | first symbol << 16 | symbols) and the number of occurrences.  Words are compared
+ *                  with their representative symbol by symbol: *collision != 0 (caller zeroes it) reports a 64-bit
+ *                  hash collision — the table is then unusable and the caller trains on the plain corpus.
+ * bpe_word_pack    copies U distinct words (loc[i] as above) to position dst_off[i] of pseudo-sequence dst_seq[i]
+ *                  of a second corpus in the same chunk-major layout (first symbol flagged as a word start) and
+ *                  pads the last chunk of each of the P pseudo-sequences (dst_len[P] symbols each).
+ * The merge loop then runs on the packed corpus with weight[P] = occurrences of the words of each pseudo-sequence
+ * (words of equal count are packed together): bpe_count_pairs / bpe_apply_merge / bpe_train_step multiply their
+ * count updates by weight[seq] (NULL = 1). */
+int bpe_word_totals(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* totals,
+                    void* stream);
+int bpe_word_table(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* keys, uint64_t* rep,
+                   int32_t* count, int64_t table_size, int32_t* collision, void* stream);
+int bpe_word_pack(const uint16_t* src, int64_t src_stride, const uint64_t* loc, const int32_t* dst_seq,
+                  const int32_t* dst_off, int64_t U, uint16_t* dst, const int32_t* dst_len, int64_t P,
+                  int64_t dst_stride, void* stream);
+
 /* Pair signatures for bpe_train_step (optional, sig = NULL scans every sequence): uint32
  * [bpe_signature_words()][n_stride], bit hash(a, b) of sequence s set when s holds (or ever held) the
  * in-word pair (a, b).  The scan for a merge reads one 4-byte column and skips the sequences whose bit

@@ -370,3 +370,54 @@ def test_vocab_limits_are_reported_up_front():
     bins = torch.randint(0, 256, (64, 20), device="cuda")
     with pytest.raises(NotImplementedError, match="trainer's limit"):
         FIGBPE(vocab_size=20000, show_progress=False).fit_from_bins(bins)
+
+
+@pytest.mark.parametrize("kind", ["repetitive", "iid", "letters", "bins1000"])
+def test_word_dedup_gives_the_same_table(kind):
+    """Training on the distinct pre-tokens with counts (what BpeTrainer does) must give exactly
+    the table of the plain run and of the oracle — on a repetitive corpus (few distinct trajectories drawn many
+    times), on an i.i.d. one, on long repeated-symbol words and on 2-byte symbols."""
+    from beast_tokenizer_b200 import FIGBPE
+    rng = np.random.default_rng(31)
+    if kind == "repetitive":
+        base = np.clip(rng.normal(128, 30, (300, 140)).round(), 0, 255).astype(np.int64)
+        bins, vocab = base[rng.integers(0, 300, 20000)], 1200
+    elif kind == "iid":
+        bins, vocab = np.clip(rng.normal(128, 28, (8000, 140)).round(), 0, 255).astype(np.int64), 900
+    elif kind == "letters":
+        bins, vocab = rng.choice([97, 97, 97, 98, 99, 32], (3000, 60)) + 7, 500
+    else:
+        base = np.clip(rng.normal(500, 120, (500, 140)).round(), 0, 999).astype(np.int64)
+        bins, vocab = np.concatenate([base[rng.integers(0, 500, 5000)], rng.integers(0, 1000, (500, 140))]), 1800
+    o = OracleBPE.train(bins, vocab)
+    dev_bins = torch.from_numpy(bins).cuda()
+    tables = {}
+    for mode in (True, False, "auto"):
+        st = FIGBPE(vocab_size=vocab, show_progress=False, dedup=mode).fit_from_bins(dev_bins)
+        tables[mode] = (st.tokenizer.merges_txt(), st.tokenizer.vocab_json())
+        stats = st.tokenizer.dedup_stats
+        if mode is True:
+            assert stats["applied"] and stats["distinct_symbols"] <= stats["symbols"], stats
+            if kind == "repetitive":
+                assert stats["distinct_symbol_ratio"] < 0.1, stats
+        if mode is False:
+            assert stats is None
+    assert tables[True] == tables[False] == tables["auto"] == (o.merges_txt(), o.vocab_json())
+    # the exact host-driven loop (progress display off the fast path is no longer a separate loop; force it through
+    # a vocabulary that re-creates an existing token string is covered elsewhere) also takes the weights:
+    from beast_tokenizer_b200.beast_bpe_trainer import GpuBpeEngine, _Collective, build_alphabet, scan_bins_gpu
+    mn, mx, seen = scan_bins_gpu(dev_bins, _Collective(enabled=False))
+    tokens, b2i = build_alphabet(mn, mx, seen)
+    engs = [GpuBpeEngine(dev_bins, mn, b2i, vocab, mx - mn, None, d) for d in (True, False)]
+    assert engs[0].weight is not None and engs[1].weight is None
+    assert torch.equal(engs[0].hist, engs[1].hist)                 # weighted initial counts == plain counts
+    n_tok = len(tokens)
+    for step in range(40):
+        picks = [e.argmax(n_tok) for e in engs]
+        assert picks[0] == picks[1]
+        cnt, a, b = picks[0]
+        for e in engs:
+            e.merge(a, b, n_tok)
+            e.apply_delta(a, b, n_tok)
+        n_tok += 1
+    assert torch.equal(engs[0].hist, engs[1].hist)
