@@ -189,9 +189,10 @@ class GpuBpeEngine:
             return
         sym2 = torch.empty(((cap + 7) // 8, P, 8), device=dev, dtype=torch.int16)
         len2 = plen.to(torch.int32)
-        _lib.check(lib.bpe_word_pack(_lib.ptr(self.sym), self.stride, _lib.ptr(rep.contiguous()),
-                                     _lib.ptr(pid.to(torch.int32)), _lib.ptr(off.to(torch.int32)), U, _lib.ptr(sym2),
-                                     _lib.ptr(len2), P, P, _lib.stream_ptr(dev)), "bpe_word_pack")
+        # named temporaries: a tensor created inside the call would be freed (and its block reused) before the launch
+        rep_c, pid32, off32 = rep.contiguous(), pid.to(torch.int32), off.to(torch.int32)
+        _lib.check(lib.bpe_word_pack(_lib.ptr(self.sym), self.stride, _lib.ptr(rep_c), _lib.ptr(pid32), _lib.ptr(off32),
+                                     U, _lib.ptr(sym2), _lib.ptr(len2), P, P, _lib.stream_ptr(dev)), "bpe_word_pack")
         self.sym, self.len, self.N, self.stride = sym2, len2, P, P
         self.weight = cnt[first].to(torch.int32).contiguous()
         self.work = torch.zeros(4 + 2 * P, device=dev, dtype=torch.int32)
