@@ -119,9 +119,11 @@ class GpuBpeEngine:
                        "bpe_count_pairs")
 
     # ------------------------------------------------------------------ word de-duplication
-    def _word_table(self, n_seq: int):
-        """Hash table over the words of the first n_seq sequences -> (rep locations, counts) of the distinct words,
-        or None on a hash collision (exactness is never traded: the caller keeps the plain corpus)."""
+    def _word_table(self, n_seq: int, expect_distinct: Optional[int] = None):
+        """Hash table over the words of the first n_seq sequences -> (locations, counts) of the distinct words
+        (unordered), or None on a hash collision (exactness is never traded: the caller keeps the plain corpus).
+        expect_distinct sizes the table (an estimate from a sample); when it proves too small the pass is repeated
+        with the safe bound, the number of words."""
         dev, lib = self.dev, self.lib
         st = _lib.stream_ptr(dev)
         totals = torch.zeros(2, device=dev, dtype=torch.int64)
@@ -130,32 +132,48 @@ class GpuBpeEngine:
         words, symbols = (int(v) for v in totals.tolist())
         if words == 0:
             return None
-        size = 1 << max(10, (2 * words - 1).bit_length())
-        keys = torch.zeros(size, device=dev, dtype=torch.int64)
-        rep = torch.full((size,), -1, device=dev, dtype=torch.int64)          # 0xff..ff
-        count = torch.zeros(size, device=dev, dtype=torch.int32)
-        collision = torch.zeros(1, device=dev, dtype=torch.int32)
-        _lib.check(lib.bpe_word_table(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(keys),
-                                      _lib.ptr(rep), _lib.ptr(count), size, _lib.ptr(collision), st), "bpe_word_table")
-        slots = torch.nonzero(count, as_tuple=False).flatten()
-        if int(collision.item()):
+        for bound in ([min(int(expect_distinct), words)] if expect_distinct else []) + [words]:
+            size = 1 << max(10, (2 * bound - 1).bit_length())
+            keys = torch.zeros(size, device=dev, dtype=torch.int64)
+            rep = torch.empty(size, device=dev, dtype=torch.int64)
+            count = torch.zeros(size, device=dev, dtype=torch.int32)
+            flags = torch.zeros(4, device=dev, dtype=torch.int32)
+            _lib.check(lib.bpe_word_insert(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(keys),
+                                           _lib.ptr(rep), _lib.ptr(count), size, _lib.ptr(flags), st), "bpe_word_insert")
+            status, distinct = flags[:2].tolist()
+            if status != 3 and distinct <= size // 2:
+                break
+            if bound == words:
+                return None
+        if status:
             return None
-        return rep[slots], count[slots], words, symbols
+        loc = torch.empty(distinct, device=dev, dtype=torch.int64)
+        cnt = torch.empty(distinct, device=dev, dtype=torch.int32)
+        _lib.check(lib.bpe_word_emit(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(keys),
+                                     _lib.ptr(rep), _lib.ptr(count), size, _lib.ptr(flags), _lib.ptr(loc), _lib.ptr(cnt), st),
+                   "bpe_word_emit")
+        status, _, emitted = flags[:3].tolist()
+        if status or emitted != distinct:
+            return None
+        return loc, cnt, words, symbols
 
     def _dedup_words(self, force: bool):
         """Replace the symbolised corpus by its distinct words, packed into pseudo-sequences of equal-count words,
         with one weight per pseudo-sequence.  "auto": only when a sample says the corpus is repetitive enough."""
         dev, lib = self.dev, self.lib
-        if not force and self.N > 2 * self.DEDUP_SAMPLE:
+        expect = None
+        if self.N > 2 * self.DEDUP_SAMPLE:
             probe = self._word_table(self.DEDUP_SAMPLE)
             if probe is None:
                 return
             rep, cnt, words, symbols = probe
             ratio = float((rep & 0xFFFF).sum().item()) / max(symbols, 1)
             self.dedup_stats = {"sampled_sequences": self.DEDUP_SAMPLE, "sample_distinct_symbol_ratio": ratio, "applied": False}
-            if ratio >= self.DEDUP_KEEP:
+            if not force and ratio >= self.DEDUP_KEEP:
                 return
-        full = self._word_table(self.N)
+            # distinct words grow sub-linearly with the corpus: the sample's rate bounds the table from above
+            expect = int(rep.numel() * (self.N / self.DEDUP_SAMPLE)) + 1024
+        full = self._word_table(self.N, expect)
         if full is None:
             self.dedup_stats = {"applied": False, "reason": "64-bit word hash collision: trained on the plain corpus"}
             return
@@ -169,7 +187,7 @@ class GpuBpeEngine:
         if not force and ratio >= self.DEDUP_KEEP:
             return
         # order by count (descending), pack words of equal count into pseudo-sequences of ~DEDUP_PACK symbols
-        cnt, order = torch.sort(cnt, descending=True, stable=True)
+        cnt, order = torch.sort(cnt.to(torch.int64), descending=True)
         rep, lens = rep[order], lens[order]
         U = int(rep.numel())
         excl = torch.cumsum(lens, 0) - lens                                   # symbols before word i

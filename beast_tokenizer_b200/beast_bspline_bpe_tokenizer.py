@@ -36,6 +36,22 @@ def _coerce_bpe(tokenizer) -> B200ByteLevelBPE:
     raise TypeError("Expected a ByteLevelBPETokenizer instance.")
 
 
+def _split_rows(flat_h: np.ndarray, off_h: np.ndarray) -> List[List[int]]:
+    """CSR -> the ragged List[List[int]] the reference returns.  One tolist() of the whole id array and pointer-copy
+    slices of it; the cyclic collector is paused meanwhile (tens of thousands of fresh lists would trigger repeated
+    full collections that find nothing).  What remains is CPython creating one int object per id."""
+    import gc
+    off = off_h.tolist()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        big = flat_h.tolist()
+        return [big[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 class BEASTBsplineBPETokenizer(BEASTBsplineTokenizer):
     """B-Spline tokenizer augmented with a learned Byte-Pair encoder."""
 
@@ -174,10 +190,11 @@ class BEASTBsplineBPETokenizer(BEASTBsplineTokenizer):
         result: List[Optional[List[int]]] = [None] * n
         for idx, bins in groups:
             flat, offsets = self._discrete_to_bpe_csr(bins)
-            flat_h, off_h = flat.cpu().numpy(), offsets.cpu().numpy()
-            rows = [flat_h[off_h[i]:off_h[i + 1]].tolist() for i in range(bins.shape[0])]
+            rows = _split_rows(flat.cpu().numpy(), offsets.cpu().numpy())
+            if idx is None:
+                return rows
             for j, r in enumerate(rows):
-                result[j if idx is None else idx[j]] = r
+                result[idx[j]] = r
         return result  # type: ignore[return-value]
 
     def _ids_to_csr(self, tokens: Iterable[TokenLike], dev):

@@ -6,10 +6,11 @@
 // and over) that is the largest algorithmic saving of the trainer.  Here:
 //
 //   table    every word of the symbolised corpus is hashed (64 bits over its symbol ids and length) into an
-//            open-addressing table: pass 1 claims the slot (atomicCAS on the key) and elects the word with the
-//            smallest (sequence, position) as the slot's representative (atomicMin on the packed location);
-//            pass 2 finds the slot again, compares the word with the representative SYMBOL BY SYMBOL (a 64-bit
-//            hash collision is reported, never trusted: the caller then trains on the plain corpus) and counts;
+//            open-addressing table: pass 1 claims the slot (atomicCAS on the key; the winner becomes the slot's
+//            representative) and counts the occurrences; pass 2 finds the slot again, the representative appends
+//            (location, count) to the list of distinct words, every other word is compared with the
+//            representative SYMBOL BY SYMBOL (a 64-bit hash collision is reported, never trusted: the caller
+//            then trains on the plain corpus);
 //   pack     the distinct words are ordered by count (host side: torch sort / scans over U elements) and packed,
 //            words of EQUAL count together, into pseudo-sequences of the same chunk-major layout the merge loop
 //            already walks; one int32 weight per pseudo-sequence = the count of its words.
@@ -94,43 +95,65 @@ bpe_word_total_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ 
     }
 }
 
-// pass 1 (COUNT = false): claim slots, elect representatives.  pass 2 (COUNT = true): verify + count.
-template <bool COUNT>
+// pass 1 (EMIT = false): claim slots (atomicCAS on the key; the winner stores its location as the slot's
+// representative) and count occurrences.  pass 2 (EMIT = true): every word finds its slot again; the
+// representative appends (location, count) to the list of distinct words, every other word is compared with the
+// representative symbol by symbol.  flags[0]: 1 = hash collision, 2 = internal error, 3 = table too small;
+// flags[1] (pass 1) = slots claimed; flags[2] (pass 2) = distinct words emitted.
+constexpr int kMaxProbes = 1 << 12;
+template <bool EMIT>
 __global__ void __launch_bounds__(256)
 bpe_word_table_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
                       unsigned long long* __restrict__ keys, unsigned long long* __restrict__ rep,
-                      int* __restrict__ count, unsigned long long mask, int* __restrict__ collision) {
+                      int* __restrict__ count, unsigned long long mask, int* __restrict__ flags,
+                      unsigned long long* __restrict__ out_loc, int* __restrict__ out_cnt) {
+    int claimed = 0;
+    const unsigned int lane = threadIdx.x & 31u;
     for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
          seq += (long long)gridDim.x * blockDim.x) {
         for_each_word(sym, len, seq, n_stride, [&](unsigned long long key, int start, int wl) {
             const unsigned long long loc = word_loc(seq, start, wl);
             unsigned long long slot = key & mask;
+            bool won = false;
+            int probes = 0;
             for (;;) {
                 unsigned long long k = keys[slot];
-                if (!COUNT && k == 0ull) {
+                if (!EMIT && k == 0ull) {
                     const unsigned long long old = atomicCAS(&keys[slot], 0ull, key);
-                    k = old == 0ull ? key : old;
+                    won = old == 0ull;
+                    k = won ? key : old;
                 }
                 if (k == key) break;
-                if (COUNT && k == 0ull) { atomicExch(collision, 2); return; }   // cannot happen after pass 1
+                if (EMIT && k == 0ull) { atomicExch(&flags[0], 2); return; }     // cannot happen after pass 1
+                if (++probes > kMaxProbes) { atomicExch(&flags[0], 3); return; } // table (nearly) full
                 slot = (slot + 1) & mask;
             }
-            if (!COUNT) {
-                atomicMin(&rep[slot], loc);
+            if (!EMIT) {
+                if (won) { rep[slot] = loc; ++claimed; }
+                atomicAdd(&count[slot], 1);
                 return;
             }
             const unsigned long long r = rep[slot];
-            if (r != loc) {                                  // another word owns the slot: it must be the SAME word
-                const long long rseq = (long long)(r >> 32);
-                const int rstart = (int)((r >> 16) & 0xffffu), rlen = (int)(r & 0xffffu);
-                bool same = rlen == wl;
-                for (int q = 0; same && q < wl; ++q)
-                    same = (sym_at(sym, start + q, seq, n_stride) & kIdMask) == (sym_at(sym, rstart + q, rseq, n_stride) & kIdMask);
-                if (!same) { atomicExch(collision, 1); return; }
+            if (r == loc) {                                  // the representative lists the distinct word
+                const unsigned int m = __activemask();       // opportunistic warp aggregation of the append
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if ((int)lane == leader) base = atomicAdd(&flags[2], __popc(m));
+                base = __shfl_sync(m, base, leader);
+                const int idx = base + __popc(m & ((1u << lane) - 1u));
+                out_loc[idx] = loc;
+                out_cnt[idx] = count[slot];
+                return;
             }
-            atomicAdd(&count[slot], 1);
+            const long long rseq = (long long)(r >> 32);     // another word owns the slot: it must be the SAME word
+            const int rstart = (int)((r >> 16) & 0xffffu), rlen = (int)(r & 0xffffu);
+            bool same = rlen == wl;
+            for (int q = 0; same && q < wl; ++q)
+                same = (sym_at(sym, start + q, seq, n_stride) & kIdMask) == (sym_at(sym, rstart + q, rseq, n_stride) & kIdMask);
+            if (!same) atomicExch(&flags[0], 1);
         });
     }
+    if (!EMIT && claimed) atomicAdd(&flags[1], claimed);
 }
 
 // One thread per distinct word: copy its symbols from the corpus into its pseudo-sequence.
@@ -188,19 +211,36 @@ extern "C" int bpe_word_totals(const uint16_t* sym, const int32_t* len, int64_t 
     return BEAST_OK;
 }
 
-extern "C" int bpe_word_table(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* keys,
-                              uint64_t* rep, int32_t* count, int64_t table_size, int32_t* collision, void* stream) {
-    if (N == 0) return BEAST_OK;
-    if (!sym || !len || !keys || !rep || !count || !collision) return BEAST_E_NULL;
-    if (N < 0 || n_stride < N || N > 0xffffffffLL || table_size < 2 || (table_size & (table_size - 1))) return BEAST_E_SHAPE;
+static int word_table_args(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, const void* keys,
+                           const void* rep, const void* count, int64_t table_size, const void* flags) {
+    if (!sym || !len || !keys || !rep || !count || !flags) return BEAST_E_NULL;
+    if (N < 0 || n_stride < N || N > 0x7fffffffLL || table_size < 2 || (table_size & (table_size - 1))) return BEAST_E_SHAPE;
     if ((uintptr_t)sym & 15u) return BEAST_E_ALIGN;
-    cudaStream_t st = (cudaStream_t)stream;
-    const unsigned long long mask = (unsigned long long)table_size - 1ull;
-    bpe_word_table_kernel<false><<<dedup_grid(N), 256, 0, st>>>(sym, len, N, n_stride, (unsigned long long*)keys,
-                                                                (unsigned long long*)rep, count, mask, collision);
-    bpe_word_table_kernel<true><<<dedup_grid(N), 256, 0, st>>>(sym, len, N, n_stride, (unsigned long long*)keys,
-                                                               (unsigned long long*)rep, count, mask, collision);
-    count_launch(2);
+    return BEAST_OK;
+}
+
+extern "C" int bpe_word_insert(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* keys,
+                               uint64_t* rep, int32_t* count, int64_t table_size, int32_t* flags, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (int rc = word_table_args(sym, len, N, n_stride, keys, rep, count, table_size, flags)) return rc;
+    bpe_word_table_kernel<false><<<dedup_grid(N), 256, 0, (cudaStream_t)stream>>>(
+        sym, len, N, n_stride, (unsigned long long*)keys, (unsigned long long*)rep, count,
+        (unsigned long long)table_size - 1ull, flags, nullptr, nullptr);
+    count_launch();
+    BEAST_CHECK_LAUNCH();
+    return BEAST_OK;
+}
+
+extern "C" int bpe_word_emit(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, const uint64_t* keys,
+                             const uint64_t* rep, const int32_t* count, int64_t table_size, int32_t* flags,
+                             uint64_t* out_loc, int32_t* out_cnt, void* stream) {
+    if (N == 0) return BEAST_OK;
+    if (int rc = word_table_args(sym, len, N, n_stride, keys, rep, count, table_size, flags)) return rc;
+    if (!out_loc || !out_cnt) return BEAST_E_NULL;
+    bpe_word_table_kernel<true><<<dedup_grid(N), 256, 0, (cudaStream_t)stream>>>(
+        sym, len, N, n_stride, (unsigned long long*)keys, (unsigned long long*)rep, (int*)count,
+        (unsigned long long)table_size - 1ull, flags, (unsigned long long*)out_loc, out_cnt);
+    count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
 }

@@ -261,12 +261,15 @@ int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int
 /* Word de-duplication in front of the merge loop (what BpeTrainer does with the strings FIGBPE hands it,
  * beast/beast_bpe_trainer.py:61-74: distinct pre-tokens with counts).  csrc/bpe_dedup.cu.
  * bpe_word_totals  totals[0] = pre-tokens, totals[1] = symbols of the symbolised corpus (device, 2 x uint64).
- * bpe_word_table   open-addressing table over the words: keys / rep uint64 [table_size], count int32 [table_size];
- *                  table_size a power of two >= 2 x words; the caller zeroes keys and count and fills rep with
- *                  0xff..ff.  After the call every occupied slot holds the location of its representative word
- *                  (sequence << 32 | first symbol << 16 | symbols) and the number of occurrences.  Words are compared
- *                  with their representative symbol by symbol: *collision != 0 (caller zeroes it) reports a 64-bit
- *                  hash collision — the table is then unusable and the caller trains on the plain corpus.
+ * bpe_word_insert  pass 1 over an open-addressing table (keys / rep uint64 [table_size], count int32 [table_size];
+ *                  table_size a power of two, at least 2 x the distinct words; the caller zeroes keys, count and
+ *                  flags [3]): claims a slot per distinct word, stores its first finder's location
+ *                  (sequence << 32 | first symbol << 16 | symbols) in rep and counts the occurrences.
+ *                  flags[1] = slots claimed; flags[0] = 3 when the table is too small (retry with a larger one).
+ * bpe_word_emit    pass 2: the representative of every slot appends (location, count) to out_loc / out_cnt
+ *                  [flags[1]]; flags[2] = entries written.  Every other word is compared with its representative
+ *                  symbol by symbol: flags[0] = 1 reports a 64-bit hash collision — the table is then unusable and
+ *                  the caller trains on the plain corpus.
  * bpe_word_pack    copies U distinct words (loc[i] as above) to position dst_off[i] of pseudo-sequence dst_seq[i]
  *                  of a second corpus in the same chunk-major layout (first symbol flagged as a word start) and
  *                  pads the last chunk of each of the P pseudo-sequences (dst_len[P] symbols each).
@@ -275,8 +278,11 @@ int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int
  * count updates by weight[seq] (NULL = 1). */
 int bpe_word_totals(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* totals,
                     void* stream);
-int bpe_word_table(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* keys, uint64_t* rep,
-                   int32_t* count, int64_t table_size, int32_t* collision, void* stream);
+int bpe_word_insert(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* keys, uint64_t* rep,
+                    int32_t* count, int64_t table_size, int32_t* flags, void* stream);
+int bpe_word_emit(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, const uint64_t* keys,
+                  const uint64_t* rep, const int32_t* count, int64_t table_size, int32_t* flags, uint64_t* out_loc,
+                  int32_t* out_cnt, void* stream);
 int bpe_word_pack(const uint16_t* src, int64_t src_stride, const uint64_t* loc, const int32_t* dst_seq,
                   const int32_t* dst_off, int64_t U, uint16_t* dst, const int32_t* dst_len, int64_t P,
                   int64_t dst_stride, void* stream);
