@@ -187,21 +187,27 @@ class GpuBpeEngine:
         if not force and ratio >= self.DEDUP_KEEP:
             return
         # order by count (descending), pack words of equal count into pseudo-sequences of ~DEDUP_PACK symbols
-        cnt, order = torch.sort(cnt.to(torch.int64), descending=True)
+        # (a dozen O(U) torch scans / gathers; no scatter, no cummax)
+        cnt, order = torch.sort(cnt, descending=True)
         rep, lens = rep[order], lens[order]
         U = int(rep.numel())
-        excl = torch.cumsum(lens, 0) - lens                                   # symbols before word i
+        incl = torch.cumsum(lens, 0)
+        excl = incl - lens                                                    # symbols before word i
         new_group = torch.ones(U, device=dev, dtype=torch.bool)
         new_group[1:] = cnt[1:] != cnt[:-1]
-        group_start = torch.cummax(torch.where(new_group, excl, torch.zeros_like(excl)), 0).values
+        gid = torch.cumsum(new_group, 0) - 1
+        group_start = excl[torch.nonzero(new_group, as_tuple=False).flatten()][gid]
         bin_in_group = (excl - group_start) // self.DEDUP_PACK
-        new_bin = new_group.clone()
+        new_bin = new_group
         new_bin[1:] |= bin_in_group[1:] != bin_in_group[:-1]
-        pid = torch.cumsum(new_bin.to(torch.int64), 0) - 1                   # pseudo-sequence of word i
-        P = int(pid[-1].item()) + 1
         first = torch.nonzero(new_bin, as_tuple=False).flatten()              # first word of every pseudo-sequence
-        off = excl - excl[first][pid]
-        plen = torch.zeros(P, device=dev, dtype=torch.int64).scatter_add_(0, pid, lens)
+        P = int(first.numel())
+        pid = torch.cumsum(new_bin, 0) - 1                                    # pseudo-sequence of word i
+        bin_start = excl[first]
+        off = excl - bin_start[pid]
+        plen = torch.empty(P, device=dev, dtype=torch.int64)
+        plen[:-1] = bin_start[1:] - bin_start[:-1]
+        plen[-1] = incl[-1] - bin_start[-1]
         cap = int(plen.max().item())
         if cap > 32767 or P > 0x7FFFFFFF:
             return
@@ -282,11 +288,11 @@ class _FastRun:
         self.enqueued = 0
         dev = eng.dev
         with torch.cuda.device(dev):
-            self.ctl = torch.zeros(16, device=dev, dtype=torch.int32)
-            self.ctl[4] = n_tokens
+            # control block, double-buffered by iteration parity (iteration i reads ctl[i & 1], writes the other)
+            self.ctl = torch.zeros((2, 16), device=dev, dtype=torch.int32)
+            self.ctl[0, 4] = n_tokens
             self.log = torch.zeros(4 * max(self.max_merges, 1), device=dev, dtype=torch.int32)
             eng.result.zero_()
-            eng.work[:4].zero_()
             # count deltas, double-buffered by merge parity: the peers' copy when sharded over NVLink
             self.delta = delta if delta is not None else torch.zeros(8 * eng.V, device=dev, dtype=torch.int32)
             # Pair signatures (two 4-byte column reads per merge tell which sequences can hold the pair).  The
@@ -319,9 +325,9 @@ class _FastRun:
                 n = min(n, int(limit))
             _lib.check(eng.lib.bpe_train_step(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, eng.V,
                                               _lib.ptr(eng.hist), _lib.ptr(self.delta), _lib.ptr(self.ctl),
-                                              _lib.ptr(self.log), _lib.ptr(eng.result), _lib.ptr(eng.work),
+                                              _lib.ptr(self.log), _lib.ptr(eng.result),
                                               self.vocab_size, self.min_frequency, self.max_merges,
-                                              _lib.ptr(self.sig) if i >= self.SIG_START else None, int(n),
+                                              _lib.ptr(self.sig) if i >= self.SIG_START else None, int(i), int(n),
                                               C.byref(self.peers) if self.peers is not None else None,
                                               _lib.ptr(eng.weight), st),
                        "bpe_train_step")
@@ -329,10 +335,10 @@ class _FastRun:
         return n
 
     def merges_done(self) -> int:
-        return int(self.ctl[5].item())                      # synchronises: progress display only
+        return int(self.ctl[self.enqueued & 1, 5].item())   # synchronises: progress display only
 
     def finish(self):
-        ctl_h = self.ctl.cpu().tolist()
+        ctl_h = self.ctl[self.enqueued & 1].cpu().tolist()
         if ctl_h[8]:
             raise _lib.BeastB200Error("sharded BPE training: a peer GPU did not publish its merge epoch within 5 s "
                                       "(ranks out of step or peer memory not reachable)")

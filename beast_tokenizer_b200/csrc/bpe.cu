@@ -385,83 +385,78 @@ __device__ __forceinline__ uint16_t chunk_get(const uint4& w, int j) {        //
     return (uint16_t)((j & 1) ? (word >> 16) : (word & 0xffffu));
 }
 
-// Scan kernel (pass 1): for every sequence the first position q0 whose id is a and whose successor is
-// b inside the same pre-token (b with the word-start bit clear is the 16-bit value b itself; padding
-// never matches).  One thread per sequence, the warp walks the chunks in lock step (512 contiguous
-// bytes per step).  SWAR search, two symbols per 32-bit word: most chunks contain no `a` at all and cost
-// four XOR-AND-ADD-ANDN groups.  Sequences with a hit are appended to the work list (warp-aggregated
-// atomic) — typically well under 1 % of the corpus after the first hundred merges.
-template <bool DEEP>
-__global__ void __launch_bounds__(256)
-bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
-                int a, int b, const BpeCtl* __restrict__ ctl, int* __restrict__ work_count, int* __restrict__ work_seq,
-                int* __restrict__ work_q0, const unsigned int* __restrict__ sig, int tile_size) {
-    if (ctl) {
-        if (ctl->done) return;
-        a = ctl->a; b = ctl->b;
-    }
-    // signature column of this pair: sequences whose bit is clear cannot contain (a, b) and are never read
-    const unsigned int sh = sig_hash((unsigned int)a, (unsigned int)b), sh2 = sig_hash2((unsigned int)a, (unsigned int)b);
-    const unsigned int* sig_col = sig ? sig + (long long)(sh >> 5) * n_stride : nullptr;
-    const unsigned int* sig_col2 = sig ? sig + (long long)(sh2 >> 5) * n_stride : nullptr;
-    const unsigned int sig_bit = 1u << (sh & 31u), sig_bit2 = 1u << (sh2 & 31u);
-    const uint4* sym4 = (const uint4*)sym;
-    const int lane = threadIdx.x & 31;
+// First position q0 whose id is a and whose successor is b inside the same pre-token (b with the word-start
+// bit clear is the 16-bit value b itself; padding never matches), or -1.  One lane per sequence, the warp walks
+// the chunks in LOCK STEP (512 contiguous bytes per step; all 32 lanes must call).  SWAR search, two symbols per
+// 32-bit word: most chunks contain no `a` at all and cost four XOR-AND-ADD-ANDN groups.  `deep`: four independent
+// 128-bit loads in flight per lane (few rows: the walk is a chain of dependent round trips) instead of two.
+__device__ __forceinline__ int find_first_pair(const uint4* __restrict__ sym4, long long n_stride, long long seq,
+                                               bool valid, int n, int a, int b, bool deep) {
     const unsigned int A2 = (unsigned int)a | ((unsigned int)a << 16);
     const unsigned int B2 = (unsigned int)b | ((unsigned int)b << 16);
-    // one warp, 32 sequences (`valid` lanes), chunks walked in lock step; hits go to the work list
-    auto scan_warp = [&](long long seq, bool valid, bool deep) {
-        const int n = valid ? len[seq] : 0;
-        const int nch = (n + kChunk - 1) >> 3;
-        const long long row0 = valid ? seq : 0;
-        const int nch_max = warp_max_i(nch);
-        int q0 = -1;
-        unsigned int carry = 0;                               // bit 15: previous chunk ended with `a`
-        auto test_chunk = [&](const uint4& w, int ci) {
-            const unsigned int wd[4] = {w.x, w.y, w.z, w.w};
-            unsigned int fa[4];                               // bit 15 / 31: half-word has id == a
+    const int nch = valid ? (n + kChunk - 1) >> 3 : 0;
+    const long long row0 = valid ? seq : 0;
+    const int nch_max = warp_max_i(nch);
+    int q0 = -1;
+    unsigned int carry = 0;                               // bit 15: previous chunk ended with `a`
+    auto test_chunk = [&](const uint4& w, int ci) {
+        const unsigned int wd[4] = {w.x, w.y, w.z, w.w};
+        unsigned int fa[4];                               // bit 15 / 31: half-word has id == a
 #pragma unroll
-            for (int k = 0; k < 4; ++k) fa[k] = ~(((wd[k] ^ A2) & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
-            if (carry | fa[0] | fa[1] | fa[2] | fa[3]) {
+        for (int k = 0; k < 4; ++k) fa[k] = ~(((wd[k] ^ A2) & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+        if (carry | fa[0] | fa[1] | fa[2] | fa[3]) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned int y = wd[k] ^ B2;            // fb: half-word == b exactly
-                    const unsigned int fb = ~((((y & 0x7fff7fffu) + 0x7fff7fffu)) | y) & 0x80008000u;
-                    const unsigned int h = ((fa[k] << 16) | (k ? fa[k - 1] >> 16 : carry)) & fb;
-                    if (h && q0 < 0) q0 = ci * kChunk + 2 * k + ((h & 0x8000u) ? 0 : 1) - 1;
-                }
-            }
-            carry = fa[3] >> 16;
-        };
-        const uint4 pad = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (deep) {
-            // survivors of the signature filter: few rows, the walk is a chain of dependent round trips —
-            // four independent 128-bit loads in flight per lane (the bytes past a hit are negligible here)
-            for (int ci = 0; ci < nch_max; ci += 4) {
-                if (ci < nch && q0 < 0) {
-                    const uint4 w0 = __ldcs(&sym4[(long long)ci * n_stride + row0]);
-                    const uint4 w1 = ci + 1 < nch ? __ldcs(&sym4[(long long)(ci + 1) * n_stride + row0]) : pad;
-                    const uint4 w2 = ci + 2 < nch ? __ldcs(&sym4[(long long)(ci + 2) * n_stride + row0]) : pad;
-                    const uint4 w3 = ci + 3 < nch ? __ldcs(&sym4[(long long)(ci + 3) * n_stride + row0]) : pad;
-                    test_chunk(w0, ci);
-                    if (q0 < 0) test_chunk(w1, ci + 1);
-                    if (q0 < 0) test_chunk(w2, ci + 2);
-                    if (q0 < 0) test_chunk(w3, ci + 3);
-                }
-                if (__all_sync(0xffffffffu, q0 >= 0 || ci + 4 >= nch)) break;
-            }
-        } else {
-            for (int ci = 0; ci < nch_max; ci += 2) {         // whole corpus: two loads in flight per lane
-                if (ci < nch && q0 < 0) {
-                    // streaming (evict-first) loads: the corpus pass must not push the V x V histogram out of L2
-                    const uint4 w0 = __ldcs(&sym4[(long long)ci * n_stride + row0]);
-                    const uint4 w1 = ci + 1 < nch ? __ldcs(&sym4[(long long)(ci + 1) * n_stride + row0]) : pad;
-                    test_chunk(w0, ci);
-                    if (q0 < 0) test_chunk(w1, ci + 1);
-                }
-                if (__all_sync(0xffffffffu, q0 >= 0 || ci + 2 >= nch)) break;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int y = wd[k] ^ B2;            // fb: half-word == b exactly
+                const unsigned int fb = ~((((y & 0x7fff7fffu) + 0x7fff7fffu)) | y) & 0x80008000u;
+                const unsigned int h = ((fa[k] << 16) | (k ? fa[k - 1] >> 16 : carry)) & fb;
+                if (h && q0 < 0) q0 = ci * kChunk + 2 * k + ((h & 0x8000u) ? 0 : 1) - 1;
             }
         }
+        carry = fa[3] >> 16;
+    };
+    const uint4 pad = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (deep) {
+        for (int ci = 0; ci < nch_max; ci += 4) {
+            if (ci < nch && q0 < 0) {
+                const uint4 w0 = __ldcs(&sym4[(long long)ci * n_stride + row0]);
+                const uint4 w1 = ci + 1 < nch ? __ldcs(&sym4[(long long)(ci + 1) * n_stride + row0]) : pad;
+                const uint4 w2 = ci + 2 < nch ? __ldcs(&sym4[(long long)(ci + 2) * n_stride + row0]) : pad;
+                const uint4 w3 = ci + 3 < nch ? __ldcs(&sym4[(long long)(ci + 3) * n_stride + row0]) : pad;
+                test_chunk(w0, ci);
+                if (q0 < 0) test_chunk(w1, ci + 1);
+                if (q0 < 0) test_chunk(w2, ci + 2);
+                if (q0 < 0) test_chunk(w3, ci + 3);
+            }
+            if (__all_sync(0xffffffffu, q0 >= 0 || ci + 4 >= nch)) break;
+        }
+    } else {
+        for (int ci = 0; ci < nch_max; ci += 2) {         // whole corpus: two loads in flight per lane
+            if (ci < nch && q0 < 0) {
+                // streaming (evict-first) loads: the corpus pass must not push the V x V histogram out of L2
+                const uint4 w0 = __ldcs(&sym4[(long long)ci * n_stride + row0]);
+                const uint4 w1 = ci + 1 < nch ? __ldcs(&sym4[(long long)(ci + 1) * n_stride + row0]) : pad;
+                test_chunk(w0, ci);
+                if (q0 < 0) test_chunk(w1, ci + 1);
+            }
+            if (__all_sync(0xffffffffu, q0 >= 0 || ci + 2 >= nch)) break;
+        }
+    }
+    return q0;
+}
+
+// Scan kernel of the host-driven loop (bpe_apply_merge): sequences with a hit are appended to the work list
+// (warp-aggregated atomic), the rewrite kernel below consumes it.
+__global__ void __launch_bounds__(256)
+bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
+                int a, int b, int* __restrict__ work_count, int* __restrict__ work_seq, int* __restrict__ work_q0) {
+    const uint4* sym4 = (const uint4*)sym;
+    const int lane = threadIdx.x & 31;
+    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N;
+         base += (long long)gridDim.x * blockDim.x) {
+        const long long seq = base + lane;
+        const bool valid = seq < N;
+        const int q0 = find_first_pair(sym4, n_stride, seq, valid, valid ? len[seq] : 0, a, b, false);
         const unsigned int hits = __ballot_sync(0xffffffffu, q0 >= 0);
         if (hits) {
             int slot0 = 0;
@@ -473,49 +468,6 @@ bpe_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, l
                 work_q0[slot] = q0;
             }
         }
-    };
-    if (!sig_col) {
-        for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < N;
-             base += (long long)gridDim.x * blockDim.x)
-            scan_warp(base + lane, base + lane < N, false);
-        return;
-    }
-    // With signatures: a block filters a tile of kScanTile sequences down to the ones whose bit is set
-    // (one coalesced 4-byte column read), compacts them in shared memory, and only those are walked —
-    // by full warps, so the number of chunk walks drops with the pass rate, not just the bytes.
-    __shared__ int s_list[kScanTile];
-    __shared__ int s_n;
-    for (long long tile = (long long)blockIdx.x * tile_size; tile < N; tile += (long long)gridDim.x * tile_size) {
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-        // all signature words of the tile first (up to 16 loads in flight per thread), then the ballots
-        unsigned int pass_bits = 0;
-#pragma unroll
-        for (int r = 0; r < kScanTile / 256; ++r) {
-            const int k = threadIdx.x + r * 256;
-            const long long seq = tile + k;
-            if (k < tile_size && seq < N && (__ldg(sig_col + seq) & sig_bit) && (__ldg(sig_col2 + seq) & sig_bit2))
-                pass_bits |= 1u << r;
-        }
-        for (int r = 0; r * 256 < tile_size; ++r) {
-            const int k = threadIdx.x + r * 256;
-            const bool pass = (pass_bits >> r) & 1u;
-            const unsigned int m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_n, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = k;
-            }
-        }
-        __syncthreads();
-        const int n_pass = s_n;
-        for (int i0 = threadIdx.x & ~31; i0 < n_pass; i0 += blockDim.x) {
-            const int i = i0 + lane;
-            const bool valid = i < n_pass;
-            scan_warp(valid ? tile + s_list[i] : 0, valid, DEEP);
-        }
-        __syncthreads();
     }
 }
 
@@ -769,15 +721,10 @@ __device__ __forceinline__ void flush_delta_block(const int* s_delta, int* __res
 
 __global__ void __launch_bounds__(256)
 bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long n_stride, int a, int b, int c, int V,
-                   const BpeCtl* __restrict__ ctl, const int* __restrict__ work_count,
+                   const int* __restrict__ work_count,
                    const int* __restrict__ work_seq, const int* __restrict__ work_q0, int* __restrict__ delta,
                    unsigned int* __restrict__ sig, const int* __restrict__ weight) {
     extern __shared__ int s_delta[];
-    if (ctl) {
-        if (ctl->done) return;
-        a = ctl->a; b = ctl->b; c = ctl->c;
-        delta += ((ctl->n_merges - 1) & 1) * 4 * V;           // double-buffered by merge parity (peers may still read the other half)
-    }
     const int n_work = *work_count;
     if (n_work > kDirectDeltaWork && (long long)blockIdx.x * blockDim.x >= n_work) return;       // nothing for this block
     if (n_work <= kDirectDeltaWork) {
@@ -849,7 +796,7 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
 // pass — which needs nothing from the peers — hides the NVLink round trip; then every block waits for its own
 // flags and the fold pass sums the ranks' delta blocks with peer loads.  The histogram replicas stay identical, so
 // every rank picks the same merge without a broadcast.
-// (One block of 1024 threads per SM writes its maximum to partial[block]; bpe_pick_kernel finishes.)
+// (One block of 1024 threads per SM writes its maximum to partial[block]; every block of bpe_merge_kernel reduces them.)
 __global__ void __launch_bounds__(1024)
 bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int* __restrict__ delta,
                    unsigned long long* __restrict__ partial, const __grid_constant__ BpePeersDev peers) {
@@ -944,7 +891,7 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int*
         };
         // 4 x n_active special entries, one per thread: which = 0 column a (j, a), 1 row b (b, j), 2 column c
         // (j, c), 3 row c (c, j).  An entry on two of the lines belongs to the first one in that order and takes
-        // both deltas; the delta half itself is cleared by bpe_pick_kernel before it is written again.
+        // both deltas; the delta half itself is cleared by the iteration head two merges later.
         const unsigned int nthreads = gridDim.x * blockDim.x;
         for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * (unsigned int)n_active; i += nthreads) {
             const int which = (int)(i / (unsigned int)n_active), j = (int)(i - (unsigned int)which * n_active);
@@ -964,6 +911,12 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int*
             consider(x, y, v);
         }
     }
+    {   // the half that the rewrite of THIS merge fills: it held merge m - 2, which every rank has consumed (the
+        // peers published epoch m — awaited above — after their fold of m - 2)
+        int4* d4 = (int4*)(delta + (ctl->n_merges & 1) * 4 * V);
+        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned int)V; i += gridDim.x * blockDim.x)
+            d4[i] = make_int4(0, 0, 0, 0);
+    }
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other > best ? other : best;
@@ -973,23 +926,39 @@ bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int*
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < warps_per_block; ++w) best = s_best[w] > best ? s_best[w] : best;
-        partial[blockIdx.x] = best;                          // plain store: bpe_pick_kernel runs after this grid
+        partial[blockIdx.x] = best;                          // plain store: bpe_merge_kernel runs after this grid
     }
 }
 
-// Second half of the iteration head: reduce the per-block maxima, apply BpeTrainer's stop rules (vocabulary
-// full, count < min_frequency), assign the next id, log the merge.  One small block; keeping it a separate
-// launch costs ~2 us, whereas a last-block-done ticket inside the arg-max grid costs ten times that in
-// same-address atomics, fences and barrier waits.
+// Second kernel of an iteration: pick + scan + rewrite fused.
+//   pick     EVERY block reduces the per-block maxima of the iteration head and applies BpeTrainer's stop rules
+//            (vocabulary full, count < min_frequency) itself — the state is read from ctl_in and the new state
+//            written (by block 0) to the OTHER control block, so no block waits for another; block 0 logs the merge;
+//   scan     a block filters a tile of <= kScanTile sequences by the pair's two signature columns, compacts the
+//            survivors in shared memory and walks only those (lane per sequence, lock step) for the first hit;
+//   rewrite  the hits of a warp's batch are rewritten at once, one WARP per sequence (no global work list, no
+//            third launch).  Count changes go straight to the global delta half as fire-and-forget reductions when
+//            the tile has few survivors, to block-private 4 x V shared-memory counters (flushed once) when it is dense.
+constexpr int kDenseTile = 96;           // survivors per tile from which the block-private counters pay
+template <bool DEEP>
 __global__ void __launch_bounds__(256)
-bpe_pick_kernel(const unsigned long long* __restrict__ partial, int n_partial, BpeCtl* __restrict__ ctl,
-                int* __restrict__ log, int V, int vocab_size, int min_frequency, int max_merges,
-                int* __restrict__ work_count, int* __restrict__ delta) {
-    if (ctl->done) return;
-    {   // the half that the rewrite of THIS merge fills: it held merge m - 2, which every rank (peers included:
-        // they published epoch m after their fold of m - 2) has consumed
-        int4* d4 = (int4*)(delta + (ctl->n_merges & 1) * 4 * V);
-        for (int i = threadIdx.x; i < V; i += blockDim.x) d4[i] = make_int4(0, 0, 0, 0);
+bpe_merge_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long N, long long n_stride, int V,
+                 const BpeCtl* __restrict__ ctl_in, BpeCtl* __restrict__ ctl_out,
+                 const unsigned long long* __restrict__ partial, int n_partial, int* __restrict__ log,
+                 int vocab_size, int min_frequency, int max_merges, int* __restrict__ delta_base,
+                 unsigned int* __restrict__ sig, const int* __restrict__ weight, int tile_size) {
+    extern __shared__ int s_delta[];
+    __shared__ uint16_t s_out[8][32 * kChunk + kChunk];
+    __shared__ int s_list[kScanTile];
+    __shared__ int s_n;
+    __shared__ unsigned long long s_best[8];
+    __shared__ int s_pick[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---------------- pick
+    const BpeCtl cur = *ctl_in;
+    if (cur.done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *ctl_out = cur;
+        return;
     }
     unsigned long long best = 0;
     for (int i = threadIdx.x; i < n_partial; i += blockDim.x) best = partial[i] > best ? partial[i] : best;
@@ -997,28 +966,109 @@ bpe_pick_kernel(const unsigned long long* __restrict__ partial, int n_partial, B
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other > best ? other : best;
     }
-    __shared__ unsigned long long s_best[8];
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    if (lane == 0) s_best[warp] = best;
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_best[w] > best ? s_best[w] : best;
-    const unsigned long long key = best;
-    *work_count = 0;
-    ctl->has_delta = 0;
-    const int count = (int)(key >> 32);
-    if (key == 0 || count < 1 || count < min_frequency || ctl->n_tokens >= vocab_size || ctl->n_merges >= max_merges ||
-        ctl->err) {
-        ctl->done = 1;
-        return;
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_best[w] > best ? s_best[w] : best;
+        const int count = (int)(best >> 32);
+        const bool stop = best == 0 || count < 1 || count < min_frequency || cur.n_tokens >= vocab_size ||
+                          cur.n_merges >= max_merges || cur.err;
+        BpeCtl next = cur;
+        next.has_delta = 0;
+        if (stop) next.done = 1;
+        else {
+            const unsigned int flat = 0xffffffffu - (unsigned int)(best & 0xffffffffu);
+            next.a = (int)(flat / (unsigned int)V);
+            next.b = (int)(flat % (unsigned int)V);
+            next.c = cur.n_tokens;
+            next.count = count;
+            next.n_tokens = cur.n_tokens + 1;
+            next.n_merges = cur.n_merges + 1;
+            next.has_delta = 1;
+        }
+        s_pick[0] = next.a; s_pick[1] = next.b; s_pick[2] = next.c; s_pick[3] = stop ? 1 : 0;
+        if (blockIdx.x == 0) {
+            *ctl_out = next;
+            if (!stop) {
+                int* e = log + 4 * cur.n_merges;
+                e[0] = next.a; e[1] = next.b; e[2] = next.c; e[3] = count;
+            }
+        }
     }
-    const unsigned int flat = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
-    ctl->a = (int)(flat / (unsigned int)V);
-    ctl->b = (int)(flat % (unsigned int)V);
-    ctl->c = ctl->n_tokens++;
-    ctl->count = count;
-    ctl->has_delta = 1;
-    int* e = log + 4 * ctl->n_merges++;
-    e[0] = ctl->a; e[1] = ctl->b; e[2] = ctl->c; e[3] = count;
+    __syncthreads();
+    if (s_pick[3]) return;
+    const int a = s_pick[0], b = s_pick[1], c = s_pick[2];
+    int* delta = delta_base + (cur.n_merges & 1) * 4 * V;     // double-buffered by merge parity (peers still read the other half)
+    // ---------------- scan + rewrite, tile by tile
+    const unsigned int sh = sig_hash((unsigned int)a, (unsigned int)b), sh2 = sig_hash2((unsigned int)a, (unsigned int)b);
+    const unsigned int* sig_col = sig ? sig + (long long)(sh >> 5) * n_stride : nullptr;
+    const unsigned int* sig_col2 = sig ? sig + (long long)(sh2 >> 5) * n_stride : nullptr;
+    const unsigned int sig_bit = 1u << (sh & 31u), sig_bit2 = 1u << (sh2 & 31u);
+    const uint4* sym4 = (const uint4*)sym;
+    bool used_smem = false;
+    for (long long tile = (long long)blockIdx.x * tile_size; tile < N; tile += (long long)gridDim.x * tile_size) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        // all signature words of the tile first (up to 16 loads in flight per thread), then the ballots
+        unsigned int pass_bits = 0;
+#pragma unroll
+        for (int r = 0; r < kScanTile / 256; ++r) {
+            const int k = threadIdx.x + r * 256;
+            const long long seq = tile + k;
+            if (k < tile_size && seq < N &&
+                (!sig_col || ((__ldg(sig_col + seq) & sig_bit) && (__ldg(sig_col2 + seq) & sig_bit2))))
+                pass_bits |= 1u << r;
+        }
+        for (int r = 0; r * 256 < tile_size; ++r) {
+            const int k = threadIdx.x + r * 256;
+            const bool pass = (pass_bits >> r) & 1u;
+            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+            }
+        }
+        __syncthreads();
+        const int n_pass = s_n;
+        const bool dense = n_pass > kDenseTile;
+        if (dense && !used_smem) {                            // block-uniform: n_pass is shared
+            zero_delta_block(s_delta, V);
+            used_smem = true;
+            __syncthreads();
+        }
+        int* target = dense ? s_delta : delta;
+        for (int i0 = threadIdx.x & ~31; i0 < n_pass; i0 += blockDim.x) {
+            const int i = i0 + lane;
+            const bool valid = i < n_pass;
+            const long long my_seq = valid ? tile + s_list[i] : 0;
+            const int my_n = valid ? len[my_seq] : 0;
+            const int my_w = (valid && weight) ? weight[my_seq] : 1;
+            const int my_q0 = find_first_pair(sym4, n_stride, my_seq, valid, my_n, a, b, DEEP);
+            unsigned int hits = __ballot_sync(0xffffffffu, my_q0 >= 0);
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const long long seq = __shfl_sync(0xffffffffu, my_seq, k);
+                const int q0 = __shfl_sync(0xffffffffu, my_q0, k), n = __shfl_sync(0xffffffffu, my_n, k);
+                const int wgt = __shfl_sync(0xffffffffu, my_w, k);
+                if (hits) {                                   // pull the next hit's chunks towards L1 meanwhile
+                    const int k2 = __ffs(hits) - 1;
+                    const long long seq2 = __shfl_sync(0xffffffffu, my_seq, k2);
+                    const int ci2 = (__shfl_sync(0xffffffffu, my_q0, k2) >> 3) + lane;
+                    const int nch2 = (__shfl_sync(0xffffffffu, my_n, k2) + kChunk - 1) >> 3;
+                    if (ci2 < nch2) asm volatile("prefetch.global.L1 [%0];" ::"l"(&sym4[(long long)ci2 * n_stride + seq2]));
+                }
+                const int chunks_left = ((n + kChunk - 1) >> 3) - (q0 >> 3);
+                if (chunks_left <= 32) rewrite_sequence_warp(sym, len, seq, q0, n, n_stride, a, b, c, V, target, sig, s_out[warp], wgt);
+                else if (lane == 0) rewrite_sequence(sym, len, seq, q0, n_stride, a, b, c, V, target, sig, wgt);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    if (used_smem) flush_delta_block(s_delta, delta, V);
 }
 
 // hist += delta (after the optional cross-GPU sum), then the merged pair is gone for good.
@@ -1638,8 +1688,8 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
     cudaError_t e = cudaMemsetAsync(work_count, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     const int grid = merge_grid(N);
-    bpe_scan_kernel<false><<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, nullptr, work_count, work_seq, work_q0, nullptr, 0);
-    bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta,
+    bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, work_count, work_seq, work_q0);
+    bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, work_count, work_seq, work_q0, delta,
                                                 nullptr, weight);
     count_launch(2);
     BEAST_CHECK_LAUNCH();
@@ -1669,21 +1719,29 @@ extern "C" int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int
     return BEAST_OK;
 }
 
-// `iters` iterations of the sync-free training loop, each: iterate (arg-max + fold of the previous merge's delta,
-// summed over the peers' blocks when sharded) -> pick (stop rules, next id, log) -> scan (work list) -> rewrite
-// (fills delta[merge & 1]).  The caller enqueues up to (vocab_size - alphabet) iterations without reading anything
-// back; ctl / log are read once at the end.
+// `iters` iterations of the sync-free training loop, each TWO launches: the iteration head (arg-max + fold of the
+// previous merge's delta, summed over the peers' blocks when sharded) and the fused pick + scan + rewrite (fills
+// delta[merge & 1]).  The control block is double-buffered by iteration parity (first_iter = index of the first
+// iteration of this call): iteration i reads ctl[i & 1] and writes ctl[(i + 1) & 1].  The caller enqueues up to
+// (vocab_size - alphabet) iterations without reading anything back; ctl / log are read once at the end.
+static int merge_smem_attr(size_t smem) {
+    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
+    static size_t granted_deep[kMaxDevices] = {}, granted_flat[kMaxDevices] = {};
+    if (int rc = opt_in_smem(bpe_merge_kernel<true>, smem, granted_deep)) return rc;
+    return opt_in_smem(bpe_merge_kernel<false>, smem, granted_flat);
+}
+
 extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
-                              int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work,
-                              int32_t vocab_size, int32_t min_frequency, int32_t max_merges, uint32_t* sig,
+                              int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t vocab_size,
+                              int32_t min_frequency, int32_t max_merges, uint32_t* sig, int32_t first_iter,
                               int32_t iters, const bpe_peers_t* peers_h, const int32_t* weight, void* stream) {
-    if (!hist || !delta || !ctl || !log || !result || !work) return BEAST_E_NULL;
+    if (!hist || !delta || !ctl || !log || !result) return BEAST_E_NULL;
     if (N > 0 && (!sym || !len)) return BEAST_E_NULL;
-    if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL) return BEAST_E_SHAPE;
-    if ((uintptr_t)delta & 15u) return BEAST_E_ALIGN;
+    if (V < 1 || V > 32767 || (long long)V * V > 0xffffffffLL || first_iter < 0) return BEAST_E_SHAPE;
+    if (((uintptr_t)delta & 15u) || ((uintptr_t)ctl & 15u)) return BEAST_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)4 * V * sizeof(int);
-    int rc = rewrite_smem_attr(smem);
+    int rc = merge_smem_attr(smem);
     if (rc != BEAST_OK) return rc;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -1702,35 +1760,30 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
         if (peers.delta[peers.rank] != delta) return BEAST_E_SHAPE;
     }
     if (peers_h && peers_h->grid_blocks > 0 && peers_h->grid_blocks < n_part) n_part = peers_h->grid_blocks;
-    int* work_count = work;                  // work = {count, pad[3], seq[N], q0[N]}
-    int* work_seq = work + 4;
-    int* work_q0 = work + 4 + N;
     // tile of the signature scan: large enough to fill warps with survivors, small enough to use every SM
     // (a multiple of the block size, so every thread takes part in the ballots)
     long long tile = ((N / ((long long)sms * 2) + 255) / 256) * 256;
     if (tile < 256) tile = 256;
     if (tile > kScanTile) tile = kScanTile;
-    const int grid = merge_grid(N > 0 ? N : 1);
+    long long grid = (N + tile - 1) / tile;
+    if (grid > (long long)sms * 4) grid = (long long)sms * 4;
+    if (grid < 1) grid = 1;
     // small shards are latency-bound (few tiles per SM): walk the survivors with four loads in flight; large
     // ones are better off with two (measured: 65 k sequences 0.056 -> 0.053 s, 1.6 M sequences 0.214 -> 0.228 s)
-    const int deep_walk = N <= (1 << 19) ? 1 : 0;
-    // `iters` iterations back to back (nothing happens between them on the host, sharded or not)
+    const bool deep_walk = N <= (1 << 19);
+    BpeCtl* ctl2 = (BpeCtl*)ctl;
     for (int it = 0; it < (iters < 1 ? 1 : iters); ++it) {
-        bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, (BpeCtl*)ctl, delta, (unsigned long long*)result, peers);
-        bpe_pick_kernel<<<1, 256, 0, st>>>((const unsigned long long*)result, n_part, (BpeCtl*)ctl, log, V, vocab_size,
-                                           min_frequency, max_merges, work_count, delta);
+        const int i = first_iter + it;
+        BpeCtl* cin = ctl2 + (i & 1);
+        BpeCtl* cout = ctl2 + ((i + 1) & 1);
+        bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, cin, delta, (unsigned long long*)result, peers);
+        if (deep_walk)
+            bpe_merge_kernel<true><<<(unsigned)grid, 256, smem, st>>>(sym, len, N, n_stride, V, cin, cout,
+                (const unsigned long long*)result, n_part, log, vocab_size, min_frequency, max_merges, delta, sig, weight, (int)tile);
+        else
+            bpe_merge_kernel<false><<<(unsigned)grid, 256, smem, st>>>(sym, len, N, n_stride, V, cin, cout,
+                (const unsigned long long*)result, n_part, log, vocab_size, min_frequency, max_merges, delta, sig, weight, (int)tile);
         count_launch(2);
-        if (N > 0) {
-            if (deep_walk)
-                bpe_scan_kernel<true><<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count,
-                                                            work_seq, work_q0, sig, (int)tile);
-            else
-                bpe_scan_kernel<false><<<grid, 256, 0, st>>>(sym, len, N, n_stride, 0, 0, (const BpeCtl*)ctl, work_count,
-                                                             work_seq, work_q0, sig, (int)tile);
-            bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, (const BpeCtl*)ctl, work_count,
-                                                        work_seq, work_q0, delta, sig, weight);
-            count_launch(2);
-        }
     }
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
