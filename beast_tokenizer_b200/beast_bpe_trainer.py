@@ -325,7 +325,7 @@ class _FastRun:
                 n = min(n, int(limit))
             _lib.check(eng.lib.bpe_train_step(_lib.ptr(eng.sym), _lib.ptr(eng.len), eng.N, eng.stride, eng.V,
                                               _lib.ptr(eng.hist), _lib.ptr(self.delta), _lib.ptr(self.ctl),
-                                              _lib.ptr(self.log), _lib.ptr(eng.result),
+                                              _lib.ptr(self.log), _lib.ptr(eng.result), _lib.ptr(eng.work),
                                               self.vocab_size, self.min_frequency, self.max_merges,
                                               _lib.ptr(self.sig) if i >= self.SIG_START else None, int(i), int(n),
                                               C.byref(self.peers) if self.peers is not None else None,

@@ -245,20 +245,21 @@ int beast_peer_open(const void* handle_h, void** ptr_out);
 int beast_peer_close(void* ptr);
 int beast_peer_free(void* ptr);
 
-/* Sync-free training loop: one iteration = two launches: (1) iterate: arg-max of the histogram, folding the
- * previous merge's delta (summed over the peers when sharded) on the way, and clearing the delta half of the coming
- * merge; (2) merge: every block picks the merge from the per-block maxima (BpeTrainer's stop rules: vocabulary
- * full / count < min_frequency; next id; block 0 logs it), then scans its tiles of sequences for the pair (signature
- * filter) and rewrites the hits at once, count changes into delta[merge & 1].
+/* Sync-free training loop: one iteration = three launches: (1) iterate: arg-max of the histogram, folding the
+ * previous merge's delta (summed over the peers when sharded) on the way, clearing the delta half of the coming
+ * merge and the work list; (2) pick + scan: every block picks the merge from the per-block maxima (BpeTrainer's stop
+ * rules: vocabulary full / count < min_frequency; next id; block 0 logs it), then scans its tiles of sequences for the
+ * pair (signature filter) into the work list; (3) rewrite: the listed sequences, count changes into delta[merge & 1].
  * ctl: int32 [2][16] device block, double-buffered by iteration parity — iteration i reads ctl[i & 1] = {a, b, c, count,
  * n_tokens, n_merges, done, has_delta, err, ...} and writes ctl[(i + 1) & 1]; the caller sets ctl[0].n_tokens =
  * alphabet size and zeroes the rest; first_iter = index of the first iteration enqueued by this call.
- * delta: int32 [2][4*V] (== peers->delta[peers->rank] when sharded); log: int32 [4 * max_merges] receives (a, b,
- * new_id, count) per merge; result: arg-max scratch, 256 x uint64 (per-block maxima).  Nothing is read back until
- * the end (ctl[(first_iter + iters) & 1]).  iters: iterations enqueued by this call.  peers_h: NULL (or world == 1) =
- * unsharded.  weight: int32 [N] multiplicity of every (pseudo-)sequence, NULL = 1 (see word de-duplication below). */
+ * delta: int32 [2][4*V] (== peers->delta[peers->rank] when sharded); work: int32 [4 + 2*N] scratch; log: int32
+ * [4 * max_merges] receives (a, b, new_id, count) per merge; result: arg-max scratch, 256 x uint64 (per-block maxima).
+ * Nothing is read back until the end (ctl[(first_iter + iters) & 1]).  iters: iterations enqueued by this call.
+ * peers_h: NULL (or world == 1) = unsharded.  weight: int32 [N] multiplicity of every (pseudo-)sequence, NULL = 1
+ * (see word de-duplication below). */
 int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int32_t V, int32_t* hist,
-                   int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t vocab_size,
+                   int32_t* delta, void* ctl, int32_t* log, uint64_t* result, int32_t* work, int32_t vocab_size,
                    int32_t min_frequency, int32_t max_merges, uint32_t* sig, int32_t first_iter, int32_t iters,
                    const bpe_peers_t* peers_h, const int32_t* weight, void* stream);
 
