@@ -55,6 +55,16 @@ class _Plan:
             _lib.check(lib.beast_plan_create(C.byref(desc), C.byref(handle)), "beast_plan_create")
         self.handle = handle
         self._lib = lib
+        self._workspaces = {}
+
+    def minmax_workspace(self) -> torch.Tensor:
+        """Zero-initialised scratch of beast_fit_minmax_ws_f32, one per (plan, stream)."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._workspaces.get(key)
+        if ws is None:
+            n = int(self._lib.beast_fit_minmax_workspace_bytes(self.handle)) // 4
+            ws = self._workspaces[key] = torch.zeros(max(n, 1), device=self.device, dtype=torch.float32)
+        return ws
 
     def __del__(self):
         try:
@@ -309,29 +319,36 @@ class BEASTBsplineTokenizer(TokenizerBase):
         # batch, so small loader batches (32 in the reference's training script) are gathered on the device and
         # fitted ~4 096 at a time: one K1 launch per chunk instead of one per batch.
         dev = self._cuda()
-        pending, pending_rows = [], 0
+        pending, pending_rows, pending_key = [], 0, None
+        T, D, gatherable = self.times.numel(), self.num_dof, not self._has_conditions
 
         def flush():
             nonlocal pending_rows
             if pending:
-                params.append(self.compute_weights(pending[0] if len(pending) == 1 else torch.cat(pending, dim=0)))
+                x = pending[0] if len(pending) == 1 else torch.cat(pending, dim=0)     # one copy kernel / memcpy pass
+                params.append(self.compute_weights(x[..., :D] if x.shape[2] != D else x))
                 pending.clear()
                 pending_rows = 0
 
+        # the per-batch work is a handful of Python operations (the loader's 3 125 batches of 32 are otherwise bound
+        # by ~3 us of tensor-op dispatch each); conversion, slicing and the upload happen once per ~4 096 rows
         for batch in iterator:
-            if "actions" not in batch:
-                raise KeyError("Expected batch to contain an 'actions' entry.")
-            act_chunks = batch["actions"][..., : self.num_dof]
-            gather = (torch.is_tensor(act_chunks) and act_chunks.dim() == 3 and act_chunks.shape[1] == self.times.numel()
-                      and act_chunks.shape[2] == self.num_dof and not self._has_conditions)
-            if gather:
-                pending.append(act_chunks.to(dev, torch.float32))
-                pending_rows += act_chunks.shape[0]
+            try:
+                x = batch["actions"]
+            except KeyError:
+                raise KeyError("Expected batch to contain an 'actions' entry.") from None
+            if gatherable and type(x) is torch.Tensor and x.dim() == 3 and x.shape[1] == T and x.shape[2] >= D:
+                key = (x.device, x.dtype, x.shape[2])
+                if key != pending_key:
+                    flush()
+                    pending_key = key
+                pending.append(x)
+                pending_rows += x.shape[0]
                 if pending_rows >= 4096:
                     flush()
             else:                                   # odd shapes raise here, as they would per batch; boundary-condition
                 flush()                             # tokenizers keep the reference's "state of the last batch" semantics
-                params.append(self.compute_weights(act_chunks))
+                params.append(self.compute_weights(x[..., : self.num_dof]))
             sample_count += 1
             if sample_count >= sample_limit:
                 if verbose:
@@ -457,15 +474,21 @@ class BEASTBsplineTokenizer(TokenizerBase):
         dev = plan.device
         x = self._prep_trajs(demos, dev)
         n = self.num_dof * self.num_basis
-        lo = torch.empty(n, device=dev, dtype=torch.float32)
-        hi = torch.empty(n, device=dev, dtype=torch.float32)
+        # one launch, results written straight into the w_min / w_max buffers when they live on this device
+        direct = (self.w_min.device == dev and self.w_max.device == dev and self.w_min.dtype == torch.float32
+                  and self.w_max.dtype == torch.float32 and self.w_min.is_contiguous() and self.w_max.is_contiguous())
+        lo = self.w_min if direct else torch.empty(n, device=dev, dtype=torch.float32)
+        hi = self.w_max if direct else torch.empty(n, device=dev, dtype=torch.float32)
+        ws = plan.minmax_workspace()
         with torch.cuda.device(dev):
-            _lib.check(plan._lib.beast_fit_minmax_f32(plan.handle, _lib.ptr(x), x.shape[0], _lib.ptr(lo), _lib.ptr(hi), 0,
-                                                      _lib.stream_ptr(dev)), "beast_fit_minmax_f32")
+            _lib.check(plan._lib.beast_fit_minmax_ws_f32(plan.handle, _lib.ptr(x), x.shape[0], _lib.ptr(lo), _lib.ptr(hi), 0,
+                                                         _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr(dev)),
+                       "beast_fit_minmax_ws_f32")
         self._remember_boundary(x, plan)
         _dist.allreduce_minmax(lo, hi, self._group(process_group), implicit=False)
-        self.w_min.copy_(lo.to(self.w_min.device))
-        self.w_max.copy_(hi.to(self.w_max.device))
+        if not direct:
+            self.w_min.copy_(lo.to(self.w_min.device))
+            self.w_max.copy_(hi.to(self.w_max.device))
 
     def _minmax(self, weights):
         dev = weights.device

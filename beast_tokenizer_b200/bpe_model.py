@@ -74,6 +74,48 @@ def utf8_len(max_shift: int) -> int:
     return 1 if max_shift < 0x80 else 2 if max_shift < 0x800 else 3
 
 
+def token_char_entry(tb: bytes):
+    """One row of the decode kernel's per-token character table (csrc/bpe.cu: bpe_decode_warp_kernel fast path): what
+    the sequential UTF-8 state machine of A.6 does with this token's bytes, precomputed.  Returns 4 x uint32:
+    x, y, z = six 16-bit slots with the token's characters in order (the last one = the partial accumulator when the
+    token ends inside a character); w = characters started | bytes still needed << 3 | leading continuation bytes << 5
+    | slow << 7 | payload of the leading continuation bytes << 8.  slow = the token cannot be described this way (more
+    than 6 characters or 3 leading continuation bytes, an invalid or 4-byte lead, a stray continuation byte): sequences
+    holding it decode on the byte-level path, which also reports the reference's errors."""
+    SLOW = (0, 0, 0, 0x80)
+    i, lead_cont, lead_bits = 0, 0, 0
+    while i < len(tb) and (tb[i] & 0xC0) == 0x80:
+        lead_bits = (lead_bits << 6) | (tb[i] & 0x3F)
+        lead_cont += 1
+        i += 1
+    if lead_cont > 3:
+        return SLOW
+    cps, pending, acc = [], 0, 0
+    for b in tb[i:]:
+        if pending:
+            if (b & 0xC0) != 0x80:
+                return SLOW
+            acc = (acc << 6) | (b & 0x3F)
+            pending -= 1
+            if pending == 0:
+                cps.append(acc)
+        elif b < 0x80:
+            cps.append(b)
+        elif (b & 0xE0) == 0xC0:
+            acc, pending = b & 0x1F, 1
+        elif (b & 0xF0) == 0xE0:
+            acc, pending = b & 0x0F, 2
+        else:                      # 4-byte leads decode above U+FFFF (never a shifted bin), 0xF8.. and stray
+            return SLOW            # continuation bytes are invalid: the byte-level path reports them
+    if pending:
+        cps.append(acc)
+    if len(cps) > 6 or any(c > 0xFFFF for c in cps):
+        return SLOW
+    slots = cps + [0] * (6 - len(cps))
+    meta = len(cps) | (pending << 3) | (lead_cont << 5) | (lead_bits << 8)
+    return (slots[0] | (slots[1] << 16), slots[2] | (slots[3] << 16), slots[4] | (slots[5] << 16), meta)
+
+
 class Encoding:
     """Minimal stand-in for tokenizers.Encoding (only `.ids` is used by the reference)."""
 
@@ -222,8 +264,10 @@ class B200ByteLevelBPE:
             chunks.append(tb)
             off[i + 1] = off[i] + len(tb)
         blob = np.frombuffer(b"".join(chunks) or b"\x00", dtype=np.uint8).copy()
+        tab = np.stack([token_char_entry(tb) for tb in chunks]).astype(np.uint32)
         t = dict(V=V, b2i=torch.from_numpy(b2i).to(dev), rank=torch.from_numpy(rank.view(np.int32)).to(dev),
-                 off=torch.from_numpy(off).to(dev), blob=torch.from_numpy(blob).to(dev))
+                 off=torch.from_numpy(off).to(dev), blob=torch.from_numpy(blob).to(dev),
+                 tab=torch.from_numpy(tab.view(np.int32)).to(dev))
         self._dev_tables[key] = t
         return t
 
@@ -287,8 +331,8 @@ class B200ByteLevelBPE:
         declen = torch.empty(N, device=dev, dtype=torch.int32)
         with torch.cuda.device(dev):
             _lib.check(lib.bpe_decode(_lib.ptr(flat), _lib.ptr(offsets), N, L, int(min_token), _lib.ptr(t["off"]),
-                                      _lib.ptr(t["blob"]), t["V"], _lib.ptr(bins), _lib.ptr(status), _lib.ptr(declen),
-                                      _lib.stream_ptr(dev)), "bpe_decode")
+                                      _lib.ptr(t["blob"]), _lib.ptr(t["tab"]), t["V"], _lib.ptr(bins), _lib.ptr(status),
+                                      _lib.ptr(declen), _lib.stream_ptr(dev)), "bpe_decode")
         return bins, status, declen
 
     # ------------------------------------------------------------------ HF-shaped convenience (single strings, on the GPU)

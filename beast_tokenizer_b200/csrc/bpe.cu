@@ -1431,8 +1431,8 @@ __device__ __forceinline__ int utf8_lead_len(int b) {
 __global__ void __launch_bounds__(256)
 bpe_decode_warp_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
                        long long min_token, const int* __restrict__ tok_off, const uint8_t* __restrict__ tok_bytes,
-                       int n_vocab, long long* __restrict__ bins_out, int* __restrict__ status_out,
-                       int* __restrict__ declen_out, int cap, int warp_bytes) {
+                       const uint4* __restrict__ tok_tab, int n_vocab, long long* __restrict__ bins_out,
+                       int* __restrict__ status_out, int* __restrict__ declen_out, int cap, int warp_bytes) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint8_t* s_b = s_raw + (size_t)warp * warp_bytes;
@@ -1440,6 +1440,71 @@ bpe_decode_warp_kernel(const int* __restrict__ flat, const long long* __restrict
     const unsigned int FULL = 0xffffffffu, lt = (1u << lane) - 1u;
     for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
         const long long p0 = offsets[seq], p1 = offsets[seq + 1];
+        if (tok_tab) {
+            // ---- fast path: one lane per TOKEN.  The table holds, per token, its complete characters (<= 6
+            // codepoints), the continuation bytes it starts with (they finish the previous token's last
+            // character) and how many its own last character still needs.  A sequence decodes here when every
+            // id is in range, no token is flagged slow and every boundary matches (needed == supplied); the
+            // character index of a token is a prefix sum of the tokens' character counts.  Anything else —
+            // stray / missing continuation bytes, ids out of range, long tokens — falls through to the
+            // byte-level path below, which also decides WHICH error the sequence has.
+            bool bad = false;
+            int cnt_f = 0;
+            uint4 cur = make_uint4(0u, 0u, 0u, 0x80u);
+            if (p0 + lane < p1) {
+                const int id = flat[p0 + lane];
+                if (id >= 0 && id < n_vocab) cur = __ldg(tok_tab + id);
+            }
+            if (p1 > p0 && __shfl_sync(FULL, (cur.w >> 5) & 3u, 0) != 0u) bad = true;   // text starts inside a character
+            for (long long q0 = p0; q0 < p1; q0 += 32) {
+                const bool have = q0 + lane < p1;
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);                 // beyond the end: supplies nothing, needs nothing
+                if (q0 + 32 + lane < p1) {
+                    nxt.w = 0x80u;
+                    const int id = flat[q0 + 32 + lane];
+                    if (id >= 0 && id < n_vocab) nxt = __ldg(tok_tab + id);
+                }
+                const unsigned int meta = have ? cur.w : 0u;
+                unsigned int nmeta = __shfl_down_sync(FULL, meta, 1);
+                const unsigned int nmeta0 = __shfl_sync(FULL, nxt.w, 0);
+                if (lane == 31) nmeta = nmeta0;
+                const int nst = (int)(meta & 7u), need = (int)((meta >> 3) & 3u);
+                if ((meta & 0x80u) || need != (int)((nmeta >> 5) & 3u)) bad = true;
+                int inc = nst;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const int at = cnt_f + inc - nst;
+                const unsigned int c[6] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16, cur.z & 0xffffu, cur.z >> 16};
+                const unsigned int tail = ((nmeta >> 8) & 0x3ffffu);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if (k < nst && at + k < L) {
+                        unsigned int v = c[k];
+                        if (k == nst - 1 && need) v = (v << (6 * need)) | tail;
+                        s_cp[at + k] = (uint16_t)v;
+                    }
+                }
+                cnt_f += __shfl_sync(FULL, inc, 31);
+                cur = nxt;
+            }
+            if (!__any_sync(FULL, bad)) {
+                __syncwarp();
+                if (lane == 0) { status_out[seq] = cnt_f != L ? 3 : 0; declen_out[seq] = cnt_f; }
+                long long* out = bins_out + seq * L;
+                if ((L & 1) == 0 && (((uintptr_t)out) & 15u) == 0) {
+                    for (int i = 2 * lane; i < L; i += 64)
+                        *(longlong2*)(out + i) = make_longlong2((long long)s_cp[i] + min_token, (long long)s_cp[i + 1] + min_token);
+                } else {
+                    for (int i = lane; i < L; i += 32) out[i] = (long long)s_cp[i] + min_token;
+                }
+                __syncwarp();
+                continue;
+            }
+            __syncwarp();
+        }
         int B = 0, status = 0, cnt = 0;
         bool bad_tok = false, overflow = false;
         for (long long q0 = p0; q0 < p1; q0 += 32) {
@@ -1885,11 +1950,12 @@ extern "C" int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int
 }
 
 extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,
-                          const int32_t* tok_off, const uint8_t* tok_bytes, int32_t n_vocab, int64_t* bins_out,
-                          int32_t* status_out, int32_t* declen_out, void* stream) {
+                          const int32_t* tok_off, const uint8_t* tok_bytes, const void* tok_tab, int32_t n_vocab,
+                          int64_t* bins_out, int32_t* status_out, int32_t* declen_out, void* stream) {
     if (N == 0) return BEAST_OK;
     if (!offsets || !tok_off || !tok_bytes || !bins_out || !status_out || !declen_out) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_vocab < 1) return BEAST_E_SHAPE;
+    if ((uintptr_t)tok_tab & 15u) return BEAST_E_ALIGN;
     {   // one warp per sequence; BEAST_B200_BPE_THREAD_DECODE=1 (or rows too long for shared memory) takes the
         // one-thread-per-sequence kernel
         const int cap = 4 * L + 64;                          // a valid sequence has at most 3 L bytes
@@ -1910,8 +1976,8 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
             long long grid = (N + warps - 1) / warps;
             if (grid > sms * per_sm) grid = sms * per_sm;
             bpe_decode_warp_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
-                flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out,
-                status_out, declen_out, cap, (int)warp_bytes);
+                flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, (const uint4*)tok_tab, n_vocab,
+                (long long*)bins_out, status_out, declen_out, cap, (int)warp_bytes);
             count_launch();
             BEAST_CHECK_LAUNCH();
             return BEAST_OK;

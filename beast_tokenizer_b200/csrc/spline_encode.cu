@@ -52,8 +52,10 @@ struct EncArgs {
     long long* tokens_out;
     const float* w_min;
     const float* w_max;
-    float* bmin;           // optional [D*NB]: column min / max of the coefficients (order-preserving atomics)
+    float* bmin;           // optional [D*NB]: column min / max of the coefficients
     float* bmax;
+    float* mm_ws;          // workspace of the single-launch reduction: [grid][2][D*NB] per-CTA partials + ticket; NULL = atomics
+    int mm_accumulate;     // fold the existing contents of bmin / bmax into the result
     long long offset;
     float vm1;
     int D, n_joint, S, n_tiles;
@@ -221,9 +223,40 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
                 atomic_max_f32(&s_mx[slot * NB + k], tmax[k]);
             }
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(kEncGroups + 1), "r"(kEncGroups * kEncGroupWarps * 32) : "memory");
-        for (int c = tid; c < D * NB; c += kEncGroups * kEncGroupWarps * 32) {
-            if (s_mn[c] <= s_mx[c]) { atomic_min_f32(a.bmin + c, s_mn[c]); atomic_max_f32(a.bmax + c, s_mx[c]); }
+        constexpr int kComputeThreads = kEncGroups * kEncGroupWarps * 32;
+        asm volatile("bar.sync %0, %1;" ::"r"(kEncGroups + 1), "r"(kComputeThreads) : "memory");
+        const int n_col = D * NB;
+        if (a.mm_ws == nullptr) {
+            for (int c = tid; c < n_col; c += kComputeThreads) {
+                if (s_mn[c] <= s_mx[c]) { atomic_min_f32(a.bmin + c, s_mn[c]); atomic_max_f32(a.bmax + c, s_mx[c]); }
+            }
+        } else {
+            // single-launch reduction: every CTA stores its partials, the LAST one to arrive (ticket) combines
+            // them and writes the result with plain stores — no initialisation pass, no float atomics, and the
+            // caller can pass the tokenizer's own w_min / w_max as the destination
+            float* part = a.mm_ws + (size_t)blockIdx.x * 2 * n_col;
+            unsigned int* ticket = (unsigned int*)(a.mm_ws + (size_t)gridDim.x * 2 * n_col);
+            for (int c = tid; c < n_col; c += kComputeThreads) { part[c] = s_mn[c]; part[n_col + c] = s_mx[c]; }
+            __threadfence();
+            asm volatile("bar.sync %0, %1;" ::"r"(kEncGroups + 1), "r"(kComputeThreads) : "memory");
+            __shared__ int s_last;
+            if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+            asm volatile("bar.sync %0, %1;" ::"r"(kEncGroups + 1), "r"(kComputeThreads) : "memory");
+            if (s_last) {
+                __threadfence();
+                for (int c = tid; c < n_col; c += kComputeThreads) {
+                    float mn = a.mm_accumulate ? a.bmin[c] : __int_as_float(0x7f800000);
+                    float mx = a.mm_accumulate ? a.bmax[c] : __int_as_float(0xff800000);
+                    for (unsigned int bk = 0; bk < gridDim.x; ++bk) {
+                        const float* q = a.mm_ws + (size_t)bk * 2 * n_col;
+                        mn = fminf(mn, __ldcg(q + c));
+                        mx = fmaxf(mx, __ldcg(q + n_col + c));
+                    }
+                    a.bmin[c] = mn;
+                    a.bmax[c] = mx;
+                }
+                if (tid == 0) *ticket = 0u;                    // ready for the next launch
+            }
         }
     }
 }
@@ -326,7 +359,7 @@ static bool grip_structure(const float* pg, float* pgv, int* gstart) {
 template <int T, int NB, int DT>
 static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int S, const float* w_min,
                        const float* w_max, long long offset, float* params_out, long long* tokens_out,
-                       float* bmin, float* bmax, cudaStream_t st) {
+                       float* bmin, float* bmax, float* mm_ws, int mm_accumulate, cudaStream_t st) {
     EncTables<T, NB> tab;
     constexpr int NBP = EncTables<T, NB>::NBP;
     for (int t = 0; t < T; ++t)
@@ -340,6 +373,7 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
     EncArgs a;
     a.traj = traj; a.params_out = params_out; a.tokens_out = tokens_out;
     a.w_min = w_min; a.w_max = w_max; a.bmin = bmin; a.bmax = bmax; a.offset = offset; a.vm1 = (float)(p->V - 1);
+    a.mm_ws = mm_ws; a.mm_accumulate = mm_accumulate;
     a.D = p->D; a.n_joint = p->n_joint; a.S = S; a.n_tiles = (int)n_tiles;
     for (int i = 0; i < BEAST_MAX_SLOTS; ++i) a.slot_to_dof[i] = i < p->D ? p->slot_to_dof[i] : 0;
     // outputs (12 B * NB per column) alias the 4*T B per column input tile
@@ -359,7 +393,7 @@ static int launch_fast(const Plan* p, const float* traj, long long n_tiles, int 
 // Shared body of beast_encode_f32 / beast_fit_minmax_f32.
 static int encode_impl(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
                        long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* mm_ws = nullptr, int mm_accumulate = 1, bool* fast_ran = nullptr) {
     const int T = p->T, D = p->D, nb = p->nb;
     long long done = 0;
     if (T == 50 && nb == 10 && !fast_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
@@ -369,12 +403,12 @@ static int encode_impl(const Plan* p, const float* traj, long long B, const floa
             const long long n_tiles = B / S;
             int rc;
             if (D == 14)
-                rc = launch_fast<50, 10, 14>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
+                rc = launch_fast<50, 10, 14>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, mm_ws, mm_accumulate, st);
             else if (D == 7)
-                rc = launch_fast<50, 10, 7>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
+                rc = launch_fast<50, 10, 7>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, mm_ws, mm_accumulate, st);
             else
-                rc = launch_fast<50, 10, 0>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
-            if (rc == BEAST_OK) done = n_tiles * S;
+                rc = launch_fast<50, 10, 0>(p, traj, n_tiles, S, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, mm_ws, mm_accumulate, st);
+            if (rc == BEAST_OK) { done = n_tiles * S; if (fast_ran) *fast_ran = true; }
             else if (rc != BEAST_E_UNSUPPORTED) return rc;
         }
     }
@@ -416,20 +450,51 @@ extern "C" int beast_encode_f32(const beast_plan_t* plan, const float* traj, int
 
 extern "C" int beast_fit_minmax_f32(const beast_plan_t* plan, const float* traj, int64_t B, float* min_out,
                                     float* max_out, int32_t accumulate, void* stream) {
+    return beast_fit_minmax_ws_f32(plan, traj, B, min_out, max_out, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int64_t beast_fit_minmax_workspace_bytes(const beast_plan_t* plan) {
+    const Plan* p = (const Plan*)plan;
+    if (!p) return 0;
+    return ((int64_t)p->num_sms * 2 * p->D * p->nb + 4) * (int64_t)sizeof(float);
+}
+
+extern "C" int beast_fit_minmax_ws_f32(const beast_plan_t* plan, const float* traj, int64_t B, float* min_out,
+                                       float* max_out, int32_t accumulate, void* workspace, int64_t workspace_bytes,
+                                       void* stream) {
     const Plan* p = (const Plan*)plan;
     if (!p || !min_out || !max_out) return BEAST_E_NULL;
     if (B < 0) return BEAST_E_SHAPE;
+    if (B > 0 && !traj) return BEAST_E_NULL;
+    if ((uintptr_t)traj & 3u) return BEAST_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = p->D * p->nb;
-    if (!accumulate) {
-        bounds_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(min_out, max_out, n);
-        count_launch();
-        BEAST_CHECK_LAUNCH();
+    float* ws = (workspace && workspace_bytes >= beast_fit_minmax_workspace_bytes(plan) && !((uintptr_t)workspace & 3u))
+                    ? (float*)workspace : nullptr;
+    // With a workspace the tiled kernel reduces in ONE launch (its last CTA combines the per-CTA partials and writes
+    // min_out / max_out with plain stores, folding the previous contents in when accumulate != 0); the ragged tail
+    // then accumulates with atomics.  Without one (or when no full tile exists) the outputs are initialised first.
+    const int S = (kEncColumns / p->D) & ~3;
+    const bool tiled = ws && p->T == 50 && p->nb == 10 && !fast_disabled() && S >= 4 && B >= S && aligned16(traj);
+    if (!tiled) {
+        if (!accumulate) {
+            bounds_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(min_out, max_out, n);
+            count_launch();
+            BEAST_CHECK_LAUNCH();
+        }
+        if (B == 0) return BEAST_OK;
+        return encode_impl(p, traj, B, nullptr, nullptr, 0, nullptr, nullptr, min_out, max_out, st);
     }
-    if (B == 0) return BEAST_OK;
-    if (!traj) return BEAST_E_NULL;
-    if ((uintptr_t)traj & 3u) return BEAST_E_ALIGN;
-    return encode_impl(p, traj, B, nullptr, nullptr, 0, nullptr, nullptr, min_out, max_out, st);
+    bool fast_ran = false;
+    const long long n_full = (B / S) * S;
+    int rc = encode_impl(p, traj, n_full, nullptr, nullptr, 0, nullptr, nullptr, min_out, max_out, st, ws, accumulate ? 1 : 0,
+                         &fast_ran);
+    if (rc != BEAST_OK) return rc;
+    if (!fast_ran) return BEAST_E_UNSUPPORTED;
+    if (n_full < B)
+        rc = encode_impl(p, traj + n_full * (long long)p->T * p->D, B - n_full, nullptr, nullptr, 0, nullptr, nullptr, min_out,
+                         max_out, st);
+    return rc;
 }
 
 extern "C" int beast_quantize_f32(const beast_plan_t* plan, const float* params, int64_t B, const float* w_min,

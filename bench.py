@@ -523,6 +523,108 @@ def bounds_leg(tok, dev, with_cpu=False):
     return out
 
 
+def shipped_shape_leg(dev, with_cpu):
+    """The reference's own shipped configuration (train.sh / train/train_beast.py:34-36): 50 basis functions, degree 0,
+    1000 bins, actions [10, 32] — 1600 tokens per trajectory; write-bound: 1 280 B read, 12 800 B of int64 tokens +
+    6 400 B of coefficients written per trajectory on encode, the reverse on decode."""
+    import torch
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    from beast_tokenizer_b200.synth import synth, synth_device
+    Ts, Ds, NBs, Vs = 10, 32, 50, 1000
+    tok = BEASTBsplineTokenizer(num_dof=Ds, num_basis=NBs, seq_len=Ts, vocab_size=Vs, degree_p=0, device=str(dev))
+    n = 32768
+    x = synth_device(n, Ts, Ds, 11, dev)
+    tok.update_weights_bounds(x)
+    tokens, _ = tok.encode(x)
+    rec = tok.reconstruct_traj(tokens)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps = 10
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        tokens, _ = tok.encode(x)
+    ev[1].record()
+    for _ in range(reps):
+        rec = tok.reconstruct_traj(tokens)
+    ev[2].record()
+    torch.cuda.synchronize()
+    enc_ms, dec_ms = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+    enc_bytes = 4 * Ts * Ds + 8 * NBs * Ds + 4 * NBs * Ds
+    dec_bytes = 8 * NBs * Ds + 4 * Ts * Ds
+    peak, _ = measured_peak()
+    out = {"workload": f"num_dof=32 num_basis=50 seq_len=10 vocab=1000 degree_p=0 (reference train.sh), batch {n}, device-resident, "
+                       "through BEASTBsplineTokenizer.encode / reconstruct_traj (allocations included)",
+           "encode": {"ms": enc_ms, "traj_per_s": n / (enc_ms * 1e-3), "bytes_per_traj": enc_bytes,
+                      "GBps": enc_bytes * n / (enc_ms * 1e-3) / 1e9, "frac_of_measured_hbm": enc_bytes * n / (enc_ms * 1e-3) / 1e9 / peak},
+           "reconstruct_traj": {"ms": dec_ms, "traj_per_s": n / (dec_ms * 1e-3), "bytes_per_traj": dec_bytes,
+                                "GBps": dec_bytes * n / (dec_ms * 1e-3) / 1e9,
+                                "frac_of_measured_hbm": dec_bytes * n / (dec_ms * 1e-3) / 1e9 / peak},
+           "max_abs_reconstruction_error": float((rec - x).abs().max().item())}
+    if with_cpu:
+        from oracle.reference_port_torch import ReferencePort
+        use_all_host_threads()
+        port = ReferencePort(num_dof=Ds, num_basis=NBs, seq_len=Ts, vocab_size=Vs, degree_p=0)
+        port.w_min, port.w_max = tok.w_min.cpu(), tok.w_max.cpu()
+        xs = synth(32, Ts, Ds, seed=12)
+        t0 = time.perf_counter()
+        tk, _ = port.encode(xs)
+        t1 = time.perf_counter()
+        port.reconstruct_traj(tk)
+        t2 = time.perf_counter()
+        mine, _ = tok.encode(xs)
+        out["cpu_reference"] = {"kind": "port", "batch": 32, "encode_traj_per_s": 32 / (t1 - t0), "reconstruct_traj_per_s": 32 / (t2 - t1),
+                                "cores": cpu_threads(), "tokens_equal_fraction": float((mine.cpu() == tk).float().mean().item()),
+                                "note": "one loader batch of 32: the reference solves one 1600 x 1600 system per trajectory"}
+    return out
+
+
+def cfg1_latency_leg(dev, with_cpu):
+    """BASELINE configs[0]: num_dof=7, 32 trajectories — per-call latency of encode + reconstruct_traj through the
+    public API (host tensor in, host tensor out, synchronised), next to the reference's CPU path."""
+    import torch
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer
+    from beast_tokenizer_b200.synth import synth
+    tok = BEASTBsplineTokenizer(num_dof=7, num_basis=10, seq_len=50, vocab_size=256, gripper_indices=[6], device=str(dev))
+    x = synth(32, 50, 7, seed=0)
+
+    def call():
+        tokens, _ = tok.encode(x)
+        return tok.reconstruct_traj(tokens).cpu()
+
+    for _ in range(5):
+        call()
+    torch.cuda.synchronize()
+    reps = 200
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        call()
+    us = 1e6 * (time.perf_counter() - t0) / reps
+    xd = x.to(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        tokens, _ = tok.encode(xd)
+        tok.reconstruct_traj(tokens)
+    ev1.record()
+    torch.cuda.synchronize()
+    out = {"workload": "num_dof=7 num_basis=10 seq_len=50 vocab=256 gripper_indices=[6], batch 32, encode + reconstruct_traj",
+           "api_host_to_host_us_per_call": us, "traj_per_s": 32 / (us * 1e-6),
+           "device_resident_us_per_call": 1e3 * ev0.elapsed_time(ev1) / reps}
+    if with_cpu:
+        from oracle.reference_port_torch import ReferencePort
+        use_all_host_threads()
+        port = ReferencePort(num_dof=7, num_basis=10, seq_len=50, vocab_size=256, degree_p=4, gripper_indices=[6])
+        port_step(port, x)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            port_step(port, x)
+        cpu_us = 1e6 * (time.perf_counter() - t0) / 20
+        out["cpu_reference"] = {"kind": "port", "us_per_call": cpu_us, "traj_per_s": 32 / (cpu_us * 1e-6), "cores": cpu_threads()}
+        out["speedup_per_call"] = cpu_us / us
+    return out
+
+
 def synth_bins_sample(tok, dev):
     from beast_tokenizer_b200.synth import synth_device
     return tok.encode(synth_device(BPE_CPU_SAMPLE, T, D, 1000, dev), respect_llm_vocab_size=False)[0]
@@ -609,8 +711,20 @@ def main():
         dec((j + 2) % R)
         ev[j][2].record()
     torch.cuda.synchronize()
-    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    dec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    enc_alt_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    dec_alt_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    # ... and K launches of ONE kernel back to back between two events (rotating buffer sets, no event record between
+    # the launches): the kernel's average launch duration without the two event records that bracket every launch above
+    e3 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e3[0].record()
+    for j in range(K):
+        enc(j % R)
+    e3[1].record()
+    for j in range(K):
+        dec(j % R)
+    e3[2].record()
+    torch.cuda.synchronize()
+    enc_ms, dec_ms = e3[0].elapsed_time(e3[1]) / K, e3[1].elapsed_time(e3[2]) / K
 
     # (b) throughput: exactly K steps back to back, captured once into a CUDA graph (the launches are
     # the same C-ABI calls; the graph only removes the host launch gap between 60 us kernels)
@@ -723,6 +837,10 @@ def main():
     sampler.join(timeout=1.0)
 
     bounds = bounds_leg(tok, dev, with_cpu=world == 1 and not args.no_cpu_baseline) if rank == 0 else None
+    shipped = cfg1 = None
+    if rank == 0 and world == 1:
+        shipped = shipped_shape_leg(dev, with_cpu=not args.no_cpu_baseline)
+        cfg1 = cfg1_latency_leg(dev, with_cpu=not args.no_cpu_baseline)
     bpe_train = bpe_apply = None
     if not args.no_bpe:
         del xs, toks, pars, outs, xh
@@ -731,9 +849,9 @@ def main():
                                         cpu_full=not args.no_bpe_cpu_full)
 
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms, copy_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_ms, enc_ms, dec_ms, copy_ms, enc_alt_ms, dec_alt_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, enc_ms, dec_ms, copy_ms = [float(v) for v in t.tolist()]
+        ms_total, e2e_ms, enc_ms, dec_ms, copy_ms, enc_alt_ms, dec_alt_ms = [float(v) for v in t.tolist()]
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -758,10 +876,16 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "encode_fast_kernel (K1)", "achieved": enc_gbs, "peak": peak,
                          "unit": "GB/s", "frac": enc_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_launch": ENC_BYTES * B, "ms_per_launch": enc_ms},
+                         "bytes_per_launch": ENC_BYTES * B, "ms_per_launch": enc_ms,
+                         "timing": f"CUDA events around {K} back-to-back launches of this kernel on the launching stream",
+                         "ms_per_launch_alternating": enc_alt_ms, "frac_alternating": ENC_BYTES * B / (enc_alt_ms * 1e-3) / 1e9 / peak,
+                         "alternating": "events around EVERY launch of the K1, K3, K1, ... step sequence (includes two event records per launch)",
+                         "step_frac": (ENC_BYTES + DEC_BYTES) * B / (ms_total / K * 1e-3) / 1e9 / peak},
             "roofline_decode": {"bound": "hbm", "kernel": "decode_fast_kernel (K3)", "achieved": dec_gbs, "peak": peak,
                                 "unit": "GB/s", "frac": dec_gbs / peak, "traffic": None,
-                                "bytes_per_launch": DEC_BYTES * B, "ms_per_launch": dec_ms},
+                                "bytes_per_launch": DEC_BYTES * B, "ms_per_launch": dec_ms,
+                                "ms_per_launch_alternating": dec_alt_ms,
+                                "frac_alternating": DEC_BYTES * B / (dec_alt_ms * 1e-3) / 1e9 / peak},
             "kernel_rates": {"encode_traj_per_s": B / (enc_ms * 1e-3), "decode_traj_per_s": B / (dec_ms * 1e-3)},
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
@@ -774,6 +898,10 @@ def main():
                 pass
         if bounds is not None:
             line["bounds"] = bounds
+        if shipped is not None:
+            line["shipped_shape"] = shipped
+        if cfg1 is not None:
+            line["cfg1_latency"] = cfg1
         if bpe_train is not None:
             line["bpe_train"] = bpe_train
         if bpe_apply is not None:

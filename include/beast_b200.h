@@ -156,6 +156,13 @@ int beast_minmax_f32(const float* x, int64_t rows, int32_t cols,
  * trajectories — K1 without any output but 2 x D*nb floats (2 800 B read per trajectory). */
 int beast_fit_minmax_f32(const beast_plan_t* plan, const float* traj, int64_t B, float* min_out,
                          float* max_out, int32_t accumulate, void* stream);
+/* Same in ONE launch: with a zero-initialised workspace of beast_fit_minmax_workspace_bytes(plan) bytes (per-CTA
+ * partials + a ticket that the kernel resets itself; one workspace per concurrent stream) the last CTA to finish
+ * combines the partials and writes min_out / max_out with plain stores — no initialisation pass, no float atomics; the
+ * destination may be the tokenizer's own w_min / w_max buffers.  workspace == NULL behaves as beast_fit_minmax_f32. */
+int64_t beast_fit_minmax_workspace_bytes(const beast_plan_t* plan);
+int beast_fit_minmax_ws_f32(const beast_plan_t* plan, const float* traj, int64_t B, float* min_out, float* max_out,
+                            int32_t accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* update_weights_bounds_per_batch (:384-389): w_min[i] = bmin[i] where bmin[i] < w_min[i]-hyst,
  * w_max[i] = bmax[i] where bmax[i] > w_max[i]+hyst. */
@@ -205,7 +212,12 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  *                min_token + max_shift (the two range ValueErrors of bpe_tokenizer.py:182-192).
  * bpe_compact    padded rows -> CSR flat int32 (offsets = exclusive scan of len, by the caller).
  * bpe_decode     CSR ids -> bins [N, L] int64 (A.6); status 1 = unknown id, 2 = invalid UTF-8,
- *                3 = decoded length != L (bpe_tokenizer.py:241-244); declen_out = decoded length. */
+ *                3 = decoded length != L (bpe_tokenizer.py:241-244); declen_out = decoded length.
+ *                tok_tab (nullable, 16 bytes per token): the per-token character table of the fast path —
+ *                x, y, z = six 16-bit codepoints (the token's complete characters; the last one holds the partial
+ *                accumulator when it is cut off), w = meta: bits 0-2 characters started, 3-4 continuation bytes the
+ *                last character still needs, 5-6 continuation bytes the token begins with, 7 = not representable
+ *                (take the byte-level path), 8-25 payload of the leading continuation bytes. */
 int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, int64_t* minmax, int32_t* seen,
                   int32_t* err, int32_t phase, void* stream);
 int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
@@ -305,8 +317,8 @@ int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int
 int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int32_t* len, const int64_t* offsets,
                 int64_t N, int32_t* flat, void* stream);
 int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,
-               const int32_t* tok_off, const uint8_t* tok_bytes, int32_t n_vocab, int64_t* bins_out,
-               int32_t* status_out, int32_t* declen_out, void* stream);
+               const int32_t* tok_off, const uint8_t* tok_bytes, const void* tok_tab, int32_t n_vocab,
+               int64_t* bins_out, int32_t* status_out, int32_t* declen_out, void* stream);
 
 /* Device self-test of the exact invariant-divisor division inside K1 / K3 (csrc/common.cuh) against
  * IEEE division: n_divisors random divisors x 2^24 + 2^22 numerators each, and float(tok)/(V-1)

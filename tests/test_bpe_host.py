@@ -360,3 +360,88 @@ def test_parallel_utf8_decode_rules_match_the_state_machine():
         assert s1 == s2, (bs, L, s1, s2)
         if s1 in (0, 3):
             assert c1 == c2 and o1 == o2, (bs, L)
+
+
+def test_token_character_table_matches_the_state_machine():
+    """The decode kernel's fast path (csrc/bpe.cu: bpe_decode_warp_kernel) works per TOKEN from a precomputed table
+    (bpe_model.token_char_entry): complete characters, leading continuation bytes, bytes the last character still
+    needs.  Restated here lane by lane and compared with the sequential UTF-8 state machine on random token
+    sequences: whenever the fast path accepts a sequence it must give the sequential decoder's characters; it must
+    accept valid text cut into tokens at character boundaries, and text cut inside characters whenever the rest of a
+    cut character lies in the next token (a character spread over three tokens takes the byte-level path)."""
+    from beast_tokenizer_b200.bpe_model import token_char_entry
+    rng = np.random.default_rng(13)
+
+    def sequential(bs):
+        out, pending, acc = [], 0, 0
+        for bt in bs:
+            if pending:
+                if (bt & 0xC0) != 0x80:
+                    return None
+                acc = (acc << 6) | (bt & 0x3F)
+                pending -= 1
+                if pending == 0:
+                    if acc > 0xFFFF:
+                        return None
+                    out.append(acc)
+            elif bt < 0x80:
+                out.append(bt)
+            elif (bt & 0xE0) == 0xC0:
+                acc, pending = bt & 0x1F, 1
+            elif (bt & 0xF0) == 0xE0:
+                acc, pending = bt & 0x0F, 2
+            elif (bt & 0xF8) == 0xF0:
+                acc, pending = bt & 0x07, 3
+            else:
+                return None
+        return None if pending else out
+
+    def fast(tokens):
+        ent = [token_char_entry(t) for t in tokens]
+        if not ent:
+            return []
+        meta = [e[3] for e in ent]
+        if any(m & 0x80 for m in meta) or (meta[0] >> 5) & 3:
+            return None
+        out = []
+        for i, e in enumerate(ent):
+            nst, need = meta[i] & 7, (meta[i] >> 3) & 3
+            nmeta = meta[i + 1] if i + 1 < len(ent) else 0
+            if need != (nmeta >> 5) & 3:
+                return None
+            cps = [e[0] & 0xffff, e[0] >> 16, e[1] & 0xffff, e[1] >> 16, e[2] & 0xffff, e[2] >> 16][:nst]
+            if need:
+                cps[-1] = ((cps[-1] << (6 * need)) | ((nmeta >> 8) & 0x3ffff)) & 0xffff
+            out += cps
+        return out
+
+    accepted = 0
+    for trial in range(4000):
+        if trial % 2 == 0:      # valid text (1-, 2-, 3-byte characters) cut at arbitrary byte positions
+            text = "".join(chr(int(v)) for v in rng.choice([rng.integers(1, 128), rng.integers(128, 0x800), rng.integers(0x800, 0xD800)],
+                                                              int(rng.integers(1, 30))))
+            bs = text.encode("utf-8")
+            cuts = sorted(set(rng.integers(1, len(bs), int(rng.integers(0, len(bs)))).tolist())) if len(bs) > 1 else []
+            if trial % 4 == 0:      # cut at character boundaries only
+                cuts = [c for c in cuts if (bs[c] & 0xC0) != 0x80]
+            toks = [bs[a:b] for a, b in zip([0] + cuts, cuts + [len(bs)])]
+            want = sequential(bs)
+            got = fast(toks)
+            assert want == [ord(c) for c in text]
+            assert got is None or got == want, (toks, got, want)
+            short = all(sum(1 for b in t if (b & 0xC0) != 0x80) <= 6 for t in toks)
+            # a cut character is completed by the NEXT token alone unless that token is nothing but continuation bytes
+            # and the character needs more
+            chained = any(all((b & 0xC0) == 0x80 for b in t) and i + 1 < len(toks) and (toks[i + 1][0] & 0xC0) == 0x80
+                          for i, t in enumerate(toks))
+            if short and not chained:
+                assert got == want, (toks, got, want)
+                accepted += 1
+        else:                   # garbage bytes: the fast path may refuse, but must never disagree
+            pool = [0x41, 0x7A, 0xC3, 0xA9, 0x80, 0xBF, 0xE2, 0x82, 0xAC, 0xF0, 0x9F, 0x98, 0xF8, 0xFF, 0xC2]
+            toks = [bytes(int(v) for v in rng.choice(pool, int(rng.integers(1, 5)))) for _ in range(int(rng.integers(1, 12)))]
+            want = sequential(b"".join(toks))
+            got = fast(toks)
+            if got is not None:
+                assert want == got, (toks, got, want)
+    assert accepted > 1000
