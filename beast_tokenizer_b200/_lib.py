@@ -95,7 +95,7 @@ _SIGNATURES = {
                              C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bpe_compact": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "bpe_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                             C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "beast_selftest_div": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "beast_colselect_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.c_int32, c_f32p,
                                       C.c_void_p, C.c_void_p]),

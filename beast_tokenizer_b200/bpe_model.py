@@ -77,8 +77,8 @@ def utf8_len(max_shift: int) -> int:
 def token_char_entry(tb: bytes):
     """One row of the decode kernel's per-token character table (csrc/bpe.cu: bpe_decode_warp_kernel fast path): what
     the sequential UTF-8 state machine of A.6 does with this token's bytes, precomputed.  Returns 4 x uint32:
-    x, y, z = six 16-bit slots with the token's characters in order (the last one = the partial accumulator when the
-    token ends inside a character); w = characters started | bytes still needed << 3 | leading continuation bytes << 5
+    x, y, z = six 16-bit slots with the token's characters in order (the last one = the partial accumulator, already
+    shifted by the missing continuation bytes, when the token ends inside a character); w = characters started | bytes still needed << 3 | leading continuation bytes << 5
     | slow << 7 | payload of the leading continuation bytes << 8.  slow = the token cannot be described this way (more
     than 6 characters or 3 leading continuation bytes, an invalid or 4-byte lead, a stray continuation byte): sequences
     holding it decode on the byte-level path, which also reports the reference's errors."""
@@ -108,7 +108,7 @@ def token_char_entry(tb: bytes):
         else:                      # 4-byte leads decode above U+FFFF (never a shifted bin), 0xF8.. and stray
             return SLOW            # continuation bytes are invalid: the byte-level path reports them
     if pending:
-        cps.append(acc)
+        cps.append(acc << (6 * pending))            # pre-shifted: the kernel ORs the next token's leading payload in
     if len(cps) > 6 or any(c > 0xFFFF for c in cps):
         return SLOW
     slots = cps + [0] * (6 - len(cps))
@@ -265,9 +265,13 @@ class B200ByteLevelBPE:
             off[i + 1] = off[i] + len(tb)
         blob = np.frombuffer(b"".join(chunks) or b"\x00", dtype=np.uint8).copy()
         tab = np.stack([token_char_entry(tb) for tb in chunks]).astype(np.uint32)
+        slots = 6
+        fits2 = ((tab[:, 3] & 0x80) != 0) | ((tab[:, 3] & 7) <= 2)
+        if bool(fits2.all()):                     # at most two characters per token: 8-byte entries {c0 | c1 << 16, meta}
+            tab, slots = np.ascontiguousarray(tab[:, [0, 3]]), 2
         t = dict(V=V, b2i=torch.from_numpy(b2i).to(dev), rank=torch.from_numpy(rank.view(np.int32)).to(dev),
                  off=torch.from_numpy(off).to(dev), blob=torch.from_numpy(blob).to(dev),
-                 tab=torch.from_numpy(tab.view(np.int32)).to(dev))
+                 tab=torch.from_numpy(tab.view(np.int32)).to(dev), tab_slots=slots)
         self._dev_tables[key] = t
         return t
 
@@ -331,8 +335,8 @@ class B200ByteLevelBPE:
         declen = torch.empty(N, device=dev, dtype=torch.int32)
         with torch.cuda.device(dev):
             _lib.check(lib.bpe_decode(_lib.ptr(flat), _lib.ptr(offsets), N, L, int(min_token), _lib.ptr(t["off"]),
-                                      _lib.ptr(t["blob"]), _lib.ptr(t["tab"]), t["V"], _lib.ptr(bins), _lib.ptr(status),
-                                      _lib.ptr(declen), _lib.stream_ptr(dev)), "bpe_decode")
+                                      _lib.ptr(t["blob"]), _lib.ptr(t["tab"]), t["tab_slots"], t["V"], _lib.ptr(bins),
+                                      _lib.ptr(status), _lib.ptr(declen), _lib.stream_ptr(dev)), "bpe_decode")
         return bins, status, declen
 
     # ------------------------------------------------------------------ HF-shaped convenience (single strings, on the GPU)

@@ -1417,6 +1417,102 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
     }
 }
 
+// ---------------------------------------------------------------- decode (K5b), fast path: one lane per TOKEN
+// The table holds, per token, what the sequential UTF-8 state machine (A.6) does with its bytes: its characters
+// (the last one pre-shifted by the continuation bytes it still needs), the continuation bytes the token starts
+// with (they finish the previous token's last character) and their payload.  A sequence decodes here when every id
+// is in range, no token is flagged slow and every boundary matches (needed == supplied); a token's character index
+// is a prefix sum of the tokens' character counts.  Anything else — stray / missing continuation bytes, ids out of
+// range, tokens of more than SLOTS characters — is flagged (status kDecodeNeedsBytes) and decoded by the byte-level
+// kernel below, which also decides WHICH of the reference's errors the sequence has.
+//   SLOTS = 2: 8-byte entries {c0 | c1 << 16, meta}; SLOTS = 6: 16-byte entries {c0|c1, c2|c3, c4|c5, meta};
+//   meta = characters started | bytes still needed << 3 | leading continuation bytes << 5 | slow << 7 | payload << 8.
+constexpr int kDecodeNeedsBytes = 0x100;
+template <int SLOTS>
+__global__ void __launch_bounds__(256, 8)
+bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
+                        long long min_token, const void* __restrict__ tok_tab, int n_vocab,
+                        long long* __restrict__ bins_out, int* __restrict__ status_out, int* __restrict__ declen_out) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int LP = (L + 7) & ~7;
+    uint16_t* s_cp = (uint16_t*)s_raw + (size_t)warp * LP;
+    const unsigned int FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    struct Entry { unsigned int c01, c23, c45, meta; };
+    auto load_entry = [&](int id, bool in_range) -> Entry {
+        Entry e{0u, 0u, 0u, 0u};                               // beyond the end: supplies nothing, needs nothing
+        if (!in_range) return e;
+        if (id < 0 || id >= n_vocab) { e.meta = 0x80u; return e; }
+        if (SLOTS == 2) { const uint2 t = __ldg((const uint2*)tok_tab + id); e.c01 = t.x; e.meta = t.y; }
+        else { const uint4 t = __ldg((const uint4*)tok_tab + id); e.c01 = t.x; e.c23 = t.y; e.c45 = t.z; e.meta = t.w; }
+        return e;
+    };
+    for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
+        const long long p0 = offsets[seq];
+        const int n = (int)(offsets[seq + 1] - p0);
+        const int* ids = flat + p0;
+        bool bad = false;
+        int cnt = 0;
+        Entry cur = load_entry(lane < n ? ids[lane] : 0, lane < n);
+        if (n > 0 && (__shfl_sync(FULL, cur.meta, 0) & 0x60u)) bad = true;          // the text starts inside a character
+        for (int g0 = 0; g0 < n; g0 += 32) {
+            const int qn = g0 + 32 + lane;
+            const Entry nxt = load_entry(qn < n ? ids[qn] : 0, qn < n);              // in flight while this group is decoded
+            const unsigned int meta = cur.meta;
+            unsigned int nmeta = __shfl_down_sync(FULL, meta, 1);
+            const unsigned int nmeta0 = __shfl_sync(FULL, nxt.meta, 0);
+            if (lane == 31) nmeta = nmeta0;
+            const int nst = (int)(meta & 7u);
+            const unsigned int need = (meta >> 3) & 3u;
+            if ((meta & 0x80u) || need != ((nmeta >> 5) & 3u)) bad = true;
+            const unsigned int tail = need ? ((nmeta >> 8) & 0x3ffffu) : 0u;
+            int at, total;
+            if (SLOTS == 2) {                                   // counts of 0 / 1 / 2: two ballots
+                const unsigned int b1 = __ballot_sync(FULL, nst >= 1), b2 = __ballot_sync(FULL, nst >= 2);
+                at = cnt + __popc(b1 & lt) + __popc(b2 & lt);
+                total = __popc(b1) + __popc(b2);
+                unsigned int v0 = cur.c01 & 0xffffu, v1 = cur.c01 >> 16;
+                if (nst == 1) v0 |= tail;
+                if (nst == 2) v1 |= tail;
+                if (nst >= 1 && at < L) s_cp[at] = (uint16_t)v0;
+                if (nst >= 2 && at + 1 < L) s_cp[at + 1] = (uint16_t)v1;
+            } else {
+                int inc = nst;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                at = cnt + inc - nst;
+                total = __shfl_sync(FULL, inc, 31);
+                const unsigned int c[6] = {cur.c01 & 0xffffu, cur.c01 >> 16, cur.c23 & 0xffffu, cur.c23 >> 16,
+                                           cur.c45 & 0xffffu, cur.c45 >> 16};
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if (k < nst && at + k < L) s_cp[at + k] = (uint16_t)(k == nst - 1 ? c[k] | tail : c[k]);
+            }
+            cnt += total;
+            cur = nxt;
+        }
+        if (__any_sync(FULL, bad)) {
+            if (lane == 0) status_out[seq] = kDecodeNeedsBytes;
+            continue;
+        }
+        __syncwarp();
+        if (lane == 0) { status_out[seq] = cnt != L ? 3 : 0; declen_out[seq] = cnt; }
+        long long* out = bins_out + seq * L;
+        if ((L & 1) == 0 && (((uintptr_t)bins_out) & 15u) == 0) {
+            for (int i = 2 * lane; i < L; i += 64) {
+                const unsigned int two = *(const unsigned int*)(s_cp + i);
+                *(longlong2*)(out + i) = make_longlong2((long long)(two & 0xffffu) + min_token, (long long)(two >> 16) + min_token);
+            }
+        } else {
+            for (int i = lane; i < L; i += 32) out[i] = (long long)s_cp[i] + min_token;
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------- decode (K5b), one warp per sequence
 // Lanes read the ids (coalesced), a warp scan of the token byte lengths places every token's bytes in
 // shared memory, then UTF-8 is decoded in parallel: a byte that is not a continuation byte starts a
@@ -1431,8 +1527,8 @@ __device__ __forceinline__ int utf8_lead_len(int b) {
 __global__ void __launch_bounds__(256)
 bpe_decode_warp_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
                        long long min_token, const int* __restrict__ tok_off, const uint8_t* __restrict__ tok_bytes,
-                       const uint4* __restrict__ tok_tab, int n_vocab, long long* __restrict__ bins_out,
-                       int* __restrict__ status_out, int* __restrict__ declen_out, int cap, int warp_bytes) {
+                       int n_vocab, long long* __restrict__ bins_out, int* __restrict__ status_out,
+                       int* __restrict__ declen_out, int cap, int warp_bytes, int only_flagged) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint8_t* s_b = s_raw + (size_t)warp * warp_bytes;
@@ -1440,71 +1536,7 @@ bpe_decode_warp_kernel(const int* __restrict__ flat, const long long* __restrict
     const unsigned int FULL = 0xffffffffu, lt = (1u << lane) - 1u;
     for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
         const long long p0 = offsets[seq], p1 = offsets[seq + 1];
-        if (tok_tab) {
-            // ---- fast path: one lane per TOKEN.  The table holds, per token, its complete characters (<= 6
-            // codepoints), the continuation bytes it starts with (they finish the previous token's last
-            // character) and how many its own last character still needs.  A sequence decodes here when every
-            // id is in range, no token is flagged slow and every boundary matches (needed == supplied); the
-            // character index of a token is a prefix sum of the tokens' character counts.  Anything else —
-            // stray / missing continuation bytes, ids out of range, long tokens — falls through to the
-            // byte-level path below, which also decides WHICH error the sequence has.
-            bool bad = false;
-            int cnt_f = 0;
-            uint4 cur = make_uint4(0u, 0u, 0u, 0x80u);
-            if (p0 + lane < p1) {
-                const int id = flat[p0 + lane];
-                if (id >= 0 && id < n_vocab) cur = __ldg(tok_tab + id);
-            }
-            if (p1 > p0 && __shfl_sync(FULL, (cur.w >> 5) & 3u, 0) != 0u) bad = true;   // text starts inside a character
-            for (long long q0 = p0; q0 < p1; q0 += 32) {
-                const bool have = q0 + lane < p1;
-                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);                 // beyond the end: supplies nothing, needs nothing
-                if (q0 + 32 + lane < p1) {
-                    nxt.w = 0x80u;
-                    const int id = flat[q0 + 32 + lane];
-                    if (id >= 0 && id < n_vocab) nxt = __ldg(tok_tab + id);
-                }
-                const unsigned int meta = have ? cur.w : 0u;
-                unsigned int nmeta = __shfl_down_sync(FULL, meta, 1);
-                const unsigned int nmeta0 = __shfl_sync(FULL, nxt.w, 0);
-                if (lane == 31) nmeta = nmeta0;
-                const int nst = (int)(meta & 7u), need = (int)((meta >> 3) & 3u);
-                if ((meta & 0x80u) || need != (int)((nmeta >> 5) & 3u)) bad = true;
-                int inc = nst;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                const int at = cnt_f + inc - nst;
-                const unsigned int c[6] = {cur.x & 0xffffu, cur.x >> 16, cur.y & 0xffffu, cur.y >> 16, cur.z & 0xffffu, cur.z >> 16};
-                const unsigned int tail = ((nmeta >> 8) & 0x3ffffu);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    if (k < nst && at + k < L) {
-                        unsigned int v = c[k];
-                        if (k == nst - 1 && need) v = (v << (6 * need)) | tail;
-                        s_cp[at + k] = (uint16_t)v;
-                    }
-                }
-                cnt_f += __shfl_sync(FULL, inc, 31);
-                cur = nxt;
-            }
-            if (!__any_sync(FULL, bad)) {
-                __syncwarp();
-                if (lane == 0) { status_out[seq] = cnt_f != L ? 3 : 0; declen_out[seq] = cnt_f; }
-                long long* out = bins_out + seq * L;
-                if ((L & 1) == 0 && (((uintptr_t)out) & 15u) == 0) {
-                    for (int i = 2 * lane; i < L; i += 64)
-                        *(longlong2*)(out + i) = make_longlong2((long long)s_cp[i] + min_token, (long long)s_cp[i + 1] + min_token);
-                } else {
-                    for (int i = lane; i < L; i += 32) out[i] = (long long)s_cp[i] + min_token;
-                }
-                __syncwarp();
-                continue;
-            }
-            __syncwarp();
-        }
+        if (only_flagged && status_out[seq] != kDecodeNeedsBytes) continue;   // decoded by the per-token fast kernel
         int B = 0, status = 0, cnt = 0;
         bool bad_tok = false, overflow = false;
         for (long long q0 = p0; q0 < p1; q0 += 32) {
@@ -1950,34 +1982,57 @@ extern "C" int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int
 }
 
 extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,
-                          const int32_t* tok_off, const uint8_t* tok_bytes, const void* tok_tab, int32_t n_vocab,
-                          int64_t* bins_out, int32_t* status_out, int32_t* declen_out, void* stream) {
+                          const int32_t* tok_off, const uint8_t* tok_bytes, const void* tok_tab, int32_t tok_tab_slots,
+                          int32_t n_vocab, int64_t* bins_out, int32_t* status_out, int32_t* declen_out, void* stream) {
     if (N == 0) return BEAST_OK;
     if (!offsets || !tok_off || !tok_bytes || !bins_out || !status_out || !declen_out) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_vocab < 1) return BEAST_E_SHAPE;
+    if (tok_tab && tok_tab_slots != 2 && tok_tab_slots != 6) return BEAST_E_SHAPE;
     if ((uintptr_t)tok_tab & 15u) return BEAST_E_ALIGN;
-    {   // one warp per sequence; BEAST_B200_BPE_THREAD_DECODE=1 (or rows too long for shared memory) takes the
-        // one-thread-per-sequence kernel
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int force_thread = -1;
+    if (force_thread < 0) { const char* env = getenv("BEAST_B200_BPE_THREAD_DECODE"); force_thread = (env && env[0] == '1') ? 1 : 0; }
+    int only_flagged = 0;
+    if (tok_tab && !force_thread && L <= 8192) {
+        // fast path: one lane per token from the per-token character table; sequences it cannot describe are flagged
+        const size_t smem = (size_t)8 * (((size_t)L + 7) & ~(size_t)7) * 2;
+        static size_t granted2[kMaxDevices] = {}, granted6[kMaxDevices] = {};
+        int rc = tok_tab_slots == 2 ? opt_in_smem(bpe_decode_token_kernel<2>, smem, granted2)
+                                    : opt_in_smem(bpe_decode_token_kernel<6>, smem, granted6);
+        if (rc) return rc;
+        long long grid = (N + 7) / 8;
+        if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+        if (tok_tab_slots == 2)
+            bpe_decode_token_kernel<2><<<(unsigned)grid, 256, smem, st>>>(flat, (const long long*)offsets, N, L, min_token, tok_tab,
+                                                                         n_vocab, (long long*)bins_out, status_out, declen_out);
+        else
+            bpe_decode_token_kernel<6><<<(unsigned)grid, 256, smem, st>>>(flat, (const long long*)offsets, N, L, min_token, tok_tab,
+                                                                         n_vocab, (long long*)bins_out, status_out, declen_out);
+        count_launch();
+        BEAST_CHECK_LAUNCH();
+        only_flagged = 1;
+    }
+    {   // byte-level path, one warp per sequence (all sequences, or only the ones the fast kernel flagged);
+        // BEAST_B200_BPE_THREAD_DECODE=1 (or rows too long for shared memory) takes the one-thread-per-sequence kernel
         const int cap = 4 * L + 64;                          // a valid sequence has at most 3 L bytes
         const size_t warp_bytes = (((size_t)cap + 15) & ~(size_t)15) + (((size_t)L * 2 + 15) & ~(size_t)15);
         int warps = (int)((200 * 1024) / warp_bytes);
         if (warps > 8) warps = 8;
-        const char* env = getenv("BEAST_B200_BPE_THREAD_DECODE");
-        if (warps >= 1 && !(env && env[0] == '1')) {
+        if (warps >= 1 && !force_thread) {
             const size_t smem = warp_bytes * warps;
             static size_t granted_w[kMaxDevices] = {};
             if (int rc = opt_in_smem(bpe_decode_warp_kernel, smem, granted_w)) return rc;
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
             if (per_sm > 2048 / (warps * 32)) per_sm = 2048 / (warps * 32);
             if (per_sm < 1) per_sm = 1;
             long long grid = (N + warps - 1) / warps;
             if (grid > sms * per_sm) grid = sms * per_sm;
-            bpe_decode_warp_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
-                flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, (const uint4*)tok_tab, n_vocab,
-                (long long*)bins_out, status_out, declen_out, cap, (int)warp_bytes);
+            bpe_decode_warp_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(
+                flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out,
+                status_out, declen_out, cap, (int)warp_bytes, only_flagged);
             count_launch();
             BEAST_CHECK_LAUNCH();
             return BEAST_OK;
@@ -1989,7 +2044,7 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
     static size_t granted[kMaxDevices] = {};
     if (int rc = opt_in_smem(bpe_decode_kernel, smem, granted)) return rc;
     const long long grid = (N + rows - 1) / rows;
-    bpe_decode_kernel<<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
+    bpe_decode_kernel<<<(unsigned)grid, kBpeBlock, smem, st>>>(
         flat, (const long long*)offsets, N, L, min_token, tok_off, tok_bytes, n_vocab, (long long*)bins_out, status_out,
         declen_out, rows);
     count_launch();

@@ -213,11 +213,12 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  * bpe_compact    padded rows -> CSR flat int32 (offsets = exclusive scan of len, by the caller).
  * bpe_decode     CSR ids -> bins [N, L] int64 (A.6); status 1 = unknown id, 2 = invalid UTF-8,
  *                3 = decoded length != L (bpe_tokenizer.py:241-244); declen_out = decoded length.
- *                tok_tab (nullable, 16 bytes per token): the per-token character table of the fast path —
- *                x, y, z = six 16-bit codepoints (the token's complete characters; the last one holds the partial
- *                accumulator when it is cut off), w = meta: bits 0-2 characters started, 3-4 continuation bytes the
- *                last character still needs, 5-6 continuation bytes the token begins with, 7 = not representable
- *                (take the byte-level path), 8-25 payload of the leading continuation bytes. */
+ *                tok_tab (nullable): the per-token character table of the fast path (one lane per token; sequences it
+ *                cannot describe are decoded by the byte-level kernel in a second launch).  tok_tab_slots = 6:
+ *                16 bytes per token {c0|c1<<16, c2|c3<<16, c4|c5<<16, meta}; tok_tab_slots = 2: 8 bytes {c0|c1<<16, meta}.
+ *                c = the token's characters (16-bit codepoints; the last one pre-shifted when it is cut off),
+ *                meta = characters started | continuation bytes the last character still needs << 3 | continuation
+ *                bytes the token begins with << 5 | not representable << 7 | payload of those leading bytes << 8. */
 int bpe_scan_bins(const int64_t* bins, int64_t n, int64_t min_token, int64_t* minmax, int32_t* seen,
                   int32_t* err, int32_t phase, void* stream);
 int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, const int16_t* byte_to_id,
@@ -317,8 +318,8 @@ int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int
 int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int32_t* len, const int64_t* offsets,
                 int64_t N, int32_t* flat, void* stream);
 int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,
-               const int32_t* tok_off, const uint8_t* tok_bytes, const void* tok_tab, int32_t n_vocab,
-               int64_t* bins_out, int32_t* status_out, int32_t* declen_out, void* stream);
+               const int32_t* tok_off, const uint8_t* tok_bytes, const void* tok_tab, int32_t tok_tab_slots,
+               int32_t n_vocab, int64_t* bins_out, int32_t* status_out, int32_t* declen_out, void* stream);
 
 /* Device self-test of the exact invariant-divisor division inside K1 / K3 (csrc/common.cuh) against
  * IEEE division: n_divisors random divisors x 2^24 + 2^22 numerators each, and float(tok)/(V-1)

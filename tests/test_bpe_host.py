@@ -411,7 +411,7 @@ def test_token_character_table_matches_the_state_machine():
                 return None
             cps = [e[0] & 0xffff, e[0] >> 16, e[1] & 0xffff, e[1] >> 16, e[2] & 0xffff, e[2] >> 16][:nst]
             if need:
-                cps[-1] = ((cps[-1] << (6 * need)) | ((nmeta >> 8) & 0x3ffff)) & 0xffff
+                cps[-1] = (cps[-1] | ((nmeta >> 8) & 0x3ffff)) & 0xffff
             out += cps
         return out
 
