@@ -49,6 +49,7 @@ _SIGNATURES = {
     "beast_plan_destroy": (C.c_int, [C.c_void_p]),
     "beast_version": (C.c_char_p, []),
     "beast_launch_count": (C.c_int64, []),
+    "beast_debug_disable_fast": (C.c_int, [C.c_int32]),
     "beast_encode_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_f32p, c_i64p, C.c_void_p]),
     "beast_quantize_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, c_i64p, C.c_void_p]),
     "beast_normalize_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_void_p]),

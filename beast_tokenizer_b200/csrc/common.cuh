@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "beast_b200.h"
 
 #ifndef __CUDA_ARCH__
@@ -32,12 +33,32 @@ struct Plan {
     float* knots_joint_d;  // [nc+degree_p+1]
     float* knots_grip_d;   // [nb+1]
     int* slot_to_dof_d;
+    // Band tables of the tiled kernels (csrc/spline_tiled.cu), pairs [lo, hi): the non-zero range of every projector
+    // row (encode: samples t of basis k) and of every basis row (decode: basis k of sample t); the terms outside are
+    // exact zeros, skipping them leaves the fp32 sums unchanged.  Layout: enc_joint[2*nb], enc_grip[2*nb],
+    // dec_joint[2*T], dec_grip[2*T].
+    int* bands_d;
     int num_sms;
     int max_smem_optin;
 };
 
+// Tiled kernels for any geometry on the tokenizer's own times (csrc/spline_tiled.cu); BEAST_E_UNSUPPORTED when a
+// trajectory's working set does not fit shared memory (the caller then takes the one-thread-per-column kernels).
+int launch_encode_tiled(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
+                        long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
+                        cudaStream_t st);
+int launch_decode_tiled(const Plan* p, const long long* tokens, const float* params, long long B, const float* w_min,
+                        const float* w_max, long long offset, const float* init_p, float* out, cudaStream_t st);
+
 extern long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += n; }
+// 1 = take the one-thread-per-column reference kernels only (beast_debug_disable_fast, or BEAST_B200_DISABLE_FAST=1
+// read once at the first call): the parity tests compare them with the tiled / bulk-copy kernels bit for bit.
+extern int g_disable_fast;
+inline bool fast_paths_disabled() {
+    if (g_disable_fast < 0) { const char* e = getenv("BEAST_B200_DISABLE_FAST"); g_disable_fast = (e && e[0] == '1') ? 1 : 0; }
+    return g_disable_fast == 1;
+}
 
 // ---------------------------------------------------------------- quantiser (bit-exact contract)
 // beast/beast_bspline_tokenizer.py:419 (clamp) + beast/utils.py:12-16: every step is one

@@ -6,6 +6,7 @@
 
 namespace beast {
 long long g_launch_count = 0;
+int g_disable_fast = -1;
 }
 using beast::Plan;
 
@@ -18,6 +19,11 @@ static float* dup_h(const float* src, size_t n) {
 
 extern "C" const char* beast_version(void) { return "beast_b200 0.1 sm_100a"; }
 extern "C" int64_t beast_launch_count(void) { return beast::g_launch_count; }
+extern "C" int beast_debug_disable_fast(int32_t flag) {
+    const int prev = beast::g_disable_fast == 1 ? 1 : 0;
+    beast::g_disable_fast = flag ? 1 : 0;
+    return prev;
+}
 
 extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out) {
     if (!d || !out) return BEAST_E_NULL;
@@ -73,6 +79,31 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
     e = cudaMemcpy(p->dev_block, host, total * sizeof(float), cudaMemcpyHostToDevice);
     free(host);
     if (e != cudaSuccess) { beast_plan_destroy((beast_plan_t*)p); return (int)e; }
+    {   // band tables: non-zero range of every projector row [k][t] and of every basis row [t][k]
+        const int T = p->T, nb = p->nb;
+        const size_t n_band = (size_t)4 * nb + (size_t)4 * T;
+        int* bands = (int*)calloc(n_band, sizeof(int));
+        if (!bands) { beast_plan_destroy((beast_plan_t*)p); return BEAST_E_NOMEM; }
+        auto row_band = [](const float* row, int n, int stride, int* lo_hi) {
+            int lo = n, hi = 0;
+            for (int i = 0; i < n; ++i)
+                if (row[(size_t)i * stride] != 0.0f) { if (i < lo) lo = i; hi = i + 1; }
+            if (lo >= hi) lo = hi = 0;
+            lo_hi[0] = lo; lo_hi[1] = hi;
+        };
+        for (int k = 0; k < nb; ++k) {
+            row_band(p->proj_joint_h + (size_t)k * T, T, 1, bands + 2 * k);
+            if (has_grip) row_band(p->proj_grip_h + (size_t)k * T, T, 1, bands + 2 * nb + 2 * k);
+        }
+        for (int t = 0; t < T; ++t) {
+            if (p->nc == nb) row_band(p->phi_joint_h + (size_t)t * nb, nb, 1, bands + 4 * nb + 2 * t);
+            if (has_grip) row_band(p->phi_grip_h + (size_t)t * nb, nb, 1, bands + 4 * nb + 2 * T + 2 * t);
+        }
+        e = cudaMalloc((void**)&p->bands_d, n_band * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(p->bands_d, bands, n_band * sizeof(int), cudaMemcpyHostToDevice);
+        free(bands);
+        if (e != cudaSuccess) { beast_plan_destroy((beast_plan_t*)p); return (int)e; }
+    }
     *out = (beast_plan_t*)p;
     return BEAST_OK;
 }
@@ -82,6 +113,7 @@ extern "C" int beast_plan_destroy(beast_plan_t* plan) {
     Plan* p = (Plan*)plan;
     free(p->proj_joint_h); free(p->proj_grip_h); free(p->phi_joint_h); free(p->phi_grip_h);
     if (p->dev_block) cudaFree(p->dev_block);
+    if (p->bands_d) cudaFree(p->bands_d);
     delete p;
     return BEAST_OK;
 }

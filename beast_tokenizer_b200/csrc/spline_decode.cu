@@ -259,11 +259,6 @@ dequantize_kernel(const long long* __restrict__ tokens, long long n, int D, int 
     }
 }
 
-static bool dec_fast_disabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("BEAST_B200_DISABLE_FAST"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
 static inline bool dec_aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 static int dec_grid_for(long long n, int block, int num_sms) {
     long long g = (n + block - 1) / block;
@@ -367,7 +362,7 @@ extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens,
     cudaStream_t st = (cudaStream_t)stream;
     const int T = p->T, D = p->D, nb = p->nb;
     long long done = 0;
-    if (T == 50 && nb == 10 && p->nc == nb && !dec_fast_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
+    if (T == 50 && nb == 10 && p->nc == nb && !fast_paths_disabled() && dec_aligned16(tokens) && dec_aligned16(traj_out) &&
         (!init_p || dec_aligned16(init_p))) {
         const int S = (kDecColumns / D) & ~3;
         if (S >= 4 && B >= S) {
@@ -382,6 +377,13 @@ extern "C" int beast_decode_f32(const beast_plan_t* plan, const int64_t* tokens,
             if (rc == BEAST_OK) done = n_tiles * S;
             else if (rc != BEAST_E_UNSUPPORTED) return rc;
         }
+    }
+    if (done < B && !fast_paths_disabled()) {
+        const int rc = launch_decode_tiled(p, (const long long*)tokens + done * (long long)D * nb, nullptr, B - done, w_min,
+                                           w_max, offset, init_p ? init_p + done * D : nullptr,
+                                           traj_out + done * (long long)T * D, st);
+        if (rc == BEAST_OK) done = B;
+        else if (rc != BEAST_E_UNSUPPORTED) return rc;
     }
     if (done < B)
         return launch_generic(p, (const long long*)tokens + done * (long long)D * nb, nullptr, B - done, T, nullptr,
@@ -409,6 +411,10 @@ extern "C" int beast_eval_f32(const beast_plan_t* plan, const float* params, int
     if (B == 0) return BEAST_OK;
     const int tq = times ? Tq : p->T;
     if (tq == 0) return BEAST_OK;
+    if (!times && !fast_paths_disabled()) {
+        const int rc = launch_decode_tiled(p, nullptr, params, B, nullptr, nullptr, 0, init_p, traj_out, (cudaStream_t)stream);
+        if (rc != BEAST_E_UNSUPPORTED) return rc;
+    }
     return launch_generic(p, nullptr, params, B, tq, times, nullptr, nullptr, 0, init_p, nullptr, nullptr, traj_out,
                           (cudaStream_t)stream);
 }

@@ -316,11 +316,6 @@ quantize_kernel(const float* __restrict__ params, long long n, int D, int nb, co
     }
 }
 
-static bool fast_disabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("BEAST_B200_DISABLE_FAST"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
@@ -396,7 +391,7 @@ static int encode_impl(const Plan* p, const float* traj, long long B, const floa
                        cudaStream_t st, float* mm_ws = nullptr, int mm_accumulate = 1, bool* fast_ran = nullptr) {
     const int T = p->T, D = p->D, nb = p->nb;
     long long done = 0;
-    if (T == 50 && nb == 10 && !fast_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
+    if (T == 50 && nb == 10 && !fast_paths_disabled() && aligned16(traj) && (!params_out || aligned16(params_out)) &&
         (!tokens_out || aligned16(tokens_out))) {
         const int S = (kEncColumns / D) & ~3;
         if (S >= 4 && B >= S) {
@@ -411,6 +406,14 @@ static int encode_impl(const Plan* p, const float* traj, long long B, const floa
             if (rc == BEAST_OK) { done = n_tiles * S; if (fast_ran) *fast_ran = true; }
             else if (rc != BEAST_E_UNSUPPORTED) return rc;
         }
+    }
+    if (done < B && !fast_paths_disabled()) {
+        // any other geometry (and long ragged tails): tiles of trajectories through shared memory
+        const int rc = launch_encode_tiled(p, traj + done * (long long)T * D, B - done, w_min, w_max, offset,
+                                           params_out ? params_out + done * (long long)D * nb : nullptr,
+                                           tokens_out ? tokens_out + done * (long long)D * nb : nullptr, bmin, bmax, st);
+        if (rc == BEAST_OK) done = B;
+        else if (rc != BEAST_E_UNSUPPORTED) return rc;
     }
     if (done < B) {
         const long long ncol = (B - done) * D;
@@ -475,7 +478,7 @@ extern "C" int beast_fit_minmax_ws_f32(const beast_plan_t* plan, const float* tr
     // min_out / max_out with plain stores, folding the previous contents in when accumulate != 0); the ragged tail
     // then accumulates with atomics.  Without one (or when no full tile exists) the outputs are initialised first.
     const int S = (kEncColumns / p->D) & ~3;
-    const bool tiled = ws && p->T == 50 && p->nb == 10 && !fast_disabled() && S >= 4 && B >= S && aligned16(traj);
+    const bool tiled = ws && p->T == 50 && p->nb == 10 && !fast_paths_disabled() && S >= 4 && B >= S && aligned16(traj);
     if (!tiled) {
         if (!accumulate) {
             bounds_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(min_out, max_out, n);

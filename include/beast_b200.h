@@ -81,6 +81,10 @@ int beast_plan_destroy(beast_plan_t* plan);
 const char* beast_version(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t beast_launch_count(void);
+/* Test hook: flag != 0 makes the spline entry points take the one-thread-per-column reference kernels only (as
+ * BEAST_B200_DISABLE_FAST=1 does from the environment); returns the previous setting.  The parity tests compare the
+ * tiled / bulk-copy kernels with them bit for bit. */
+int beast_debug_disable_fast(int32_t flag);
 
 /* ---- K1: fused fit + quantise.  Replaces BEASTBsplineTokenizer.encode
  * (beast/beast_bspline_tokenizer.py:399-428) and compute_weights (:344-360):

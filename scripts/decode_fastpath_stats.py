@@ -11,8 +11,8 @@ bins = torch.cat([tok.encode(synth_device(100000, 50, 14, 1000 + c, dev))[0] for
 st = FIGBPE(vocab_size=2048, show_progress=False).fit_from_bins(bins)
 m = st.tokenizer
 flat, off, status = m.encode_bins(bins[:262144], st.min_token, st.max_token)
-tab = m._tables(dev)["tab"].view(-1, 4)
-meta = tab[:, 3]
+t_ = m._tables(dev); tab = t_["tab"].view(-1, 2 if t_["tab_slots"] == 2 else 4)
+meta = tab[:, -1]
 slow = (meta & 0x80) != 0
 nst, need, lead = meta & 7, (meta >> 3) & 3, (meta >> 5) & 3
 print("vocab", len(m.tokens), "slow tokens", int(slow.sum()), "max chars", int(nst.max()), "tokens with need>0", int((need > 0).sum()),
