@@ -29,10 +29,17 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
     float* par = y + (size_t)S * row_in;                      // [S][D][nb]   (coefficient layout '(d t)')
     float* s_mn = par + (size_t)S * row_out;                  // [D*nb] x 2 when bmin
     float* s_mx = s_mn + row_out;
+    float* qtab = s_mn;                                       // ... or the quantiser constants [D*nb][4] when tokens
     const bool want_mm = bmin != nullptr, want_par = params_out != nullptr, want_tok = tokens_out != nullptr;
     const int tid = threadIdx.x;
     if (want_mm)
         for (int c = tid; c < row_out; c += kTiledThreads) { s_mn[c] = __int_as_float(0x7f800000); s_mx[c] = __int_as_float(0xff800000); }
+    if (want_tok)                                             // per-column constants of the exact quantiser, once per CTA
+        for (int c = tid; c < row_out; c += kTiledThreads) {
+            QuantCol qc;
+            qc.init(w_min[c], w_max[c]);
+            qtab[4 * c] = qc.lo; qtab[4 * c + 1] = qc.hi; qtab[4 * c + 2] = qc.scale; qtab[4 * c + 3] = qc.rcp;
+        }
     const long long n_tiles = (B + S - 1) / S;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * S;
@@ -48,22 +55,29 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
             }
         }
         __syncthreads();
-        // phase 2: one output per thread and step, token order (k major, slot minor): coalesced token stores
+        // phase 2: one (trajectory, slot) column per thread, k ascending: for a fixed k the lanes of a warp hold
+        // adjacent slots, so the int64 token stores of a step are contiguous runs; index arithmetic once per column
         const int n_out = ns * row_out;
-        for (int o = tid; o < n_out; o += kTiledThreads) {
-            const int tr = o / row_out, r = o - tr * row_out;
-            const int k = r / D, slot = r - k * D;
+        for (int col = tid; col < ns * D; col += kTiledThreads) {
+            const int tr = col / D, slot = col - tr * D;
             const bool joint = slot < n_joint;
-            const float* P = (joint ? Pj : Pg) + (size_t)k * T;
-            const int* band = bands + (joint ? 0 : 2 * nb) + 2 * k;
-            const float* col = y + (size_t)tr * row_in + slot_to_dof[slot];
-            float acc = 0.0f;
-            for (int t = band[0]; t < band[1]; ++t) acc = fmaf(__ldg(P + t), col[t * D], acc);
-            const int c = slot * nb + k;
-            if (want_par || want_mm) par[(size_t)tr * row_out + c] = acc;
-            if (want_tok) {
-                const float lo = __ldg(w_min + c), hi = __ldg(w_max + c);
-                tokens_out[(b0 + tr) * row_out + r] = quantize_one(acc, lo, hi, quant_scale(lo, hi), vm1) + offset;
+            const float* P = joint ? Pj : Pg;
+            const int* band = bands + (joint ? 0 : 2 * nb);
+            const float* ycol = y + (size_t)tr * row_in + slot_to_dof[slot];
+            float* pcol = par + (size_t)tr * row_out + slot * nb;
+            long long* tcol = want_tok ? tokens_out + (b0 + tr) * row_out + slot : nullptr;
+            const float* qcol = qtab + (size_t)slot * nb * 4;
+            for (int k = 0; k < nb; ++k) {
+                const int t0 = band[2 * k], t1 = band[2 * k + 1];
+                const float* Pk = P + (size_t)k * T;
+                float acc = 0.0f;
+                for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), ycol[t * D], acc);
+                if (want_par || want_mm) pcol[k] = acc;
+                if (want_tok) {
+                    QuantCol qc;
+                    qc.lo = qcol[4 * k]; qc.hi = qcol[4 * k + 1]; qc.scale = qcol[4 * k + 2]; qc.rcp = qcol[4 * k + 3];
+                    tcol[(size_t)k * D] = quantize_col(acc, qc, vm1) + offset;
+                }
             }
         }
         if (want_par || want_mm) {
@@ -108,34 +122,46 @@ decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restric
     float* c_s = smem_f;                                      // [S][nb][D]   (token order: slot minor)
     float* o_s = c_s + (size_t)S * row_in;                    // [S][T][D]
     const int tid = threadIdx.x;
+    const float rcp_vm1 = __frcp_rn(vm1);                     // exact invariant division by V - 1 (common.cuh)
     const long long n_tiles = (B + S - 1) / S;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * S;
         const int ns = (int)((B - b0) < S ? (B - b0) : S);
         __syncthreads();
-        const int n_in = ns * row_in;
-        for (int i = tid; i < n_in; i += kTiledThreads) {     // phase 1: coefficients of the tile, '(t d)' order
-            const int tr = i / row_in, r = i - tr * row_in;
-            const int k = r / D, slot = r - k * D;
-            const int c = slot * nb + k;
-            float v;
-            if (FROM_TOKENS) v = dequantize_one(__ldcs(tokens + b0 * row_in + i) - offset, __ldg(w_min + c), __ldg(w_max + c), vm1);
-            else v = params[(b0 + tr) * row_in + c];
-            if (k == 0 && init_p && slot < n_joint) v = init_p[(b0 + tr) * D + slot_to_dof[slot]];
-            c_s[i] = v;
+        // phase 1: one (trajectory, slot) column per thread, k ascending (adjacent lanes = adjacent slots: the int64
+        // token loads of a step are contiguous runs); coefficients land in token order [k][slot]
+        for (int col = tid; col < ns * D; col += kTiledThreads) {
+            const int tr = col / D, slot = col - tr * D;
+            const bool pin0 = init_p != nullptr && slot < n_joint;
+            float* ccol = c_s + (size_t)tr * row_in + slot;
+            if (FROM_TOKENS) {
+                const long long* tcol = tokens + (b0 + tr) * row_in + slot;
+                const float* lo = w_min + slot * nb;
+                const float* hi = w_max + slot * nb;
+                for (int k = 0; k < nb; ++k)
+                    ccol[(size_t)k * D] = dequantize_fast(__ldcs(tcol + (size_t)k * D) - offset, __ldg(lo + k), __ldg(hi + k), vm1, rcp_vm1);
+            } else {
+                const float* pcol = params + (b0 + tr) * row_in + slot * nb;
+                for (int k = 0; k < nb; ++k) ccol[(size_t)k * D] = pcol[k];
+            }
+            if (pin0) ccol[0] = init_p[(b0 + tr) * D + slot_to_dof[slot]];
         }
         __syncthreads();
+        // phase 2: the same columns, t ascending over the non-zero band of every basis row
         const int n_out = ns * row_out;
-        for (int o = tid; o < n_out; o += kTiledThreads) {    // phase 2: one sample per thread, slot minor
-            const int tr = o / row_out, r = o - tr * row_out;
-            const int t = r / D, slot = r - t * D;
+        for (int col = tid; col < ns * D; col += kTiledThreads) {
+            const int tr = col / D, slot = col - tr * D;
             const bool joint = slot < n_joint;
-            const float* phi = (joint ? phi_j : phi_g) + (size_t)t * nb;
-            const int* band = bands + 4 * nb + (joint ? 0 : 2 * T) + 2 * t;
-            const float* col = c_s + (size_t)tr * row_in + slot;
-            float acc = 0.0f;
-            for (int k = band[0]; k < band[1]; ++k) acc = fmaf(__ldg(phi + k), col[k * D], acc);
-            o_s[(size_t)tr * row_out + t * D + slot_to_dof[slot]] = acc;
+            const float* phi = joint ? phi_j : phi_g;
+            const int* band = bands + 4 * nb + (joint ? 0 : 2 * T);
+            const float* ccol = c_s + (size_t)tr * row_in + slot;
+            float* ocol = o_s + (size_t)tr * row_out + slot_to_dof[slot];
+            for (int t = 0; t < T; ++t) {
+                const float* row = phi + (size_t)t * nb;
+                float acc = 0.0f;
+                for (int k = band[2 * t]; k < band[2 * t + 1]; ++k) acc = fmaf(__ldg(row + k), ccol[(size_t)k * D], acc);
+                ocol[(size_t)t * D] = acc;
+            }
         }
         __syncthreads();
         float* dst = out + b0 * row_out;                      // phase 3: contiguous rows out
@@ -149,12 +175,12 @@ decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restric
 
 static int tile_rows(size_t bytes_per_traj, size_t extra, int max_smem) {
     // three CTAs per SM when possible: ~70 KB each
-    size_t budget = 70 * 1024;
+    size_t budget = 104 * 1024;                          // two CTAs per SM
     if (budget > (size_t)max_smem) budget = (size_t)max_smem;
     if (bytes_per_traj + extra > budget) budget = (size_t)max_smem;
     if (bytes_per_traj + extra > budget) return 0;
     size_t s = (budget - extra) / bytes_per_traj;
-    if (s > 32) s = 32;
+    if (s > 64) s = 64;
     return (int)s;
 }
 
@@ -163,7 +189,8 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
                         cudaStream_t st) {
     const int T = p->T, D = p->D, nb = p->nb;
     const size_t per_traj = ((size_t)T * D + (size_t)D * nb) * sizeof(float);
-    const size_t extra = bmin ? (size_t)2 * D * nb * sizeof(float) : 0;
+    if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // the two tables share one shared-memory region
+    const size_t extra = (bmin ? (size_t)2 : tokens_out ? (size_t)4 : (size_t)0) * D * nb * sizeof(float);
     const int S = tile_rows(per_traj, extra, p->max_smem_optin);
     if (S < 1 || !p->bands_d) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)S * per_traj + extra;
