@@ -14,9 +14,14 @@
 
 namespace beast {
 
-constexpr int kTiledThreads = 256;
+constexpr int kTiledThreads = 512;
 
-// encode: tile of trajectories -> coefficients, tokens, optional column min / max
+// encode: tile of trajectories -> coefficients, tokens, optional column min / max.
+// Per CTA, once: tab[r] = k | slot << 16 for every token position r = k*D + slot of a trajectory, the quantiser
+// constants of every column, the bands.  Per tile: (1) the samples, one contiguous run; (2) one TOKEN per thread and
+// step in token order — consecutive threads store consecutive int64 tokens — each a sum over the band of projector row
+// k (shared-memory samples), quantised exactly; the coefficient goes to its '(d t)' place in shared memory;
+// (3) coefficients leave as one contiguous run.
 __global__ void __launch_bounds__(kTiledThreads)
 encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, int nb, int n_joint,
                     const int* __restrict__ slot_to_dof, const float* __restrict__ Pj, const float* __restrict__ Pg,
@@ -25,26 +30,33 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
                     float* __restrict__ bmin, float* __restrict__ bmax, int S) {
     extern __shared__ __align__(16) float smem_f[];
     const int row_in = T * D, row_out = D * nb;
-    float* y = smem_f;                                        // [S][T][D]
-    float* par = y + (size_t)S * row_in;                      // [S][D][nb]   (coefficient layout '(d t)')
-    float* s_mn = par + (size_t)S * row_out;                  // [D*nb] x 2 when bmin
-    float* s_mx = s_mn + row_out;
-    float* qtab = s_mn;                                       // ... or the quantiser constants [D*nb][4] when tokens
+    float* y = smem_f;                                          // [S][T][D]
+    float* par = y + (((size_t)S * row_in + 3) & ~(size_t)3);   // [S][D][nb]  (coefficient layout '(d t)'), 16-byte aligned
+    float* qtab = par + (((size_t)S * row_out + 3) & ~(size_t)3);   // [D*nb][4] quantiser constants, or [2][D*nb] min / max
+    float* s_mn = qtab;
+    float* s_mx = qtab + row_out;
+    int* tab = (int*)(qtab + (size_t)4 * row_out);              // [D*nb] k | slot << 16 | (joint ? 0 : 1 << 31)
+    int* s_band = tab + row_out;                                // [2][2*nb]
+    int* s_dof = s_band + 4 * nb;                               // [D]
     const bool want_mm = bmin != nullptr, want_par = params_out != nullptr, want_tok = tokens_out != nullptr;
     const int tid = threadIdx.x;
-    if (want_mm)
-        for (int c = tid; c < row_out; c += kTiledThreads) { s_mn[c] = __int_as_float(0x7f800000); s_mx[c] = __int_as_float(0xff800000); }
-    if (want_tok)                                             // per-column constants of the exact quantiser, once per CTA
-        for (int c = tid; c < row_out; c += kTiledThreads) {
+    for (int r = tid; r < row_out; r += kTiledThreads) {
+        const int k = r / D, slot = r - k * D;
+        tab[r] = k | (slot << 16) | (slot < n_joint ? 0 : (int)0x80000000u);
+        if (want_mm) { s_mn[r] = __int_as_float(0x7f800000); s_mx[r] = __int_as_float(0xff800000); }
+        else if (want_tok) {
             QuantCol qc;
-            qc.init(w_min[c], w_max[c]);
-            qtab[4 * c] = qc.lo; qtab[4 * c + 1] = qc.hi; qtab[4 * c + 2] = qc.scale; qtab[4 * c + 3] = qc.rcp;
+            qc.init(w_min[r], w_max[r]);                        // r runs over all columns c = slot*nb + k as well
+            qtab[4 * r] = qc.lo; qtab[4 * r + 1] = qc.hi; qtab[4 * r + 2] = qc.scale; qtab[4 * r + 3] = qc.rcp;
         }
+    }
+    for (int i = tid; i < 4 * nb; i += kTiledThreads) s_band[i] = bands[i];
+    for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = slot_to_dof[i];
     const long long n_tiles = (B + S - 1) / S;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * S;
         const int ns = (int)((B - b0) < S ? (B - b0) : S);
-        __syncthreads();                                      // previous tile's staging has been drained
+        __syncthreads();                                      // tables ready / previous tile's staging drained
         {   // phase 1: the tile's samples, contiguous in global memory
             const float* src = traj + b0 * row_in;
             const int n = ns * row_in;
@@ -55,28 +67,28 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
             }
         }
         __syncthreads();
-        // phase 2: one (trajectory, slot) column per thread, k ascending: for a fixed k the lanes of a warp hold
-        // adjacent slots, so the int64 token stores of a step are contiguous runs; index arithmetic once per column
         const int n_out = ns * row_out;
-        for (int col = tid; col < ns * D; col += kTiledThreads) {
-            const int tr = col / D, slot = col - tr * D;
-            const bool joint = slot < n_joint;
-            const float* P = joint ? Pj : Pg;
-            const int* band = bands + (joint ? 0 : 2 * nb);
-            const float* ycol = y + (size_t)tr * row_in + slot_to_dof[slot];
-            float* pcol = par + (size_t)tr * row_out + slot * nb;
-            long long* tcol = want_tok ? tokens_out + (b0 + tr) * row_out + slot : nullptr;
-            const float* qcol = qtab + (size_t)slot * nb * 4;
-            for (int k = 0; k < nb; ++k) {
-                const int t0 = band[2 * k], t1 = band[2 * k + 1];
-                const float* Pk = P + (size_t)k * T;
+        for (int tr = 0; tr < ns; ++tr) {                     // phase 2
+            const float* ytr = y + (size_t)tr * row_in;
+            float* ptr = par + (size_t)tr * row_out;
+            long long* ttr = want_tok ? tokens_out + (b0 + tr) * row_out : nullptr;
+#pragma unroll 2
+            for (int r = tid; r < row_out; r += kTiledThreads) {
+                const int e = tab[r];
+                const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
+                const bool grip = e < 0;
+                const float* Pk = (grip ? Pg : Pj) + (size_t)k * T;
+                const int t0 = s_band[(grip ? 2 * nb : 0) + 2 * k], t1 = s_band[(grip ? 2 * nb : 0) + 2 * k + 1];
+                const float* col = ytr + s_dof[slot];
                 float acc = 0.0f;
-                for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), ycol[t * D], acc);
-                if (want_par || want_mm) pcol[k] = acc;
+                for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), col[t * D], acc);
+                const int c = slot * nb + k;
+                if (want_par || want_mm) ptr[c] = acc;
                 if (want_tok) {
+                    const float4 q = *(const float4*)(qtab + 4 * c);
                     QuantCol qc;
-                    qc.lo = qcol[4 * k]; qc.hi = qcol[4 * k + 1]; qc.scale = qcol[4 * k + 2]; qc.rcp = qcol[4 * k + 3];
-                    tcol[(size_t)k * D] = quantize_col(acc, qc, vm1) + offset;
+                    qc.lo = q.x; qc.hi = q.y; qc.scale = q.z; qc.rcp = q.w;
+                    ttr[r] = quantize_col(acc, qc, vm1) + offset;
                 }
             }
         }
@@ -90,7 +102,7 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
                     for (int i = tid; i < n_out; i += kTiledThreads) dst[i] = par[i];
                 }
             }
-            if (want_mm) {                                    // a thread owns columns c, c + 256, ...: no atomics needed
+            if (want_mm) {                                    // a thread owns columns c, c + blockDim, ...: no atomics needed
                 for (int c = tid; c < row_out; c += kTiledThreads) {
                     float mn = s_mn[c], mx = s_mx[c];
                     for (int tr = 0; tr < ns; ++tr) {
@@ -109,7 +121,10 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
     }
 }
 
-// decode: tile of token rows (or coefficient rows) -> trajectories
+// decode: tile of token rows (or coefficient rows) -> trajectories.
+// Per tile: (1) one TOKEN per thread and step in token order (contiguous int64 loads), dequantised exactly into shared
+// memory; (2) one output SAMPLE per thread and step in output order (contiguous fp32 stores): the sum over the band of
+// basis row t against the slot's coefficients.
 template <bool FROM_TOKENS>
 __global__ void __launch_bounds__(kTiledThreads)
 decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restrict__ params, long long B, int T, int D,
@@ -119,56 +134,65 @@ decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restric
                     float* __restrict__ out, int S) {
     extern __shared__ __align__(16) float smem_f[];
     const int row_in = D * nb, row_out = T * D;
-    float* c_s = smem_f;                                      // [S][nb][D]   (token order: slot minor)
-    float* o_s = c_s + (size_t)S * row_in;                    // [S][T][D]
+    float* c_s = smem_f;                                        // [S][nb][D]   (token order: slot minor)
+    float* lohi = c_s + (((size_t)S * row_in + 3) & ~(size_t)3);    // [D*nb][2] bounds in token order
+    int* tab_in = (int*)(lohi + (size_t)2 * row_in);            // [D*nb] k | slot << 16
+    int* tab_out = tab_in + row_in;                             // [T*D]  t | slot << 16 | grip << 31, output order [t][dof]
+    int* s_band = tab_out + row_out;                            // [2][2*T]
+    int* s_dof = s_band + 4 * T;                                // [D]
     const int tid = threadIdx.x;
-    const float rcp_vm1 = __frcp_rn(vm1);                     // exact invariant division by V - 1 (common.cuh)
+    const float rcp_vm1 = __frcp_rn(vm1);                       // exact invariant division by V - 1 (common.cuh)
+    for (int r = tid; r < row_in; r += kTiledThreads) {
+        const int k = r / D, slot = r - k * D;
+        tab_in[r] = k | (slot << 16);
+        if (FROM_TOKENS) { lohi[2 * r] = w_min[slot * nb + k]; lohi[2 * r + 1] = w_max[slot * nb + k]; }
+    }
+    for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = slot_to_dof[i];
+    for (int i = tid; i < 4 * T; i += kTiledThreads) s_band[i] = bands[4 * nb + i];
+    __syncthreads();
+    for (int q = tid; q < row_out; q += kTiledThreads) {
+        const int t = q / D, dof = q - t * D;
+        int slot = 0;
+        for (int sidx = 0; sidx < D; ++sidx) if (s_dof[sidx] == dof) slot = sidx;
+        tab_out[q] = t | (slot << 16) | (slot < n_joint ? 0 : (int)0x80000000u);
+    }
     const long long n_tiles = (B + S - 1) / S;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * S;
         const int ns = (int)((B - b0) < S ? (B - b0) : S);
         __syncthreads();
-        // phase 1: one (trajectory, slot) column per thread, k ascending (adjacent lanes = adjacent slots: the int64
-        // token loads of a step are contiguous runs); coefficients land in token order [k][slot]
-        for (int col = tid; col < ns * D; col += kTiledThreads) {
-            const int tr = col / D, slot = col - tr * D;
-            const bool pin0 = init_p != nullptr && slot < n_joint;
-            float* ccol = c_s + (size_t)tr * row_in + slot;
-            if (FROM_TOKENS) {
-                const long long* tcol = tokens + (b0 + tr) * row_in + slot;
-                const float* lo = w_min + slot * nb;
-                const float* hi = w_max + slot * nb;
-                for (int k = 0; k < nb; ++k)
-                    ccol[(size_t)k * D] = dequantize_fast(__ldcs(tcol + (size_t)k * D) - offset, __ldg(lo + k), __ldg(hi + k), vm1, rcp_vm1);
-            } else {
-                const float* pcol = params + (b0 + tr) * row_in + slot * nb;
-                for (int k = 0; k < nb; ++k) ccol[(size_t)k * D] = pcol[k];
+        for (int tr = 0; tr < ns; ++tr) {                     // phase 1
+            float* ctr = c_s + (size_t)tr * row_in;
+            const long long* ttr = FROM_TOKENS ? tokens + (b0 + tr) * row_in : nullptr;
+            const float* ptr = FROM_TOKENS ? nullptr : params + (b0 + tr) * row_in;
+            const float* ip = init_p ? init_p + (b0 + tr) * D : nullptr;
+#pragma unroll 2
+            for (int r = tid; r < row_in; r += kTiledThreads) {
+                const int e = tab_in[r];
+                const int k = e & 0xffff, slot = e >> 16;
+                float v;
+                if (FROM_TOKENS) v = dequantize_fast(__ldcs(ttr + r) - offset, lohi[2 * r], lohi[2 * r + 1], vm1, rcp_vm1);
+                else v = ptr[slot * nb + k];
+                if (k == 0 && ip && slot < n_joint) v = ip[s_dof[slot]];
+                ctr[r] = v;
             }
-            if (pin0) ccol[0] = init_p[(b0 + tr) * D + slot_to_dof[slot]];
         }
         __syncthreads();
-        // phase 2: the same columns, t ascending over the non-zero band of every basis row
-        const int n_out = ns * row_out;
-        for (int col = tid; col < ns * D; col += kTiledThreads) {
-            const int tr = col / D, slot = col - tr * D;
-            const bool joint = slot < n_joint;
-            const float* phi = joint ? phi_j : phi_g;
-            const int* band = bands + 4 * nb + (joint ? 0 : 2 * T);
-            const float* ccol = c_s + (size_t)tr * row_in + slot;
-            float* ocol = o_s + (size_t)tr * row_out + slot_to_dof[slot];
-            for (int t = 0; t < T; ++t) {
-                const float* row = phi + (size_t)t * nb;
+        for (int tr = 0; tr < ns; ++tr) {                     // phase 2
+            const float* ctr = c_s + (size_t)tr * row_in;
+            float* otr = out + (b0 + tr) * row_out;
+#pragma unroll 2
+            for (int q = tid; q < row_out; q += kTiledThreads) {
+                const int e = tab_out[q];
+                const int t = e & 0xffff, slot = (e >> 16) & 0x7fff;
+                const bool grip = e < 0;
+                const float* row = (grip ? phi_g : phi_j) + (size_t)t * nb;
+                const int k0 = s_band[(grip ? 2 * T : 0) + 2 * t], k1 = s_band[(grip ? 2 * T : 0) + 2 * t + 1];
+                const float* col = ctr + slot;
                 float acc = 0.0f;
-                for (int k = band[2 * t]; k < band[2 * t + 1]; ++k) acc = fmaf(__ldg(row + k), ccol[(size_t)k * D], acc);
-                ocol[(size_t)t * D] = acc;
+                for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(row + k), col[(size_t)k * D], acc);
+                __stcs(otr + q, acc);
             }
-        }
-        __syncthreads();
-        float* dst = out + b0 * row_out;                      // phase 3: contiguous rows out
-        if ((((uintptr_t)dst) & 15u) == 0 && (n_out & 3) == 0) {
-            for (int i = tid; i < (n_out >> 2); i += kTiledThreads) __stcs((float4*)dst + i, ((const float4*)o_s)[i]);
-        } else {
-            for (int i = tid; i < n_out; i += kTiledThreads) dst[i] = o_s[i];
         }
     }
 }
@@ -190,7 +214,9 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
     const int T = p->T, D = p->D, nb = p->nb;
     const size_t per_traj = ((size_t)T * D + (size_t)D * nb) * sizeof(float);
     if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // the two tables share one shared-memory region
-    const size_t extra = (bmin ? (size_t)2 : tokens_out ? (size_t)4 : (size_t)0) * D * nb * sizeof(float);
+    if (nb > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
+    // quantiser constants / min-max (4 floats per column), token-position table, bands, slot map
+    const size_t extra = ((size_t)5 * D * nb + (size_t)4 * nb + D) * sizeof(float) + 64;
     const int S = tile_rows(per_traj, extra, p->max_smem_optin);
     if (S < 1 || !p->bands_d) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)S * per_traj + extra;
@@ -214,10 +240,12 @@ int launch_decode_tiled(const Plan* p, const long long* tokens, const float* par
                         const float* w_max, long long offset, const float* init_p, float* out, cudaStream_t st) {
     const int T = p->T, D = p->D, nb = p->nb;
     if (p->nc != nb || !p->bands_d) return BEAST_E_UNSUPPORTED;           // pinned control points: generic kernel
-    const size_t per_traj = ((size_t)T * D + (size_t)D * nb) * sizeof(float);
-    const int S = tile_rows(per_traj, 0, p->max_smem_optin);
+    if (nb > 0xffff || T > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
+    const size_t per_traj = (size_t)D * nb * sizeof(float);
+    const size_t extra = ((size_t)3 * D * nb + (size_t)T * D + (size_t)4 * T + D) * sizeof(float) + 64;
+    const int S = tile_rows(per_traj, extra, p->max_smem_optin);
     if (S < 1) return BEAST_E_UNSUPPORTED;
-    const size_t smem = (size_t)S * per_traj;
+    const size_t smem = (size_t)S * per_traj + extra;
     static size_t granted_t[kMaxDevices] = {}, granted_p[kMaxDevices] = {};
     if (int rc = tokens ? opt_in_smem(decode_tiled_kernel<true>, smem, granted_t) : opt_in_smem(decode_tiled_kernel<false>, smem, granted_p))
         return rc;
