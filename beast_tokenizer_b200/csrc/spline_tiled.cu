@@ -31,22 +31,25 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
     extern __shared__ __align__(16) float smem_f[];
     const int row_in = T * D, row_out = D * nb;
     float* y = smem_f;                                          // [S][T][D]
-    float* par = y + (((size_t)S * row_in + 3) & ~(size_t)3);   // [S][D][nb]  (coefficient layout '(d t)'), 16-byte aligned
-    float* qtab = par + (((size_t)S * row_out + 3) & ~(size_t)3);   // [D*nb][4] quantiser constants, or [2][D*nb] min / max
+    const int pitch = nb | 1, prow = D * pitch;                 // odd pitch: the '(d t)' staging is free of bank conflicts
+    float* par = y + (((size_t)S * row_in + 3) & ~(size_t)3);   // [S][D][pitch] coefficients, slot major
+    float* qtab = par + (((size_t)S * prow + 3) & ~(size_t)3);  // [D*nb][4] quantiser constants in TOKEN order, or [2][D*nb] min / max
     float* s_mn = qtab;
     float* s_mx = qtab + row_out;
-    int* tab = (int*)(qtab + (size_t)4 * row_out);              // [D*nb] k | slot << 16 | (joint ? 0 : 1 << 31)
-    int* s_band = tab + row_out;                                // [2][2*nb]
+    int* tab = (int*)(qtab + (size_t)4 * row_out);              // [D*nb] token position r -> k | slot << 16 | (joint ? 0 : 1 << 31)
+    int* ctab = tab + row_out;                                  // [D*nb] column c = slot*nb + k -> slot*pitch + k
+    int* s_band = ctab + row_out;                               // [2][2*nb]
     int* s_dof = s_band + 4 * nb;                               // [D]
     const bool want_mm = bmin != nullptr, want_par = params_out != nullptr, want_tok = tokens_out != nullptr;
     const int tid = threadIdx.x;
     for (int r = tid; r < row_out; r += kTiledThreads) {
         const int k = r / D, slot = r - k * D;
         tab[r] = k | (slot << 16) | (slot < n_joint ? 0 : (int)0x80000000u);
+        ctab[r] = (r / nb) * pitch + (r % nb);                  // r read as a column index here
         if (want_mm) { s_mn[r] = __int_as_float(0x7f800000); s_mx[r] = __int_as_float(0xff800000); }
         else if (want_tok) {
             QuantCol qc;
-            qc.init(w_min[r], w_max[r]);                        // r runs over all columns c = slot*nb + k as well
+            qc.init(w_min[slot * nb + k], w_max[slot * nb + k]);
             qtab[4 * r] = qc.lo; qtab[4 * r + 1] = qc.hi; qtab[4 * r + 2] = qc.scale; qtab[4 * r + 3] = qc.rcp;
         }
     }
@@ -67,12 +70,11 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
             }
         }
         __syncthreads();
-        const int n_out = ns * row_out;
         for (int tr = 0; tr < ns; ++tr) {                     // phase 2
             const float* ytr = y + (size_t)tr * row_in;
-            float* ptr = par + (size_t)tr * row_out;
+            float* ptr = par + (size_t)tr * prow;
             long long* ttr = want_tok ? tokens_out + (b0 + tr) * row_out : nullptr;
-#pragma unroll 2
+#pragma unroll 4
             for (int r = tid; r < row_out; r += kTiledThreads) {
                 const int e = tab[r];
                 const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
@@ -82,10 +84,9 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
                 const float* col = ytr + s_dof[slot];
                 float acc = 0.0f;
                 for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), col[t * D], acc);
-                const int c = slot * nb + k;
-                if (want_par || want_mm) ptr[c] = acc;
+                if (want_par || want_mm) ptr[slot * pitch + k] = acc;
                 if (want_tok) {
-                    const float4 q = *(const float4*)(qtab + 4 * c);
+                    const float4 q = *(const float4*)(qtab + 4 * r);
                     QuantCol qc;
                     qc.lo = q.x; qc.hi = q.y; qc.scale = q.z; qc.rcp = q.w;
                     ttr[r] = quantize_col(acc, qc, vm1) + offset;
@@ -95,18 +96,19 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
         if (want_par || want_mm) {
             __syncthreads();
             if (want_par) {                                   // phase 3: coefficients leave as contiguous rows
-                float* dst = params_out + b0 * row_out;
-                if ((((uintptr_t)dst) & 15u) == 0 && (n_out & 3) == 0) {
-                    for (int i = tid; i < (n_out >> 2); i += kTiledThreads) __stcs((float4*)dst + i, ((const float4*)par)[i]);
-                } else {
-                    for (int i = tid; i < n_out; i += kTiledThreads) dst[i] = par[i];
+                for (int tr = 0; tr < ns; ++tr) {
+                    float* dst = params_out + (b0 + tr) * row_out;
+                    const float* src = par + (size_t)tr * prow;
+#pragma unroll 4
+                    for (int c = tid; c < row_out; c += kTiledThreads) __stcs(dst + c, src[ctab[c]]);
                 }
             }
             if (want_mm) {                                    // a thread owns columns c, c + blockDim, ...: no atomics needed
                 for (int c = tid; c < row_out; c += kTiledThreads) {
                     float mn = s_mn[c], mx = s_mx[c];
+                    const int pc = ctab[c];
                     for (int tr = 0; tr < ns; ++tr) {
-                        const float v = par[(size_t)tr * row_out + c];
+                        const float v = par[(size_t)tr * prow + pc];
                         mn = fminf(mn, v); mx = fmaxf(mx, v);
                     }
                     s_mn[c] = mn; s_mx[c] = mx;
@@ -166,7 +168,7 @@ decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restric
             const long long* ttr = FROM_TOKENS ? tokens + (b0 + tr) * row_in : nullptr;
             const float* ptr = FROM_TOKENS ? nullptr : params + (b0 + tr) * row_in;
             const float* ip = init_p ? init_p + (b0 + tr) * D : nullptr;
-#pragma unroll 2
+#pragma unroll 4
             for (int r = tid; r < row_in; r += kTiledThreads) {
                 const int e = tab_in[r];
                 const int k = e & 0xffff, slot = e >> 16;
@@ -181,7 +183,7 @@ decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restric
         for (int tr = 0; tr < ns; ++tr) {                     // phase 2
             const float* ctr = c_s + (size_t)tr * row_in;
             float* otr = out + (b0 + tr) * row_out;
-#pragma unroll 2
+#pragma unroll 4
             for (int q = tid; q < row_out; q += kTiledThreads) {
                 const int e = tab_out[q];
                 const int t = e & 0xffff, slot = (e >> 16) & 0x7fff;
@@ -212,11 +214,11 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
                         long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
                         cudaStream_t st) {
     const int T = p->T, D = p->D, nb = p->nb;
-    const size_t per_traj = ((size_t)T * D + (size_t)D * nb) * sizeof(float);
+    const size_t per_traj = ((size_t)T * D + (size_t)D * (nb | 1)) * sizeof(float);
     if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // the two tables share one shared-memory region
     if (nb > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
-    // quantiser constants / min-max (4 floats per column), token-position table, bands, slot map
-    const size_t extra = ((size_t)5 * D * nb + (size_t)4 * nb + D) * sizeof(float) + 64;
+    // quantiser constants / min-max (4 floats per column), token-position and column tables, bands, slot map
+    const size_t extra = ((size_t)6 * D * nb + (size_t)4 * nb + D) * sizeof(float) + 64;
     const int S = tile_rows(per_traj, extra, p->max_smem_optin);
     if (S < 1 || !p->bands_d) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)S * per_traj + extra;
