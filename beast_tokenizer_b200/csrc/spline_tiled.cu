@@ -38,14 +38,22 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
     float* s_mx = qtab + row_out;
     int* tab = (int*)(qtab + (size_t)4 * row_out);              // [D*nb] token position r -> k | slot << 16 | (joint ? 0 : 1 << 31)
     int* ctab = tab + row_out;                                  // [D*nb] column c = slot*nb + k -> slot*pitch + k
-    int* s_band = ctab + row_out;                               // [2][2*nb]
+    int* ztok = ctab + row_out;                                 // [D*nb] token of a zero coefficient, token order (empty projector rows)
+    int* s_band = ztok + row_out;                               // [2][2*nb]
     int* s_dof = s_band + 4 * nb;                               // [D]
     const bool want_mm = bmin != nullptr, want_par = params_out != nullptr, want_tok = tokens_out != nullptr;
     const int tid = threadIdx.x;
     for (int r = tid; r < row_out; r += kTiledThreads) {
         const int k = r / D, slot = r - k * D;
-        tab[r] = k | (slot << 16) | (slot < n_joint ? 0 : (int)0x80000000u);
+        const bool grip_r = slot >= n_joint;
+        const bool empty = bands[(grip_r ? 2 * nb : 0) + 2 * k] >= bands[(grip_r ? 2 * nb : 0) + 2 * k + 1];
+        // bits 0-13 k, 14 = projector row k is all zero (the coefficient is exactly 0 for every trajectory), 16-30 slot, 31 gripper
+        tab[r] = k | (empty ? 0x4000 : 0) | (slot << 16) | (grip_r ? (int)0x80000000u : 0);
         ctab[r] = (r / nb) * pitch + (r % nb);                  // r read as a column index here
+        if (want_tok) {
+            const float lo0 = w_min[slot * nb + k], hi0 = w_max[slot * nb + k];
+            ztok[r] = (int)quantize_one(0.0f, lo0, hi0, quant_scale(lo0, hi0), vm1);
+        }
         if (want_mm) { s_mn[r] = __int_as_float(0x7f800000); s_mx[r] = __int_as_float(0xff800000); }
         else if (want_tok) {
             QuantCol qc;
@@ -77,9 +85,14 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
 #pragma unroll 4
             for (int r = tid; r < row_out; r += kTiledThreads) {
                 const int e = tab[r];
-                const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
+                const int k = e & 0x3fff, slot = (e >> 16) & 0x7fff;
+                if (e & 0x4000) {                             // empty projector row: coefficient 0, token a per-column constant
+                    if (want_par || want_mm) ptr[slot * pitch + k] = 0.0f;
+                    if (want_tok) ttr[r] = (long long)ztok[r] + offset;
+                    continue;
+                }
                 const bool grip = e < 0;
-                const float* Pk = (grip ? Pg : Pj) + (size_t)k * T;
+                const float* Pk = (grip ? Pg : Pj) + k * T;
                 const int t0 = s_band[(grip ? 2 * nb : 0) + 2 * k], t1 = s_band[(grip ? 2 * nb : 0) + 2 * k + 1];
                 const float* col = ytr + s_dof[slot];
                 float acc = 0.0f;
@@ -128,7 +141,7 @@ encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, i
 // memory; (2) one output SAMPLE per thread and step in output order (contiguous fp32 stores): the sum over the band of
 // basis row t against the slot's coefficients.
 template <bool FROM_TOKENS>
-__global__ void __launch_bounds__(kTiledThreads)
+__global__ void __launch_bounds__(kTiledThreads, 4)
 decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restrict__ params, long long B, int T, int D,
                     int nb, int n_joint, const int* __restrict__ slot_to_dof, const float* __restrict__ phi_j,
                     const float* __restrict__ phi_g, const int* __restrict__ bands, const float* __restrict__ w_min,
@@ -199,9 +212,7 @@ decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restric
     }
 }
 
-static int tile_rows(size_t bytes_per_traj, size_t extra, int max_smem) {
-    // three CTAs per SM when possible: ~70 KB each
-    size_t budget = 104 * 1024;                          // two CTAs per SM
+static int tile_rows(size_t bytes_per_traj, size_t extra, int max_smem, size_t budget) {
     if (budget > (size_t)max_smem) budget = (size_t)max_smem;
     if (bytes_per_traj + extra > budget) budget = (size_t)max_smem;
     if (bytes_per_traj + extra > budget) return 0;
@@ -216,10 +227,10 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
     const int T = p->T, D = p->D, nb = p->nb;
     const size_t per_traj = ((size_t)T * D + (size_t)D * (nb | 1)) * sizeof(float);
     if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // the two tables share one shared-memory region
-    if (nb > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
-    // quantiser constants / min-max (4 floats per column), token-position and column tables, bands, slot map
-    const size_t extra = ((size_t)6 * D * nb + (size_t)4 * nb + D) * sizeof(float) + 64;
-    const int S = tile_rows(per_traj, extra, p->max_smem_optin);
+    if (nb > 0x3fff || D > 0x7fff || p->V > 0x7fffffff) return BEAST_E_UNSUPPORTED;
+    // quantiser constants / min-max (4 floats per column), token-position, column and zero-token tables, bands, slot map
+    const size_t extra = ((size_t)7 * D * nb + (size_t)4 * nb + D) * sizeof(float) + 64;
+    const int S = tile_rows(per_traj, extra, p->max_smem_optin, 104 * 1024);
     if (S < 1 || !p->bands_d) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)S * per_traj + extra;
     static size_t granted[kMaxDevices] = {};
@@ -245,7 +256,7 @@ int launch_decode_tiled(const Plan* p, const long long* tokens, const float* par
     if (nb > 0xffff || T > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
     const size_t per_traj = (size_t)D * nb * sizeof(float);
     const size_t extra = ((size_t)3 * D * nb + (size_t)T * D + (size_t)4 * T + D) * sizeof(float) + 64;
-    const int S = tile_rows(per_traj, extra, p->max_smem_optin);
+    const int S = tile_rows(per_traj, extra, p->max_smem_optin, 54 * 1024);   // four CTAs per SM: the token loads need the warps
     if (S < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = (size_t)S * per_traj + extra;
     static size_t granted_t[kMaxDevices] = {}, granted_p[kMaxDevices] = {};
