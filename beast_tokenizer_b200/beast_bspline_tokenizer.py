@@ -3,7 +3,12 @@
 
 Same constructor, methods, return types, exceptions and on-disk format; underneath, the
 movement-primitive library, the per-trajectory LU solve and the elementwise quantiser are
-replaced by the C-ABI kernels of libbeast_b200.so (include/beast_b200.h):
+replaced by the C-ABI kernels of libbeast_b200.so (include/beast_b200.h).
+
+Limits next to the reference (also in README "Out of scope"): the three visualize_* methods raise
+NotImplementedError (plotting); num_dof <= 64 (BEAST_MAX_DOF); init / end condition orders 0, 1, 2 only;
+non-finite trajectories are not rejected — the fused min / max and the clamp use IEEE fmin / fmax, which
+drop a NaN where torch.min / torch.clamp would propagate it.  Entry points:
 
     encode / compute_weights / encode_continuous  -> beast_encode_f32 (+ quantize / normalize)
     decode / reconstruct_traj(_continuous)        -> beast_decode_f32 / _times / dequantize / eval
@@ -113,6 +118,7 @@ class BEASTBsplineTokenizer(TokenizerBase):
         self.use_bpe = use_bpe
 
         self.times = make_times(duration, seq_len)
+        self._times_version = 0
         self._plan_cache = None
         # sharded fitting is opt-in (set_process_group): an implicit collective inside update_weights_bounds /
         # fit_parameters would hang every caller that fits on one rank of an initialised job
@@ -161,7 +167,9 @@ class BEASTBsplineTokenizer(TokenizerBase):
 
     def _plan(self) -> _Plan:
         dev = self._cuda()
-        key = (dev, self.times.data_ptr(), int(self.times.numel()), int(self.vocab_size))
+        # `times` is part of the geometry: update_times() bumps the version; in-place edits of tok.times are picked up
+        # through the content hash of the (short) vector
+        key = (dev, self._times_version, hash(self.times.numpy().tobytes()), int(self.vocab_size))
         if self._plan_cache is None or self._plan_cache[0] != key:
             consts = build_constants(self.times, self.duration, self.num_basis, self.degree_p,
                                      self.joint_indices, self.gripper_indices,
@@ -523,6 +531,7 @@ class BEASTBsplineTokenizer(TokenizerBase):
 
     def update_times(self, times):
         self.times = times.detach().to("cpu", torch.float32).reshape(-1).contiguous()
+        self._times_version += 1
         self._plan_cache = None
 
     # ------------------------------------------------------------------ encoding
@@ -710,6 +719,20 @@ class BEASTBsplineTokenizer(TokenizerBase):
         return out
 
     # ------------------------------------------------------------------ evaluation
+    def _no_plotting(self, name):
+        raise NotImplementedError(
+            f"{name} is matplotlib plotting around encode -> reconstruct_traj (reference beast_bspline_tokenizer.py:600-720), "
+            "outside the B200 hot path; use compute_reconstruction_error(raw_traj, return_tokens=True) and plot the result")
+
+    def visualize_reconstruction_error(self, raw_traj, max_vis_samples=5, update_bounds=True, save_path=None):
+        self._no_plotting("visualize_reconstruction_error")
+
+    def visualize_reconstruction_error_with_llm_tokenizer(self, raw_traj, save_path=None):
+        self._no_plotting("visualize_reconstruction_error_with_llm_tokenizer")
+
+    def visualize_reconstruction_error_with_cont_tokenizer(self, raw_traj, save_path=None):
+        self._no_plotting("visualize_reconstruction_error_with_cont_tokenizer")
+
     def compute_reconstruction_error(self, raw_traj, return_tokens: bool = False):
         """(mean squared error, mean signed error) of encode -> reconstruct (reference :589-597).
         `return_tokens=True` also returns the tokens — the call train/eval.py:34 makes upstream, where

@@ -1936,6 +1936,7 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     const size_t warp_bytes = ((size_t)8 * M + 2 * (size_t)((L + 1) & ~1) + 2 * (size_t)(L + 2) + 15) & ~(size_t)15;
     int warps = (int)((200 * 1024) / warp_bytes);
     if (warps > 8) warps = 8;
+    // test hook, re-read per call (the tests toggle it): one getenv is noise next to a launch
     const char* env = getenv("BEAST_B200_BPE_THREAD_ENCODE");
     if (warps >= 1 && !(env && env[0] == '1')) {
         const size_t smem = warp_bytes * warps;
@@ -1993,8 +1994,9 @@ extern "C" int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static int force_thread = -1;
-    if (force_thread < 0) { const char* env = getenv("BEAST_B200_BPE_THREAD_DECODE"); force_thread = (env && env[0] == '1') ? 1 : 0; }
+    // test hook, re-read per call (the tests toggle it between calls): one getenv is noise next to a launch
+    const char* env_thread = getenv("BEAST_B200_BPE_THREAD_DECODE");
+    const int force_thread = (env_thread && env_thread[0] == '1') ? 1 : 0;
     int only_flagged = 0;
     if (tok_tab && !force_thread && L <= 8192) {
         // fast path: one lane per token from the per-token character table; sequences it cannot describe are flagged

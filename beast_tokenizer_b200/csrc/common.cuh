@@ -176,12 +176,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kernel fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (kernel fails with an error) instead of hanging the GPU.  The bound is wall
+// time on the global timer (60 s): a healthy launch that is merely descheduled (time-slicing with another process,
+// MPS oversubscription, a debugger) never comes near it, whereas SM-clock ticks keep running while descheduled.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();            // ~2 s at 2 GHz
+        if ((++spins & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 60000000000ull) __trap();
+        }
     }
 }
 // global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)

@@ -20,11 +20,15 @@ from .beast_bspline_tokenizer import BEASTBsplineTokenizer
 from .synth import SyntheticLoader
 
 
-def _limit_batches(loader: Iterable[Any], max_batches: int) -> Iterator[Any]:
+def _limit_batches(loader: Iterable[Any], max_batches) -> Iterator[Any]:
+    """Reference train/train_beast.py:16-24: None or <= 0 means the whole loader."""
+    if max_batches is None or max_batches <= 0:
+        yield from loader
+        return
     for i, batch in enumerate(loader):
-        if i >= max_batches:
-            break
         yield batch
+        if i + 1 >= max_batches:
+            break
 
 
 def evaluate_from_path(dataloader, dataset_name: str, tokenizer_path: str, is_bpe_tokenizer: bool = True,
