@@ -80,7 +80,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-constexpr unsigned long long kPeerWaitNs = 5000000000ull;     // a peer that stays silent for 5 s is reported, not waited for
+constexpr unsigned long long kPeerWaitNs = 5000000000ull;
+// Programmatic dependent launch: the three kernels of a merge iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the blocks of the next kernel are scheduled while the
+// previous one drains; pdl_wait() blocks until the previous grid has completed and its writes are visible,
+// pdl_launch() lets the next grid start being scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }     // a peer that stays silent for 5 s is reported, not waited for
 
 
 // GPT-2 pre-tokeniser character classes for codepoints 0..255
@@ -726,6 +732,8 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
                    unsigned int* __restrict__ sig, const int* __restrict__ weight) {
     extern __shared__ int s_delta[];
     if (ctl) {                                                // the state the scan kernel's pick wrote
+        pdl_wait();
+        pdl_launch();
         if (ctl->done) return;
         a = ctl->a; b = ctl->b; c = ctl->c;
         delta += ((ctl->n_merges - 1) & 1) * 4 * V;           // double-buffered by merge parity (peers may still read the other half)
@@ -806,6 +814,8 @@ __global__ void __launch_bounds__(1024)
 bpe_iterate_kernel(int* __restrict__ hist, int V, BpeCtl* __restrict__ ctl, int* __restrict__ delta,
                    unsigned long long* __restrict__ partial, int* __restrict__ work_count,
                    const __grid_constant__ BpePeersDev peers) {
+    pdl_wait();
+    pdl_launch();
     if (ctl->done) return;
     const int n_active = ctl->n_tokens;
     const bool fold = ctl->has_delta != 0;
@@ -960,6 +970,8 @@ bpe_pick_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ l
     __shared__ unsigned long long s_best[8];
     __shared__ int s_pick[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
+    pdl_launch();
     // ---------------- pick
     const BpeCtl cur = *ctl_in;
     if (cur.done) {
@@ -1858,21 +1870,48 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
     // ones are better off with two (measured: 65 k sequences 0.056 -> 0.053 s, 1.6 M sequences 0.214 -> 0.228 s)
     const bool deep_walk = N <= (1 << 19);
     BpeCtl* ctl2 = (BpeCtl*)ctl;
+    static int use_pdl = -1;
+    if (use_pdl < 0) { const char* e = getenv("BEAST_B200_BPE_NO_PDL"); use_pdl = (e && e[0] == '1') ? 0 : 1; }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    auto config = [&](unsigned g, unsigned b, size_t sm) {
+        cudaLaunchConfig_t c;
+        memset(&c, 0, sizeof(c));
+        c.gridDim = dim3(g); c.blockDim = dim3(b); c.dynamicSmemBytes = sm; c.stream = st;
+        c.attrs = attr; c.numAttrs = use_pdl ? 1 : 0;
+        return c;
+    };
+    const unsigned long long* partial = (const unsigned long long*)result;
+    const uint16_t* csym = sym;
+    const int32_t* clen = len;
+    const unsigned int* csig = sig;
+    const int tile_i = (int)tile;
     for (int it = 0; it < (iters < 1 ? 1 : iters); ++it) {
         const int i = first_iter + it;
         BpeCtl* cin = ctl2 + (i & 1);
         BpeCtl* cout = ctl2 + ((i + 1) & 1);
-        bpe_iterate_kernel<<<n_part, 1024, 0, st>>>(hist, V, cin, delta, (unsigned long long*)result, work_count, peers);
+        const BpeCtl* ccin = cin;
+        const BpeCtl* ccout = cout;
+        cudaLaunchConfig_t c1 = config((unsigned)n_part, 1024, 0);
+        cudaError_t e = cudaLaunchKernelEx(&c1, bpe_iterate_kernel, hist, V, cin, delta, (unsigned long long*)result, work_count, peers);
+        if (e != cudaSuccess) return (int)e;
+        cudaLaunchConfig_t c2 = config((unsigned)grid, 256, 0);
         if (deep_walk)
-            bpe_pick_scan_kernel<true><<<grid, 256, 0, st>>>(sym, len, N, n_stride, V, cin, cout, (const unsigned long long*)result,
-                n_part, log, vocab_size, min_frequency, max_merges, work_count, work_seq, work_q0, sig, (int)tile);
+            e = cudaLaunchKernelEx(&c2, bpe_pick_scan_kernel<true>, csym, clen, (long long)N, (long long)n_stride, V, ccin, cout, partial,
+                                   n_part, log, vocab_size, min_frequency, max_merges, work_count, work_seq, work_q0, csig, tile_i);
         else
-            bpe_pick_scan_kernel<false><<<grid, 256, 0, st>>>(sym, len, N, n_stride, V, cin, cout, (const unsigned long long*)result,
-                n_part, log, vocab_size, min_frequency, max_merges, work_count, work_seq, work_q0, sig, (int)tile);
+            e = cudaLaunchKernelEx(&c2, bpe_pick_scan_kernel<false>, csym, clen, (long long)N, (long long)n_stride, V, ccin, cout, partial,
+                                   n_part, log, vocab_size, min_frequency, max_merges, work_count, work_seq, work_q0, csig, tile_i);
+        if (e != cudaSuccess) return (int)e;
         count_launch(2);
         if (N > 0) {
-            bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, 0, 0, 0, V, cout, work_count, work_seq, work_q0,
-                                                        delta, sig, weight);
+            cudaLaunchConfig_t c3 = config((unsigned)grid, 256, smem);
+            const int* cwc = work_count;
+            const int* cws = work_seq;
+            const int* cwq = work_q0;
+            e = cudaLaunchKernelEx(&c3, bpe_rewrite_kernel, sym, len, (long long)n_stride, 0, 0, 0, V, ccout, cwc, cws, cwq, delta, sig, weight);
+            if (e != cudaSuccess) return (int)e;
             count_launch();
         }
     }
