@@ -345,6 +345,16 @@ def bpe_legs(tok, dev, rank, world, dist, with_cpu, cpu_full=False):
              "encode_seq_per_s": nb / (ev[0].elapsed_time(ev[1]) * 1e-3),
              "decode_seq_per_s": nb / (ev[1].elapsed_time(ev[2]) * 1e-3),
              "ids_per_sequence": float(flat.numel()) / nb, "round_trip_exact": bool(torch.equal(back, mp))}
+    # roofline of the two apply paths: 8 B x 140 bins + 4 B x ids per sequence, against the measured HBM peak
+    peak, _ = measured_peak()
+    seq_bytes = 8 * mp.shape[1] + 4 * float(flat.numel()) / nb
+    for name, secs in (("encode", ev[0].elapsed_time(ev[1]) * 1e-3), ("decode", ev[1].elapsed_time(ev[2]) * 1e-3)):
+        gbs = seq_bytes * nb / secs / 1e9
+        apply[f"roofline_bpe_{name}"] = {"bound": "hbm" if name == "decode" else "issue (ncu: 4 300 warp instructions per sequence)",
+                                        "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                        "bytes_per_sequence": seq_bytes, "ms": secs * 1e3,
+                                        "path": "_discrete_to_bpe_csr (bpe_encode + cumsum + bpe_compact)" if name == "encode"
+                                        else "_bpe_csr_to_discrete (bpe_decode: per-token table kernel + flagged fallback)"}
     if with_cpu:
         ref = bpe_apply_cpu_reference(btok, mp[:4096].cpu())
         if ref is not None:
