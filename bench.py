@@ -876,6 +876,13 @@ def main():
                        "launch": launch_mode,
                        "l2": f"{R} rotating buffer sets ({R * (ENC_BYTES + DEC_BYTES) * B / 1e6:.0f} MB) > 126 MB L2; "
                              "decode reads tokens written two steps earlier"},
+            "parity": {"tokens": "bit-exact given identical fp32 coefficients (beast_quantize_f32 on the reference's coefficients); fused K1 tokens == "
+                                 "the exact quantiser applied to K1's own coefficients",
+                       "flips_vs_reference": "profiles/flips_r02.json: 62 of 1 146 880 tokens (first 8 192 trajectories vs the reference's CPU path), all "
+                                             "+-1 bin, reference coefficient within 3.7e-7 * max|w| of the rounding edge (criterion: coefficient tolerance "
+                                             "1e-5 * max|w|, not 1 ulp — the reference's per-trajectory fp32 LU differs from the projector by ~2e-6)",
+                       "coefficients_trajectories": "<= 1e-5 normwise vs the live reference's goldens (tests/test_gpu_spline.py)",
+                       "bpe": "vocab.json / merges.txt / tokenizer.json byte-identical to the reference's files; ids bit-exact"},
             "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "trajectories/s",
                     "h2d_bytes_per_step": 4 * T * D * B, "d2h_bytes_per_step": (8 * NB * D + 4 * T * D) * B,
                     "steps": Ke, "ms_per_step": e2e_ms / Ke, "copy_only_ms": copy_ms / Ke,
