@@ -1238,9 +1238,12 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
             const long long v = row[i] - min_token;
             if (v < 0) st |= 1;
             else if (v > max_shift) st |= 2;
+            if (v == 39) st |= 4;                              // an apostrophe: the contraction rule may apply
             cp[i] = (uint16_t)(v < 0 ? 0 : (v > 0xD7FF ? 0xD7FF : v));
         }
         st = __reduce_or_sync(FULL, st);
+        const bool apos = (st & 4) != 0;                       // warp-uniform: most sequences hold none and skip the look-back
+        st &= 3;
         __syncwarp();
         if (st) {
             if (lane == 0) { status_out[seq] = st; len_out[seq] = 0; }
@@ -1254,7 +1257,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
             int bt[3];
             const int nbt = utf8_encode(cp[i], bt);
             for (int r = 0; r < nbt; ++r) ns += s_b2i[bt[r]] >= 0;
-            const bool t = token_start(cp, i, L, s_cls, cls_tab);
+            const bool t = apos ? token_start(cp, i, L, s_cls, cls_tab) : base_start(cp, i, L, s_cls, cls_tab);
             nst += t;
             if (t && i - p0 < 32) smask |= 1u << (i - p0);
         }
@@ -1267,7 +1270,8 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
         const int total = (int)(__shfl_sync(FULL, inc, 31) >> 16);
         int off = (int)((inc - packed) >> 16), w = (int)((inc - packed) & 0xffffu);
         for (int i = p0; i < p1; ++i) {
-            const bool t = i - p0 < 32 ? ((smask >> (i - p0)) & 1u) != 0 : token_start(cp, i, L, s_cls, cls_tab);
+            const bool t = i - p0 < 32 ? ((smask >> (i - p0)) & 1u) != 0
+                                       : (apos ? token_start(cp, i, L, s_cls, cls_tab) : base_start(cp, i, L, s_cls, cls_tab));
             w += t;
             int bt[3];
             const int nbt = utf8_encode(cp[i], bt);
@@ -1441,7 +1445,7 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
 //   meta = characters started | bytes still needed << 3 | leading continuation bytes << 5 | slow << 7 | payload << 8.
 constexpr int kDecodeNeedsBytes = 0x100;
 template <int SLOTS>
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(256, SLOTS == 2 ? 8 : 5)
 bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
                         long long min_token, const void* __restrict__ tok_tab, int n_vocab,
                         long long* __restrict__ bins_out, int* __restrict__ status_out, int* __restrict__ declen_out) {
@@ -1465,14 +1469,13 @@ bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restric
         const int* ids = flat + p0;
         bool bad = false;
         int cnt = 0;
-        Entry cur = load_entry(lane < n ? ids[lane] : 0, lane < n);
-        if (n > 0 && (__shfl_sync(FULL, cur.meta, 0) & 0x60u)) bad = true;          // the text starts inside a character
-        for (int g0 = 0; g0 < n; g0 += 32) {
-            const int qn = g0 + 32 + lane;
-            const Entry nxt = load_entry(qn < n ? ids[qn] : 0, qn < n);              // in flight while this group is decoded
+        // two groups of 32 tokens per step: their id and table loads are issued together, the next step's are in flight
+        Entry curA = load_entry(lane < n ? ids[lane] : 0, lane < n);
+        Entry curB = load_entry(32 + lane < n ? ids[32 + lane] : 0, 32 + lane < n);
+        if (n > 0 && (__shfl_sync(FULL, curA.meta, 0) & 0x60u)) bad = true;         // the text starts inside a character
+        auto decode_group = [&](const Entry& cur, unsigned int nmeta0) {
             const unsigned int meta = cur.meta;
             unsigned int nmeta = __shfl_down_sync(FULL, meta, 1);
-            const unsigned int nmeta0 = __shfl_sync(FULL, nxt.meta, 0);
             if (lane == 31) nmeta = nmeta0;
             const int nst = (int)(meta & 7u);
             const unsigned int need = (meta >> 3) & 3u;
@@ -1504,7 +1507,15 @@ bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restric
                     if (k < nst && at + k < L) s_cp[at + k] = (uint16_t)(k == nst - 1 ? c[k] | tail : c[k]);
             }
             cnt += total;
-            cur = nxt;
+        };
+        for (int g0 = 0; g0 < n; g0 += 64) {
+            const int qa = g0 + 64 + lane, qb = g0 + 96 + lane;
+            const Entry nxtA = load_entry(qa < n ? ids[qa] : 0, qa < n);
+            const Entry nxtB = load_entry(qb < n ? ids[qb] : 0, qb < n);
+            decode_group(curA, __shfl_sync(FULL, curB.meta, 0));
+            decode_group(curB, __shfl_sync(FULL, nxtA.meta, 0));
+            curA = nxtA;
+            curB = nxtB;
         }
         if (__any_sync(FULL, bad)) {
             if (lane == 0) status_out[seq] = kDecodeNeedsBytes;
