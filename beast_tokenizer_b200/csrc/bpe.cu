@@ -1445,7 +1445,7 @@ bpe_decode_kernel(const int* __restrict__ flat, const long long* __restrict__ of
 //   meta = characters started | bytes still needed << 3 | leading continuation bytes << 5 | slow << 7 | payload << 8.
 constexpr int kDecodeNeedsBytes = 0x100;
 template <int SLOTS>
-__global__ void __launch_bounds__(256, SLOTS == 2 ? 8 : 5)
+__global__ void __launch_bounds__(256, 8)
 bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restrict__ offsets, long long N, int L,
                         long long min_token, const void* __restrict__ tok_tab, int n_vocab,
                         long long* __restrict__ bins_out, int* __restrict__ status_out, int* __restrict__ declen_out) {
@@ -1469,13 +1469,14 @@ bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restric
         const int* ids = flat + p0;
         bool bad = false;
         int cnt = 0;
-        // two groups of 32 tokens per step: their id and table loads are issued together, the next step's are in flight
-        Entry curA = load_entry(lane < n ? ids[lane] : 0, lane < n);
-        Entry curB = load_entry(32 + lane < n ? ids[32 + lane] : 0, 32 + lane < n);
-        if (n > 0 && (__shfl_sync(FULL, curA.meta, 0) & 0x60u)) bad = true;         // the text starts inside a character
-        auto decode_group = [&](const Entry& cur, unsigned int nmeta0) {
+        Entry cur = load_entry(lane < n ? ids[lane] : 0, lane < n);
+        if (n > 0 && (__shfl_sync(FULL, cur.meta, 0) & 0x60u)) bad = true;          // the text starts inside a character
+        for (int g0 = 0; g0 < n; g0 += 32) {
+            const int qn = g0 + 32 + lane;
+            const Entry nxt = load_entry(qn < n ? ids[qn] : 0, qn < n);              // in flight while this group is decoded
             const unsigned int meta = cur.meta;
             unsigned int nmeta = __shfl_down_sync(FULL, meta, 1);
+            const unsigned int nmeta0 = __shfl_sync(FULL, nxt.meta, 0);
             if (lane == 31) nmeta = nmeta0;
             const int nst = (int)(meta & 7u);
             const unsigned int need = (meta >> 3) & 3u;
@@ -1507,15 +1508,7 @@ bpe_decode_token_kernel(const int* __restrict__ flat, const long long* __restric
                     if (k < nst && at + k < L) s_cp[at + k] = (uint16_t)(k == nst - 1 ? c[k] | tail : c[k]);
             }
             cnt += total;
-        };
-        for (int g0 = 0; g0 < n; g0 += 64) {
-            const int qa = g0 + 64 + lane, qb = g0 + 96 + lane;
-            const Entry nxtA = load_entry(qa < n ? ids[qa] : 0, qa < n);
-            const Entry nxtB = load_entry(qb < n ? ids[qb] : 0, qb < n);
-            decode_group(curA, __shfl_sync(FULL, curB.meta, 0));
-            decode_group(curB, __shfl_sync(FULL, nxtA.meta, 0));
-            curA = nxtA;
-            curB = nxtB;
+            cur = nxt;
         }
         if (__any_sync(FULL, bad)) {
             if (lane == 0) status_out[seq] = kDecodeNeedsBytes;
