@@ -4,12 +4,12 @@
 token that differs is listed with the distance of the reference coefficient from the rounding edge — in bins, in
 coefficient units and in ulps of the coefficient — next to the coefficient difference that caused it.
 
-    python scripts/flips_report.py [sample=8192] > gpurun_out/flips_r02.json
+    python tests/flips_report.py [sample=8192] > gpurun_out/flips_r02.json
 """
 import json, math, os, sys
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root (the oracle may only be used from tests/, smoke() and bench.py)
 from beast_tokenizer_b200 import BEASTBsplineTokenizer
 from beast_tokenizer_b200.synth import SyntheticLoader, synth
 from oracle.reference_port_torch import ReferencePort

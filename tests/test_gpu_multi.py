@@ -42,6 +42,20 @@ def _worker(rank, world, port, q):
             full = torch.cat([chunk(c) for c in range(n_chunks)])
             ref = FIGBPE(vocab_size=1024, show_progress=False, device=f"cuda:{rank}", process_group=False).fit_from_bins(full)
             out["ref"] = (ref.tokenizer.merges_txt(), ref.tokenizer.vocab_json(), ref.min_token, ref.max_token)
+        # uneven shards, one of them EMPTY (the last rank holds no sequence at all): same table as the unsharded run
+        os.environ["BEAST_B200_BPE_NO_PEER"] = "0"
+        if rank == world - 1:
+            uneven = shard[:0]
+        else:
+            uneven = torch.cat([chunk(c) for c in range(n_chunks) if c % (world - 1) == rank])[: 3000 + 997 * rank]
+        st = FIGBPE(vocab_size=700, show_progress=False, device=f"cuda:{rank}").fit_from_bins(uneven)
+        out["uneven"] = (st.tokenizer.merges_txt(), st.tokenizer.vocab_json(), st.min_token, st.max_token)
+        parts = [None] * world
+        dist.all_gather_object(parts, uneven.cpu())
+        if rank == 0:
+            ref = FIGBPE(vocab_size=700, show_progress=False, device=f"cuda:{rank}", process_group=False).fit_from_bins(
+                torch.cat(parts).to(dev))
+            out["uneven_ref"] = (ref.tokenizer.merges_txt(), ref.tokenizer.vocab_json(), ref.min_token, ref.max_token)
         # sharded bounds: every rank passes its shard of the trajectories
         xs = [synth_device(3000, 50, 14, 77 + c, dev) for c in range(world)]
         tok.set_process_group("world")
@@ -87,6 +101,7 @@ def test_sharded_trainer_and_bounds_match_unsharded(world):
         assert r["peer"][:4] == ref, f"rank {r['rank']}: peer-fused sharded merge table differs from the unsharded one"
         assert r["nccl"][:4] == ref, f"rank {r['rank']}: NCCL-per-merge sharded merge table differs"
         assert "peer-fused" in (r["peer"][4] or ""), r["peer"][4]          # the NVLink path really ran
+        assert r["uneven"] == by_rank[0]["uneven_ref"], f"rank {r['rank']}: uneven / empty shards give a different table"
         for key in ("minmax", "quant"):
             lo, hi = r[key]
             lo0, hi0 = by_rank[0][key + "_ref"]
