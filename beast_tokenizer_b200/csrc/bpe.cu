@@ -33,7 +33,6 @@ namespace beast {
 // sequence holds or ever held (bits are only added, so the set is a superset).  Stored word-major
 // (sig[word * n_stride + seq]) so that the scan for one pair reads a single 4-byte column.
 constexpr int kScanTile = 2048;          // sequences filtered per block and step by the signature scan
-constexpr long long kPersistMaxN = 400000;  // (pseudo-)sequences up to which the merge loop runs as one cooperative kernel
 constexpr int kDirectDeltaWork = 1 << 17; // rewrite: work lists up to this size are rewritten one warp per sequence
 constexpr int kGlobalDeltaWork = 1 << 14; // ... and up to this size their count changes go straight to the global delta block // rewrite: work lists up to this size update the global delta directly
 constexpr int kSigWords = 64;
@@ -1133,9 +1132,9 @@ bpe_pick_scan_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ l
                          min_frequency, max_merges, work_count, work_seq, work_q0, sig, tile_size);
 }
 
-// The whole merge loop in ONE cooperative kernel (small corpora: sharded runs, de-duplicated repetitive data): the
-// three phases of an iteration are separated by grid barriers (~1.5 us each) instead of kernel boundaries, and the
-// host enqueues one launch per block of up to 256 merges.  One 1024-thread block per SM; the scan and rewrite phases
+// The whole merge loop in ONE cooperative kernel (opt-in, BEAST_B200_BPE_LOOP=persistent): the three phases of an
+// iteration are separated by grid barriers instead of kernel boundaries, and the host enqueues one launch per block of
+// up to 256 merges.  Slower than the PDL-chained launches on every size measured (see bpe_train_step).  One 1024-thread block per SM; the scan and rewrite phases
 // run as four 256-thread virtual blocks per block (VBlock), the code is the stand-alone kernels' code.
 struct LoopArgs {
     uint16_t* sym; int* len; long long N, n_stride; int V;
@@ -1986,12 +1985,14 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
         c.attrs = attr; c.numAttrs = use_pdl ? 1 : 0;
         return c;
     };
-    // small corpora (sharded runs, de-duplicated repetitive data): the whole block of iterations in ONE cooperative
-    // kernel, grid barriers instead of kernel boundaries (BEAST_B200_BPE_LOOP = launches | persistent | auto)
+    // BEAST_B200_BPE_LOOP=persistent: the whole block of iterations in ONE cooperative kernel, grid barriers instead of
+    // kernel boundaries.  Measured SLOWER than the PDL-chained launches (200 k-sequence shard 62.6 vs 40.2 ms, 12 000
+    // pseudo-sequences 54.3 vs 31.3 ms: three grid barriers of a 148 x 1024-thread grid cost more than three
+    // programmatic launch boundaries), so it is opt-in; kept because it is the same device code and is tested.
     const char* loop_env = getenv("BEAST_B200_BPE_LOOP");      // re-read per call: the tests run both forms in one process
-    const int loop_mode = (loop_env && loop_env[0] == 'l') ? 0 : (loop_env && loop_env[0] == 'p') ? 1 : 2;
+    const int loop_mode = (loop_env && loop_env[0] == 'p') ? 1 : 0;
     const size_t loop_smem = (size_t)64 * V + (size_t)4 * 8 * kRewriteOut * sizeof(uint16_t);
-    if ((loop_mode == 1 || (loop_mode == 2 && N <= kPersistMaxN)) && loop_smem <= 176 * 1024) {
+    if (loop_mode == 1 && loop_smem <= 176 * 1024) {
         static size_t granted_ld[kMaxDevices] = {}, granted_lf[kMaxDevices] = {};
         int rc2 = deep_walk ? opt_in_smem(bpe_loop_kernel<true>, loop_smem, granted_ld) : opt_in_smem(bpe_loop_kernel<false>, loop_smem, granted_lf);
         int per_sm = 0, coop = 0, dev = 0;
