@@ -775,7 +775,8 @@ def main():
     # ---- end-to-end leg: public API, pinned host input, results back on the host.  The step is the same
     # 65 536-trajectory batch, fed as 8 chunks over 3 streams so that the H2D copy of one chunk, the
     # kernels of another and the D2H copies of a third overlap (PCIe is full duplex).
-    n_chunks, n_streams = 8, 3
+    n_chunks = int(os.environ.get("BEAST_BENCH_E2E_CHUNKS", "8"))
+    n_streams = int(os.environ.get("BEAST_BENCH_E2E_STREAMS", "3"))
     cb = B // n_chunks
     xh = [synth(B, T, D, seed=50 + 1000 * rank + i).pin_memory() for i in range(2)]
     tok_h = torch.empty((B, NB * D), dtype=torch.int64).pin_memory()
@@ -888,7 +889,7 @@ def main():
                     "steps": Ke, "ms_per_step": e2e_ms / Ke, "copy_only_ms": copy_ms / Ke,
                     "frac_of_copy_only": copy_ms / e2e_ms,
                     "path": "BEASTBsplineTokenizer.encode(pinned host) -> reconstruct_traj -> tokens+trajectories to pinned host; "
-                            "8 chunks over 3 CUDA streams (H2D / kernels / D2H overlapped)", "timer": "host clock, all streams synchronised"},
+                            f"{n_chunks} chunks over {n_streams} CUDA streams (H2D / kernels / D2H overlapped)", "timer": "host clock, all streams synchronised"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "encode_fast_kernel (K1)", "achieved": enc_gbs, "peak": peak,
