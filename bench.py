@@ -570,6 +570,37 @@ def shipped_shape_leg(dev, with_cpu):
                                 "GBps": dec_bytes * n / (dec_ms * 1e-3) / 1e9,
                                 "frac_of_measured_hbm": dec_bytes * n / (dec_ms * 1e-3) / 1e9 / peak},
            "max_abs_reconstruction_error": float((rec - x).abs().max().item())}
+    # the BPE stage of the same configuration (train.sh: --bpe-vocab-size 2048): 1 600-bin sequences, 2-byte UTF-8 symbols
+    from beast_tokenizer_b200 import FIGBPE
+    n_bpe = 16384
+    bins = tokens[:n_bpe]
+    fig = FIGBPE(vocab_size=2048, show_progress=False, device=str(dev), process_group=False)
+    fig.fit_from_bins(bins[:1024])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st = fig.fit_from_bins(bins)
+    torch.cuda.synchronize()
+    bpe_s = time.perf_counter() - t0
+    flat, offs, status = st.tokenizer.encode_bins(bins, st.min_token, st.max_token)
+    back, st2, _ = st.tokenizer.decode_ids(flat, offs, bins.shape[1], st.min_token)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    flat, offs, status = st.tokenizer.encode_bins(bins, st.min_token, st.max_token)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    back, st2, _ = st.tokenizer.decode_ids(flat, offs, bins.shape[1], st.min_token)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    out["bpe"] = {"sequences": n_bpe, "bins_per_sequence": int(bins.shape[1]), "vocab": 2048, "merges": len(st.tokenizer.merges),
+                  "train_seconds": bpe_s, "merges_per_s": len(st.tokenizer.merges) / bpe_s,
+                  "encode_seq_per_s": n_bpe / (t1 - t0), "decode_seq_per_s": n_bpe / (t2 - t1),
+                  "ids_per_sequence": float(flat.numel()) / n_bpe, "round_trip_exact": bool(torch.equal(back, bins)),
+                  "dedup": getattr(st.tokenizer, "dedup_stats", None)}
+    if with_cpu:
+        cpu = hf_train_cpu(bins.cpu().numpy(), 2048)
+        out["bpe"]["cpu_reference"] = {"engine": cpu["engine"], "seconds": cpu["seconds"], "merges_per_s": cpu["merges"] / cpu["seconds"],
+                                       "merge_table_identical": cpu["merges_txt"] == st.tokenizer.merges_txt(),
+                                       "speedup_1gpu": cpu["seconds"] / bpe_s}
     if with_cpu:
         from oracle.reference_port_torch import ReferencePort
         use_all_host_threads()
