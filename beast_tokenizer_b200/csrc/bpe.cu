@@ -1314,7 +1314,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                        long long max_shift, const short* __restrict__ byte_to_id,
                        const uint8_t* __restrict__ cls_tab, const unsigned int* __restrict__ rank_tab, int V,
                        uint16_t* __restrict__ ids_out, int out_stride, int* __restrict__ len_out,
-                       int* __restrict__ status_out, int M, int warp_bytes) {
+                       int* __restrict__ status_out, int M, int warp_bytes, int key2_off) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ short s_b2i[256];
     __shared__ uint8_t s_cls[256];
@@ -1327,6 +1327,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
     uint16_t* wid = sym + M;
     uint16_t* cp = wid + M;
     uint16_t* wbeg = cp + ((L + 1) & ~1);
+    unsigned int* key2 = (unsigned int*)(mine + key2_off);      // ping-pong buffer of the cooperative long-word path
     const int P = (L + 31) >> 5;
     const unsigned int FULL = 0xffffffffu, NONE = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     for (long long seq = (long long)blockIdx.x * nw + warp; seq < N; seq += (long long)gridDim.x * nw) {
@@ -1403,11 +1404,77 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
         // loops of the merge code serialise, so words are handed out longest class first (>= 7 symbols, 3-6, 2; finer classes cost more in ballots than they save):
         // the lanes of one round then run words of similar length.  Single symbols need no work at all.
         // (`sym` is free after phase C and holds the order list.)
+        // Long words (>= kCoopWord symbols: the reference's shipped 1000-bin / 50-basis configuration produces words of
+        // ~60 symbols, runs of one character class) are merged by the WHOLE WARP, one word at a time and one RANK per
+        // step: the ranks a word's merges are applied in never decrease (a pair created by a merge involves the new
+        // token, whose rules were all learned later), so "lowest rank, leftmost first, one merge at a time" equals
+        // "for the lowest rank present, merge ALL its occurrences left to right".  A step is a strided min-scan, the
+        // left-to-right resolution of overlapping candidates by run parity, a compaction by ballot prefix sums and
+        // the re-evaluation of the pair ranks — all lanes busy, all rank look-ups of a step in flight together — instead
+        // of one lane's O(length) scan + shift per single merge.
+        int n_long = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int wq = w0 + lane;
+            const int wl = wq < nwords ? wbeg[wq + 1] - wbeg[wq] : 0;
+            const bool in = wl >= kCoopWord;
+            const unsigned int m = __ballot_sync(FULL, in);
+            if (in) cp[n_long + __popc(m & lt_mask)] = (uint16_t)wq;     // `cp` is free after phase B
+            n_long += __popc(m);
+        }
+        __syncwarp();
+        for (int li = 0; li < n_long; ++li) {
+            const int wq = cp[li];
+            const int b = wbeg[wq];
+            int n = wbeg[wq + 1] - b;
+            unsigned int* cur = key + b;
+            unsigned int* nxt = key2 + b;
+            for (;;) {
+                unsigned int best = 0xffffu;                  // lowest rank present
+                for (int q = lane; q + 1 < n; q += 32) best = min(best, cur[q] >> 16);
+                best = __reduce_min_sync(FULL, best);
+                if (best == 0xffffu) break;
+                int out_n = 0;
+                unsigned int m_prev = 0;                      // was the last position of the previous chunk a match
+                for (int q0 = 0; q0 < n; q0 += 32) {
+                    const int q = q0 + lane;
+                    const unsigned int slot = q < n ? cur[q] : NONE;
+                    const bool cand = q + 1 < n && (slot >> 16) == best;
+                    const unsigned int C = __ballot_sync(FULL, cand);
+                    // match[q] = cand[q] and not match[q-1]: inside a run of candidates the matches alternate from the
+                    // run's first position (from its second when the run continues a matched position of the last chunk)
+                    const unsigned int zeros_below = ~C & lt_mask;
+                    const int run_start = zeros_below ? 32 - __clz(zeros_below) : 0;
+                    const bool match = cand && ((((lane - run_start) + ((run_start == 0) ? (int)m_prev : 0)) & 1) == 0);
+                    const unsigned int Mb = __ballot_sync(FULL, match);
+                    const bool dropped = q < n && (lane == 0 ? m_prev != 0 : ((Mb >> (lane - 1)) & 1u) != 0);
+                    const bool kept = q < n && !dropped;
+                    const unsigned int K = __ballot_sync(FULL, kept);
+                    if (kept) {
+                        unsigned int v = slot & 0xffffu;
+                        if (match) v = __ldg(&rank_tab[(size_t)v * V + (cur[q + 1] & 0xffffu)]) & 0xffffu;   // the merged token
+                        nxt[out_n + __popc(K & lt_mask)] = v;
+                    }
+                    out_n += __popc(K);
+                    m_prev = (Mb >> 31) & 1u;
+                }
+                __syncwarp();
+                n = out_n;
+                for (int q = lane; q < n; q += 32) {          // pair ranks of the shorter word
+                    const unsigned int me = nxt[q];
+                    const unsigned int r = q + 1 < n ? __ldg(&rank_tab[(size_t)me * V + nxt[q + 1]]) : NONE;
+                    cur[q] = (r & 0xffff0000u) | me;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) wid[b] = (uint16_t)n;              // final length, kept in the word's own segment
+            __syncwarp();
+        }
         int n_order = 0;
         for (int cls = 0; cls < 3; ++cls) {
             for (int w0 = 0; w0 < nwords; w0 += 32) {
                 const int wq = w0 + lane;
-                const int wl = wq < nwords ? wbeg[wq + 1] - wbeg[wq] : 0;
+                int wl = wq < nwords ? wbeg[wq + 1] - wbeg[wq] : 0;
+                if (wl >= kCoopWord) wl = 0;                  // done above
                 const bool in = cls == 0 ? wl >= 7 : (cls == 1 ? (wl >= 3 && wl <= 6) : wl == 2);
                 const unsigned int m = __ballot_sync(FULL, in);
                 if (in) sym[n_order + __popc(m & lt_mask)] = (uint16_t)wq;
@@ -2107,7 +2174,8 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     if (M > 65535) return BEAST_E_SHAPE;
     // one warp per sequence, working arrays in shared memory; sequences too long for that (or
     // BEAST_B200_BPE_THREAD_ENCODE=1) take the one-thread-per-sequence kernel
-    const size_t warp_bytes = ((size_t)8 * M + 2 * (size_t)((L + 1) & ~1) + 2 * (size_t)(L + 2) + 15) & ~(size_t)15;
+    const size_t key2_off = ((size_t)8 * M + 2 * (size_t)((L + 1) & ~1) + 2 * (size_t)(L + 2) + 3) & ~(size_t)3;
+    const size_t warp_bytes = (key2_off + (size_t)4 * M + 15) & ~(size_t)15;
     int warps = (int)((200 * 1024) / warp_bytes);
     if (warps > 8) warps = 8;
     // test hook, re-read per call (the tests toggle it): one getenv is noise next to a launch
@@ -2126,7 +2194,7 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
         if (grid > sms * per_sm) grid = sms * per_sm;
         bpe_encode_warp_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
             (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
-            len_out, status_out, M, (int)warp_bytes);
+            len_out, status_out, M, (int)warp_bytes, (int)key2_off);
         count_launch();
         BEAST_CHECK_LAUNCH();
         return BEAST_OK;

@@ -7,6 +7,7 @@ namespace beast {
 constexpr int kBpeBlock = 128;
 constexpr uint16_t kWordStart = 0x8000u;
 constexpr uint16_t kIdMask = 0x7fffu;
+constexpr int kCoopWord = 24;            // pre-tokens from this many symbols on are merged by the whole warp, one rank per step
 constexpr int kMaxWordLong = 8192;       // longest pre-token (in symbols) of the thread-per-sequence encode kernel
 
 // Corpus layout ("chunk-major"): the symbols of sequence `seq` live in 16-byte chunks of 8,
