@@ -445,3 +445,65 @@ def test_token_character_table_matches_the_state_machine():
             if got is not None:
                 assert want == got, (toks, got, want)
     assert accepted > 1000
+
+
+def test_rank_order_batch_merging_equals_one_merge_at_a_time():
+    """The cooperative long-word path of the encode kernel (csrc/bpe.cu: bpe_encode_warp_kernel, phase D) applies, per
+    step, ALL occurrences of the lowest-rank pair present, left to right (overlapping candidates — runs of one symbol —
+    alternate from the run's first position), instead of HF's 'lowest rank, leftmost first, one merge at a time'.
+    The two are equal because a merge only creates pairs that involve the new token, whose rules were learned later
+    (higher rank).  Restated here on random words and random merge tables that respect that property."""
+    rng = np.random.default_rng(3)
+
+    def one_at_a_time(word, rank, new_id):
+        w = list(word)
+        while True:
+            best, bp = None, -1
+            for q in range(len(w) - 1):
+                r = rank.get((w[q], w[q + 1]))
+                if r is not None and (best is None or r < best):
+                    best, bp = r, q
+            if best is None:
+                return w
+            w[bp:bp + 2] = [new_id[(w[bp], w[bp + 1])]]
+
+    def batch_by_rank(word, rank, new_id):
+        w = list(word)
+        while True:
+            ranks = [rank.get((w[q], w[q + 1])) for q in range(len(w) - 1)]
+            present = [r for r in ranks if r is not None]
+            if not present:
+                return w
+            best = min(present)
+            cand = [r == best for r in ranks] + [False]
+            # chunked run-parity resolution, as the kernel does it (32 positions per step, carry = last position matched)
+            match, m_prev = [False] * len(w), False
+            for q0 in range(0, len(w), 32):
+                C = cand[q0:q0 + 32]
+                for lane, c in enumerate(C):
+                    zeros_below = [i for i in range(lane) if not C[i]]
+                    run_start = zeros_below[-1] + 1 if zeros_below else 0
+                    match[q0 + lane] = c and ((lane - run_start) + (int(m_prev) if run_start == 0 else 0)) % 2 == 0
+                m_prev = match[min(q0 + 31, len(w) - 1)] if q0 + 32 <= len(w) else False
+            out, q = [], 0
+            while q < len(w):
+                if match[q]:
+                    out.append(new_id[(w[q], w[q + 1])]); q += 2
+                else:
+                    out.append(w[q]); q += 1
+            w = out
+
+    for trial in range(300):
+        n_alpha = int(rng.integers(2, 6))
+        rank, new_id, n_tok = {}, {}, n_alpha
+        for r in range(int(rng.integers(1, 25))):       # every rule pairs EXISTING tokens: pairs of a new token rank later
+            a, b = int(rng.integers(0, n_tok)), int(rng.integers(0, n_tok))
+            if (a, b) in rank:
+                continue
+            rank[(a, b)] = r
+            new_id[(a, b)] = n_tok
+            n_tok += 1
+        word = rng.integers(0, n_alpha, int(rng.integers(1, 150))).tolist()
+        if trial % 3 == 0:                              # long runs of one symbol: the overlapping-candidate case
+            word = ([0] * int(rng.integers(30, 100))) + word
+        assert batch_by_rank(word, rank, new_id) == one_at_a_time(word, rank, new_id), (word, rank)
