@@ -547,7 +547,7 @@ def shipped_shape_leg(dev, with_cpu):
     tok.update_weights_bounds(x)
     tokens, _ = tok.encode(x)
     rec = tok.reconstruct_traj(tokens)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     reps = 10
     torch.cuda.synchronize()
     ev[0].record()
@@ -558,12 +558,40 @@ def shipped_shape_leg(dev, with_cpu):
         rec = tok.reconstruct_traj(tokens)
     ev[2].record()
     torch.cuda.synchronize()
-    enc_ms, dec_ms = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+    api_enc_ms, api_dec_ms = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+    # the same kernels through the C ABI on preallocated buffers (what the roofline fraction is computed from; the API
+    # path above also pays torch's allocation of 630 MB of outputs per call)
+    from beast_tokenizer_b200 import _lib
+    plan = tok._plan()
+    lo, hi = tok._bounds(dev)
+    toks_b = torch.empty((n, NBs * Ds), device=dev, dtype=torch.int64)
+    pars_b = torch.empty((n, NBs * Ds), device=dev, dtype=torch.float32)
+    out_b = torch.empty((n, Ts, Ds), device=dev, dtype=torch.float32)
+    def enc_raw():
+        _lib.check(plan._lib.beast_encode_f32(plan.handle, _lib.ptr(x), n, _lib.ptr(lo), _lib.ptr(hi), 0, _lib.ptr(pars_b),
+                                              _lib.ptr(toks_b), _lib.stream_ptr(dev)), "encode")
+    def dec_raw():
+        _lib.check(plan._lib.beast_decode_f32(plan.handle, _lib.ptr(toks_b), n, _lib.ptr(lo), _lib.ptr(hi), 0, None,
+                                              _lib.ptr(out_b), _lib.stream_ptr(dev)), "decode")
+    enc_raw(); dec_raw()
+    torch.cuda.synchronize()
+    ev[2].record()
+    for _ in range(reps):
+        enc_raw()
+    ev[3].record()
+    for _ in range(reps):
+        dec_raw()
+    ev[4].record()
+    torch.cuda.synchronize()
+    enc_ms, dec_ms = ev[2].elapsed_time(ev[3]) / reps, ev[3].elapsed_time(ev[4]) / reps
+    assert torch.equal(toks_b, tokens) and torch.equal(out_b, rec)
     enc_bytes = 4 * Ts * Ds + 8 * NBs * Ds + 4 * NBs * Ds
     dec_bytes = 8 * NBs * Ds + 4 * Ts * Ds
     peak, _ = measured_peak()
-    out = {"workload": f"num_dof=32 num_basis=50 seq_len=10 vocab=1000 degree_p=0 (reference train.sh), batch {n}, device-resident, "
-                       "through BEASTBsplineTokenizer.encode / reconstruct_traj (allocations included)",
+    out = {"workload": f"num_dof=32 num_basis=50 seq_len=10 vocab=1000 degree_p=0 (reference train.sh), batch {n}, device-resident; "
+                       "C-ABI calls on preallocated buffers, CUDA events around 10 back-to-back launches",
+           "api_path_ms": {"encode": api_enc_ms, "reconstruct_traj": api_dec_ms,
+                           "note": "BEASTBsplineTokenizer.encode / reconstruct_traj incl. torch's allocation of the outputs (630 MB per encode)"},
            "encode": {"ms": enc_ms, "traj_per_s": n / (enc_ms * 1e-3), "bytes_per_traj": enc_bytes,
                       "GBps": enc_bytes * n / (enc_ms * 1e-3) / 1e9, "frac_of_measured_hbm": enc_bytes * n / (enc_ms * 1e-3) / 1e9 / peak},
            "reconstruct_traj": {"ms": dec_ms, "traj_per_s": n / (dec_ms * 1e-3), "bytes_per_traj": dec_bytes,
