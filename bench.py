@@ -591,7 +591,8 @@ def shipped_shape_leg(dev, with_cpu):
     out = {"workload": f"num_dof=32 num_basis=50 seq_len=10 vocab=1000 degree_p=0 (reference train.sh), batch {n}, device-resident; "
                        "C-ABI calls on preallocated buffers, CUDA events around 10 back-to-back launches",
            "api_path_ms": {"encode": api_enc_ms, "reconstruct_traj": api_dec_ms,
-                           "note": "BEASTBsplineTokenizer.encode / reconstruct_traj incl. torch's allocation of the outputs (630 MB per encode)"},
+                           "note": "BEASTBsplineTokenizer.encode / reconstruct_traj incl. torch's allocation of the outputs (630 MB per encode); depends on "
+                                   "the caching allocator's state inside this long process — 0.21 ms per encode in a fresh one (scripts/api_alloc_probe.py)"},
            "encode": {"ms": enc_ms, "traj_per_s": n / (enc_ms * 1e-3), "bytes_per_traj": enc_bytes,
                       "GBps": enc_bytes * n / (enc_ms * 1e-3) / 1e9, "frac_of_measured_hbm": enc_bytes * n / (enc_ms * 1e-3) / 1e9 / peak},
            "reconstruct_traj": {"ms": dec_ms, "traj_per_s": n / (dec_ms * 1e-3), "bytes_per_traj": dec_bytes,
