@@ -218,22 +218,6 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
     int m = 0, i = 0;
     // sequences of unequal length arrive padded to L; the text of this one ends at row_len[seq]
     const int Lr = row_len ? min(max(row_len[seq], 0), L) : L;
-    // eight symbols are gathered in registers and leave as ONE 16-byte chunk store (the chunk-major layout puts the
-    // chunks of neighbouring sequences side by side: a warp's store covers 512 contiguous bytes instead of 32 sectors)
-    uint4* sym4 = (uint4*)sym;
-    unsigned long long lo = 0ull, hi = 0ull;
-    auto push = [&](uint16_t x) {
-        const int k = m & 7;
-        if (k < 4) lo |= (unsigned long long)x << (16 * k);
-        else hi |= (unsigned long long)x << (16 * (k - 4));
-        ++m;
-        if ((m & 7) == 0) {
-            sym4[(long long)((m >> 3) - 1) * n_stride + seq] =
-                make_uint4((unsigned int)lo, (unsigned int)(lo >> 32), (unsigned int)hi, (unsigned int)(hi >> 32));
-            lo = 0ull;
-            hi = 0ull;
-        }
-    };
     while (i < Lr) {
         const int pl = pretoken_len(cp, i, Lr, cls_tab);
         uint16_t flag = kWordStart;
@@ -242,15 +226,13 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
             const int nbt = utf8_encode(cp[q], bt);
             for (int r = 0; r < nbt; ++r) {
                 const int id = s_b2i[bt[r]];
-                if (id >= 0) { push((uint16_t)id | flag); flag = 0; }
+                if (id >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)id | flag; flag = 0; ++m; }
             }
         }
         i += pl;
     }
     len[seq] = m;
-    const int n_real = m;
-    while (m & 7) push(kPad);                                 // pad and flush the last chunk
-    (void)n_real;
+    for (int q = m; q & 7; ++q) sym[sym_index(q, seq, n_stride)] = kPad;      // pad the last chunk
 }
 
 // ---------------------------------------------------------------- pair histogram
@@ -1894,7 +1876,6 @@ extern "C" int bpe_symbolize(const int64_t* bins, int64_t N, int32_t L, int64_t 
     if (N == 0) return BEAST_OK;
     if (!bins || !byte_to_id || !cls_tab || !sym || !len || !err) return BEAST_E_NULL;
     if (N < 0 || L < 1 || n_stride < N || 3 * L > 32767) return BEAST_E_SHAPE;
-    if ((uintptr_t)sym & 15u) return BEAST_E_ALIGN;
     const int rows = stage_rows_per_block(L);
     if (rows < 1) return BEAST_E_UNSUPPORTED;
     const size_t smem = stage_smem(L, rows);
