@@ -33,7 +33,8 @@ B2U = bytes_to_unicode()
 U2B = {c: b for b, c in enumerate(B2U)}
 
 MAX_SHIFT = 0xD7FF                      # shifted bins are codepoints below the surrogate range
-MAX_APPLY_VOCAB = 16384                 # dense V x V rank table of the encode kernel: 1 GiB at this size
+MAX_APPLY_VOCAB = 65535                 # token ids are 16 bits wide in the encode kernel
+DENSE_RANK_VOCAB = 4096                 # up to here the merge ranks live in a dense V x V table (64 MB), beyond in a hash of the merges
 # letters added to Unicode after Python 3.12's tables (15.0) that the reference's regex engine already knows
 _NEWER_LETTERS = (7305, 7306, 42955, 42956, 42957, 42970, 42971, 42972)
 _WHITE_SPACE = {9, 10, 11, 12, 13, 32, 133, 160, 5760, 8232, 8233, 8239, 8287, 12288} | set(range(8192, 8203))
@@ -238,17 +239,34 @@ class B200ByteLevelBPE:
             return self._dev_tables[key]
         V = len(self.tokens)
         if V > MAX_APPLY_VOCAB:
-            raise _lib.BeastB200Error(
-                f"BPE vocabulary of {V} entries: the encode kernel looks merge ranks up in a dense V x V uint32 table "
-                f"({4 * V * V / 2**30:.1f} GiB here); vocabularies up to {MAX_APPLY_VOCAB} entries (1 GiB) are supported")
+            raise _lib.BeastB200Error(f"BPE vocabulary of {V} entries: token ids are 16 bits wide in the encode / decode kernels "
+                                      f"(up to {MAX_APPLY_VOCAB} entries)")
         b2i = np.full(256, -1, dtype=np.int16)
         for b in range(256):
             b2i[b] = self._vocab.get(chr(B2U[b]), -1)
-        rank = np.full(V * V, 0xFFFFFFFF, dtype=np.uint32)
-        for r, (a, b, c) in enumerate(self.merges):
-            k = a * V + b
-            if rank[k] == 0xFFFFFFFF:
-                rank[k] = (r << 16) | c
+        if V <= DENSE_RANK_VOCAB:
+            hash_bits = 0
+            rank = np.full(V * V, 0xFFFFFFFF, dtype=np.uint32)
+            for r, (a, b, c) in enumerate(self.merges):
+                k = a * V + b
+                if rank[k] == 0xFFFFFFFF:
+                    rank[k] = (r << 16) | c
+        else:
+            # large vocabularies: an open-addressing hash of the merges only (O(#merges) memory; the dense table would
+            # take 4 V^2 bytes — 4.3 GB at V = 32 768); same slot function and probing as csrc/bpe.cu: rank_lookup
+            if len(self.merges) > 0xFFFE:
+                raise _lib.BeastB200Error("more than 65 534 merges do not fit the 16-bit rank field of the encode kernel")
+            hash_bits = max(10, int(2 * max(len(self.merges), 1) - 1).bit_length())
+            size, mask = 1 << hash_bits, (1 << hash_bits) - 1
+            table = np.full((size, 2), 0xFFFFFFFF, dtype=np.uint32)
+            for r, (a, b, c) in enumerate(self.merges):
+                key = (a << 16) | b
+                slot = ((key * 0x9E3779B1) & 0xFFFFFFFF) >> (32 - hash_bits)
+                while table[slot, 0] != 0xFFFFFFFF and table[slot, 0] != key:
+                    slot = (slot + 1) & mask
+                if table[slot, 0] == 0xFFFFFFFF:              # the first rule of a pair wins, as in the dense table
+                    table[slot] = (key, (r << 16) | c)
+            rank = table.reshape(-1)
         off = np.zeros(V + 1, dtype=np.int32)
         chunks = []
         special_ids = {self._vocab[t] for t in self.special_tokens}
@@ -269,7 +287,7 @@ class B200ByteLevelBPE:
         fits2 = ((tab[:, 3] & 0x80) != 0) | ((tab[:, 3] & 7) <= 2)
         if bool(fits2.all()):                     # at most two characters per token: 8-byte entries {c0 | c1 << 16, meta}
             tab, slots = np.ascontiguousarray(tab[:, [0, 3]]), 2
-        t = dict(V=V, b2i=torch.from_numpy(b2i).to(dev), rank=torch.from_numpy(rank.view(np.int32)).to(dev),
+        t = dict(V=V, hash_bits=hash_bits, b2i=torch.from_numpy(b2i).to(dev), rank=torch.from_numpy(rank.view(np.int32)).to(dev),
                  off=torch.from_numpy(off).to(dev), blob=torch.from_numpy(blob).to(dev),
                  tab=torch.from_numpy(tab.view(np.int32)).to(dev), tab_slots=slots)
         self._dev_tables[key] = t
@@ -297,8 +315,8 @@ class B200ByteLevelBPE:
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(lib.bpe_encode(_lib.ptr(bins), N, L, int(min_token), max_shift, _lib.ptr(t["b2i"]),
-                                      _lib.ptr(class_table_device(dev)), _lib.ptr(t["rank"]), t["V"], _lib.ptr(padded),
-                                      stride, _lib.ptr(lens), _lib.ptr(status), st), "bpe_encode")
+                                      _lib.ptr(class_table_device(dev)), _lib.ptr(t["rank"]), t["V"], t["hash_bits"],
+                                      _lib.ptr(padded), stride, _lib.ptr(lens), _lib.ptr(status), st), "bpe_encode")
             offsets = torch.zeros(N + 1, device=dev, dtype=torch.int64)
             torch.cumsum(lens, 0, out=offsets[1:])
             total = int(offsets[-1].item()) if N else 0

@@ -1197,6 +1197,23 @@ bpe_apply_delta_kernel(int* __restrict__ hist, int* __restrict__ delta, int a, i
 }
 
 // ---------------------------------------------------------------- encode (K5a)
+// Merge-rank look-up: rank << 16 | new_id of the pair (a, b), 0xffffffff when it is no merge.  Two table forms:
+// dense V x V uint32 (hash_bits == 0: 16 MB at V = 2048, L2-resident) or, for large vocabularies, an open-addressing hash
+// of the merges only (2^hash_bits uint2 slots {a << 16 | b, rank << 16 | new_id}, empty key 0xffffffff): O(#merges) memory.
+__device__ __forceinline__ unsigned int rank_lookup(const unsigned int* __restrict__ tab, int V, int hash_bits,
+                                                    unsigned int a, unsigned int b) {
+    if (hash_bits == 0) return __ldg(&tab[(size_t)a * V + b]);
+    const unsigned int key = (a << 16) | b, mask = (1u << hash_bits) - 1u;
+    const uint2* ht = (const uint2*)tab;
+    unsigned int slot = (key * 0x9E3779B1u) >> (32 - hash_bits);
+    for (;;) {
+        const uint2 e = __ldg(&ht[slot]);
+        if (e.x == key) return e.y;
+        if (e.x == 0xffffffffu) return 0xffffffffu;
+        slot = (slot + 1) & mask;
+    }
+}
+
 // rank_tab[a*V + b] = rank << 16 | new_id, or 0xffffffff.  One thread per sequence; the word being
 // merged lives in local memory with its pair keys cached, so a merge costs one scan + two lookups.
 template <int MAXW, typename CP>
@@ -1204,7 +1221,7 @@ __global__ void __launch_bounds__(kBpeBlock)
 bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long long min_token, long long max_shift,
                   const short* __restrict__ byte_to_id, const uint8_t* __restrict__ cls_tab,
                   const unsigned int* __restrict__ rank_tab, int V, uint16_t* __restrict__ ids_out, int out_stride,
-                  int* __restrict__ len_out, int* __restrict__ status_out, int rows) {
+                  int* __restrict__ len_out, int* __restrict__ status_out, int rows, int hash_bits) {
     extern __shared__ uint8_t s_raw[];
     const int LP = L + 1;
     CP* s_cp = (CP*)s_raw;
@@ -1237,7 +1254,7 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
             }
         }
         i += pl;
-        for (int q = 0; q + 1 < wl; ++q) key[q] = __ldg(&rank_tab[(size_t)w[q] * V + w[q + 1]]);
+        for (int q = 0; q + 1 < wl; ++q) key[q] = rank_lookup(rank_tab, V, hash_bits, w[q], w[q + 1]);
         while (wl >= 2) {
             unsigned int best = 0xffffffffu, best_rank = 0xffffffffu;
             int bp = -1;
@@ -1249,8 +1266,8 @@ bpe_encode_kernel(const long long* __restrict__ bins, long long N, int L, long l
             w[bp] = (uint16_t)(best & 0xffffu);
             for (int q = bp + 1; q + 1 < wl; ++q) { w[q] = w[q + 1]; key[q] = key[q + 1]; }
             --wl;
-            if (bp > 0) key[bp - 1] = __ldg(&rank_tab[(size_t)w[bp - 1] * V + w[bp]]);
-            if (bp + 1 < wl) key[bp] = __ldg(&rank_tab[(size_t)w[bp] * V + w[bp + 1]]);
+            if (bp > 0) key[bp - 1] = rank_lookup(rank_tab, V, hash_bits, w[bp - 1], w[bp]);
+            if (bp + 1 < wl) key[bp] = rank_lookup(rank_tab, V, hash_bits, w[bp], w[bp + 1]);
         }
         for (int q = 0; q < wl; ++q) out[m++] = w[q];
     }
@@ -1314,7 +1331,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                        long long max_shift, const short* __restrict__ byte_to_id,
                        const uint8_t* __restrict__ cls_tab, const unsigned int* __restrict__ rank_tab, int V,
                        uint16_t* __restrict__ ids_out, int out_stride, int* __restrict__ len_out,
-                       int* __restrict__ status_out, int M, int warp_bytes, int key2_off) {
+                       int* __restrict__ status_out, int M, int warp_bytes, int key2_off, int hash_bits) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ short s_b2i[256];
     __shared__ uint8_t s_cls[256];
@@ -1391,7 +1408,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                 // slot = rank of the pair (s, s+1) in the high half (0xffff: none), symbol s in the low half
                 const unsigned int me = sym[s];
                 const unsigned int r = (s + 1 < total && wid[s + 1] == wid[s])
-                                           ? __ldg(&rank_tab[(size_t)me * V + sym[s + 1]]) : NONE;
+                                           ? rank_lookup(rank_tab, V, hash_bits, me, sym[s + 1]) : NONE;
                 key[s] = (r & 0xffff0000u) | me;
             }
             const unsigned int m = __ballot_sync(FULL, isb);
@@ -1451,7 +1468,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                     const unsigned int K = __ballot_sync(FULL, kept);
                     if (kept) {
                         unsigned int v = slot & 0xffffu;
-                        if (match) v = __ldg(&rank_tab[(size_t)v * V + (cur[q + 1] & 0xffffu)]) & 0xffffu;   // the merged token
+                        if (match) v = rank_lookup(rank_tab, V, hash_bits, v, cur[q + 1] & 0xffffu) & 0xffffu;   // the merged token
                         nxt[out_n + __popc(K & lt_mask)] = v;
                     }
                     out_n += __popc(K);
@@ -1461,7 +1478,7 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                 n = out_n;
                 for (int q = lane; q < n; q += 32) {          // pair ranks of the shorter word
                     const unsigned int me = nxt[q];
-                    const unsigned int r = q + 1 < n ? __ldg(&rank_tab[(size_t)me * V + nxt[q + 1]]) : NONE;
+                    const unsigned int r = q + 1 < n ? rank_lookup(rank_tab, V, hash_bits, me, nxt[q + 1]) : NONE;
                     cur[q] = (r & 0xffff0000u) | me;
                 }
                 __syncwarp();
@@ -1499,15 +1516,15 @@ bpe_encode_warp_kernel(const long long* __restrict__ bins, long long N, int L, l
                 }
                 if (bp < 0) break;
                 const unsigned int left = best & 0xffffu, right = wk[bp + 1] & 0xffffu;
-                const unsigned int nid = __ldg(&rank_tab[(size_t)left * V + right]) & 0xffffu;
+                const unsigned int nid = rank_lookup(rank_tab, V, hash_bits, left, right) & 0xffffu;
                 for (int q = bp + 1; q + 1 < wl; ++q) wk[q] = wk[q + 1];
                 --wl;
                 unsigned int r = 0xffff0000u;
-                if (bp + 1 < wl) r = __ldg(&rank_tab[(size_t)nid * V + (wk[bp + 1] & 0xffffu)]) & 0xffff0000u;
+                if (bp + 1 < wl) r = rank_lookup(rank_tab, V, hash_bits, nid, wk[bp + 1] & 0xffffu) & 0xffff0000u;
                 wk[bp] = r | nid;
                 if (bp > 0) {
                     const unsigned int ls = wk[bp - 1] & 0xffffu;
-                    wk[bp - 1] = (__ldg(&rank_tab[(size_t)ls * V + nid]) & 0xffff0000u) | ls;
+                    wk[bp - 1] = (rank_lookup(rank_tab, V, hash_bits, ls, nid) & 0xffff0000u) | ls;
                 }
             }
             wid[b] = (uint16_t)wl;                           // final length, kept in the word's own segment
@@ -2163,12 +2180,13 @@ extern "C" int beast_peer_free(void* ptr) {
 
 extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
                           const int16_t* byte_to_id, const uint8_t* cls_tab, const uint32_t* rank_tab, int32_t V,
-                          uint16_t* ids_padded, int32_t out_stride, int32_t* len_out, int32_t* status_out,
-                          void* stream) {
+                          int32_t hash_bits, uint16_t* ids_padded, int32_t out_stride, int32_t* len_out,
+                          int32_t* status_out, void* stream) {
     if (N == 0) return BEAST_OK;
     if (!bins || !byte_to_id || !cls_tab || !rank_tab || !ids_padded || !len_out || !status_out) return BEAST_E_NULL;
     const int mult = max_shift < 0x80 ? 1 : (max_shift < 0x800 ? 2 : 3);       // UTF-8 bytes per bin
-    if (N < 0 || L < 1 || mult * L > kMaxWordLong || out_stride < mult * L || V < 1 || V > 65535 || max_shift > 0xD7FF)
+    if (N < 0 || L < 1 || mult * L > kMaxWordLong || out_stride < mult * L || V < 1 || V > 65535 || max_shift > 0xD7FF ||
+        hash_bits < 0 || hash_bits > 30 || ((uintptr_t)rank_tab & 7u))
         return BEAST_E_SHAPE;
     const int M = mult * L;
     if (M > 65535) return BEAST_E_SHAPE;
@@ -2194,7 +2212,7 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
         if (grid > sms * per_sm) grid = sms * per_sm;
         bpe_encode_warp_kernel<<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
             (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
-            len_out, status_out, M, (int)warp_bytes, (int)key2_off);
+            len_out, status_out, M, (int)warp_bytes, (int)key2_off, hash_bits);
         count_launch();
         BEAST_CHECK_LAUNCH();
         return BEAST_OK;
@@ -2207,7 +2225,7 @@ extern "C" int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min
     const long long grid = (N + rows - 1) / rows;
     bpe_encode_kernel<kMaxWordLong, uint16_t><<<(unsigned)grid, kBpeBlock, smem, (cudaStream_t)stream>>>(
         (const long long*)bins, N, L, min_token, max_shift, byte_to_id, cls_tab, rank_tab, V, ids_padded, out_stride,
-        len_out, status_out, rows);
+        len_out, status_out, rows, hash_bits);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;

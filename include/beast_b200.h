@@ -211,7 +211,10 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  *                work: int32 [4 + 2*N] scratch (list length, sequence ids, first-hit positions).
  * bpe_apply_delta  hist += delta (after the cross-GPU sum when sharded); hist[a][b] = 0; delta = 0.
  * bpe_encode     bins -> ids: per pre-token repeatedly merge the lowest-rank pair, leftmost first (A.5).
- *                rank_tab[a*V + b] = rank << 16 | new_id or 0xffffffff.  ids_padded [N, out_stride >= 2L]
+ *                rank_tab: hash_bits == 0: dense [a*V + b] = rank << 16 | new_id or 0xffffffff; hash_bits > 0: an
+ *                open-addressing hash of the merges only, 2^hash_bits uint2 slots {a << 16 | b, rank << 16 | new_id}, empty
+ *                key 0xffffffff, slot = (key * 0x9E3779B1) >> (32 - hash_bits), linear probing (large vocabularies:
+ *                O(#merges) memory instead of 4 V^2 bytes).  ids_padded [N, out_stride >= 2L]
  *                uint16, len_out [N], status_out [N]: bit 0 = bin below min_token, bit 1 = bin above
  *                min_token + max_shift (the two range ValueErrors of bpe_tokenizer.py:182-192).
  * bpe_compact    padded rows -> CSR flat int32 (offsets = exclusive scan of len, by the caller).
@@ -318,7 +321,8 @@ int bpe_build_signatures(const uint16_t* sym, const int32_t* len, int64_t N, int
                          void* stream);
 int bpe_encode(const int64_t* bins, int64_t N, int32_t L, int64_t min_token, int64_t max_shift,
                const int16_t* byte_to_id, const uint8_t* cls_tab, const uint32_t* rank_tab, int32_t V,
-               uint16_t* ids_padded, int32_t out_stride, int32_t* len_out, int32_t* status_out, void* stream);
+               int32_t hash_bits, uint16_t* ids_padded, int32_t out_stride, int32_t* len_out, int32_t* status_out,
+               void* stream);
 int bpe_compact(const uint16_t* ids_padded, int32_t stride, const int32_t* len, const int64_t* offsets,
                 int64_t N, int32_t* flat, void* stream);
 int bpe_decode(const int32_t* flat, const int64_t* offsets, int64_t N, int32_t L, int64_t min_token,

@@ -447,3 +447,35 @@ def test_persistent_loop_kernel_equals_the_launch_chain(kind, monkeypatch):
     o = OracleBPE.train(bins, vocab)
     for key, val in out.items():
         assert val == (o.merges_txt(), o.vocab_json()), key
+
+
+@pytest.mark.parametrize("kind", ["normal", "bins1000", "letters"])
+def test_hashed_rank_table_gives_the_same_ids(kind, monkeypatch):
+    """Vocabularies above 4 096 entries keep their merge ranks in an open-addressing hash of the merges (O(#merges)
+    memory) instead of the dense V x V table.  Forced here on ordinary models: ids must equal the dense-table ids and
+    the oracle's, in the warp-per-sequence kernel (lane-per-word and cooperative long-word paths) and in the
+    one-thread-per-sequence kernel."""
+    from beast_tokenizer_b200 import FIGBPE, B200ByteLevelBPE, bpe_model
+    rng = np.random.default_rng(51)
+    if kind == "normal":
+        bins, vocab = np.clip(rng.normal(128, 28, (6000, 140)).round(), 0, 255).astype(np.int64), 1200
+    elif kind == "bins1000":
+        bins, vocab = np.clip(rng.normal(500, 120, (3000, 100)).round(), 0, 999).astype(np.int64), 1800
+    else:
+        bins, vocab = rng.choice([97, 97, 97, 98, 99, 32], (2000, 90)) + 7, 400      # long words, runs of one symbol
+    dev_bins = torch.from_numpy(bins).cuda()
+    st = FIGBPE(vocab_size=vocab, show_progress=False).fit_from_bins(dev_bins)
+    o = OracleBPE.train(bins, vocab)
+    test = torch.from_numpy(np.concatenate([bins[:300], rng.permuted(bins[:300], axis=1)])).cuda()
+    dense = st.tokenizer.encode_bins(test, st.min_token, st.max_token)
+    assert st.tokenizer._tables(test.device)["hash_bits"] == 0
+    monkeypatch.setattr(bpe_model, "DENSE_RANK_VOCAB", 0)
+    hashed_model = B200ByteLevelBPE(st.tokenizer.tokens, st.tokenizer.merges)
+    for thread_kernel in ("0", "1"):
+        monkeypatch.setenv("BEAST_B200_BPE_THREAD_ENCODE", thread_kernel)
+        hashed = hashed_model.encode_bins(test, st.min_token, st.max_token)
+        assert hashed_model._tables(test.device)["hash_bits"] > 0
+        assert torch.equal(hashed[0], dense[0]) and torch.equal(hashed[1], dense[1])
+    fl, of = dense[0].cpu().numpy(), dense[1].cpu().numpy()
+    for i in range(0, 600, 13):
+        assert fl[of[i]:of[i + 1]].tolist() == o.encode(test[i].cpu().numpy() - o.min_token)
