@@ -31,8 +31,9 @@ except Exception:  # pragma: no cover
 
 ArrayLike = Union[Sequence[int], np.ndarray, torch.Tensor]
 
-# dense V x V histogram + 16*V bytes of shared-memory delta counters per block (csrc/bpe.cu: bpe_rewrite_kernel)
-MAX_TRAIN_VOCAB = 12800
+# symbol ids are 15 bits wide in the corpus (bit 15 = word start); the pair histogram is dense V x V int32 (4.3 GB at the limit;
+# above 12 800 entries the rewrite kernel has no room for block-private counters and reduces into the global delta block)
+MAX_TRAIN_VOCAB = 32766
 
 
 @dataclass
@@ -466,9 +467,9 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
     V = max(int(vocab_size), len(tokens))
     if V > MAX_TRAIN_VOCAB:
         raise NotImplementedError(
-            f"bpe_vocab_size {V} is above the trainer's limit of {MAX_TRAIN_VOCAB}: the merge loop keeps a dense "
-            f"V x V int32 pair histogram ({4 * V * V / 2**30:.1f} GiB here) and 16*V bytes of per-block shared-memory "
-            "counters (reference FIGBPE default is 1024; BASELINE config 2048)")
+            f"bpe_vocab_size {V} is above the trainer's limit of {MAX_TRAIN_VOCAB}: symbol ids are 15 bits wide in the corpus and "
+            f"the merge loop keeps a dense V x V int32 pair histogram ({4 * V * V / 2**30:.1f} GiB here; reference FIGBPE "
+            "default is 1024, BASELINE config 2048)")
     make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token, row_len, dedup)
                            if engine_factory is GpuBpeEngine else engine_factory(bins, min_token, byte_to_id, V))
     eng = make_engine()

@@ -765,7 +765,7 @@ rewrite_body(const VBlock& vb, int* s_delta, uint16_t (*s_out)[kRewriteOut],
         // pulled towards L1 while entry k is rewritten
         const long long stride = (long long)vb.nblocks * nw;
         const uint4* sym4 = (const uint4*)sym;
-        const bool use_smem = n_work > kGlobalDeltaWork;
+        const bool use_smem = n_work > kGlobalDeltaWork && s_delta != nullptr;   // nullptr: 4 x V counters do not fit shared memory
         if (use_smem) {
             if ((long long)vb.bid * nw >= n_work) return;        // no entry for this block
             zero_delta_block(vb, s_delta, V);
@@ -805,14 +805,19 @@ rewrite_body(const VBlock& vb, int* s_delta, uint16_t (*s_out)[kRewriteOut],
         }
         return;
     }
-    zero_delta_block(vb, s_delta, V);
-    vb_sync(vb);
+    if (s_delta != nullptr) {
+        zero_delta_block(vb, s_delta, V);
+        vb_sync(vb);
+    }
+    int* target = s_delta != nullptr ? s_delta : delta;         // very large vocabularies: straight to the global block
     for (long long i = (long long)vb.bid * vb.nthreads + vb.tid; i < n_work;
          i += (long long)vb.nblocks * vb.nthreads)
-        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, s_delta, sig,
+        rewrite_sequence(sym, len, work_seq[i], work_q0[i], n_stride, a, b, c, V, target, sig,
                          weight ? weight[work_seq[i]] : 1);
-    vb_sync(vb);
-    flush_delta_block(vb, s_delta, delta, V);
+    if (s_delta != nullptr) {
+        vb_sync(vb);
+        flush_delta_block(vb, s_delta, delta, V);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -826,7 +831,11 @@ bpe_rewrite_kernel(uint16_t* __restrict__ sym, int* __restrict__ len, long long 
         pdl_wait();
         pdl_launch();
     }
-    rewrite_body(real_block(), s_delta, s_out, sym, len, n_stride, a, b, c, V, ctl, work_count, work_seq, work_q0, delta, sig, weight);
+    // V < 0: launched without the 16 |V|-byte dynamic shared memory (vocabularies above 12 800 entries)
+    const bool has_smem = V > 0;
+    V = V > 0 ? V : -V;
+    rewrite_body(real_block(), has_smem ? s_delta : nullptr, s_out, sym, len, n_stride, a, b, c, V, ctl, work_count, work_seq, work_q0,
+                 delta, sig, weight);
 }
 
 // Iteration head of the sync-free loop: arg-max of the histogram, folding the delta block of the previous merge
@@ -1956,7 +1965,7 @@ static int merge_grid(long long n) {
 }
 
 static int rewrite_smem_attr(size_t smem) {
-    if (smem > 200 * 1024) return BEAST_E_UNSUPPORTED;
+    if (smem > 200 * 1024) return BEAST_OK;               // launched without block-private counters (V passed negated)
     static size_t granted[kMaxDevices] = {};
     return opt_in_smem(bpe_rewrite_kernel, smem, granted);
 }
@@ -1979,8 +1988,9 @@ extern "C" int bpe_apply_merge(uint16_t* sym, int32_t* len, int64_t N, int64_t n
     if (e != cudaSuccess) return (int)e;
     const int grid = merge_grid(N);
     bpe_scan_kernel<<<grid, 256, 0, st>>>(sym, len, N, n_stride, a, b, work_count, work_seq, work_q0);
-    bpe_rewrite_kernel<<<grid, 256, smem, st>>>(sym, len, n_stride, a, b, c, V, nullptr, work_count, work_seq, work_q0, delta,
-                                                nullptr, weight);
+    const bool big_v = smem > 200 * 1024;                  // no room for block-private counters: global reductions only
+    bpe_rewrite_kernel<<<grid, 256, big_v ? 0 : smem, st>>>(sym, len, n_stride, a, b, c, big_v ? -V : V, nullptr, work_count, work_seq,
+                                                            work_q0, delta, nullptr, weight);
     count_launch(2);
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -2125,11 +2135,13 @@ extern "C" int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_
         if (e != cudaSuccess) return (int)e;
         count_launch(2);
         if (N > 0) {
-            cudaLaunchConfig_t c3 = config((unsigned)grid, 256, smem);
+            const bool big_v = smem > 200 * 1024;          // no room for block-private counters: global reductions only
+            cudaLaunchConfig_t c3 = config((unsigned)grid, 256, big_v ? 0 : smem);
+            const int v_arg = big_v ? -V : V;
             const int* cwc = work_count;
             const int* cws = work_seq;
             const int* cwq = work_q0;
-            e = cudaLaunchKernelEx(&c3, bpe_rewrite_kernel, sym, len, (long long)n_stride, 0, 0, 0, V, ccout, cwc, cws, cwq, delta, sig, weight);
+            e = cudaLaunchKernelEx(&c3, bpe_rewrite_kernel, sym, len, (long long)n_stride, 0, 0, 0, v_arg, ccout, cwc, cws, cwq, delta, sig, weight);
             if (e != cudaSuccess) return (int)e;
             count_launch();
         }

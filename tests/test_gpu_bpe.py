@@ -369,7 +369,39 @@ def test_vocab_limits_are_reported_up_front():
     from beast_tokenizer_b200 import FIGBPE
     bins = torch.randint(0, 256, (64, 20), device="cuda")
     with pytest.raises(NotImplementedError, match="trainer's limit"):
-        FIGBPE(vocab_size=20000, show_progress=False).fit_from_bins(bins)
+        FIGBPE(vocab_size=40000, show_progress=False).fit_from_bins(bins)
+
+
+def test_large_vocabulary_trains_and_applies():
+    """bpe_vocab_size above 12 800 (no block-private delta counters in the rewrite kernel) and above 4 096 (hashed merge
+    ranks in the encode kernel): the table must equal the library's, ids must round-trip."""
+    tk = pytest.importorskip("tokenizers")
+    from tokenizers import ByteLevelBPETokenizer
+    from tokenizers.trainers import BpeTrainer
+    from beast_tokenizer_b200 import FIGBPE
+    rng = np.random.default_rng(61)
+    base = rng.integers(0, 3000, (600, 80))
+    bins = np.concatenate([base[rng.integers(0, 600, 9000)], rng.integers(0, 3000, (3000, 80))])    # repeats => many merges
+    vocab = 14500
+    st = FIGBPE(vocab_size=vocab, show_progress=False).fit_from_bins(torch.from_numpy(bins).cuda())
+    mn, mx = int(bins.min()), int(bins.max())
+    hf = ByteLevelBPETokenizer()
+    trainer = BpeTrainer(vocab_size=vocab, min_frequency=2, show_progress=False, special_tokens=[],
+                         initial_alphabet=[chr(i) for i in range(mx - mn + 1)], max_token_length=10000)
+    hf._tokenizer.train_from_iterator(["".join(map(chr, r - mn)) for r in bins], trainer=trainer)
+    model = json.loads(hf._tokenizer.to_str())["model"]
+    hf_merges = [m if isinstance(m, str) else " ".join(m) for m in model["merges"]]
+    assert len(st.tokenizer.merges) > 9000
+    assert [f"{a} {b}" for a, b in st.tokenizer.merge_strings()] == hf_merges
+    assert st.tokenizer.get_vocab() == hf.get_vocab()
+    test = torch.from_numpy(bins[:400]).cuda()
+    flat, offs, status = st.tokenizer.encode_bins(test, st.min_token, st.max_token)
+    assert st.tokenizer._tables(test.device)["hash_bits"] > 0 and int(status.max()) == 0
+    fl, of = flat.cpu().numpy(), offs.cpu().numpy()
+    for i in range(0, 400, 17):
+        assert fl[of[i]:of[i + 1]].tolist() == hf.encode("".join(map(chr, bins[i] - mn)), add_special_tokens=False).ids
+    back, stt, _ = st.tokenizer.decode_ids(flat, offs, 80, st.min_token)
+    assert int(stt.max()) == 0 and torch.equal(back, test)
 
 
 @pytest.mark.parametrize("kind", ["repetitive", "iid", "letters", "bins1000"])
