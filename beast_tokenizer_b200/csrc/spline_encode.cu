@@ -192,7 +192,9 @@ encode_fast_kernel(const __grid_constant__ EncTables<T, NB> tab, const __grid_co
 #pragma unroll
             for (int k = 0; k < NB; ++k) { tmin[k] = fminf(tmin[k], acc[k]); tmax[k] = fmaxf(tmax[k], acc[k]); }
         }
-        group_barrier(group);                              // every column of the tile has been read
+        // every column of the tile has been read before the outputs overwrite it (the reduction-only launch of
+        // update_weights_bounds writes nothing: its warps release the stage one by one and run ahead)
+        if (want_tok || want_par) group_barrier(group);
         if (active) {
             if (want_tok) {
                 long long* to = (long long*)stage + tl * (NB * D) + slot;
