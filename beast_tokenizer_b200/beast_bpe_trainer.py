@@ -82,7 +82,7 @@ class GpuBpeEngine:
     DEDUP_PACK = int(__import__("os").environ.get("BEAST_B200_DEDUP_PACK", "64"))   # symbols per pseudo-sequence of packed distinct words (plus one straddling word)
 
     def __init__(self, bins: torch.Tensor, min_token: int, byte_to_id: np.ndarray, V: int, max_shift: int = 255,
-                 row_len: Optional[torch.Tensor] = None, dedup="auto"):
+                 row_len: Optional[torch.Tensor] = None, dedup="auto", seen_bytes: Optional[np.ndarray] = None):
         self.lib = _lib.load()
         self.dev = bins.device
         self.N, self.L = bins.shape
@@ -111,7 +111,9 @@ class GpuBpeEngine:
             self.dedup_stats = None
             if dedup and self.N > 0:
                 self._dedup_words(force=dedup is True)
-            used = np.unique(byte_to_id[byte_to_id >= 0]).astype(np.int16)   # ids before any merge (byte-level symbols)
+            # ids before any merge: the byte-level symbols of the bytes the corpus holds (all mapped bytes when unknown)
+            live = byte_to_id >= 0 if seen_bytes is None else (byte_to_id >= 0) & (np.asarray(seen_bytes) != 0)
+            used = np.unique(byte_to_id[live]).astype(np.int16)
             used_d = torch.from_numpy(used).to(self.dev)
             n_ids = int(used[-1]) + 1 if used.size else 0
             _lib.check(self.lib.bpe_count_pairs(_lib.ptr(self.sym), _lib.ptr(self.len), self.N, self.stride, V,
@@ -133,25 +135,29 @@ class GpuBpeEngine:
         words, symbols = (int(v) for v in totals.tolist())
         if words == 0:
             return None
+        flags = torch.zeros(4, device=dev, dtype=torch.int32)
+        wlist = torch.empty((words, 4), device=dev, dtype=torch.int64)       # hash, location, first six symbols per word
+        cursor = torch.zeros(1, device=dev, dtype=torch.int64)
+        _lib.check(lib.bpe_word_list(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(wlist), words,
+                                     _lib.ptr(cursor), _lib.ptr(flags), st), "bpe_word_list")
         for bound in ([min(int(expect_distinct), words)] if expect_distinct else []) + [words]:
             size = 1 << max(10, (2 * bound - 1).bit_length())
-            keys = torch.zeros(size, device=dev, dtype=torch.int64)
-            rep = torch.empty(size, device=dev, dtype=torch.int64)
-            count = torch.zeros(size, device=dev, dtype=torch.int32)
-            flags = torch.zeros(4, device=dev, dtype=torch.int32)
-            _lib.check(lib.bpe_word_insert(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(keys),
-                                           _lib.ptr(rep), _lib.ptr(count), size, _lib.ptr(flags), st), "bpe_word_insert")
+            table = torch.zeros((size, 4), device=dev, dtype=torch.int64)    # key, representative, count | symbols
+            flags[1:].zero_()
+            _lib.check(lib.bpe_word_insert(_lib.ptr(self.sym), self.stride, _lib.ptr(wlist), words, _lib.ptr(table), size,
+                                           _lib.ptr(flags), st), "bpe_word_insert")
             status, distinct = flags[:2].tolist()
+            if status in (1, 2):
+                return None
             if status != 3 and distinct <= size // 2:
                 break
             if bound == words:
                 return None
-        if status:
-            return None
+            flags.zero_()
+        del wlist
         loc = torch.empty(distinct, device=dev, dtype=torch.int64)
         cnt = torch.empty(distinct, device=dev, dtype=torch.int32)
-        _lib.check(lib.bpe_word_emit(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(keys),
-                                     _lib.ptr(rep), _lib.ptr(count), size, _lib.ptr(flags), _lib.ptr(loc), _lib.ptr(cnt), st),
+        _lib.check(lib.bpe_word_emit(_lib.ptr(table), size, _lib.ptr(flags), _lib.ptr(loc), _lib.ptr(cnt), distinct, st),
                    "bpe_word_emit")
         status, _, emitted = flags[:3].tolist()
         if status or emitted != distinct:
@@ -470,7 +476,7 @@ def train_bpe(bins: torch.Tensor, vocab_size: int, min_frequency: int = 2, *, en
             f"bpe_vocab_size {V} is above the trainer's limit of {MAX_TRAIN_VOCAB}: symbol ids are 15 bits wide in the corpus and "
             f"the merge loop keeps a dense V x V int32 pair histogram ({4 * V * V / 2**30:.1f} GiB here; reference FIGBPE "
             "default is 1024, BASELINE config 2048)")
-    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token, row_len, dedup)
+    make_engine = lambda: (engine_factory(bins, min_token, byte_to_id, V, max_token - min_token, row_len, dedup, seen)
                            if engine_factory is GpuBpeEngine else engine_factory(bins, min_token, byte_to_id, V))
     eng = make_engine()
     coll.reduce_(eng.hist, "sum")                       # replicated global histogram

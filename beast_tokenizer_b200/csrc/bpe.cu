@@ -253,25 +253,28 @@ bpe_count_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, 
     }
 }
 
-// Same count with a block-private [A x A] histogram in shared memory, A = number of DISTINCT ids in the
-// corpus (the byte-level symbols before any merge: 194 for a 256-bin tokenizer, 150 KB; their ids are
-// sparse in [0, n_ids), so they are renumbered through `used_ids`): the ~200 pair increments per
-// sequence become shared-memory atomics, one global atomic per non-zero cell and block at the end.
+// Same count with a block-private histogram in shared memory over the A DISTINCT ids of the corpus (the
+// byte-level symbols before any merge: 194 for a 256-bin tokenizer, 150 KB; their ids are sparse in [0, n_ids),
+// so they are renumbered through `used_ids`): the ~200 pair increments per sequence become shared-memory
+// atomics, one global atomic per non-zero cell and block at the end.  When A x A counters do not fit, the rows
+// (first symbol of the pair) are dealt round-robin to `parts` blocks that read the same sequences — the corpus is
+// read `parts` times, which is cheap next to global atomics on a few hundred hot cells.
 // 128-bit chunk loads, one thread per sequence.
 __global__ void __launch_bounds__(1024)
 bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ len, long long N, long long n_stride,
-                      int V, int n_ids, const short* __restrict__ used_ids, int A, int* __restrict__ hist,
+                      int V, int n_ids, const short* __restrict__ used_ids, int A, int parts, int* __restrict__ hist,
                       const int* __restrict__ weight) {
-    extern __shared__ int s_hist[];                          // [A*A] counters, then u16 inverse map [n_ids]
-    const int cells = A * A;
+    extern __shared__ int s_hist[];                          // [rows*A] counters, then u16 inverse map [n_ids]
+    const int rows = (A + parts - 1) / parts, part = (int)(blockIdx.x % (unsigned int)parts);
+    const int cells = rows * A;
     unsigned short* s_inv = (unsigned short*)(s_hist + cells);
     for (int i = threadIdx.x; i < cells; i += blockDim.x) s_hist[i] = 0;
     for (int i = threadIdx.x; i < n_ids; i += blockDim.x) s_inv[i] = 0xffffu;
     __syncthreads();
     for (int i = threadIdx.x; i < A; i += blockDim.x) s_inv[used_ids[i]] = (unsigned short)i;
     __syncthreads();
-    for (long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x; seq < N;
-         seq += (long long)gridDim.x * blockDim.x) {
+    const long long group = blockIdx.x / (unsigned int)parts, groups = gridDim.x / (unsigned int)parts;
+    for (long long seq = group * blockDim.x + threadIdx.x; seq < N; seq += groups * blockDim.x) {
         const int n = len[seq];
         const int wgt = weight ? weight[seq] : 1;
         unsigned int prev = 0xffffu;
@@ -284,7 +287,10 @@ bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ 
                 const unsigned int cur = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
                 const unsigned int id = cur & kIdMask;
                 const unsigned int ci = id < (unsigned int)n_ids ? s_inv[id] : 0xffffu;
-                if (prev != 0xffffu && ci != 0xffffu && !(cur & kWordStart)) atomicAdd(&s_hist[prev * A + ci], wgt);
+                if (prev != 0xffffu && ci != 0xffffu && !(cur & kWordStart)) {
+                    if (parts == 1) atomicAdd(&s_hist[prev * A + ci], wgt);
+                    else if ((int)(prev % (unsigned int)parts) == part) atomicAdd(&s_hist[(prev / (unsigned int)parts) * A + ci], wgt);
+                }
                 prev = ci;
             }
         }
@@ -292,7 +298,8 @@ bpe_count_smem_kernel(const uint16_t* __restrict__ sym, const int* __restrict__ 
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
         const int v = s_hist[i];
-        if (v) atomicAdd(&hist[(long long)used_ids[i / A] * V + used_ids[i % A]], v);
+        const int first = (i / A) * parts + part;
+        if (v && first < A) atomicAdd(&hist[(long long)used_ids[first] * V + used_ids[i % A]], v);
     }
 }
 
@@ -1921,20 +1928,27 @@ extern "C" int bpe_count_pairs(const uint16_t* sym, const int32_t* len, int64_t 
     if (N == 0) return BEAST_OK;
     if (!sym || !len || !hist) return BEAST_E_NULL;
     if (N < 0 || V < 1 || V > 32767 || n_ids < 0 || n_ids > V || n_used < 0 || n_used > n_ids) return BEAST_E_SHAPE;
-    const size_t smem = (size_t)n_used * n_used * sizeof(int) + (((size_t)n_ids * 2 + 15) & ~(size_t)15);
-    if (used_ids && n_used > 0 && smem <= 200 * 1024 && ((uintptr_t)sym & 15u) == 0) {
-        static size_t granted[kMaxDevices] = {};
-        if (int rc = opt_in_smem(bpe_count_smem_kernel, smem, granted)) return rc;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        long long grid = (N + 1023) / 1024;
-        if (grid > sms) grid = sms;
-        bpe_count_smem_kernel<<<(unsigned)grid, 1024, smem, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, n_ids,
-                                                                                   used_ids, n_used, hist, weight);
-        count_launch();
-        BEAST_CHECK_LAUNCH();
-        return BEAST_OK;
+    if (used_ids && n_used > 0 && ((uintptr_t)sym & 15u) == 0) {
+        const size_t map = ((size_t)n_ids * 2 + 15) & ~(size_t)15;
+        int parts = 1;
+        auto bytes = [&](int p) { return (size_t)((n_used + p - 1) / p) * n_used * sizeof(int) + map; };
+        while (parts < 8 && bytes(parts) > 200 * 1024) ++parts;
+        if (bytes(parts) <= 200 * 1024) {
+            const size_t smem = bytes(parts);
+            static size_t granted[kMaxDevices] = {};
+            if (int rc = opt_in_smem(bpe_count_smem_kernel, smem, granted)) return rc;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            long long groups = (N + 1023) / 1024;
+            if (groups > sms / parts) groups = sms / parts;
+            if (groups < 1) groups = 1;
+            bpe_count_smem_kernel<<<(unsigned)(groups * parts), 1024, smem, (cudaStream_t)stream>>>(
+                sym, len, N, n_stride, V, n_ids, used_ids, n_used, parts, hist, weight);
+            count_launch();
+            BEAST_CHECK_LAUNCH();
+            return BEAST_OK;
+        }
     }
     bpe_count_kernel<<<bpe_grid(N, 256), 256, 0, (cudaStream_t)stream>>>(sym, len, N, n_stride, V, hist, weight);
     count_launch();

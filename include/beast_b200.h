@@ -201,8 +201,9 @@ int beast_colselect_f32(const float* x, int64_t rows, int32_t cols,
  *                sequence s ends at row_len[s].
  * bpe_count_pairs  hist[a*V + b] += #adjacent (a, b) inside pre-tokens (int32, V x V).  Optional hint:
  *                used_ids[n_used] = the distinct ids that can occur in sym (ascending, all < n_ids: the
- *                byte-level symbols before any merge) — when n_used^2 counters fit in shared memory the
- *                count runs on block-private histograms; NULL / 0 = global atomics.
+ *                byte-level symbols before any merge; an id of sym that is missing from the list is NOT counted) —
+ *                the count then runs on block-private shared-memory histograms, the rows dealt to up to 8 blocks
+ *                per group of sequences when n_used^2 counters do not fit in one; NULL / 0 = global atomics.
  * bpe_argmax     result = count << 32 | (0xffffffff - (a*V + b)) of the best pair (0 if none): maximum
  *                count, ties -> smallest (a, b) (BpeTrainer's heap order).
  * bpe_apply_merge  replace (a, b) by c left to right, non-overlapping, compacting in place; the count
@@ -286,15 +287,21 @@ int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int
 /* Word de-duplication in front of the merge loop (what BpeTrainer does with the strings FIGBPE hands it,
  * beast/beast_bpe_trainer.py:61-74: distinct pre-tokens with counts).  csrc/bpe_dedup.cu.
  * bpe_word_totals  totals[0] = pre-tokens, totals[1] = symbols of the symbolised corpus (device, 2 x uint64).
- * bpe_word_insert  pass 1 over an open-addressing table (keys / rep uint64 [table_size], count int32 [table_size];
- *                  table_size a power of two, at least 2 x the distinct words; the caller zeroes keys, count and
- *                  flags [3]): claims a slot per distinct word, stores its first finder's location
- *                  (sequence << 32 | first symbol << 16 | symbols) in rep and counts the occurrences.
- *                  flags[1] = slots claimed; flags[0] = 3 when the table is too small (retry with a larger one).
- * bpe_word_emit    pass 2: the representative of every slot appends (location, count) to out_loc / out_cnt
- *                  [flags[1]]; flags[2] = entries written.  Every other word is compared with its representative
- *                  symbol by symbol: flags[0] = 1 reports a 64-bit hash collision — the table is then unusable and
- *                  the caller trains on the plain corpus.
+ * bpe_word_list    the flat list of the corpus' words: words [W][4] uint64 = (64-bit hash over symbol ids and length,
+ *                  location = sequence << 32 | first symbol << 16 | symbols, the first six symbol ids + 1 in the
+ *                  upper 32 + 64 bits of the rest), W = totals[0], in no particular order;
+ *                  cursor: one device uint64 of scratch (zeroed by the call); flags[0] = 2 reports W too small.
+ * bpe_word_insert  one thread per word over an open-addressing table of 32-byte slots (table: uint64
+ *                  [table_size][4] = key, representative location, count | two symbols, four symbols; 32-byte aligned; table_size a
+ *                  power of two, at least 2 x the distinct words; the caller zeroes table and flags [3]): an empty
+ *                  slot is claimed with one 128-bit compare-and-swap of (hash, location), occurrences are counted,
+ *                  and every word that is not the slot's representative is compared with it symbol by symbol (against the
+ *                  slot's copy of the first six symbols, else in the corpus):
+ *                  flags[0] = 1 reports a 64-bit hash collision — the table is then unusable and the caller trains
+ *                  on the plain corpus; flags[0] = 3 = table too small (retry with a larger one); flags[1] = slots
+ *                  claimed.
+ * bpe_word_emit    reads the distinct words off the table: (location, count) of every claimed slot to out_loc /
+ *                  out_cnt [capacity >= flags[1]]; flags[2] = entries written.
  * bpe_word_pack    copies U distinct words (loc[i] as above) to position dst_off[i] of pseudo-sequence dst_seq[i]
  *                  of a second corpus in the same chunk-major layout (first symbol flagged as a word start) and
  *                  pads the last chunk of each of the P pseudo-sequences (dst_len[P] symbols each).
@@ -303,11 +310,12 @@ int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int
  * count updates by weight[seq] (NULL = 1). */
 int bpe_word_totals(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* totals,
                     void* stream);
-int bpe_word_insert(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* keys, uint64_t* rep,
-                    int32_t* count, int64_t table_size, int32_t* flags, void* stream);
-int bpe_word_emit(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, const uint64_t* keys,
-                  const uint64_t* rep, const int32_t* count, int64_t table_size, int32_t* flags, uint64_t* out_loc,
-                  int32_t* out_cnt, void* stream);
+int bpe_word_list(const uint16_t* sym, const int32_t* len, int64_t N, int64_t n_stride, uint64_t* words, int64_t W,
+                  uint64_t* cursor, int32_t* flags, void* stream);
+int bpe_word_insert(const uint16_t* sym, int64_t n_stride, const uint64_t* words, int64_t W, uint64_t* table,
+                    int64_t table_size, int32_t* flags, void* stream);
+int bpe_word_emit(const uint64_t* table, int64_t table_size, int32_t* flags, uint64_t* out_loc, int32_t* out_cnt,
+                  int64_t capacity, void* stream);
 int bpe_word_pack(const uint16_t* src, int64_t src_stride, const uint64_t* loc, const int32_t* dst_seq,
                   const int32_t* dst_off, int64_t U, uint16_t* dst, const int32_t* dst_len, int64_t P,
                   int64_t dst_stride, void* stream);
