@@ -141,7 +141,7 @@ class GpuBpeEngine:
         _lib.check(lib.bpe_word_list(_lib.ptr(self.sym), _lib.ptr(self.len), n_seq, self.stride, _lib.ptr(wlist), words,
                                      _lib.ptr(cursor), _lib.ptr(flags), st), "bpe_word_list")
         for bound in ([min(int(expect_distinct), words)] if expect_distinct else []) + [words]:
-            size = 1 << max(10, (2 * bound - 1).bit_length())
+            size = 1 << max(10, (bound + bound // 2 - 1).bit_length())   # load factor <= 2/3 (linear probing)
             table = torch.zeros((size, 4), device=dev, dtype=torch.int64)    # key, representative, count | symbols
             flags[1:].zero_()
             _lib.check(lib.bpe_word_insert(_lib.ptr(self.sym), self.stride, _lib.ptr(wlist), words, _lib.ptr(table), size,
@@ -149,7 +149,7 @@ class GpuBpeEngine:
             status, distinct = flags[:2].tolist()
             if status in (1, 2):
                 return None
-            if status != 3 and distinct <= size // 2:
+            if status != 3 and distinct <= size - size // 4:
                 break
             if bound == words:
                 return None

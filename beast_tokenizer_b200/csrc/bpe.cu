@@ -215,24 +215,83 @@ bpe_symbolize_kernel(const long long* __restrict__ bins, long long N, int L, lon
     if (threadIdx.x >= rows || seq >= N) return;
     if (s_status[threadIdx.x]) *err = 1;
     const uint16_t* cp = s_cp + threadIdx.x * LP;
-    int m = 0, i = 0;
     // sequences of unequal length arrive padded to L; the text of this one ends at row_len[seq]
     const int Lr = row_len ? min(max(row_len[seq], 0), L) : L;
-    while (i < Lr) {
-        const int pl = pretoken_len(cp, i, Lr, cls_tab);
-        uint16_t flag = kWordStart;
-        for (int q = i; q < i + pl; ++q) {
-            int bt[3];
-            const int nbt = utf8_encode(cp[q], bt);
-            for (int r = 0; r < nbt; ++r) {
-                const int id = s_b2i[bt[r]];
-                if (id >= 0) { sym[sym_index(m, seq, n_stride)] = (uint16_t)id | flag; flag = 0; ++m; }
+    // pretoken_len's rules as ONE pass with constant work per codepoint (the lanes of a warp hold different
+    // sequences: nested run loops made the warp execute every lane's path, ~630 instructions per codepoint):
+    // run_cls = class of the run being extended (-1: the next codepoint opens a pre-token), ws_run = inside a
+    // whitespace run of two or more, skip = codepoints left of a contraction ('s 't 're 've 'm 'll 'd).
+    int m = 0, run_cls = -1, skip = 0;
+    bool ws_run = false;
+    unsigned long long lo = 0ull, hi = 0ull;                 // the open chunk of eight symbols
+    unsigned int pending = 0u;
+    int c = Lr > 0 ? cp[0] : 0, k = Lr > 0 ? cp_class(c, cls_tab) : 0;
+    for (int p = 0; p < Lr; ++p) {
+        const bool has1 = p + 1 < Lr;
+        const int c1 = has1 ? cp[p + 1] : 0;
+        const int k1 = has1 ? cp_class(c1, cls_tab) : -1;
+        bool start;
+        if (skip > 0) {
+            start = false;
+            --skip;
+        } else if (k == CLS_S) {
+            const bool next_s = k1 == CLS_S;
+            if (!ws_run) {                                   // a whitespace run opens a pre-token
+                start = true;
+                if (next_s) ws_run = true;
+                else run_cls = (has1 && c == 32) ? k1 : -1;  // " ?X+": one blank joins the run behind it
+            } else if (next_s || !has1) {
+                start = false;                               // \s+(?!\S): inside the run, or the run ends the text
+            } else {                                         // ... which leaves the run's last blank to the next match
+                start = true;
+                ws_run = false;
+                run_cls = c == 32 ? k1 : -1;
+            }
+        } else if (k == run_cls) {
+            start = false;
+        } else {
+            start = true;
+            run_cls = k;
+            if (c == 39 && has1) {
+                const int c2 = p + 2 < Lr ? cp[p + 2] : 0;
+                int cl = 0;
+                if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') cl = 2;
+                else if ((c1 == 'r' && c2 == 'e') || (c1 == 'v' && c2 == 'e') || (c1 == 'l' && c2 == 'l')) cl = 3;
+                if (cl) { skip = cl - 1; run_cls = -1; }
             }
         }
-        i += pl;
+        if (start) pending = kWordStart;
+        int bt[3];
+        const int nbt = utf8_encode(c, bt);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r >= nbt) break;
+            const int id = s_b2i[bt[r]];
+            if (id < 0) continue;
+            const unsigned long long v = (unsigned long long)((unsigned int)id | pending);
+            pending = 0u;
+            const int pos = m & 7;
+            if (pos < 4) lo |= v << (16 * pos);
+            else hi |= v << (16 * (pos - 4));
+            if (pos == 7) {
+                *(uint4*)(sym + ((long long)(m >> 3) * n_stride + seq) * kChunk) =
+                    make_uint4((unsigned int)lo, (unsigned int)(lo >> 32), (unsigned int)hi, (unsigned int)(hi >> 32));
+                lo = hi = 0ull;
+            }
+            ++m;
+        }
+        c = c1;
+        k = k1;
     }
     len[seq] = m;
-    for (int q = m; q & 7; ++q) sym[sym_index(q, seq, n_stride)] = kPad;      // pad the last chunk
+    if (m & 7) {                                             // pad the last chunk
+        for (int pos = m & 7; pos < 8; ++pos) {
+            if (pos < 4) lo |= 0xffffull << (16 * pos);
+            else hi |= 0xffffull << (16 * (pos - 4));
+        }
+        *(uint4*)(sym + ((long long)(m >> 3) * n_stride + seq) * kChunk) =
+            make_uint4((unsigned int)lo, (unsigned int)(lo >> 32), (unsigned int)hi, (unsigned int)(hi >> 32));
+    }
 }
 
 // ---------------------------------------------------------------- pair histogram

@@ -293,7 +293,7 @@ int bpe_train_step(uint16_t* sym, int32_t* len, int64_t N, int64_t n_stride, int
  *                  cursor: one device uint64 of scratch (zeroed by the call); flags[0] = 2 reports W too small.
  * bpe_word_insert  one thread per word over an open-addressing table of 32-byte slots (table: uint64
  *                  [table_size][4] = key, representative location, count | two symbols, four symbols; 32-byte aligned; table_size a
- *                  power of two, at least 2 x the distinct words; the caller zeroes table and flags [3]): an empty
+ *                  power of two above the distinct words (the trainer keeps the load below 3/4); the caller zeroes table and flags [3]): an empty
  *                  slot is claimed with one 128-bit compare-and-swap of (hash, location), occurrences are counted,
  *                  and every word that is not the slot's representative is compared with it symbol by symbol (against the
  *                  slot's copy of the first six symbols, else in the corpus):

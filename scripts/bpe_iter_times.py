@@ -13,7 +13,7 @@ coll = _Collective(enabled=False)
 mn, mx, seen = scan_bins_gpu(bins, coll)
 tokens, b2i = build_alphabet(mn, mx, seen)
 torch.cuda.synchronize(); t0 = time.perf_counter()
-eng = GpuBpeEngine(bins, mn, b2i, 2048)
+eng = GpuBpeEngine(bins, mn, b2i, 2048, mx - mn, None, "auto", seen)
 torch.cuda.synchronize(); print(f"symbolize+count: {time.perf_counter()-t0:.3f} s")
 run = eng.start_run(len(tokens), 2048, 2)
 mm = run.max_merges
@@ -27,3 +27,6 @@ log = run.finish()
 print(f"total {sum(ts):.1f} ms; live symbols at end {eng.len.sum().item()/1e6:.1f} M; merges {len(log)}")
 for i in (0, 1, 10, 50, 100, 127, 128, 150, 200, 300, 500, 800, 1200, 1700):
     if i < len(log): print(i, f"{ts[i]*1e3:.0f} us", log[i])
+edges = [0, 16, 64, 128, 256, 512, 1024, len(ts)]
+for a, b in zip(edges[:-1], edges[1:]):
+    print(f"merges [{a:4d}, {b:4d}): {sum(ts[a:b]):7.2f} ms  = {1e3 * sum(ts[a:b]) / max(b - a, 1):6.1f} us per merge")

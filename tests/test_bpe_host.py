@@ -507,3 +507,78 @@ def test_rank_order_batch_merging_equals_one_merge_at_a_time():
         if trial % 3 == 0:                              # long runs of one symbol: the overlapping-candidate case
             word = ([0] * int(rng.integers(30, 100))) + word
         assert batch_by_rank(word, rank, new_id) == one_at_a_time(word, rank, new_id), (word, rank)
+
+
+def _single_pass_word_starts(cp, cls):
+    """CPU restatement of bpe_symbolize_kernel's one-pass pre-tokenizer (csrc/bpe.cu): constant work per codepoint,
+    state = (class of the run being extended, inside a whitespace run of two or more, codepoints left of a
+    contraction)."""
+    n = len(cp)
+    S = 3
+    out = np.zeros(n, dtype=np.uint8)
+    run_cls, skip, ws_run = -1, 0, False
+    for p in range(n):
+        c, k = int(cp[p]), int(cls[cp[p]])
+        has1 = p + 1 < n
+        c1 = int(cp[p + 1]) if has1 else 0
+        k1 = int(cls[c1]) if has1 else -1
+        if skip > 0:
+            start = False
+            skip -= 1
+        elif k == S:
+            next_s = k1 == S
+            if not ws_run:
+                start = True
+                if next_s:
+                    ws_run = True
+                else:
+                    run_cls = k1 if (has1 and c == 32) else -1
+            elif next_s or not has1:
+                start = False
+            else:
+                start, ws_run = True, False
+                run_cls = k1 if c == 32 else -1
+        elif k == run_cls:
+            start = False
+        else:
+            start, run_cls = True, k
+            if c == 39 and has1:
+                c2 = int(cp[p + 2]) if p + 2 < n else 0
+                cl = 0
+                if chr(c1) in "stmd":
+                    cl = 2
+                elif (chr(c1), chr(c2)) in (("r", "e"), ("v", "e"), ("l", "l")):
+                    cl = 3
+                if cl:
+                    skip, run_cls = cl - 1, -1
+        out[p] = start
+    return out
+
+
+def test_single_pass_pretokenizer_equals_the_regex_walk():
+    """The symboliser decides pre-token starts in one pass; the oracle walks the GPT-2 regex alternatives match by
+    match (oracle/bpe_oracle.c, checked against the library in tests/test_bpe_oracle.py).  Same starts on random
+    texts dense in blanks, apostrophes, contraction letters and class changes."""
+    from oracle.bpe_oracle import unicode_classes
+    cls = unicode_classes(0x3000)
+    rng = np.random.default_rng(11)
+    pools = [
+        np.array([32, 32, 32, 9, 10, 39, 39, ord("s"), ord("t"), ord("r"), ord("e"), ord("l"), ord("v"), ord("m"), ord("d"),
+                  ord("a"), ord("7"), ord("!"), 133, 160, 178], dtype=np.uint16),
+        np.arange(0, 256, dtype=np.uint16),
+        np.concatenate([np.arange(0, 700, dtype=np.uint16), np.array([0x2000, 0x2003, 0x2028, 0x1680], dtype=np.uint16)]),
+    ]
+    checked = 0
+    for pool in pools:
+        for _ in range(1500):
+            n = int(rng.integers(0, 40))
+            cp = pool[rng.integers(0, len(pool), size=n)]
+            want = pretokenize(cp) if n else np.zeros(0, dtype=np.uint8)
+            got = _single_pass_word_starts(cp, cls)
+            if n:
+                assert got[0] == 1
+                want = want.copy()
+                want[0] = 1                                  # the oracle may leave position 0 implicit
+            np.testing.assert_array_equal(got, want, err_msg=str(cp.tolist()))
+            checked += n
+    assert checked > 50_000
