@@ -36,20 +36,72 @@ def _coerce_bpe(tokenizer) -> B200ByteLevelBPE:
     raise TypeError("Expected a ByteLevelBPETokenizer instance.")
 
 
+_PYLISTS = None
+
+
+def _pylists():
+    """The CPython helper `_pylists` (csrc/pylists.c, built in-tree by `build.py`); False when it cannot be had
+    (no compiler): the pure-Python conversions below then do the same job, slower."""
+    global _PYLISTS
+    if _PYLISTS is None:
+        try:
+            from . import _pylists as mod
+        except ImportError:
+            try:
+                from .build import build_pylists
+                build_pylists()
+                import importlib
+                importlib.invalidate_caches()
+                from . import _pylists as mod
+            except Exception:
+                mod = False
+        _PYLISTS = mod
+    return _PYLISTS
+
+
 def _split_rows(flat_h: np.ndarray, off_h: np.ndarray) -> List[List[int]]:
-    """CSR -> the ragged List[List[int]] the reference returns.  One tolist() of the whole id array and pointer-copy
-    slices of it; the cyclic collector is paused meanwhile (tens of thousands of fresh lists would trigger repeated
-    full collections that find nothing).  What remains is CPython creating one int object per id."""
+    """CSR -> the ragged List[List[int]] the reference returns.  C helper: one list per row, one shared int object per
+    distinct id.  Without it: one tolist() of the whole id array and pointer-copy slices of it, the cyclic collector
+    paused meanwhile (tens of thousands of fresh lists would trigger repeated full collections that find nothing)."""
     import gc
-    off = off_h.tolist()
     was_enabled = gc.isenabled()
     gc.disable()
     try:
+        mod = _pylists()
+        if mod:
+            return mod.split_rows(np.ascontiguousarray(flat_h, dtype=np.int32),
+                                  np.ascontiguousarray(off_h, dtype=np.int64))
+        off = off_h.tolist()
         big = flat_h.tolist()
         return [big[off[i]:off[i + 1]] for i in range(len(off) - 1)]
     finally:
         if was_enabled:
             gc.enable()
+
+
+def _flatten_rows(rows):
+    """List / tuple of lists / tuples of Python ints -> (flat int32, offsets int64 [n+1]) numpy arrays, or None when the
+    rows are of another kind (tensors, arrays, numpy scalars: the general path converts those)."""
+    mod = _pylists()
+    if mod:
+        got = mod.flatten_rows(rows)
+        if got is None:
+            return None
+        return np.frombuffer(got[0], dtype=np.int32), np.frombuffer(got[1], dtype=np.int64)
+    if not (isinstance(rows, (list, tuple)) and all(type(t) in (list, tuple) for t in rows)):
+        return None
+    lens = np.fromiter(map(len, rows), dtype=np.int64, count=len(rows))
+    try:
+        flat = np.fromiter(itertools.chain.from_iterable(rows), dtype=np.int64, count=int(lens.sum()))
+    except OverflowError:
+        raise ValueError("BPE token id out of range") from None
+    except (TypeError, ValueError):
+        return None
+    if flat.size and (flat.min() < -2 ** 31 or flat.max() >= 2 ** 31):
+        raise ValueError("BPE token id out of range")
+    offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return flat.astype(np.int32), offsets
 
 
 class BEASTBsplineBPETokenizer(BEASTBsplineTokenizer):
@@ -216,20 +268,19 @@ class BEASTBsplineBPETokenizer(BEASTBsplineTokenizer):
             token_sequences = [tokens]
         else:
             token_sequences = tokens
-        if isinstance(token_sequences, (list, tuple)) and token_sequences and \
-                all(type(t) in (list, tuple) for t in token_sequences):
+        fast = _flatten_rows(token_sequences) if isinstance(token_sequences, (list, tuple)) and token_sequences else None
+        if fast is not None:
             # the ragged List[List[int]] that encode() returns: one C-level pass instead of an int() call per id
-            lens = np.fromiter(map(len, token_sequences), dtype=np.int64, count=len(token_sequences))
-            flat = np.fromiter(itertools.chain.from_iterable(token_sequences), dtype=np.int64, count=int(lens.sum()))
-        else:
-            arrays = []
-            for token in token_sequences:
-                if isinstance(token, torch.Tensor):
-                    arrays.append(token.detach().cpu().numpy().astype(np.int64).reshape(-1))
-                else:
-                    arrays.append(np.asarray([int(t) for t in token], dtype=np.int64).reshape(-1))
-            lens = np.asarray([a.size for a in arrays], dtype=np.int64)
-            flat = np.concatenate(arrays) if arrays else np.zeros(0, dtype=np.int64)
+            flat32, offsets = fast
+            return torch.from_numpy(flat32).to(dev), torch.from_numpy(offsets).to(dev)
+        arrays = []
+        for token in token_sequences:
+            if isinstance(token, torch.Tensor):
+                arrays.append(token.detach().cpu().numpy().astype(np.int64).reshape(-1))
+            else:
+                arrays.append(np.asarray([int(t) for t in token], dtype=np.int64).reshape(-1))
+        lens = np.asarray([a.size for a in arrays], dtype=np.int64)
+        flat = np.concatenate(arrays) if arrays else np.zeros(0, dtype=np.int64)
         offsets = np.zeros(len(lens) + 1, dtype=np.int64)
         np.cumsum(lens, out=offsets[1:])
         if flat.size and (flat.min() < -2 ** 31 or flat.max() >= 2 ** 31):

@@ -9,6 +9,7 @@ import glob
 import os
 import subprocess
 import sys
+import sysconfig
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
@@ -17,6 +18,20 @@ LIB = os.path.join(PKG, "libbeast_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
+PYLISTS_SRC = os.path.join(CSRC, "pylists.c")
+PYLISTS = os.path.join(PKG, "_pylists" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pylists(force=False):
+    """The CPython helper of the list-returning BPE API (CSR <-> List[List[int]]): plain C, gcc, in-tree."""
+    if not force and os.path.exists(PYLISTS) and os.path.getmtime(PYLISTS) >= os.path.getmtime(PYLISTS_SRC):
+        return PYLISTS
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-Wall", "-I", sysconfig.get_paths()["include"],
+           PYLISTS_SRC, "-o", PYLISTS]
+    subprocess.check_call(cmd)
+    return PYLISTS
 
 
 def sources():
@@ -32,6 +47,7 @@ def _stale():
 
 
 def build(force=False, verbose=False):
+    build_pylists(force)
     if not force and not _stale():
         return LIB
     objdir = os.path.join(PKG, "build")

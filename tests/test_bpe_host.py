@@ -220,6 +220,48 @@ def test_ids_to_csr_accepts_every_container():
         T._ids_to_csr(obj, [[2 ** 40]], "cpu")
 
 
+def test_list_helpers_c_and_python_agree(monkeypatch):
+    """CSR <-> List[List[int]] (the reference's return / argument type, beast_bspline_bpe_tokenizer.py:175-247):
+    the CPython helper (csrc/pylists.c) and the pure-Python conversions must give the same lists / arrays,
+    including empty rows, ids above the shared-int cache, negative ids and the int32 range error."""
+    import beast_tokenizer_b200.beast_bspline_bpe_tokenizer as M
+    rng = np.random.default_rng(11)
+    lens = rng.integers(0, 40, 500)
+    lens[[0, 7, 499]] = 0
+    off = np.zeros(501, np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = rng.integers(0, 3000, int(off[-1])).astype(np.int32)
+    flat[:4] = [-1, 2 ** 31 - 1, 1 << 20, (1 << 20) - 1]
+    want = [flat[off[i]:off[i + 1]].tolist() for i in range(500)]
+    cmod = M._pylists()
+    assert cmod, "the in-tree CPython helper did not build / import"
+    got = {}
+    for name, mod in (("c", cmod), ("py", False)):
+        monkeypatch.setattr(M, "_PYLISTS", mod)
+        rows = M._split_rows(flat, off)
+        assert rows == want and all(type(v) is int for r in rows for v in r), name
+        f, o = M._flatten_rows(rows)
+        assert f.dtype == np.int32 and o.dtype == np.int64
+        assert np.array_equal(f, flat) and np.array_equal(o, off), name
+        f, o = M._flatten_rows(tuple(tuple(r) for r in rows))
+        assert np.array_equal(f, flat) and np.array_equal(o, off), name
+        assert M._flatten_rows([np.arange(3)]) is None, name
+        T = M.BEASTBsplineBPETokenizer                              # floats truncate like int() on either path
+        f2, o2 = T._ids_to_csr(T.__new__(T), [[1, 2.5], [np.int64(7)]], "cpu")
+        assert f2.tolist() == [1, 2, 7] and o2.tolist() == [0, 2, 3], name
+        for bad in ([[2 ** 31]], [[-2 ** 31 - 1]], [[2 ** 80]]):
+            with pytest.raises(ValueError):
+                M._flatten_rows(bad)
+        got[name] = rows
+    assert got["c"] == got["py"]
+    with pytest.raises(ValueError):
+        cmod.split_rows(flat, off[:-3].copy())           # offsets that do not cover the ids
+    bad_off = off.copy()
+    bad_off[3] = off[-1] + 1
+    with pytest.raises(ValueError):
+        cmod.split_rows(flat, bad_off)
+
+
 def test_match_resolution_by_function_composition():
     """The warp-per-sequence rewrite (csrc/bpe.cu: rewrite_sequence_warp) resolves the greedy left-to-right rule
     match[p] = cand[p] and not match[p-1] without a serial pass: every lane evaluates its 8-symbol chunk for both
