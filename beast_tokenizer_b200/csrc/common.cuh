@@ -38,6 +38,14 @@ struct Plan {
     // exact zeros, skipping them leaves the fp32 sums unchanged.  Layout: enc_joint[2*nb], enc_grip[2*nb],
     // dec_joint[2*T], dec_grip[2*T].
     int* bands_d;
+    // Work lists of the tiled kernels, token order (r = k*D + slot ascending), entries k | slot << 16 | gripper << 31:
+    // enc_list = token positions whose projector row is not empty (every other coefficient is exactly 0 for every
+    // trajectory and its token a per-column constant); dec_list = token positions whose coefficient some basis row
+    // actually reads (with more basis functions than samples most coefficients never reach a trajectory sample, so
+    // their tokens need not even be loaded).  One allocation: enc_list_d[n_enc] followed by dec_list_d[n_dec].
+    int* enc_list_d;
+    int* dec_list_d;
+    int n_enc, n_dec;
     int num_sms;
     int max_smem_optin;
 };

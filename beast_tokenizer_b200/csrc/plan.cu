@@ -101,6 +101,35 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
         }
         e = cudaMalloc((void**)&p->bands_d, n_band * sizeof(int));
         if (e == cudaSuccess) e = cudaMemcpy(p->bands_d, bands, n_band * sizeof(int), cudaMemcpyHostToDevice);
+        // work lists of the tiled kernels (see Plan): non-empty projector rows / coefficients a basis row reads
+        const int D = p->D, n_joint = p->n_joint;
+        int* lists = nullptr;
+        if (e == cudaSuccess && nb <= 0xffff && D <= 0x7fff) {
+            lists = (int*)malloc((size_t)2 * D * nb * sizeof(int) + sizeof(int));
+            char* used = (char*)calloc((size_t)2 * nb, 1);          // [joint | gripper][k]
+            if (!lists || !used) { free(lists); free(used); free(bands); beast_plan_destroy((beast_plan_t*)p); return BEAST_E_NOMEM; }
+            for (int t = 0; t < T; ++t) {
+                for (int k = bands[4 * nb + 2 * t]; k < bands[4 * nb + 2 * t + 1]; ++k) used[k] = 1;
+                for (int k = bands[4 * nb + 2 * T + 2 * t]; k < bands[4 * nb + 2 * T + 2 * t + 1]; ++k) used[nb + k] = 1;
+            }
+            int n_enc = 0, n_dec = 0;
+            int* dec = lists + (size_t)D * nb;
+            for (int k = 0; k < nb; ++k)
+                for (int slot = 0; slot < D; ++slot) {
+                    const bool grip = slot >= n_joint;
+                    const int entry = k | (slot << 16) | (grip ? (int)0x80000000u : 0);
+                    const int* b = bands + (grip ? 2 * nb : 0) + 2 * k;
+                    if (b[0] < b[1]) lists[n_enc++] = entry;
+                    if (used[(grip ? nb : 0) + k]) dec[n_dec++] = entry;
+                }
+            free(used);
+            p->n_enc = n_enc; p->n_dec = n_dec;
+            e = cudaMalloc((void**)&p->enc_list_d, ((size_t)n_enc + n_dec + 1) * sizeof(int));
+            if (e == cudaSuccess && n_enc) e = cudaMemcpy(p->enc_list_d, lists, (size_t)n_enc * sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) p->dec_list_d = p->enc_list_d + n_enc;
+            if (e == cudaSuccess && n_dec) e = cudaMemcpy(p->dec_list_d, dec, (size_t)n_dec * sizeof(int), cudaMemcpyHostToDevice);
+            free(lists);
+        }
         free(bands);
         if (e != cudaSuccess) { beast_plan_destroy((beast_plan_t*)p); return (int)e; }
     }
@@ -114,6 +143,7 @@ extern "C" int beast_plan_destroy(beast_plan_t* plan) {
     free(p->proj_joint_h); free(p->proj_grip_h); free(p->phi_joint_h); free(p->phi_grip_h);
     if (p->dev_block) cudaFree(p->dev_block);
     if (p->bands_d) cudaFree(p->bands_d);
+    if (p->enc_list_d) cudaFree(p->enc_list_d);
     delete p;
     return BEAST_OK;
 }

@@ -3,236 +3,342 @@
 // actions [10, 32]: 1 600 tokens per trajectory, 1 280 B read and 19 200 B written per encode) and of every shape the
 // T = 50 / nb = 10 bulk-copy kernels (spline_encode.cu, spline_decode.cu) do not cover.
 //
-// A CTA walks tiles of S trajectories through shared memory: global loads and stores are contiguous runs of a
-// trajectory's samples / tokens / coefficients (every buffer of the reference's layout is contiguous per trajectory),
-// the strided accesses — sample (t, dof) of a column, coefficient (slot, k) of a token — hit shared memory.  Sums run
-// over the non-zero BAND of each projector / basis row (plan.cu): a degree-0 projector row touches the few samples of
-// its interval (none at all for 40 of 50 basis functions when nb > T), a degree-p basis row p + 1 coefficients; the
-// skipped terms are exact zeros, t / k ascending with fused multiply-adds as in the other kernels, so the results are
-// bit-identical to them.
+// Sums run over the non-zero BAND of each projector / basis row (plan.cu): a degree-0 projector row touches the few
+// samples of its interval (none at all for 40 of 50 basis functions when nb > T), a degree-p basis row p + 1
+// coefficients; the skipped terms are exact zeros, t / k ascending with fused multiply-adds as in the other kernels, so
+// the results are bit-identical to them.
+//
+// Encode: a persistent CTA walks tiles of S trajectories.  The tile's samples arrive by one bulk copy (double
+// buffered: the next tile is in flight while this one is computed); tokens and coefficients are STAGED in shared memory
+// in their final global layout and leave by one bulk copy each (a tile's tokens / coefficients are one contiguous run
+// of global memory).  The staging rows are templates: a coefficient whose projector row is empty is exactly 0 for every
+// trajectory and its token a per-column constant, both written ONCE per CTA; per tile only the positions of the plan's
+// enc_list are recomputed (320 of 1 600 for the shipped shape), so the instruction stream per trajectory is the
+// useful fit + quantiser and nothing else — the copy engine moves the bytes.
+//
+// Decode: only the tokens whose coefficient some basis row reads are loaded at all (plan's dec_list: with 50 degree-0
+// basis functions over 10 samples that is one token in five, in 256-byte runs), dequantised into shared memory; then
+// one output sample per thread in output order (contiguous fp32 stores).
 #include "common.cuh"
 
 namespace beast {
 
 constexpr int kTiledThreads = 512;
 
-// encode: tile of trajectories -> coefficients, tokens, optional column min / max.
-// Per CTA, once: tab[r] = k | slot << 16 for every token position r = k*D + slot of a trajectory, the quantiser
-// constants of every column, the bands.  Per tile: (1) the samples, one contiguous run; (2) one TOKEN per thread and
-// step in token order — consecutive threads store consecutive int64 tokens — each a sum over the band of projector row
-// k (shared-memory samples), quantised exactly; the coefficient goes to its '(d t)' place in shared memory;
-// (3) coefficients leave as one contiguous run.
-__global__ void __launch_bounds__(kTiledThreads)
-encode_tiled_kernel(const float* __restrict__ traj, long long B, int T, int D, int nb, int n_joint,
-                    const int* __restrict__ slot_to_dof, const float* __restrict__ Pj, const float* __restrict__ Pg,
-                    const int* __restrict__ bands, const float* __restrict__ w_min, const float* __restrict__ w_max,
-                    float vm1, long long offset, float* __restrict__ params_out, long long* __restrict__ tokens_out,
-                    float* __restrict__ bmin, float* __restrict__ bmax, int S) {
-    extern __shared__ __align__(16) float smem_f[];
+int launch_encode_tiled_v1(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
+                           long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
+                           cudaStream_t st);
+int launch_decode_tiled_v1(const Plan* p, const long long* tokens, const float* params, long long B, const float* w_min,
+                           const float* w_max, long long offset, const float* init_p, float* out, cudaStream_t st);
+static bool tiled_v1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BEAST_B200_TILED_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+struct EncTiledArgs {
+    const float* traj;
+    long long B;
+    int T, D, nb, n_joint;
+    const int* slot_to_dof;
+    const float* Pj;
+    const float* Pg;
+    const int* bands;
+    const int* list;
+    int n_enc;
+    const float* w_min;
+    const float* w_max;
+    float vm1;
+    long long offset;
+    float* params_out;
+    long long* tokens_out;
+    float* bmin;
+    float* bmax;
+    int S, G;                 // trajectories per tile; trajectory groups per list entry (work item = entry x group)
+    uint32_t y_bytes, tok_off, par_off, q_off, list_off, band_off, dof_off, bar_off;
+    int in_bulk, tok_bulk, par_bulk;   // base pointer 16-byte aligned and full tiles a multiple of 16 bytes
+};
+
+__global__ void __launch_bounds__(kTiledThreads, 3)
+encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int T = a.T, D = a.D, nb = a.nb, S = a.S, n_enc = a.n_enc;
     const int row_in = T * D, row_out = D * nb;
-    float* y = smem_f;                                          // [S][T][D]
-    const int pitch = nb | 1, prow = D * pitch;                 // odd pitch: the '(d t)' staging is free of bank conflicts
-    float* par = y + (((size_t)S * row_in + 3) & ~(size_t)3);   // [S][D][pitch] coefficients, slot major
-    float* qtab = par + (((size_t)S * prow + 3) & ~(size_t)3);  // [D*nb][4] quantiser constants in TOKEN order, or [2][D*nb] min / max
-    float* s_mn = qtab;
-    float* s_mx = qtab + row_out;
-    int* tab = (int*)(qtab + (size_t)4 * row_out);              // [D*nb] token position r -> k | slot << 16 | (joint ? 0 : 1 << 31)
-    int* ctab = tab + row_out;                                  // [D*nb] column c = slot*nb + k -> slot*pitch + k
-    int* ztok = ctab + row_out;                                 // [D*nb] token of a zero coefficient, token order (empty projector rows)
-    int* s_band = ztok + row_out;                               // [2][2*nb]
-    int* s_dof = s_band + 4 * nb;                               // [D]
-    const bool want_mm = bmin != nullptr, want_par = params_out != nullptr, want_tok = tokens_out != nullptr;
+    float* const ybuf0 = (float*)smem;                          // [2][S][T][D] samples, double buffered
+    float* const ybuf1 = (float*)(smem + a.y_bytes);
+    long long* const tok_s = (long long*)(smem + a.tok_off);    // [S][D*nb] tokens, global layout '(t d)'
+    float* const par_s = (float*)(smem + a.par_off);            // [S][D*nb] coefficients, global layout '(d t)'
+    float* const qtab = (float*)(smem + a.q_off);               // [n_enc][4] quantiser constants, or [2][D*nb] min / max
+    float* const s_mn = qtab;
+    float* const s_mx = qtab + row_out;
+    int* const lst = (int*)(smem + a.list_off);                 // [n_enc] k | slot << 16 | gripper << 31
+    int* const s_band = (int*)(smem + a.band_off);              // [2][2*nb]
+    int* const s_dof = (int*)(smem + a.dof_off);                // [D]
+    uint64_t* const bar = (uint64_t*)(smem + a.bar_off);        // [2]
+    const bool want_tok = a.tokens_out != nullptr, want_par = a.params_out != nullptr, want_mm = a.bmin != nullptr;
+    const bool use_par = want_par || want_mm;
     const int tid = threadIdx.x;
-    for (int r = tid; r < row_out; r += kTiledThreads) {
-        const int k = r / D, slot = r - k * D;
-        const bool grip_r = slot >= n_joint;
-        const bool empty = bands[(grip_r ? 2 * nb : 0) + 2 * k] >= bands[(grip_r ? 2 * nb : 0) + 2 * k + 1];
-        // bits 0-13 k, 14 = projector row k is all zero (the coefficient is exactly 0 for every trajectory), 16-30 slot, 31 gripper
-        tab[r] = k | (empty ? 0x4000 : 0) | (slot << 16) | (grip_r ? (int)0x80000000u : 0);
-        ctab[r] = (r / nb) * pitch + (r % nb);                  // r read as a column index here
+
+    for (int i = tid; i < n_enc; i += kTiledThreads) {
+        const int e = a.list[i];
+        lst[i] = e;
         if (want_tok) {
-            const float lo0 = w_min[slot * nb + k], hi0 = w_max[slot * nb + k];
-            ztok[r] = (int)quantize_one(0.0f, lo0, hi0, quant_scale(lo0, hi0), vm1);
-        }
-        if (want_mm) { s_mn[r] = __int_as_float(0x7f800000); s_mx[r] = __int_as_float(0xff800000); }
-        else if (want_tok) {
+            const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
             QuantCol qc;
-            qc.init(w_min[slot * nb + k], w_max[slot * nb + k]);
-            qtab[4 * r] = qc.lo; qtab[4 * r + 1] = qc.hi; qtab[4 * r + 2] = qc.scale; qtab[4 * r + 3] = qc.rcp;
+            qc.init(a.w_min[slot * nb + k], a.w_max[slot * nb + k]);
+            qtab[4 * i] = qc.lo; qtab[4 * i + 1] = qc.hi; qtab[4 * i + 2] = qc.scale; qtab[4 * i + 3] = qc.rcp;
         }
     }
-    for (int i = tid; i < 4 * nb; i += kTiledThreads) s_band[i] = bands[i];
-    for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = slot_to_dof[i];
-    const long long n_tiles = (B + S - 1) / S;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long b0 = tile * S;
-        const int ns = (int)((B - b0) < S ? (B - b0) : S);
-        __syncthreads();                                      // tables ready / previous tile's staging drained
-        {   // phase 1: the tile's samples, contiguous in global memory
-            const float* src = traj + b0 * row_in;
-            const int n = ns * row_in;
-            if ((((uintptr_t)src) & 15u) == 0 && (n & 3) == 0) {
-                for (int i = tid; i < (n >> 2); i += kTiledThreads) ((float4*)y)[i] = __ldcs((const float4*)src + i);
-            } else {
-                for (int i = tid; i < n; i += kTiledThreads) y[i] = __ldcs(src + i);
-            }
+    for (int i = tid; i < 4 * nb; i += kTiledThreads) s_band[i] = a.bands[i];
+    for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = a.slot_to_dof[i];
+    if (want_tok)                                               // templates: the token of a zero coefficient everywhere
+        for (int r = tid; r < row_out; r += kTiledThreads) {
+            const int k = r / D, slot = r - k * D;
+            const float lo0 = a.w_min[slot * nb + k], hi0 = a.w_max[slot * nb + k];
+            const long long z = quantize_one(0.0f, lo0, hi0, quant_scale(lo0, hi0), a.vm1) + a.offset;
+            for (int tr = 0; tr < S; ++tr) tok_s[(size_t)tr * row_out + r] = z;
         }
+    if (use_par)
+        for (int i = tid; i < S * row_out; i += kTiledThreads) par_s[i] = 0.0f;
+    if (want_mm)                                                // a column outside the list holds 0 for every trajectory
+        for (int c = tid; c < row_out; c += kTiledThreads) { s_mn[c] = 0.0f; s_mx[c] = 0.0f; }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (want_mm)
+        for (int i = tid; i < n_enc; i += kTiledThreads) {
+            const int e = lst[i];
+            const int c = ((e >> 16) & 0x7fff) * nb + (e & 0xffff);
+            s_mn[c] = __int_as_float(0x7f800000);
+            s_mx[c] = __int_as_float(0xff800000);
+        }
+
+    const long long n_tiles = (a.B + S - 1) / S;
+    auto rows_of = [&](long long tile) { const long long rem = a.B - tile * S; return (int)(rem < S ? rem : S); };
+    auto bulk_in = [&](int ns) { return a.in_bulk && ((ns * row_in) & 3) == 0; };
+    auto issue = [&](long long tile, int buf) {                 // thread 0: the tile's samples, one bulk copy
+        const int ns = rows_of(tile);
+        if (!bulk_in(ns)) return;
+        const uint32_t bytes = (uint32_t)ns * row_in * 4u;
+        mbar_arrive_expect_tx(&bar[buf], bytes);
+        bulk_g2s(buf ? ybuf1 : ybuf0, a.traj + tile * S * row_in, bytes, &bar[buf]);
+    };
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) issue(tile, 0);
+    const int items = n_enc * a.G;
+    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+        const int buf = it & 1;
+        float* const y = buf ? ybuf1 : ybuf0;
+        const long long b0 = tile * S;
+        const int ns = rows_of(tile);
+        // the other buffer was last read before the barrier that ended the previous tile's compute phase
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
+        if (bulk_in(ns)) {
+            mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u);    // only a LAST tile can be loaded by hand: parity = use count
+        } else {
+            const float* src = a.traj + b0 * row_in;
+            for (int i = tid; i < ns * row_in; i += kTiledThreads) y[i] = __ldcs(src + i);
+        }
+        if (tid == 0) bulk_wait_read<0>();                      // the previous tile's stores have read the staging rows
         __syncthreads();
-        for (int tr = 0; tr < ns; ++tr) {                     // phase 2
-            const float* ytr = y + (size_t)tr * row_in;
-            float* ptr = par + (size_t)tr * prow;
-            long long* ttr = want_tok ? tokens_out + (b0 + tr) * row_out : nullptr;
-#pragma unroll 4
-            for (int r = tid; r < row_out; r += kTiledThreads) {
-                const int e = tab[r];
-                const int k = e & 0x3fff, slot = (e >> 16) & 0x7fff;
-                if (e & 0x4000) {                             // empty projector row: coefficient 0, token a per-column constant
-                    if (want_par || want_mm) ptr[slot * pitch + k] = 0.0f;
-                    if (want_tok) ttr[r] = (long long)ztok[r] + offset;
-                    continue;
-                }
-                const bool grip = e < 0;
-                const float* Pk = (grip ? Pg : Pj) + k * T;
-                const int t0 = s_band[(grip ? 2 * nb : 0) + 2 * k], t1 = s_band[(grip ? 2 * nb : 0) + 2 * k + 1];
-                const float* col = ytr + s_dof[slot];
+        for (int j = tid; j < items; j += kTiledThreads) {
+            const int g = j / n_enc, i = j - g * n_enc;
+            const int e = lst[i];
+            const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
+            const bool grip = e < 0;
+            const float* Pk = (grip ? a.Pg : a.Pj) + k * T;
+            const int t0 = s_band[(grip ? 2 * nb : 0) + 2 * k], t1 = s_band[(grip ? 2 * nb : 0) + 2 * k + 1];
+            const int r = k * D + slot, c = slot * nb + k;
+            const float* col0 = y + s_dof[slot];
+            QuantCol qc;
+            if (want_tok) {
+                const float4 q = *(const float4*)(qtab + 4 * i);
+                qc.lo = q.x; qc.hi = q.y; qc.scale = q.z; qc.rcp = q.w;
+            }
+            float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+            for (int tr = g; tr < ns; tr += a.G) {
+                const float* col = col0 + (size_t)tr * row_in;
                 float acc = 0.0f;
                 for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), col[t * D], acc);
-                if (want_par || want_mm) ptr[slot * pitch + k] = acc;
-                if (want_tok) {
-                    const float4 q = *(const float4*)(qtab + 4 * r);
-                    QuantCol qc;
-                    qc.lo = q.x; qc.hi = q.y; qc.scale = q.z; qc.rcp = q.w;
-                    ttr[r] = quantize_col(acc, qc, vm1) + offset;
-                }
+                if (use_par) par_s[(size_t)tr * row_out + c] = acc;
+                if (want_tok) tok_s[(size_t)tr * row_out + r] = quantize_col(acc, qc, a.vm1) + a.offset;
+                mn = fminf(mn, acc); mx = fmaxf(mx, acc);
+            }
+            if (want_mm && mn <= mx) { atomic_min_f32(&s_mn[c], mn); atomic_max_f32(&s_mx[c], mx); }
+        }
+        fence_async_smem();                                     // staging rows -> visible to the copy engine
+        __syncthreads();
+        if (want_tok) {
+            long long* dst = a.tokens_out + b0 * row_out;
+            if (a.tok_bulk && ((ns * row_out) & 1) == 0) {
+                if (tid == 0) bulk_s2g(dst, tok_s, (uint32_t)ns * row_out * 8u);
+            } else {
+                for (int i = tid; i < ns * row_out; i += kTiledThreads) __stcs(dst + i, tok_s[i]);
             }
         }
-        if (want_par || want_mm) {
-            __syncthreads();
-            if (want_par) {                                   // phase 3: coefficients leave as contiguous rows
-                for (int tr = 0; tr < ns; ++tr) {
-                    float* dst = params_out + (b0 + tr) * row_out;
-                    const float* src = par + (size_t)tr * prow;
-#pragma unroll 4
-                    for (int c = tid; c < row_out; c += kTiledThreads) __stcs(dst + c, src[ctab[c]]);
-                }
-            }
-            if (want_mm) {                                    // a thread owns columns c, c + blockDim, ...: no atomics needed
-                for (int c = tid; c < row_out; c += kTiledThreads) {
-                    float mn = s_mn[c], mx = s_mx[c];
-                    const int pc = ctab[c];
-                    for (int tr = 0; tr < ns; ++tr) {
-                        const float v = par[(size_t)tr * prow + pc];
-                        mn = fminf(mn, v); mx = fmaxf(mx, v);
-                    }
-                    s_mn[c] = mn; s_mx[c] = mx;
-                }
+        if (want_par) {
+            float* dst = a.params_out + b0 * row_out;
+            if (a.par_bulk && ((ns * row_out) & 3) == 0) {
+                if (tid == 0) bulk_s2g(dst, par_s, (uint32_t)ns * row_out * 4u);
+            } else {
+                for (int i = tid; i < ns * row_out; i += kTiledThreads) __stcs(dst + i, par_s[i]);
             }
         }
+        if (tid == 0) bulk_commit();
+        // hand-written stores of this tile read the staging rows; the next tile's writes come after its barrier
     }
+    if (tid == 0) bulk_wait_all<0>();
     if (want_mm) {
         __syncthreads();
         for (int c = tid; c < row_out; c += kTiledThreads)
-            if (s_mn[c] <= s_mx[c]) { atomic_min_f32(bmin + c, s_mn[c]); atomic_max_f32(bmax + c, s_mx[c]); }
+            if (s_mn[c] <= s_mx[c]) { atomic_min_f32(a.bmin + c, s_mn[c]); atomic_max_f32(a.bmax + c, s_mx[c]); }
     }
 }
 
+struct DecTiledArgs {
+    const long long* tokens;
+    const float* params;
+    long long B;
+    int T, D, nb, n_joint;
+    const int* slot_to_dof;
+    const float* phi_j;
+    const float* phi_g;
+    const int* bands;
+    const int* list;
+    int n_dec;
+    const float* w_min;
+    const float* w_max;
+    float vm1;
+    long long offset;
+    const float* init_p;
+    float* out;
+    int S, G1, G2;            // trajectories per tile; trajectory groups per token entry / per output sample
+};
+
 // decode: tile of token rows (or coefficient rows) -> trajectories.
-// Per tile: (1) one TOKEN per thread and step in token order (contiguous int64 loads), dequantised exactly into shared
-// memory; (2) one output SAMPLE per thread and step in output order (contiguous fp32 stores): the sum over the band of
-// basis row t against the slot's coefficients.
 template <bool FROM_TOKENS>
-__global__ void __launch_bounds__(kTiledThreads, 4)
-decode_tiled_kernel(const long long* __restrict__ tokens, const float* __restrict__ params, long long B, int T, int D,
-                    int nb, int n_joint, const int* __restrict__ slot_to_dof, const float* __restrict__ phi_j,
-                    const float* __restrict__ phi_g, const int* __restrict__ bands, const float* __restrict__ w_min,
-                    const float* __restrict__ w_max, float vm1, long long offset, const float* __restrict__ init_p,
-                    float* __restrict__ out, int S) {
+__global__ void __launch_bounds__(kTiledThreads, 3)
+decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
     extern __shared__ __align__(16) float smem_f[];
+    const int T = a.T, D = a.D, nb = a.nb, S = a.S, n_dec = a.n_dec;
     const int row_in = D * nb, row_out = T * D;
-    float* c_s = smem_f;                                        // [S][nb][D]   (token order: slot minor)
-    float* lohi = c_s + (((size_t)S * row_in + 3) & ~(size_t)3);    // [D*nb][2] bounds in token order
-    int* tab_in = (int*)(lohi + (size_t)2 * row_in);            // [D*nb] k | slot << 16
-    int* tab_out = tab_in + row_in;                             // [T*D]  t | slot << 16 | grip << 31, output order [t][dof]
+    float* c_s = smem_f;                                        // [S][nb][D] coefficients, token order (slot minor)
+    float* lohi = c_s + (((size_t)S * row_in + 3) & ~(size_t)3);    // [n_dec][2] bounds of the listed tokens
+    int* lst = (int*)(lohi + (size_t)2 * n_dec);                // [n_dec] k | slot << 16 | gripper << 31
+    int* tab_out = lst + n_dec;                                 // [T*D]  t | slot << 16 | gripper << 31, output order [t][dof]
     int* s_band = tab_out + row_out;                            // [2][2*T]
     int* s_dof = s_band + 4 * T;                                // [D]
     const int tid = threadIdx.x;
-    const float rcp_vm1 = __frcp_rn(vm1);                       // exact invariant division by V - 1 (common.cuh)
-    for (int r = tid; r < row_in; r += kTiledThreads) {
-        const int k = r / D, slot = r - k * D;
-        tab_in[r] = k | (slot << 16);
-        if (FROM_TOKENS) { lohi[2 * r] = w_min[slot * nb + k]; lohi[2 * r + 1] = w_max[slot * nb + k]; }
+    const float rcp_vm1 = __frcp_rn(a.vm1);                     // exact invariant division by V - 1 (common.cuh)
+    for (int i = tid; i < n_dec; i += kTiledThreads) {
+        const int e = a.list[i];
+        lst[i] = e;
+        if (FROM_TOKENS) {
+            const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
+            lohi[2 * i] = a.w_min[slot * nb + k];
+            lohi[2 * i + 1] = a.w_max[slot * nb + k];
+        }
     }
-    for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = slot_to_dof[i];
-    for (int i = tid; i < 4 * T; i += kTiledThreads) s_band[i] = bands[4 * nb + i];
+    for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = a.slot_to_dof[i];
+    for (int i = tid; i < 4 * T; i += kTiledThreads) s_band[i] = a.bands[4 * nb + i];
     __syncthreads();
     for (int q = tid; q < row_out; q += kTiledThreads) {
         const int t = q / D, dof = q - t * D;
         int slot = 0;
         for (int sidx = 0; sidx < D; ++sidx) if (s_dof[sidx] == dof) slot = sidx;
-        tab_out[q] = t | (slot << 16) | (slot < n_joint ? 0 : (int)0x80000000u);
+        tab_out[q] = t | (slot << 16) | (slot < a.n_joint ? 0 : (int)0x80000000u);
     }
-    const long long n_tiles = (B + S - 1) / S;
+    const long long n_tiles = (a.B + S - 1) / S;
+    const int items1 = n_dec * a.G1, items2 = row_out * a.G2;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * S;
-        const int ns = (int)((B - b0) < S ? (B - b0) : S);
-        __syncthreads();
-        for (int tr = 0; tr < ns; ++tr) {                     // phase 1
-            float* ctr = c_s + (size_t)tr * row_in;
-            const long long* ttr = FROM_TOKENS ? tokens + (b0 + tr) * row_in : nullptr;
-            const float* ptr = FROM_TOKENS ? nullptr : params + (b0 + tr) * row_in;
-            const float* ip = init_p ? init_p + (b0 + tr) * D : nullptr;
+        const int ns = (int)((a.B - b0) < S ? (a.B - b0) : S);
+        __syncthreads();                                        // tables ready / previous tile's coefficients consumed
+        for (int j = tid; j < items1; j += kTiledThreads) {     // phase 1: the listed tokens -> coefficients
+            const int g = j / n_dec, i = j - g * n_dec;
+            const int e = lst[i];
+            const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
+            const int r = k * D + slot;
+            float lo = 0.0f, hi = 0.0f;
+            if (FROM_TOKENS) { lo = lohi[2 * i]; hi = lohi[2 * i + 1]; }
+            const bool pinned = k == 0 && a.init_p != nullptr && slot < a.n_joint;
+            const int dof = s_dof[slot];
+            const int cpar = slot * nb + k;
 #pragma unroll 4
-            for (int r = tid; r < row_in; r += kTiledThreads) {
-                const int e = tab_in[r];
-                const int k = e & 0xffff, slot = e >> 16;
+            for (int tr = g; tr < ns; tr += a.G1) {
                 float v;
-                if (FROM_TOKENS) v = dequantize_fast(__ldcs(ttr + r) - offset, lohi[2 * r], lohi[2 * r + 1], vm1, rcp_vm1);
-                else v = ptr[slot * nb + k];
-                if (k == 0 && ip && slot < n_joint) v = ip[s_dof[slot]];
-                ctr[r] = v;
+                if (FROM_TOKENS) v = dequantize_fast(__ldcs(a.tokens + (b0 + tr) * row_in + r) - a.offset, lo, hi, a.vm1, rcp_vm1);
+                else v = a.params[(b0 + tr) * row_in + cpar];
+                if (pinned) v = a.init_p[(b0 + tr) * D + dof];
+                c_s[(size_t)tr * row_in + r] = v;
             }
         }
         __syncthreads();
-        for (int tr = 0; tr < ns; ++tr) {                     // phase 2
-            const float* ctr = c_s + (size_t)tr * row_in;
-            float* otr = out + (b0 + tr) * row_out;
-#pragma unroll 4
-            for (int q = tid; q < row_out; q += kTiledThreads) {
-                const int e = tab_out[q];
-                const int t = e & 0xffff, slot = (e >> 16) & 0x7fff;
-                const bool grip = e < 0;
-                const float* row = (grip ? phi_g : phi_j) + (size_t)t * nb;
-                const int k0 = s_band[(grip ? 2 * T : 0) + 2 * t], k1 = s_band[(grip ? 2 * T : 0) + 2 * t + 1];
-                const float* col = ctr + slot;
+        for (int j = tid; j < items2; j += kTiledThreads) {     // phase 2: one output sample per thread, output order
+            const int g = j / row_out, q = j - g * row_out;
+            const int e = tab_out[q];
+            const int t = e & 0xffff, slot = (e >> 16) & 0x7fff;
+            const bool grip = e < 0;
+            const float* row = (grip ? a.phi_g : a.phi_j) + (size_t)t * nb;
+            const int k0 = s_band[(grip ? 2 * T : 0) + 2 * t], k1 = s_band[(grip ? 2 * T : 0) + 2 * t + 1];
+            for (int tr = g; tr < ns; tr += a.G2) {
+                const float* col = c_s + (size_t)tr * row_in + slot;
                 float acc = 0.0f;
                 for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(row + k), col[(size_t)k * D], acc);
-                __stcs(otr + q, acc);
+                __stcs(a.out + (b0 + tr) * row_out + q, acc);
             }
         }
     }
 }
 
-static int tile_rows(size_t bytes_per_traj, size_t extra, int max_smem, size_t budget) {
-    if (budget > (size_t)max_smem) budget = (size_t)max_smem;
-    if (bytes_per_traj + extra > budget) budget = (size_t)max_smem;
-    if (bytes_per_traj + extra > budget) return 0;
-    size_t s = (budget - extra) / bytes_per_traj;
-    if (s > 64) s = 64;
-    return (int)s;
+static inline size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
+static inline int groups_for(int entries, int S) {
+    int g = entries > 0 ? (kTiledThreads + entries - 1) / entries : 1;
+    if (g > S) g = S;
+    return g < 1 ? 1 : g;
 }
 
 int launch_encode_tiled(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
                         long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
                         cudaStream_t st) {
+    if (tiled_v1()) return launch_encode_tiled_v1(p, traj, B, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
     const int T = p->T, D = p->D, nb = p->nb;
-    const size_t per_traj = ((size_t)T * D + (size_t)D * (nb | 1)) * sizeof(float);
-    if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // the two tables share one shared-memory region
-    if (nb > 0x3fff || D > 0x7fff || p->V > 0x7fffffff) return BEAST_E_UNSUPPORTED;
-    // quantiser constants / min-max (4 floats per column), token-position, column and zero-token tables, bands, slot map
-    const size_t extra = ((size_t)7 * D * nb + (size_t)4 * nb + D) * sizeof(float) + 64;
-    const int S = tile_rows(per_traj, extra, p->max_smem_optin, 104 * 1024);
-    if (S < 1 || !p->bands_d) return BEAST_E_UNSUPPORTED;
-    const size_t smem = (size_t)S * per_traj + extra;
+    if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // quantiser constants and min / max share one region
+    if (nb > 0xffff || D > 0x7fff || p->V > 0x7fffffff || !p->bands_d || !p->enc_list_d) return BEAST_E_UNSUPPORTED;
+    const size_t row_in = (size_t)T * D, row_out = (size_t)D * nb;
+    const bool use_par = params_out || bmin;
+    const size_t per_traj = 2 * row_in * 4 + (tokens_out ? row_out * 8 : 0) + (use_par ? row_out * 4 : 0);
+    const size_t q_bytes = up16(bmin ? 2 * row_out * 4 : (tokens_out ? (size_t)p->n_enc * 16 : 0));
+    const size_t extra = q_bytes + up16((size_t)p->n_enc * 4) + up16((size_t)4 * nb * 4) + up16((size_t)D * 4) + 16 + 4 * 16;
+    size_t budget = 72 * 1024;                                // three CTAs per SM
+    if (per_traj + extra > budget) budget = (size_t)p->max_smem_optin;
+    if (per_traj + extra > budget) return BEAST_E_UNSUPPORTED;
+    int S = (int)((budget - extra) / per_traj);
+    if (S > 64) S = 64;
+    if (S >= 4) S &= ~3;                                      // full tiles a multiple of 16 bytes whatever the row sizes
+    EncTiledArgs a;
+    a.traj = traj; a.B = B; a.T = T; a.D = D; a.nb = nb; a.n_joint = p->n_joint;
+    a.slot_to_dof = p->slot_to_dof_d; a.Pj = p->proj_joint_d; a.Pg = p->proj_grip_d; a.bands = p->bands_d;
+    a.list = p->enc_list_d; a.n_enc = p->n_enc;
+    a.w_min = w_min; a.w_max = w_max; a.vm1 = (float)(p->V - 1); a.offset = offset;
+    a.params_out = params_out; a.tokens_out = tokens_out; a.bmin = bmin; a.bmax = bmax;
+    a.S = S; a.G = groups_for(p->n_enc, S);
+    a.y_bytes = (uint32_t)up16((size_t)S * row_in * 4);
+    a.tok_off = 2 * a.y_bytes;
+    a.par_off = a.tok_off + (uint32_t)(tokens_out ? up16((size_t)S * row_out * 8) : 0);
+    a.q_off = a.par_off + (uint32_t)(use_par ? up16((size_t)S * row_out * 4) : 0);
+    a.list_off = a.q_off + (uint32_t)q_bytes;
+    a.band_off = a.list_off + (uint32_t)up16((size_t)p->n_enc * 4);
+    a.dof_off = a.band_off + (uint32_t)up16((size_t)4 * nb * 4);
+    a.bar_off = a.dof_off + (uint32_t)up16((size_t)D * 4);
+    const size_t smem = (size_t)a.bar_off + 16;
+    if (smem > (size_t)p->max_smem_optin) return BEAST_E_UNSUPPORTED;
+    a.in_bulk = (((uintptr_t)traj & 15u) == 0 && ((size_t)S * row_in) % 4 == 0) ? 1 : 0;
+    a.tok_bulk = (tokens_out && ((uintptr_t)tokens_out & 15u) == 0 && ((size_t)S * row_out) % 2 == 0) ? 1 : 0;
+    a.par_bulk = (params_out && ((uintptr_t)params_out & 15u) == 0 && ((size_t)S * row_out) % 4 == 0) ? 1 : 0;
     static size_t granted[kMaxDevices] = {};
     if (int rc = opt_in_smem(encode_tiled_kernel, smem, granted)) return rc;
     const long long n_tiles = (B + S - 1) / S;
@@ -240,10 +346,7 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
     if (per_sm > 2048 / kTiledThreads) per_sm = 2048 / kTiledThreads;
     if (per_sm < 1) per_sm = 1;
     long long grid = n_tiles < (long long)p->num_sms * per_sm ? n_tiles : (long long)p->num_sms * per_sm;
-    encode_tiled_kernel<<<(unsigned)grid, kTiledThreads, smem, st>>>(traj, B, T, D, nb, p->n_joint, p->slot_to_dof_d,
-                                                                    p->proj_joint_d, p->proj_grip_d, p->bands_d, w_min, w_max,
-                                                                    (float)(p->V - 1), offset, params_out, tokens_out, bmin,
-                                                                    bmax, S);
+    encode_tiled_kernel<<<(unsigned)grid, kTiledThreads, smem, st>>>(a);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -251,28 +354,36 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
 
 int launch_decode_tiled(const Plan* p, const long long* tokens, const float* params, long long B, const float* w_min,
                         const float* w_max, long long offset, const float* init_p, float* out, cudaStream_t st) {
+    if (tiled_v1()) return launch_decode_tiled_v1(p, tokens, params, B, w_min, w_max, offset, init_p, out, st);
     const int T = p->T, D = p->D, nb = p->nb;
-    if (p->nc != nb || !p->bands_d) return BEAST_E_UNSUPPORTED;           // pinned control points: generic kernel
+    if (p->nc != nb || !p->bands_d || !p->dec_list_d) return BEAST_E_UNSUPPORTED;   // pinned control points: generic kernel
     if (nb > 0xffff || T > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
-    const size_t per_traj = (size_t)D * nb * sizeof(float);
-    const size_t extra = ((size_t)3 * D * nb + (size_t)T * D + (size_t)4 * T + D) * sizeof(float) + 64;
-    const int S = tile_rows(per_traj, extra, p->max_smem_optin, 54 * 1024);   // four CTAs per SM: the token loads need the warps
-    if (S < 1) return BEAST_E_UNSUPPORTED;
+    const size_t row_in = (size_t)D * nb, row_out = (size_t)T * D;
+    const size_t per_traj = row_in * sizeof(float);
+    const size_t extra = ((size_t)3 * p->n_dec + row_out + (size_t)4 * T + D) * sizeof(float) + 64;
+    size_t budget = 72 * 1024;                                // three CTAs per SM (40 registers per thread)
+    if (per_traj + extra > budget) budget = (size_t)p->max_smem_optin;
+    if (per_traj + extra > budget) return BEAST_E_UNSUPPORTED;
+    int S = (int)((budget - extra) / per_traj);
+    if (S > 64) S = 64;
     const size_t smem = (size_t)S * per_traj + extra;
     static size_t granted_t[kMaxDevices] = {}, granted_p[kMaxDevices] = {};
     if (int rc = tokens ? opt_in_smem(decode_tiled_kernel<true>, smem, granted_t) : opt_in_smem(decode_tiled_kernel<false>, smem, granted_p))
         return rc;
+    DecTiledArgs a;
+    a.tokens = tokens; a.params = params; a.B = B; a.T = T; a.D = D; a.nb = nb; a.n_joint = p->n_joint;
+    a.slot_to_dof = p->slot_to_dof_d; a.phi_j = p->phi_joint_d; a.phi_g = p->phi_grip_d; a.bands = p->bands_d;
+    a.list = p->dec_list_d; a.n_dec = p->n_dec;
+    a.w_min = w_min; a.w_max = w_max; a.vm1 = tokens ? (float)(p->V - 1) : 0.0f; a.offset = tokens ? offset : 0;
+    a.init_p = init_p; a.out = out;
+    a.S = S; a.G1 = groups_for(p->n_dec, S); a.G2 = groups_for((int)row_out, S);
     const long long n_tiles = (B + S - 1) / S;
     long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
     if (per_sm > 2048 / kTiledThreads) per_sm = 2048 / kTiledThreads;
     if (per_sm < 1) per_sm = 1;
     long long grid = n_tiles < (long long)p->num_sms * per_sm ? n_tiles : (long long)p->num_sms * per_sm;
-    if (tokens)
-        decode_tiled_kernel<true><<<(unsigned)grid, kTiledThreads, smem, st>>>(tokens, nullptr, B, T, D, nb, p->n_joint,
-            p->slot_to_dof_d, p->phi_joint_d, p->phi_grip_d, p->bands_d, w_min, w_max, (float)(p->V - 1), offset, init_p, out, S);
-    else
-        decode_tiled_kernel<false><<<(unsigned)grid, kTiledThreads, smem, st>>>(nullptr, params, B, T, D, nb, p->n_joint,
-            p->slot_to_dof_d, p->phi_joint_d, p->phi_grip_d, p->bands_d, nullptr, nullptr, 0.0f, 0, init_p, out, S);
+    if (tokens) decode_tiled_kernel<true><<<(unsigned)grid, kTiledThreads, smem, st>>>(a);
+    else decode_tiled_kernel<false><<<(unsigned)grid, kTiledThreads, smem, st>>>(a);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
