@@ -617,10 +617,23 @@ class FIGBPE:
                       and not tokenizer._has_conditions and torch.cuda.is_available())
         staging, filled = None, 0
         T, D = (tokenizer.times.numel(), tokenizer.num_dof) if can_gather else (0, 0)
+        # HOST batches beyond the first block are gathered in one of two pinned blocks (a plain memcpy per batch) and
+        # uploaded GATHER_ROWS at a time by ONE asynchronous copy: a pageable 90 KB batch costs a synchronous staged
+        # cudaMemcpy each (~15 us), 50 000 of them were most of the wall time of the reference's loader shape
+        pinned, pin_events, pin_cur, block_on_host = None, [None, None], 0, False
 
         def flush():
-            nonlocal filled
+            nonlocal filled, pin_cur, block_on_host
             if filled:
+                if block_on_host:
+                    staging[:filled].copy_(pinned[pin_cur][:filled], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    pin_events[pin_cur] = ev
+                    pin_cur ^= 1
+                    if pin_events[pin_cur] is not None:      # the upload that last read the block we fill next
+                        pin_events[pin_cur].synchronize()
+                    block_on_host = False
                 off = offset if offset is not None else (
                     tokenizer._llm_vocab_offset() if tokenizer.llm_vocab_size is not None else 0)
                 chunks.append(tokenizer._fit(staging[:filled], want_tokens=True, offset=off)[0])
@@ -642,9 +655,16 @@ class FIGBPE:
                     data = data[: max_sequences - collected]
                 if staging is None:
                     staging = torch.empty((self.GATHER_ROWS, T, D), device=tokenizer._cuda(), dtype=torch.float32)
-                if filled + data.shape[0] > self.GATHER_ROWS:
+                via_host = data.device.type == "cpu" and collected >= self.GATHER_ROWS
+                if filled and (filled + data.shape[0] > self.GATHER_ROWS or via_host != block_on_host):
                     flush()
-                staging[filled:filled + data.shape[0]].copy_(data[..., :D], non_blocking=True)
+                if via_host:
+                    if pinned is None:
+                        pinned = [torch.empty((self.GATHER_ROWS, T, D), dtype=torch.float32).pin_memory() for _ in range(2)]
+                    pinned[pin_cur][filled:filled + data.shape[0]].copy_(data[..., :D])
+                    block_on_host = True
+                else:
+                    staging[filled:filled + data.shape[0]].copy_(data[..., :D], non_blocking=True)
                 filled += data.shape[0]
                 n_new = data.shape[0]
             else:

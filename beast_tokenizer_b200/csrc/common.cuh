@@ -46,6 +46,7 @@ struct Plan {
     int* enc_list_d;
     int* dec_list_d;
     int n_enc, n_dec;
+    int enc_band_max, dec_band_max;   // longest projector-row / basis-row band (terms per sum)
     int num_sms;
     int max_smem_optin;
 };

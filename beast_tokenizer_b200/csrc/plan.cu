@@ -112,6 +112,11 @@ extern "C" int beast_plan_create(const beast_plan_desc_t* d, beast_plan_t** out)
                 for (int k = bands[4 * nb + 2 * t]; k < bands[4 * nb + 2 * t + 1]; ++k) used[k] = 1;
                 for (int k = bands[4 * nb + 2 * T + 2 * t]; k < bands[4 * nb + 2 * T + 2 * t + 1]; ++k) used[nb + k] = 1;
             }
+            for (int k = 0; k < 2 * nb; ++k)
+                if (bands[2 * k + 1] - bands[2 * k] > p->enc_band_max) p->enc_band_max = bands[2 * k + 1] - bands[2 * k];
+            for (int t = 0; t < 2 * T; ++t)
+                if (bands[4 * nb + 2 * t + 1] - bands[4 * nb + 2 * t] > p->dec_band_max)
+                    p->dec_band_max = bands[4 * nb + 2 * t + 1] - bands[4 * nb + 2 * t];
             int n_enc = 0, n_dec = 0;
             int* dec = lists + (size_t)D * nb;
             for (int k = 0; k < nb; ++k)

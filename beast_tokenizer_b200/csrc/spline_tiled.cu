@@ -55,10 +55,14 @@ struct EncTiledArgs {
     float* bmin;
     float* bmax;
     int S, G;                 // trajectories per tile; trajectory groups per list entry (work item = entry x group)
-    uint32_t y_bytes, tok_off, par_off, q_off, list_off, band_off, dof_off, bar_off;
+    uint32_t y_bytes, tok_off, par_off, q_off, list_off, band_off, dof_off, bar_off, p_off;
     int in_bulk, tok_bulk, par_bulk;   // base pointer 16-byte aligned and full tiles a multiple of 16 bytes
+    int p_smem;                        // projectors staged in shared memory as [joint | gripper][t][k]
 };
 
+// R = trajectories per pass of a work item: 4 when the sums are long (one projector load then feeds four sums), 1 when
+// they have one or two terms (the shipped shape: nothing to share, and the compute phase sits on the tile's critical path)
+template <int R>
 __global__ void __launch_bounds__(kTiledThreads, 3)
 encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -75,6 +79,7 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
     int* const s_band = (int*)(smem + a.band_off);              // [2][2*nb]
     int* const s_dof = (int*)(smem + a.dof_off);                // [D]
     uint64_t* const bar = (uint64_t*)(smem + a.bar_off);        // [2]
+    float* const P_s = (float*)(smem + a.p_off);                // [2][T][nb] projectors, k minor (threads of a warp differ in k)
     const bool want_tok = a.tokens_out != nullptr, want_par = a.params_out != nullptr, want_mm = a.bmin != nullptr;
     const bool use_par = want_par || want_mm;
     const int tid = threadIdx.x;
@@ -91,6 +96,12 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
     }
     for (int i = tid; i < 4 * nb; i += kTiledThreads) s_band[i] = a.bands[i];
     for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = a.slot_to_dof[i];
+    if (a.p_smem)
+        for (int i = tid; i < T * nb; i += kTiledThreads) {
+            const int t = i / nb, k = i - t * nb;
+            P_s[i] = a.Pj[k * T + t];
+            if (a.Pg) P_s[T * nb + i] = a.Pg[k * T + t];
+        }
     if (want_tok)                                               // templates: the token of a zero coefficient everywhere
         for (int r = tid; r < row_out; r += kTiledThreads) {
             const int k = r / D, slot = r - k * D;
@@ -149,7 +160,9 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
             const int e = lst[i];
             const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
             const bool grip = e < 0;
-            const float* Pk = (grip ? a.Pg : a.Pj) + k * T;
+            // generic pointer + stride over t: the shared-memory copy [t][k] or the plan's global table [k][t]
+            const float* Pk = a.p_smem ? P_s + (grip ? T * nb : 0) + k : (grip ? a.Pg : a.Pj) + k * T;
+            const int pst = a.p_smem ? nb : 1;
             const int t0 = s_band[(grip ? 2 * nb : 0) + 2 * k], t1 = s_band[(grip ? 2 * nb : 0) + 2 * k + 1];
             const int r = k * D + slot, c = slot * nb + k;
             const float* col0 = y + s_dof[slot];
@@ -159,13 +172,30 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
                 qc.lo = q.x; qc.hi = q.y; qc.scale = q.z; qc.rcp = q.w;
             }
             float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-            for (int tr = g; tr < ns; tr += a.G) {
-                const float* col = col0 + (size_t)tr * row_in;
-                float acc = 0.0f;
-                for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), col[t * D], acc);
+            auto emit = [&](int tr, float acc) {
                 if (use_par) par_s[(size_t)tr * row_out + c] = acc;
                 if (want_tok) tok_s[(size_t)tr * row_out + r] = quantize_col(acc, qc, a.vm1) + a.offset;
                 mn = fminf(mn, acc); mx = fmaxf(mx, acc);
+            };
+            // R trajectories per pass: one projector load feeds R sums (each sum keeps its own t-ascending order)
+            for (int tr = g; tr < ns; tr += R * a.G) {
+                const float* cp[R];
+                float acc[R];
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const int tru = tr + u * a.G;
+                    cp[u] = col0 + (size_t)(tru < ns ? tru : ns - 1) * row_in;
+                    acc[u] = 0.0f;
+                }
+                for (int t = t0; t < t1; ++t) {
+                    const float pv = a.p_smem ? Pk[t * pst] : __ldg(Pk + t);
+                    const int o = t * D;
+#pragma unroll
+                    for (int u = 0; u < R; ++u) acc[u] = fmaf(pv, cp[u][o], acc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < R; ++u)
+                    if (tr + u * a.G < ns) emit(tr + u * a.G, acc[u]);
             }
             if (want_mm && mn <= mx) { atomic_min_f32(&s_mn[c], mn); atomic_max_f32(&s_mx[c], mx); }
         }
@@ -216,6 +246,7 @@ struct DecTiledArgs {
     const float* init_p;
     float* out;
     int S, G1, G2;            // trajectories per tile; trajectory groups per token entry / per output sample
+    int phi_smem;             // basis rows staged in shared memory as [joint | gripper][t][nb | 1]
 };
 
 // decode: tile of token rows (or coefficient rows) -> trajectories.
@@ -231,6 +262,8 @@ decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
     int* tab_out = lst + n_dec;                                 // [T*D]  t | slot << 16 | gripper << 31, output order [t][dof]
     int* s_band = tab_out + row_out;                            // [2][2*T]
     int* s_dof = s_band + 4 * T;                                // [D]
+    float* phi_s = (float*)(s_dof + D);                         // [2][T][pitch] basis rows, odd pitch
+    const int pitch = nb | 1;
     const int tid = threadIdx.x;
     const float rcp_vm1 = __frcp_rn(a.vm1);                     // exact invariant division by V - 1 (common.cuh)
     for (int i = tid; i < n_dec; i += kTiledThreads) {
@@ -244,6 +277,12 @@ decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
     }
     for (int i = tid; i < D; i += kTiledThreads) s_dof[i] = a.slot_to_dof[i];
     for (int i = tid; i < 4 * T; i += kTiledThreads) s_band[i] = a.bands[4 * nb + i];
+    if (a.phi_smem)
+        for (int i = tid; i < T * nb; i += kTiledThreads) {
+            const int t = i / nb, k = i - t * nb;
+            phi_s[t * pitch + k] = a.phi_j[i];
+            if (a.phi_g) phi_s[(T + t) * pitch + k] = a.phi_g[i];
+        }
     __syncthreads();
     for (int q = tid; q < row_out; q += kTiledThreads) {
         const int t = q / D, dof = q - t * D;
@@ -282,13 +321,25 @@ decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
             const int e = tab_out[q];
             const int t = e & 0xffff, slot = (e >> 16) & 0x7fff;
             const bool grip = e < 0;
-            const float* row = (grip ? a.phi_g : a.phi_j) + (size_t)t * nb;
+            const float* row = a.phi_smem ? phi_s + (size_t)((grip ? T : 0) + t) * pitch : (grip ? a.phi_g : a.phi_j) + (size_t)t * nb;
             const int k0 = s_band[(grip ? 2 * T : 0) + 2 * t], k1 = s_band[(grip ? 2 * T : 0) + 2 * t + 1];
-            for (int tr = g; tr < ns; tr += a.G2) {
-                const float* col = c_s + (size_t)tr * row_in + slot;
-                float acc = 0.0f;
-                for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(row + k), col[(size_t)k * D], acc);
-                __stcs(a.out + (b0 + tr) * row_out + q, acc);
+            // four trajectories per pass: one basis load feeds four sums (each keeps its own k-ascending order)
+            for (int tr = g; tr < ns; tr += 4 * a.G2) {
+                const int tr1 = tr + a.G2, tr2 = tr + 2 * a.G2, tr3 = tr + 3 * a.G2, last = ns - 1;
+                const float* c0 = c_s + (size_t)tr * row_in + slot;
+                const float* c1 = c_s + (size_t)(tr1 < last ? tr1 : last) * row_in + slot;
+                const float* c2 = c_s + (size_t)(tr2 < last ? tr2 : last) * row_in + slot;
+                const float* c3 = c_s + (size_t)(tr3 < last ? tr3 : last) * row_in + slot;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                for (int k = k0; k < k1; ++k) {
+                    const float pv = row[k];
+                    const size_t o = (size_t)k * D;
+                    a0 = fmaf(pv, c0[o], a0); a1 = fmaf(pv, c1[o], a1); a2 = fmaf(pv, c2[o], a2); a3 = fmaf(pv, c3[o], a3);
+                }
+                __stcs(a.out + (b0 + tr) * row_out + q, a0);
+                if (tr1 < ns) __stcs(a.out + (b0 + tr1) * row_out + q, a1);
+                if (tr2 < ns) __stcs(a.out + (b0 + tr2) * row_out + q, a2);
+                if (tr3 < ns) __stcs(a.out + (b0 + tr3) * row_out + q, a3);
             }
         }
     }
@@ -312,7 +363,12 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
     const bool use_par = params_out || bmin;
     const size_t per_traj = 2 * row_in * 4 + (tokens_out ? row_out * 8 : 0) + (use_par ? row_out * 4 : 0);
     const size_t q_bytes = up16(bmin ? 2 * row_out * 4 : (tokens_out ? (size_t)p->n_enc * 16 : 0));
-    const size_t extra = q_bytes + up16((size_t)p->n_enc * 4) + up16((size_t)4 * nb * 4) + up16((size_t)D * 4) + 16 + 4 * 16;
+    const size_t p_bytes = up16((size_t)2 * T * nb * 4);
+    // sums of one or two terms read every projector entry once per pass: no reuse to stage for (and the shipped shape
+    // keeps a third trajectory per tile instead); tables beyond 32 KB are read through L1 from the plan's global copy
+    const bool p_smem = p_bytes <= 32 * 1024 && p->enc_band_max > 2;
+    const size_t extra = q_bytes + up16((size_t)p->n_enc * 4) + up16((size_t)4 * nb * 4) + up16((size_t)D * 4) + 16 + 4 * 16 +
+                         (p_smem ? p_bytes : 0);
     size_t budget = 72 * 1024;                                // three CTAs per SM
     if (per_traj + extra > budget) budget = (size_t)p->max_smem_optin;
     if (per_traj + extra > budget) return BEAST_E_UNSUPPORTED;
@@ -334,19 +390,23 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
     a.band_off = a.list_off + (uint32_t)up16((size_t)p->n_enc * 4);
     a.dof_off = a.band_off + (uint32_t)up16((size_t)4 * nb * 4);
     a.bar_off = a.dof_off + (uint32_t)up16((size_t)D * 4);
-    const size_t smem = (size_t)a.bar_off + 16;
+    a.p_off = a.bar_off + 16;
+    a.p_smem = p_smem ? 1 : 0;
+    const size_t smem = (size_t)a.p_off + (p_smem ? p_bytes : 0);
     if (smem > (size_t)p->max_smem_optin) return BEAST_E_UNSUPPORTED;
     a.in_bulk = (((uintptr_t)traj & 15u) == 0 && ((size_t)S * row_in) % 4 == 0) ? 1 : 0;
     a.tok_bulk = (tokens_out && ((uintptr_t)tokens_out & 15u) == 0 && ((size_t)S * row_out) % 2 == 0) ? 1 : 0;
     a.par_bulk = (params_out && ((uintptr_t)params_out & 15u) == 0 && ((size_t)S * row_out) % 4 == 0) ? 1 : 0;
-    static size_t granted[kMaxDevices] = {};
-    if (int rc = opt_in_smem(encode_tiled_kernel, smem, granted)) return rc;
+    const bool wide = p->enc_band_max > 2;
+    static size_t granted1[kMaxDevices] = {}, granted4[kMaxDevices] = {};
+    if (int rc = wide ? opt_in_smem(encode_tiled_kernel<4>, smem, granted4) : opt_in_smem(encode_tiled_kernel<1>, smem, granted1)) return rc;
     const long long n_tiles = (B + S - 1) / S;
     long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
     if (per_sm > 2048 / kTiledThreads) per_sm = 2048 / kTiledThreads;
     if (per_sm < 1) per_sm = 1;
     long long grid = n_tiles < (long long)p->num_sms * per_sm ? n_tiles : (long long)p->num_sms * per_sm;
-    encode_tiled_kernel<<<(unsigned)grid, kTiledThreads, smem, st>>>(a);
+    if (wide) encode_tiled_kernel<4><<<(unsigned)grid, kTiledThreads, smem, st>>>(a);
+    else encode_tiled_kernel<1><<<(unsigned)grid, kTiledThreads, smem, st>>>(a);
     count_launch();
     BEAST_CHECK_LAUNCH();
     return BEAST_OK;
@@ -360,7 +420,9 @@ int launch_decode_tiled(const Plan* p, const long long* tokens, const float* par
     if (nb > 0xffff || T > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;
     const size_t row_in = (size_t)D * nb, row_out = (size_t)T * D;
     const size_t per_traj = row_in * sizeof(float);
-    const size_t extra = ((size_t)3 * p->n_dec + row_out + (size_t)4 * T + D) * sizeof(float) + 64;
+    const size_t phi_bytes = (size_t)2 * T * (nb | 1) * sizeof(float);
+    const bool phi_smem = phi_bytes <= 32 * 1024 && p->dec_band_max > 2;   // as in launch_encode_tiled
+    const size_t extra = ((size_t)3 * p->n_dec + row_out + (size_t)4 * T + D) * sizeof(float) + 64 + (phi_smem ? phi_bytes : 0);
     size_t budget = 72 * 1024;                                // three CTAs per SM (40 registers per thread)
     if (per_traj + extra > budget) budget = (size_t)p->max_smem_optin;
     if (per_traj + extra > budget) return BEAST_E_UNSUPPORTED;
@@ -377,6 +439,7 @@ int launch_decode_tiled(const Plan* p, const long long* tokens, const float* par
     a.w_min = w_min; a.w_max = w_max; a.vm1 = tokens ? (float)(p->V - 1) : 0.0f; a.offset = tokens ? offset : 0;
     a.init_p = init_p; a.out = out;
     a.S = S; a.G1 = groups_for(p->n_dec, S); a.G2 = groups_for((int)row_out, S);
+    a.phi_smem = phi_smem ? 1 : 0;
     const long long n_tiles = (B + S - 1) / S;
     long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
     if (per_sm > 2048 / kTiledThreads) per_sm = 2048 / kTiledThreads;

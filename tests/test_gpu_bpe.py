@@ -165,6 +165,37 @@ def test_fit_from_trajectories_and_files(tmp_path):
         tok3.set_bpe_tokenizer(object())
 
 
+def test_fit_from_trajectories_gathers_host_and_device_batches_in_order():
+    """Reference beast/beast_bpe_trainer.py:100-151 encodes the loader batch by batch; here small batches are gathered
+    (device batches in a device block, host batches beyond the first block in pinned blocks uploaded 4 096 rows at a
+    time).  The bins handed to the trainer must be the loader's trajectories in the loader's order, whatever mix of
+    host / device / float64 / oversized batches arrives."""
+    from beast_tokenizer_b200 import BEASTBsplineTokenizer, FIGBPE
+    from beast_tokenizer_b200.synth import synth
+    tok = BEASTBsplineTokenizer(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
+                                gripper_indices=[6, 13], device="cuda")
+    x = synth(13000, 50, 14, seed=21)
+    tok.update_weights_bounds(x)
+    want, _ = tok.encode(x)
+    cuts = list(range(0, 9600, 32)) + [9600, 9607, 9700, 9700 + 4096 + 5, 12000, 12033, 13000]
+    loader = []
+    for j, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        part = x[a:b]
+        if j % 7 == 3:
+            part = part.cuda()                         # a device batch in the middle of host batches
+        elif j % 11 == 5:
+            part = part.double()                       # converted on the way into the pinned block
+        loader.append({"actions": part} if j % 2 else part)
+    got = {}
+    fig = FIGBPE(vocab_size=300, show_progress=False, device="cuda", process_group=False)
+    fig.fit_from_bins = lambda bins: got.setdefault("bins", bins)
+    fig.fit_from_trajectories(tok, loader)
+    assert torch.equal(got["bins"], want)
+    got.clear()
+    fig.fit_from_trajectories(tok, loader, max_sequences=9000)
+    assert torch.equal(got["bins"], want[:9000])
+
+
 def test_bpe_errors():
     from beast_tokenizer_b200 import BEASTBsplineBPETokenizer
     g = load_golden("bpe_d14")
