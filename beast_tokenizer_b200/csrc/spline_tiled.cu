@@ -148,7 +148,9 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
         // the other buffer was last read before the barrier that ended the previous tile's compute phase
         if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);
         if (bulk_in(ns)) {
-            mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u);    // only a LAST tile can be loaded by hand: parity = use count
+            // one thread polls (511 spinning threads would take issue slots from the CTAs that are computing); the block
+            // barrier below orders everyone after its acquire.  Only a LAST tile can be loaded by hand: parity = use count
+            if (tid == 0) mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u);
         } else {
             const float* src = a.traj + b0 * row_in;
             for (int i = tid; i < ns * row_in; i += kTiledThreads) y[i] = __ldcs(src + i);
@@ -177,25 +179,32 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
                 if (want_tok) tok_s[(size_t)tr * row_out + r] = quantize_col(acc, qc, a.vm1) + a.offset;
                 mn = fminf(mn, acc); mx = fmaxf(mx, acc);
             };
-            // R trajectories per pass: one projector load feeds R sums (each sum keeps its own t-ascending order)
-            for (int tr = g; tr < ns; tr += R * a.G) {
-                const float* cp[R];
-                float acc[R];
-#pragma unroll
-                for (int u = 0; u < R; ++u) {
-                    const int tru = tr + u * a.G;
-                    cp[u] = col0 + (size_t)(tru < ns ? tru : ns - 1) * row_in;
-                    acc[u] = 0.0f;
+            if constexpr (R == 4) {
+                // four trajectories per pass: one projector load feeds four sums (each sum keeps its own t-ascending order)
+                for (int tr = g; tr < ns; tr += 4 * a.G) {
+                    const int tr1 = tr + a.G, tr2 = tr + 2 * a.G, tr3 = tr + 3 * a.G, last = ns - 1;
+                    const float* c0 = col0 + (size_t)tr * row_in;
+                    const float* c1 = col0 + (size_t)(tr1 < last ? tr1 : last) * row_in;
+                    const float* c2 = col0 + (size_t)(tr2 < last ? tr2 : last) * row_in;
+                    const float* c3 = col0 + (size_t)(tr3 < last ? tr3 : last) * row_in;
+                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                    for (int t = t0; t < t1; ++t) {
+                        const float pv = Pk[t * pst];
+                        const int o = t * D;
+                        a0 = fmaf(pv, c0[o], a0); a1 = fmaf(pv, c1[o], a1); a2 = fmaf(pv, c2[o], a2); a3 = fmaf(pv, c3[o], a3);
+                    }
+                    emit(tr, a0);
+                    if (tr1 < ns) emit(tr1, a1);
+                    if (tr2 < ns) emit(tr2, a2);
+                    if (tr3 < ns) emit(tr3, a3);
                 }
-                for (int t = t0; t < t1; ++t) {
-                    const float pv = a.p_smem ? Pk[t * pst] : __ldg(Pk + t);
-                    const int o = t * D;
-#pragma unroll
-                    for (int u = 0; u < R; ++u) acc[u] = fmaf(pv, cp[u][o], acc[u]);
+            } else {
+                for (int tr = g; tr < ns; tr += a.G) {
+                    const float* col = col0 + (size_t)tr * row_in;
+                    float acc = 0.0f;
+                    for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), col[t * D], acc);   // <1> never stages the projector
+                    emit(tr, acc);
                 }
-#pragma unroll
-                for (int u = 0; u < R; ++u)
-                    if (tr + u * a.G < ns) emit(tr + u * a.G, acc[u]);
             }
             if (want_mm && mn <= mx) { atomic_min_f32(&s_mn[c], mn); atomic_max_f32(&s_mx[c], mx); }
         }

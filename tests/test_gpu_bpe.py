@@ -174,10 +174,11 @@ def test_fit_from_trajectories_gathers_host_and_device_batches_in_order():
     from beast_tokenizer_b200.synth import synth
     tok = BEASTBsplineTokenizer(num_dof=14, num_basis=10, seq_len=50, vocab_size=256, gripper_zero_order=True,
                                 gripper_indices=[6, 13], device="cuda")
-    x = synth(13000, 50, 14, seed=21)
+    x = synth(15000, 50, 14, seed=21)
     tok.update_weights_bounds(x)
     want, _ = tok.encode(x)
-    cuts = list(range(0, 9600, 32)) + [9600, 9607, 9700, 9700 + 4096 + 5, 12000, 12033, 13000]
+    cuts = list(range(0, 9600, 32)) + [9600, 9607, 9700, 9700 + 4096 + 5, 14000, 14033, 15000]
+    assert cuts == sorted(cuts)
     loader = []
     for j, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
         part = x[a:b]
