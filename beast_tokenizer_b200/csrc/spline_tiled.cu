@@ -25,17 +25,6 @@ namespace beast {
 
 constexpr int kTiledThreads = 512;
 
-int launch_encode_tiled_v1(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
-                           long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
-                           cudaStream_t st);
-int launch_decode_tiled_v1(const Plan* p, const long long* tokens, const float* params, long long B, const float* w_min,
-                           const float* w_max, long long offset, const float* init_p, float* out, cudaStream_t st);
-static bool tiled_v1() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("BEAST_B200_TILED_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
 struct EncTiledArgs {
     const float* traj;
     long long B;
@@ -364,7 +353,6 @@ static inline int groups_for(int entries, int S) {
 int launch_encode_tiled(const Plan* p, const float* traj, long long B, const float* w_min, const float* w_max,
                         long long offset, float* params_out, long long* tokens_out, float* bmin, float* bmax,
                         cudaStream_t st) {
-    if (tiled_v1()) return launch_encode_tiled_v1(p, traj, B, w_min, w_max, offset, params_out, tokens_out, bmin, bmax, st);
     const int T = p->T, D = p->D, nb = p->nb;
     if (bmin && tokens_out) return BEAST_E_UNSUPPORTED;      // quantiser constants and min / max share one region
     if (nb > 0xffff || D > 0x7fff || p->V > 0x7fffffff || !p->bands_d || !p->enc_list_d) return BEAST_E_UNSUPPORTED;
@@ -423,7 +411,6 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
 
 int launch_decode_tiled(const Plan* p, const long long* tokens, const float* params, long long B, const float* w_min,
                         const float* w_max, long long offset, const float* init_p, float* out, cudaStream_t st) {
-    if (tiled_v1()) return launch_decode_tiled_v1(p, tokens, params, B, w_min, w_max, offset, init_p, out, st);
     const int T = p->T, D = p->D, nb = p->nb;
     if (p->nc != nb || !p->bands_d || !p->dec_list_d) return BEAST_E_UNSUPPORTED;   // pinned control points: generic kernel
     if (nb > 0xffff || T > 0xffff || D > 0x7fff) return BEAST_E_UNSUPPORTED;

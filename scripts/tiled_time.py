@@ -1,5 +1,5 @@
 """Time the tiled K1 / K3 (csrc/spline_tiled.cu) on several geometries through the C ABI on preallocated buffers and
-print a digest of the outputs (compare across processes: BEAST_B200_TILED_V1=1 selects the previous kernels)."""
+print a digest of the outputs (sha-1: compare across builds / processes; profiles/r02_tiled_kernels_timing.txt)."""
 import hashlib, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from beast_tokenizer_b200 import BEASTBsplineTokenizer, _lib
