@@ -52,7 +52,7 @@ struct EncTiledArgs {
 // R = trajectories per pass of a work item: 4 when the sums are long (one projector load then feeds four sums), 1 when
 // they have one or two terms (the shipped shape: nothing to share, and the compute phase sits on the tile's critical path)
 template <int R>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+__global__ void __launch_bounds__(kTiledThreads, 2)
 encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int T = a.T, D = a.D, nb = a.nb, S = a.S, n_enc = a.n_enc;
@@ -129,6 +129,9 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
     long long tile = blockIdx.x;
     if (tid == 0 && tile < n_tiles) issue(tile, 0);
     const int items = n_enc * a.G;
+    // work item j = tid + m * blockDim -> (trajectory group g, list entry i) = (j / n_enc, j % n_enc), tracked by increments:
+    // two divisions per tile instead of one per item
+    const int ne = n_enc > 0 ? n_enc : 1;
     for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
         const int buf = it & 1;
         float* const y = buf ? ybuf1 : ybuf0;
@@ -146,8 +149,10 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
         }
         if (tid == 0) bulk_wait_read<0>();                      // the previous tile's stores have read the staging rows
         __syncthreads();
-        for (int j = tid; j < items; j += kTiledThreads) {
-            const int g = j / n_enc, i = j - g * n_enc;
+        const int g_step = kTiledThreads / ne, i_step = kTiledThreads - g_step * n_enc;
+        int g = tid / ne, i = tid - g * n_enc;
+        for (int j = tid; j < items; j += kTiledThreads, g += g_step, i += i_step) {
+            if (i >= n_enc) { i -= n_enc; ++g; }
             const int e = lst[i];
             const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
             const bool grip = e < 0;
@@ -164,18 +169,18 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
             }
             float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
             auto emit = [&](int tr, float acc) {
-                if (use_par) par_s[(size_t)tr * row_out + c] = acc;
-                if (want_tok) tok_s[(size_t)tr * row_out + r] = quantize_col(acc, qc, a.vm1) + a.offset;
+                if (use_par) par_s[tr * row_out + c] = acc;
+                if (want_tok) tok_s[tr * row_out + r] = quantize_col(acc, qc, a.vm1) + a.offset;
                 mn = fminf(mn, acc); mx = fmaxf(mx, acc);
             };
             if constexpr (R == 4) {
                 // four trajectories per pass: one projector load feeds four sums (each sum keeps its own t-ascending order)
                 for (int tr = g; tr < ns; tr += 4 * a.G) {
                     const int tr1 = tr + a.G, tr2 = tr + 2 * a.G, tr3 = tr + 3 * a.G, last = ns - 1;
-                    const float* c0 = col0 + (size_t)tr * row_in;
-                    const float* c1 = col0 + (size_t)(tr1 < last ? tr1 : last) * row_in;
-                    const float* c2 = col0 + (size_t)(tr2 < last ? tr2 : last) * row_in;
-                    const float* c3 = col0 + (size_t)(tr3 < last ? tr3 : last) * row_in;
+                    const float* c0 = col0 + tr * row_in;
+                    const float* c1 = col0 + (tr1 < last ? tr1 : last) * row_in;
+                    const float* c2 = col0 + (tr2 < last ? tr2 : last) * row_in;
+                    const float* c3 = col0 + (tr3 < last ? tr3 : last) * row_in;
                     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
                     for (int t = t0; t < t1; ++t) {
                         const float pv = Pk[t * pst];
@@ -189,7 +194,7 @@ encode_tiled_kernel(const __grid_constant__ EncTiledArgs a) {
                 }
             } else {
                 for (int tr = g; tr < ns; tr += a.G) {
-                    const float* col = col0 + (size_t)tr * row_in;
+                    const float* col = col0 + tr * row_in;
                     float acc = 0.0f;
                     for (int t = t0; t < t1; ++t) acc = fmaf(__ldg(Pk + t), col[t * D], acc);   // <1> never stages the projector
                     emit(tr, acc);
@@ -248,8 +253,11 @@ struct DecTiledArgs {
 };
 
 // decode: tile of token rows (or coefficient rows) -> trajectories.
+// Two 512-thread CTAs per SM, 64 registers per thread: with three CTAs (40 registers) ptxas could not keep the four token
+// loads of a pass in flight together — it consumed the first before issuing the third — and the kernel waited on memory
+// latency (shipped shape 87 us against 51 us).
 template <bool FROM_TOKENS>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+__global__ void __launch_bounds__(kTiledThreads, 2)
 decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int T = a.T, D = a.D, nb = a.nb, S = a.S, n_dec = a.n_dec;
@@ -290,32 +298,67 @@ decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
     }
     const long long n_tiles = (a.B + S - 1) / S;
     const int items1 = n_dec * a.G1, items2 = row_out * a.G2;
+    // work item j = tid + m * blockDim -> (trajectory group, entry), tracked by increments inside a phase (two divisions
+    // per phase and tile instead of one per item; recomputed per phase so that they do not occupy registers across it)
+    const int nd = n_dec > 0 ? n_dec : 1;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * S;
         const int ns = (int)((a.B - b0) < S ? (a.B - b0) : S);
         __syncthreads();                                        // tables ready / previous tile's coefficients consumed
-        for (int j = tid; j < items1; j += kTiledThreads) {     // phase 1: the listed tokens -> coefficients
-            const int g = j / n_dec, i = j - g * n_dec;
+        // tile bases: everything below indexes them with 32-bit offsets (a tile is at most S * row < 2^20 elements)
+        const long long* tok_tile = FROM_TOKENS ? a.tokens + b0 * row_in : nullptr;
+        const float* par_tile = FROM_TOKENS ? nullptr : a.params + b0 * row_in;
+        const float* ip_tile = a.init_p ? a.init_p + b0 * D : nullptr;
+        float* out_tile = a.out + b0 * row_out;
+        const int g1_step = kTiledThreads / nd, i1_step = kTiledThreads - g1_step * n_dec;
+        int g = tid / nd, i = tid - g * n_dec;
+        for (int j = tid; j < items1; j += kTiledThreads, g += g1_step, i += i1_step) {     // phase 1: the listed tokens -> coefficients
+            if (i >= n_dec) { i -= n_dec; ++g; }
             const int e = lst[i];
             const int k = e & 0xffff, slot = (e >> 16) & 0x7fff;
             const int r = k * D + slot;
             float lo = 0.0f, hi = 0.0f;
             if (FROM_TOKENS) { lo = lohi[2 * i]; hi = lohi[2 * i + 1]; }
-            const bool pinned = k == 0 && a.init_p != nullptr && slot < a.n_joint;
-            const int dof = s_dof[slot];
             const int cpar = slot * nb + k;
-#pragma unroll 4
-            for (int tr = g; tr < ns; tr += a.G1) {
-                float v;
-                if (FROM_TOKENS) v = dequantize_fast(__ldcs(a.tokens + (b0 + tr) * row_in + r) - a.offset, lo, hi, a.vm1, rcp_vm1);
-                else v = a.params[(b0 + tr) * row_in + cpar];
-                if (pinned) v = a.init_p[(b0 + tr) * D + dof];
-                c_s[(size_t)tr * row_in + r] = v;
+            const int stride = a.G1 * row_in;
+            // four trajectories per pass, all four loads issued before the first store (the token pointer is a plain
+            // pointer: the compiler keeps a global load behind an earlier shared-memory store, which left ONE load in
+            // flight per thread)
+            for (int tr = g, off = g * row_in; tr < ns; tr += 4 * a.G1, off += 4 * stride) {
+                const int o1 = off + stride, o2 = o1 + stride, o3 = o2 + stride;
+                const bool h1 = tr + a.G1 < ns, h2 = tr + 2 * a.G1 < ns, h3 = tr + 3 * a.G1 < ns;
+                float v0, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+                if (FROM_TOKENS) {
+                    const long long q0 = __ldcs(tok_tile + off + r);
+                    const long long q1 = h1 ? __ldcs(tok_tile + o1 + r) : 0;
+                    const long long q2 = h2 ? __ldcs(tok_tile + o2 + r) : 0;
+                    const long long q3 = h3 ? __ldcs(tok_tile + o3 + r) : 0;
+                    v0 = dequantize_fast(q0 - a.offset, lo, hi, a.vm1, rcp_vm1);
+                    v1 = dequantize_fast(q1 - a.offset, lo, hi, a.vm1, rcp_vm1);
+                    v2 = dequantize_fast(q2 - a.offset, lo, hi, a.vm1, rcp_vm1);
+                    v3 = dequantize_fast(q3 - a.offset, lo, hi, a.vm1, rcp_vm1);
+                } else {
+                    v0 = par_tile[off + cpar];
+                    if (h1) v1 = par_tile[o1 + cpar];
+                    if (h2) v2 = par_tile[o2 + cpar];
+                    if (h3) v3 = par_tile[o3 + cpar];
+                }
+                c_s[off + r] = v0;
+                if (h1) c_s[o1 + r] = v1;
+                if (h2) c_s[o2 + r] = v2;
+                if (h3) c_s[o3 + r] = v3;
+            }
+            if (k == 0 && ip_tile != nullptr && slot < a.n_joint) {   // init_p pins the first joint coefficient: replaces it
+                const int dof = s_dof[slot];
+                for (int tr = g; tr < ns; tr += a.G1) c_s[tr * row_in + r] = ip_tile[tr * D + dof];
             }
         }
         __syncthreads();
-        for (int j = tid; j < items2; j += kTiledThreads) {     // phase 2: one output sample per thread, output order
-            const int g = j / row_out, q = j - g * row_out;
+        const int g2_step = kTiledThreads / row_out, q_step = kTiledThreads - g2_step * row_out;
+        int g2 = tid / row_out, q = tid - g2 * row_out;
+        for (int j = tid; j < items2; j += kTiledThreads, g2 += g2_step, q += q_step) {     // phase 2: one output sample per thread, output order
+            if (q >= row_out) { q -= row_out; ++g2; }
+            const int g = g2;
             const int e = tab_out[q];
             const int t = e & 0xffff, slot = (e >> 16) & 0x7fff;
             const bool grip = e < 0;
@@ -324,20 +367,20 @@ decode_tiled_kernel(const __grid_constant__ DecTiledArgs a) {
             // four trajectories per pass: one basis load feeds four sums (each keeps its own k-ascending order)
             for (int tr = g; tr < ns; tr += 4 * a.G2) {
                 const int tr1 = tr + a.G2, tr2 = tr + 2 * a.G2, tr3 = tr + 3 * a.G2, last = ns - 1;
-                const float* c0 = c_s + (size_t)tr * row_in + slot;
-                const float* c1 = c_s + (size_t)(tr1 < last ? tr1 : last) * row_in + slot;
-                const float* c2 = c_s + (size_t)(tr2 < last ? tr2 : last) * row_in + slot;
-                const float* c3 = c_s + (size_t)(tr3 < last ? tr3 : last) * row_in + slot;
+                const float* c0 = c_s + tr * row_in + slot;
+                const float* c1 = c_s + (tr1 < last ? tr1 : last) * row_in + slot;
+                const float* c2 = c_s + (tr2 < last ? tr2 : last) * row_in + slot;
+                const float* c3 = c_s + (tr3 < last ? tr3 : last) * row_in + slot;
                 float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
                 for (int k = k0; k < k1; ++k) {
                     const float pv = row[k];
-                    const size_t o = (size_t)k * D;
+                    const int o = k * D;
                     a0 = fmaf(pv, c0[o], a0); a1 = fmaf(pv, c1[o], a1); a2 = fmaf(pv, c2[o], a2); a3 = fmaf(pv, c3[o], a3);
                 }
-                __stcs(a.out + (b0 + tr) * row_out + q, a0);
-                if (tr1 < ns) __stcs(a.out + (b0 + tr1) * row_out + q, a1);
-                if (tr2 < ns) __stcs(a.out + (b0 + tr2) * row_out + q, a2);
-                if (tr3 < ns) __stcs(a.out + (b0 + tr3) * row_out + q, a3);
+                __stcs(out_tile + tr * row_out + q, a0);
+                if (tr1 < ns) __stcs(out_tile + tr1 * row_out + q, a1);
+                if (tr2 < ns) __stcs(out_tile + tr2 * row_out + q, a2);
+                if (tr3 < ns) __stcs(out_tile + tr3 * row_out + q, a3);
             }
         }
     }
@@ -366,7 +409,9 @@ int launch_encode_tiled(const Plan* p, const float* traj, long long B, const flo
     const bool p_smem = p_bytes <= 32 * 1024 && p->enc_band_max > 2;
     const size_t extra = q_bytes + up16((size_t)p->n_enc * 4) + up16((size_t)4 * nb * 4) + up16((size_t)D * 4) + 16 + 4 * 16 +
                          (p_smem ? p_bytes : 0);
-    size_t budget = 72 * 1024;                                // three CTAs per SM
+    // two CTAs per SM, 64 registers per thread (three CTAs at 40 registers measured 5 % slower on the shipped shape, 25 %
+    // on long sums: ptxas had no room to overlap the shared-memory loads of a pass)
+    size_t budget = 108 * 1024;
     if (per_traj + extra > budget) budget = (size_t)p->max_smem_optin;
     if (per_traj + extra > budget) return BEAST_E_UNSUPPORTED;
     int S = (int)((budget - extra) / per_traj);
@@ -419,7 +464,7 @@ int launch_decode_tiled(const Plan* p, const long long* tokens, const float* par
     const size_t phi_bytes = (size_t)2 * T * (nb | 1) * sizeof(float);
     const bool phi_smem = phi_bytes <= 32 * 1024 && p->dec_band_max > 2;   // as in launch_encode_tiled
     const size_t extra = ((size_t)3 * p->n_dec + row_out + (size_t)4 * T + D) * sizeof(float) + 64 + (phi_smem ? phi_bytes : 0);
-    size_t budget = 72 * 1024;                                // three CTAs per SM (40 registers per thread)
+    size_t budget = 108 * 1024;                               // two CTAs per SM
     if (per_traj + extra > budget) budget = (size_t)p->max_smem_optin;
     if (per_traj + extra > budget) return BEAST_E_UNSUPPORTED;
     int S = (int)((budget - extra) / per_traj);
