@@ -325,7 +325,9 @@ class BEASTBsplineTokenizer(TokenizerBase):
         sample_count = 0
         # The reference fits batch by batch; the coefficients of a trajectory do not depend on its position in a
         # batch, so small loader batches (32 in the reference's training script) are gathered on the device and
-        # fitted ~4 096 at a time: one K1 launch per chunk instead of one per batch.
+        # fitted ~4 096 at a time: one K1 launch per chunk instead of one per batch.  The gathered batches are READ at
+        # the flush (up to ~128 batches later): a loader must yield fresh tensors, as torch's DataLoader does, not one
+        # buffer it overwrites in place (FIGBPE.fit_from_trajectories copies every batch at once and has no such rule).
         dev = self._cuda()
         pending, pending_rows, pending_key = [], 0, None
         T, D, gatherable = self.times.numel(), self.num_dof, not self._has_conditions
