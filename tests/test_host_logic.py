@@ -241,7 +241,27 @@ def test_fit_parameters_gathers_small_batches():
     odd = [{"actions": torch.randn(32, 10, 5)}, {"actions": torch.randn(4, 7, 5)}, {"actions": torch.randn(8, 10, 5)}]
     tok.fit_parameters(odd, verbose=False)                       # an odd-shaped batch is passed through on its own
     assert calls == [(32, 10, 3), (4, 7, 3), (8, 10, 3)]
+    calls.clear()
+    tok.fit_parameters(batches, max_samples=0, verbose=False)    # the reference's loop fits one batch before it checks
+    assert calls == [(32, 10, 3)]
+    calls.clear()
+    grow = [{"actions": torch.randn(8, 10, 3)}] + [{"actions": torch.randn(3000, 10, 3)} for _ in range(9)]
+    tok.fit_parameters(grow, verbose=False)                      # later batches far larger than the first: bounded blocks
+    assert calls == [(6008, 10, 3), (6000, 10, 3), (6000, 10, 3), (6000, 10, 3), (3000, 10, 3)]
+    want_hi = torch.cat([b["actions"] for b in grow]).reshape(27008, -1)[:, :12].max(0).values
+    assert torch.equal(tok.w_max, want_hi)
+    calls.clear()
+    mixed = [{"actions": torch.randn(16, 10, 3)}, {"actions": torch.randn(16, 10, 3).double()},
+             {"actions": torch.randn(16, 10, 3).numpy()}]
+    tok.compute_weights = lambda x: fake_fit(torch.as_tensor(x))
+    tok.fit_parameters(mixed, verbose=False)                     # a numpy batch in the block: batch by batch, in order
+    assert calls == [(16, 10, 3)] * 3
+    calls.clear()
+    tok.fit_parameters(mixed[:2], verbose=False)                 # a change of dtype starts a new block
+    assert calls == [(16, 10, 3), (16, 10, 3)]
     with pytest.raises(KeyError):
         tok.fit_parameters([{"x": 1}], verbose=False)
+    with pytest.raises(KeyError):
+        tok.fit_parameters(batches[:3] + [{"x": 1}], verbose=False)
     with pytest.raises(RuntimeError):
         tok.fit_parameters([], verbose=False)
