@@ -6,7 +6,7 @@ beast/beast_bspline_tokenizer.py:362-378) and the exact quantile needs every ran
 (fit_parameters, :181-220).  A process group is "world" (the default group), a ProcessGroup, or False / None =
 local: the tokenizer opts in through set_process_group, it never communicates implicitly.
 """
-from typing import List, Optional
+from typing import List
 
 import torch
 

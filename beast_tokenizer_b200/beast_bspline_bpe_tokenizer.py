@@ -17,7 +17,6 @@ from typing import Iterable, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from . import _lib
 from .beast_bspline_tokenizer import CONFIG_FILENAME, BEASTBsplineTokenizer
 from .bpe_model import B200ByteLevelBPE
 

@@ -5,7 +5,6 @@ Stands in for HF `tokenizers.ByteLevelBPETokenizer` as used by the reference
 vocab.json / merges.txt / tokenizer.json files, same ids.  Applying the model (ids <-> bins) runs
 on the GPU through libbeast_b200.so (bpe_encode / bpe_decode); there is no host implementation.
 """
-import ctypes as C
 import json
 import os
 from typing import Dict, List, Optional, Sequence, Tuple

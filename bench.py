@@ -20,7 +20,6 @@ trajectories.  One step = encode (K1) of one batch + reconstruct_traj (K3) of on
 """
 import argparse
 import json
-import math
 import os
 import sys
 import threading
