@@ -265,3 +265,53 @@ def test_fit_parameters_gathers_small_batches():
         tok.fit_parameters(batches[:3] + [{"x": 1}], verbose=False)
     with pytest.raises(RuntimeError):
         tok.fit_parameters([], verbose=False)
+
+
+def test_tiled_kernel_work_lists_are_exact_shortcuts():
+    """The tiled kernels (csrc/spline_tiled.cu, lists built by csrc/plan.cu) recompute only the token positions whose
+    projector row is not empty and load only the tokens whose coefficient some basis row reads.  Restated on the host
+    tables: (a) band sums equal full sums bit for bit (the skipped terms are exact zeros, t / k ascending FMA order),
+    (b) an empty projector row gives coefficient +0.0 for any trajectory, (c) a coefficient outside every basis band
+    cannot change a trajectory sample.  Geometries: the reference's shipped shape (train.sh) and a cubic one."""
+    from beast_tokenizer_b200.basis import build_constants, make_times
+    rng = np.random.default_rng(3)
+    for T, nb, deg in ((10, 50, 0), (33, 8, 3), (64, 20, 2)):
+        c = build_constants(make_times(2 * math.pi, T), 2 * math.pi, nb, deg, list(range(3)), [])
+        P, Phi = c.proj_joint.numpy(), c.phi_joint.numpy()          # [nb, T], [T, nb]
+        assert P.dtype == np.float32 and Phi.dtype == np.float32
+
+        def band(row):
+            nz = np.nonzero(row)[0]
+            return (0, 0) if nz.size == 0 else (int(nz[0]), int(nz[-1]) + 1)
+
+        def fma_sum(coef, vals, lo, hi):                            # fp32 FMA chain, ascending index
+            acc = np.float32(0.0)
+            for i in range(lo, hi):
+                acc = np.float32(np.float64(coef[i]) * np.float64(vals[i]) + np.float64(acc))   # one rounding: an FMA
+            return acc
+
+        y = rng.standard_normal(T).astype(np.float32)
+        w = rng.standard_normal(nb).astype(np.float32)
+        used = np.zeros(nb, bool)
+        for t in range(T):
+            lo, hi = band(Phi[t])
+            used[lo:hi] = True
+            assert fma_sum(Phi[t], w, lo, hi).tobytes() == fma_sum(Phi[t], w, 0, nb).tobytes()
+        n_empty = 0
+        for k in range(nb):
+            lo, hi = band(P[k])
+            full = fma_sum(P[k], y, 0, T)
+            assert fma_sum(P[k], y, lo, hi).tobytes() == full.tobytes()
+            if lo == hi:
+                n_empty += 1
+                assert full.tobytes() == np.float32(0.0).tobytes()   # +0.0: the token is a per-column constant
+        # (c): garbage in the coefficients no basis row reads leaves every sample unchanged
+        w2 = w.copy()
+        w2[~used] = 1e30
+        for t in range(T):
+            lo, hi = band(Phi[t])
+            assert fma_sum(Phi[t], w2, lo, hi).tobytes() == fma_sum(Phi[t], w, lo, hi).tobytes()
+        if (T, nb, deg) == (10, 50, 0):
+            assert n_empty == 40 and int(used.sum()) == 10           # one token in five is recomputed / loaded
+        else:
+            assert n_empty == 0 and used.all()
